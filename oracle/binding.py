@@ -1,0 +1,305 @@
+"""ctypes binding of oracle/libczk_oracle.so.  TEST INFRASTRUCTURE ONLY.
+
+Allowed importers: tests/, __graft_entry__.smoke(), bench.py's cpu_baseline and
+`--impl reference` legs.  The product package never imports this.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = None
+
+u64p = C.POINTER(C.c_uint64)
+u8p = C.POINTER(C.c_uint8)
+
+
+def build(force: bool = False) -> Path:
+    so = _HERE / "libczk_oracle.so"
+    srcs = [_HERE / n for n in ("czk_oracle.c", "czk_oracle_groth16.inc", "fp_tmpl.h", "ec_tmpl.h", "Makefile")]
+    if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
+        subprocess.run(["make", "-C", str(_HERE), "-s"], check=True)
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = _HERE / "libczk_oracle.so"
+        if not so.exists():
+            build()
+        _LIB = C.CDLL(str(so))
+        _LIB.orc_init()
+    return _LIB
+
+
+def _p(a: np.ndarray):
+    assert a.dtype == np.uint64 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(u64p)
+
+
+def _p8(a):
+    if a is None:
+        return None
+    assert a.dtype == np.uint8 and a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(u8p)
+
+
+def cpu_threads() -> int:
+    return len(os.sched_getaffinity(0))
+
+
+# ---------------------------------------------------------------- int <-> limb arrays
+def ints_to_limbs(vals, nl: int) -> np.ndarray:
+    out = np.zeros((len(vals), nl), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        for j in range(nl):
+            out[i, j] = (v >> (64 * j)) & 0xFFFFFFFFFFFFFFFF
+    return out
+
+
+def limbs_to_ints(arr: np.ndarray):
+    arr = np.asarray(arr, dtype=np.uint64)
+    if arr.ndim == 1:
+        arr = arr[None, :]
+    return [sum(int(x) << (64 * j) for j, x in enumerate(row)) for row in arr]
+
+
+# ---------------------------------------------------------------- fields
+def _binop(name, nl):
+    def f(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, nl)
+        b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, nl)
+        r = np.empty_like(a)
+        getattr(lib(), name)(_p(r), _p(a), _p(b), C.c_size_t(a.shape[0]))
+        return r
+
+    return f
+
+
+def _unop(name, nl):
+    def f(a: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, nl)
+        r = np.empty_like(a)
+        getattr(lib(), name)(_p(r), _p(a), C.c_size_t(a.shape[0]))
+        return r
+
+    return f
+
+
+fr_mul = _binop("orc_fr_mul", 4)
+fr_add = _binop("orc_fr_add", 4)
+fr_sub = _binop("orc_fr_sub", 4)
+fr_neg = _unop("orc_fr_neg", 4)
+fr_inv = _unop("orc_fr_inv", 4)
+fr_from_repr = _unop("orc_fr_from_repr", 4)
+fr_into_repr = _unop("orc_fr_into_repr", 4)
+fq_mul = _binop("orc_fq_mul", 6)
+fq_add = _binop("orc_fq_add", 6)
+fq_sub = _binop("orc_fq_sub", 6)
+fq_inv = _unop("orc_fq_inv", 6)
+fq_from_repr = _unop("orc_fq_from_repr", 6)
+fq_into_repr = _unop("orc_fq_into_repr", 6)
+fq2_mul = _binop("orc_fq2_mul", 12)
+fq2_sqr = _unop("orc_fq2_sqr", 12)
+fq2_inv = _unop("orc_fq2_inv", 12)
+
+
+def fr_from_ints(vals) -> np.ndarray:
+    """canonical ints -> Montgomery limb array (n,4)."""
+    return fr_from_repr(ints_to_limbs([v for v in vals], 4))
+
+
+def fr_to_ints(arr) -> list:
+    return limbs_to_ints(fr_into_repr(arr))
+
+
+def fq_from_ints(vals) -> np.ndarray:
+    return fq_from_repr(ints_to_limbs(vals, 6))
+
+
+def fq_to_ints(arr) -> list:
+    return limbs_to_ints(fq_into_repr(arr))
+
+
+def params():
+    frR = np.zeros(4, np.uint64)
+    frR2 = np.zeros(4, np.uint64)
+    fqR = np.zeros(6, np.uint64)
+    fqR2 = np.zeros(6, np.uint64)
+    fri = C.c_uint64()
+    fqi = C.c_uint64()
+    lib().orc_params(_p(frR), _p(frR2), C.byref(fri), _p(fqR), _p(fqR2), C.byref(fqi))
+    return dict(fr_R=limbs_to_ints(frR)[0], fr_R2=limbs_to_ints(frR2)[0], fr_INV=fri.value,
+                fq_R=limbs_to_ints(fqR)[0], fq_R2=limbs_to_ints(fqR2)[0], fq_INV=fqi.value)
+
+
+# ---------------------------------------------------------------- groups
+class Group:
+    """g = 'g1' (12 words per affine point) or 'g2' (24 words)."""
+
+    def __init__(self, g: str):
+        self.g = g
+        self.w = 12 if g == "g1" else 24
+
+    def affine_from_ints(self, pts) -> tuple:
+        """pts: list of None | (x, y) with ints (G1) or ((x0,x1),(y0,y1)) (G2). -> (xy[n,w], inf[n])"""
+        n = len(pts)
+        flat = []
+        inf = np.zeros(n, np.uint8)
+        for i, p in enumerate(pts):
+            if p is None:
+                inf[i] = 1
+                flat += [0, 1] if self.g == "g1" else [0, 0, 1, 0]
+            elif self.g == "g1":
+                flat += [p[0], p[1]]
+            else:
+                flat += [p[0][0], p[0][1], p[1][0], p[1][1]]
+        xy = fq_from_ints(flat).reshape(n, self.w)
+        return xy, inf
+
+    def affine_to_ints(self, xy, inf=None):
+        xy = np.ascontiguousarray(xy, dtype=np.uint64).reshape(-1, self.w)
+        vals = fq_to_ints(xy.reshape(-1, 6))
+        per = self.w // 6
+        out = []
+        for i in range(xy.shape[0]):
+            if inf is not None and inf[i]:
+                out.append(None)
+            elif self.g == "g1":
+                out.append((vals[2 * i], vals[2 * i + 1]))
+            else:
+                v = vals[per * i: per * i + per]
+                out.append(((v[0], v[1]), (v[2], v[3])))
+        return out
+
+    def scalar_mul(self, base_xy, scalar_mont, base_inf=0):
+        out = np.zeros(self.w, np.uint64)
+        inf = getattr(lib(), f"orc_{self.g}_scalar_mul")(_p(out), _p(np.ascontiguousarray(base_xy, np.uint64)),
+                                                         C.c_int(int(base_inf)), _p(np.ascontiguousarray(scalar_mont, np.uint64)))
+        return out, inf
+
+    def msm(self, bases_xy, inf, scalars, montgomery=True, threads=1):
+        bases_xy = np.ascontiguousarray(bases_xy, np.uint64).reshape(-1, self.w)
+        scalars = np.ascontiguousarray(scalars, np.uint64).reshape(-1, 4)
+        n = min(bases_xy.shape[0], scalars.shape[0])
+        out = np.zeros(self.w, np.uint64)
+        r = getattr(lib(), f"orc_{self.g}_msm")(_p(out), _p(bases_xy), _p8(inf), _p(scalars), C.c_int(int(montgomery)),
+                                                C.c_size_t(n), C.c_int(threads))
+        return out, r
+
+    def msm_naive(self, bases_xy, inf, scalars_mont):
+        bases_xy = np.ascontiguousarray(bases_xy, np.uint64).reshape(-1, self.w)
+        scalars_mont = np.ascontiguousarray(scalars_mont, np.uint64).reshape(-1, 4)
+        n = min(bases_xy.shape[0], scalars_mont.shape[0])
+        out = np.zeros(self.w, np.uint64)
+        r = getattr(lib(), f"orc_{self.g}_msm_naive")(_p(out), _p(bases_xy), _p8(inf), _p(scalars_mont), C.c_size_t(n))
+        return out, r
+
+    def gen_progression(self, base_xy, k0_mont, kstep_mont, n, threads=1):
+        out = np.zeros((n, self.w), np.uint64)
+        getattr(lib(), f"orc_{self.g}_gen_progression")(_p(out), _p(np.ascontiguousarray(base_xy, np.uint64)),
+                                                        _p(np.ascontiguousarray(k0_mont, np.uint64)),
+                                                        _p(np.ascontiguousarray(kstep_mont, np.uint64)), C.c_size_t(n), C.c_int(threads))
+        return out
+
+
+G1 = Group("g1")
+G2 = Group("g2")
+
+
+# ---------------------------------------------------------------- NTT
+def ntt(data: np.ndarray, inverse=False, coset=False, threads=1) -> np.ndarray:
+    """data: (2^k, 4) Montgomery Fr.  Returns a transformed copy."""
+    a = np.array(data, dtype=np.uint64, order="C").reshape(-1, 4)
+    n = a.shape[0]
+    log_d = n.bit_length() - 1
+    assert 1 << log_d == n
+    ok = lib().orc_ntt(_p(a), C.c_uint(log_d), C.c_int(int(inverse)), C.c_int(int(coset)), C.c_int(threads))
+    assert ok
+    return a
+
+
+def serial_radix2_fft(data: np.ndarray, inverse=False) -> np.ndarray:
+    a = np.array(data, dtype=np.uint64, order="C").reshape(-1, 4)
+    n = a.shape[0]
+    log_n = n.bit_length() - 1
+    assert lib().orc_serial_radix2_fft(_p(a), C.c_uint(log_n), C.c_int(int(inverse)))
+    return a
+
+
+def poly_eval(coeffs: np.ndarray, x_mont: np.ndarray) -> np.ndarray:
+    coeffs = np.ascontiguousarray(coeffs, np.uint64).reshape(-1, 4)
+    out = np.zeros(4, np.uint64)
+    lib().orc_poly_eval(_p(out), _p(coeffs), C.c_size_t(coeffs.shape[0]), _p(np.ascontiguousarray(x_mont, np.uint64)))
+    return out
+
+
+def fr_pow_u64(a_mont, e: int) -> np.ndarray:
+    out = np.zeros(4, np.uint64)
+    lib().orc_fr_pow_u64(_p(out), _p(np.ascontiguousarray(a_mont, np.uint64)), C.c_uint64(e))
+    return out
+
+
+def domain_params(num_coeffs: int):
+    size = C.c_uint64()
+    gg = np.zeros(4, np.uint64)
+    ggi = np.zeros(4, np.uint64)
+    si = np.zeros(4, np.uint64)
+    gi = np.zeros(4, np.uint64)
+    ok = lib().orc_domain_params(C.c_size_t(num_coeffs), C.byref(size), _p(gg), _p(ggi), _p(si), _p(gi))
+    assert ok
+    return dict(size=size.value, group_gen=gg, group_gen_inv=ggi, size_inv=si, generator_inv=gi)
+
+
+def divide_by_vanishing_on_coset(data: np.ndarray, threads=1) -> np.ndarray:
+    a = np.array(data, dtype=np.uint64, order="C").reshape(-1, 4)
+    log_d = a.shape[0].bit_length() - 1
+    assert lib().orc_divide_by_vanishing_on_coset(_p(a), C.c_uint(log_d), C.c_int(threads))
+    return a
+
+
+# ---------------------------------------------------------------- seeded inputs (SplitMix64 rejection sampling)
+def splitmix64(seed: int, n: int) -> np.ndarray:
+    out = np.empty(n, dtype=np.uint64)
+    x = seed & 0xFFFFFFFFFFFFFFFF
+    M = 0xFFFFFFFFFFFFFFFF
+    for i in range(n):
+        x = (x + 0x9E3779B97F4A7C15) & M
+        z = x
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & M
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & M
+        out[i] = z ^ (z >> 31)
+    return out
+
+
+def random_fr_canonical(seed: int, n: int) -> np.ndarray:
+    """n uniform values in [0, r) as canonical limb array (n,4): vectorised rejection sampling."""
+    from . import pymodel
+
+    rng = np.random.Generator(np.random.PCG64(seed))
+    mod_limbs = ints_to_limbs([pymodel.R_MOD], 4)[0]
+    out = np.zeros((n, 4), dtype=np.uint64)
+    need = np.arange(n)
+    while need.size:
+        cand = rng.integers(0, 1 << 64, size=(need.size, 4), dtype=np.uint64)
+        cand[:, 3] &= np.uint64((1 << 61) - 1)  # 253-bit candidates
+        lt = np.zeros(need.size, dtype=bool)
+        decided = np.zeros(need.size, dtype=bool)
+        for j in (3, 2, 1, 0):
+            less = (cand[:, j] < mod_limbs[j]) & ~decided
+            greater = (cand[:, j] > mod_limbs[j]) & ~decided
+            lt |= less
+            decided |= less | greater
+        out[need[lt]] = cand[lt]
+        need = need[~lt]
+    return out
+
+
+def random_fr_mont(seed: int, n: int) -> np.ndarray:
+    return fr_from_repr(random_fr_canonical(seed, n))

@@ -1,0 +1,332 @@
+"""Python big-int model of the BLS12-377 hot path.  TEST INFRASTRUCTURE ONLY.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg may import
+this module.  It is an *independent* second model (textbook affine arithmetic
+on Python ints, O(n^2) DFT by direct evaluation) used to pin the C restatement
+in oracle/czk_oracle.c, which is the line-by-line one.
+
+What it models, and where the reference defines it (paths relative to
+/root/reference):
+  * Fr / Fq / Fq2 values                curves/bls12_377/src/fields/{fr,fq,fq2}.rs
+  * Montgomery representation           algebra/ff/src/fields/macros.rs:444-454 (from_repr),
+                                        algebra/ff/src/fields/arithmetic.rs:59-82 (into_repr)
+  * root of unity for a radix-2 domain  algebra/ff/src/fields/mod.rs:337-386 (large-subgroup branch)
+  * domain constants                    algebra/poly/src/domain/radix2/mod.rs:51-82
+  * FFT semantics out[i] = p(w^i)       algebra/poly/src/domain/radix2/mod.rs:320-360 (the reference's own test)
+  * coset FFT = distribute_powers(g)    algebra/poly/src/domain/mod.rs:139-142, g = 22
+  * short-Weierstrass group law         algebra/ec/src/models/short_weierstrass_jacobian.rs (affine meaning)
+  * MSM meaning sum s_i P_i             algebra/test-templates/src/msm.rs:16-33 (naive reference)
+"""
+from __future__ import annotations
+
+# ----------------------------------------------------------------------------
+# moduli (decimal; re-checked against the golden JSON in tests)
+R_MOD = 8444461749428370424248824938781546531375899335154063827935233455917409239041
+Q_MOD = 258664426012969094010652733694893533536393512754914660539884262666720468348340822774968888139573360124440321458177
+
+FR_LIMBS = 4
+FQ_LIMBS = 6
+FR_R = pow(2, 256, R_MOD)
+FQ_R = pow(2, 384, Q_MOD)
+FR_RINV = pow(FR_R, -1, R_MOD)
+FQ_RINV = pow(FQ_R, -1, Q_MOD)
+
+FR_TWO_ADICITY = 47
+FR_GENERATOR = 22  # multiplicative generator == coset shift
+FR_SMALL_SUBGROUP_BASE = 3
+FR_SMALL_SUBGROUP_BASE_ADICITY = 1
+# LARGE_SUBGROUP_ROOT_OF_UNITY = 11^((r-1)/(3*2^47))   (decoded from fr.rs:23-28)
+FR_LARGE_SUBGROUP_ROOT = pow(11, (R_MOD - 1) // (3 * 2**47), R_MOD)
+FR_TWO_ADIC_ROOT = pow(22, (R_MOD - 1) // 2**47, R_MOD)
+
+FQ2_NONRESIDUE = Q_MOD - 5
+G1_B = 1
+G1_GEN = (
+    81937999373150964239938255573465948239988671502647976594219695644855304257327692006745978603320413799295628339695,
+    241266749859715473739788878240585681733927191168601896383759122102112907357779751001206799952863815012735208165030,
+)
+G2_B = (0, 155198655607781456406391640216936120121836107652948796323930557600032281009004493664981332883744016074664192874906)
+G2_GEN = (
+    (233578398248691099356572568220835526895379068987715365179118596935057653620464273615301663571204657964920925606294,
+     140913150380207355837477652521042157274541796891053068589147167627541651775299824604154852141315666357241556069118),
+    (63160294768292073209381361943935198908131692476676907196754037919244929611450776219210369229519898517858833747423,
+     149157405641012693445398062341192467754805999074082136895788947234480009303640899064710353187729182149407503257491),
+)
+
+
+# ----------------------------------------------------------------------------
+# Montgomery helpers
+def fr_to_mont(x: int) -> int:
+    return x * FR_R % R_MOD
+
+
+def fr_from_mont(x: int) -> int:
+    return x * FR_RINV % R_MOD
+
+
+def fq_to_mont(x: int) -> int:
+    return x * FQ_R % Q_MOD
+
+
+def fq_from_mont(x: int) -> int:
+    return x * FQ_RINV % Q_MOD
+
+
+def to_limbs(x: int, n: int):
+    return [(x >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(n)]
+
+
+def from_limbs(limbs) -> int:
+    return sum(int(l) << (64 * i) for i, l in enumerate(limbs))
+
+
+# ----------------------------------------------------------------------------
+# radix-2 domain (algebra/poly/src/domain/radix2/mod.rs:51-82)
+def k_adicity(k: int, n: int) -> int:
+    r = 0
+    while n > 1:
+        if n % k == 0:
+            r += 1
+            n //= k
+        else:
+            return r
+    return r
+
+
+def fr_root_of_unity(n: int) -> int:
+    """get_root_of_unity(n), large-subgroup branch (ff/src/fields/mod.rs:339-367)."""
+    q = FR_SMALL_SUBGROUP_BASE
+    q_adicity = k_adicity(q, n)
+    q_part = q**q_adicity
+    two_adicity = k_adicity(2, n)
+    two_part = 1 << two_adicity
+    if n != two_part * q_part or two_adicity > FR_TWO_ADICITY or q_adicity > FR_SMALL_SUBGROUP_BASE_ADICITY:
+        raise ValueError("no root of unity of that order")
+    omega = FR_LARGE_SUBGROUP_ROOT
+    for _ in range(q_adicity, FR_SMALL_SUBGROUP_BASE_ADICITY):
+        omega = pow(omega, q, R_MOD)
+    for _ in range(two_adicity, FR_TWO_ADICITY):
+        omega = omega * omega % R_MOD
+    return omega
+
+
+class Domain:
+    def __init__(self, num_coeffs: int):
+        size = 1
+        while size < num_coeffs:
+            size *= 2
+        self.size = size
+        self.log_size = size.bit_length() - 1
+        self.group_gen = fr_root_of_unity(size)
+        self.group_gen_inv = pow(self.group_gen, -1, R_MOD)
+        self.size_inv = pow(size, -1, R_MOD)
+        self.generator_inv = pow(FR_GENERATOR, -1, R_MOD)
+
+    def vanishing_at(self, tau: int) -> int:
+        return (pow(tau, self.size, R_MOD) - 1) % R_MOD
+
+
+def _fast_dft(a, w, p):
+    """Recursive radix-2 DFT on Python ints: out[i] = sum a[j] w^(ij)."""
+    n = len(a)
+    if n == 1:
+        return list(a)
+    w2 = w * w % p
+    ev = _fast_dft(a[0::2], w2, p)
+    od = _fast_dft(a[1::2], w2, p)
+    out = [0] * n
+    t = 1
+    h = n // 2
+    for i in range(h):
+        x = t * od[i] % p
+        out[i] = (ev[i] + x) % p
+        out[i + h] = (ev[i] - x) % p
+        t = t * w % p
+    return out
+
+
+def ntt(values, inverse=False, coset=False, slow=False):
+    """The four reference transforms on canonical ints, natural order in and out.
+
+    fft:        out[i] = p(w^i)                                 (radix2/mod.rs:99-103)
+    coset fft:  out[i] = p(g w^i)                               (domain/mod.rs:139-142)
+    ifft:       inverse of fft                                  (radix2/fft.rs:26-29)
+    coset ifft: ifft then coefficient i times g^-i              (radix2/fft.rs:31-35)
+    Input shorter than the domain is zero padded (radix2/mod.rs:100-101).
+    """
+    d = Domain(max(len(values), 1))
+    a = [v % R_MOD for v in values] + [0] * (d.size - len(values))
+    n = d.size
+    if not inverse:
+        if coset:
+            gp = 1
+            for i in range(n):
+                a[i] = a[i] * gp % R_MOD
+                gp = gp * FR_GENERATOR % R_MOD
+        if slow:
+            return [sum(a[j] * pow(d.group_gen, i * j, R_MOD) for j in range(n)) % R_MOD for i in range(n)]
+        return _fast_dft(a, d.group_gen, R_MOD)
+    if slow:
+        out = [sum(a[j] * pow(d.group_gen_inv, i * j, R_MOD) for j in range(n)) % R_MOD for i in range(n)]
+    else:
+        out = _fast_dft(a, d.group_gen_inv, R_MOD)
+    out = [x * d.size_inv % R_MOD for x in out]
+    if coset:
+        gp = 1
+        for i in range(n):
+            out[i] = out[i] * gp % R_MOD
+            gp = gp * d.generator_inv % R_MOD
+    return out
+
+
+# ----------------------------------------------------------------------------
+# Fq2 = Fq[u]/(u^2 + 5)
+def fq2_add(a, b):
+    return ((a[0] + b[0]) % Q_MOD, (a[1] + b[1]) % Q_MOD)
+
+
+def fq2_sub(a, b):
+    return ((a[0] - b[0]) % Q_MOD, (a[1] - b[1]) % Q_MOD)
+
+
+def fq2_mul(a, b):
+    return ((a[0] * b[0] + FQ2_NONRESIDUE * a[1] * b[1]) % Q_MOD, (a[0] * b[1] + a[1] * b[0]) % Q_MOD)
+
+
+def fq2_inv(a):
+    # 1/(c0 + c1 u) = (c0 - c1 u)/(c0^2 - beta c1^2)
+    norm = (a[0] * a[0] - FQ2_NONRESIDUE * a[1] * a[1]) % Q_MOD
+    ni = pow(norm, -1, Q_MOD)
+    return (a[0] * ni % Q_MOD, (-a[1]) * ni % Q_MOD)
+
+
+class _F1:
+    zero = 0
+    one = 1
+    add = staticmethod(lambda a, b: (a + b) % Q_MOD)
+    sub = staticmethod(lambda a, b: (a - b) % Q_MOD)
+    mul = staticmethod(lambda a, b: a * b % Q_MOD)
+    inv = staticmethod(lambda a: pow(a, -1, Q_MOD))
+    neg = staticmethod(lambda a: (-a) % Q_MOD)
+    b = G1_B
+
+
+class _F2:
+    zero = (0, 0)
+    one = (1, 0)
+    add = staticmethod(fq2_add)
+    sub = staticmethod(fq2_sub)
+    mul = staticmethod(fq2_mul)
+    inv = staticmethod(fq2_inv)
+    neg = staticmethod(lambda a: ((-a[0]) % Q_MOD, (-a[1]) % Q_MOD))
+    b = G2_B
+
+
+# affine points: None == infinity, else (x, y)
+def _on_curve(F, P):
+    if P is None:
+        return True
+    x, y = P
+    return F.mul(y, y) == F.add(F.mul(F.mul(x, x), x), F.b)
+
+
+def _add(F, P, Q):
+    if P is None:
+        return Q
+    if Q is None:
+        return P
+    x1, y1 = P
+    x2, y2 = Q
+    if x1 == x2:
+        if y1 != y2 or y1 == F.zero:
+            return None
+        xx = F.mul(x1, x1)
+        lam = F.mul(F.add(F.add(xx, xx), xx), F.inv(F.add(y1, y1)))
+    else:
+        lam = F.mul(F.sub(y2, y1), F.inv(F.sub(x2, x1)))
+    x3 = F.sub(F.sub(F.mul(lam, lam), x1), x2)
+    y3 = F.sub(F.mul(lam, F.sub(x1, x3)), y1)
+    return (x3, y3)
+
+
+def _neg(F, P):
+    return None if P is None else (P[0], F.neg(P[1]))
+
+
+def _mul(F, P, k: int):
+    k %= R_MOD
+    acc = None
+    while k:
+        if k & 1:
+            acc = _add(F, acc, P)
+        P = _add(F, P, P)
+        k >>= 1
+    return acc
+
+
+def g1_on_curve(P):
+    return _on_curve(_F1, P)
+
+
+def g1_add(P, Q):
+    return _add(_F1, P, Q)
+
+
+def g1_neg(P):
+    return _neg(_F1, P)
+
+
+def g1_mul(P, k):
+    return _mul(_F1, P, k)
+
+
+def g2_on_curve(P):
+    return _on_curve(_F2, P)
+
+
+def g2_add(P, Q):
+    return _add(_F2, P, Q)
+
+
+def g2_neg(P):
+    return _neg(_F2, P)
+
+
+def g2_mul(P, k):
+    return _mul(_F2, P, k)
+
+
+def g1_msm_naive(bases, scalars):
+    """sum s_i P_i on affine points (algebra/test-templates/src/msm.rs:6-14)."""
+    acc = None
+    for P, s in zip(bases, scalars):
+        acc = g1_add(acc, g1_mul(P, s))
+    return acc
+
+
+def g2_msm_naive(bases, scalars):
+    acc = None
+    for P, s in zip(bases, scalars):
+        acc = g2_add(acc, g2_mul(P, s))
+    return acc
+
+
+# ----------------------------------------------------------------------------
+# reference window heuristic (ec/src/msm/variable_base.rs:21-25, msm/mod.rs:10-13, utils/src/lib.rs:65-73)
+def ark_log2(x: int) -> int:
+    if x == 0:
+        return 0
+    if x & (x - 1) == 0:
+        return x.bit_length() - 1
+    return x.bit_length()
+
+
+def ref_window(size: int) -> int:
+    return 3 if size < 32 else ark_log2(size) * 69 // 100 + 2
+
+
+def ref_msm_adds(n: int) -> int:
+    """The metric normaliser of SURVEY.md section 8(d): N*W + 2(2^c-1)W + 253."""
+    c = ref_window(n)
+    w = (253 + c - 1) // c
+    return n * w + 2 * ((1 << c) - 1) * w + 253
