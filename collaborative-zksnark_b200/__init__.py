@@ -1,0 +1,19 @@
+"""czk_b200 - B200-native hot path of collaborative-zksnark (MSM, NTT, share opening / Beaver
+multiplication, Groth16 prover loop) behind a C ABI (include/czk.h).
+
+This package is the Python host-side mirror used by the tests and the benchmark; the product is
+libczk_b200.so.  There is no CPU fallback: creating a Context without a CUDA device raises.
+"""
+from .binding import (  # noqa: F401
+    CzkError,
+    Context,
+    DeviceVec,
+    Bases,
+    load_library,
+    library_path,
+    domain_params,
+    SCHEME_PLAIN,
+    SCHEME_ADDITIVE,
+    SCHEME_SPDZ,
+)
+from .build import build as build_library  # noqa: F401

@@ -1,0 +1,398 @@
+"""ctypes binding of libczk_b200.so (include/czk.h) with a thin object layer.
+
+Names follow the reference's interface for this path:
+  Context.msm_g1 / msm_g2      <- AffineCurve::multi_scalar_mul   (algebra/ec/src/lib.rs:302-311)
+  Context.fft / ifft / coset_fft / coset_ifft  (+ *_in_place on DeviceVec)
+                               <- EvaluationDomain               (algebra/poly/src/domain/mod.rs:79-158)
+  Context.batch_open / batch_mul <- FieldShare                   (mpc-algebra/src/share/field.rs:44-46,97-127)
+  Context.net_*                <- MpcNet                         (mpc-net/src/lib.rs:28-70)
+All arrays are numpy uint64 limb arrays in the reference's Montgomery in-memory form.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+_HERE = Path(__file__).resolve().parent
+_LIB = None
+
+SCHEME_PLAIN, SCHEME_ADDITIVE, SCHEME_SPDZ = 0, 1, 2
+
+u64p = C.POINTER(C.c_uint64)
+u8p = C.POINTER(C.c_uint8)
+
+
+class CzkError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"czk error {code}: {msg}")
+        self.code = code
+
+
+def library_path() -> Path:
+    return _HERE / "libczk_b200.so"
+
+
+_SIGS = {
+    "czk_ctx_create": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "czk_ctx_destroy": (None, [C.c_void_p]),
+    "czk_last_error": (C.c_char_p, [C.c_void_p]),
+    "czk_ctx_sync": (C.c_int, [C.c_void_p]),
+    "czk_ctx_stream": (C.c_void_p, [C.c_void_p]),
+    "czk_ctx_launches": (C.c_uint64, [C.c_void_p]),
+    "czk_version": (C.c_char_p, []),
+    "czk_vec_alloc": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "czk_vec_free": (None, [C.c_void_p, C.c_void_p]),
+    "czk_vec_len": (C.c_size_t, [C.c_void_p]),
+    "czk_vec_device_ptr": (C.c_void_p, [C.c_void_p]),
+    "czk_vec_upload": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "czk_vec_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "czk_vec_copy": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "czk_vec_zero": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "czk_ntt_fr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int]),
+    "czk_ntt_fr_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int]),
+    "czk_ntt_vec": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int]),
+    "czk_domain_params": (C.c_int, [C.c_uint, u64p, u64p, u64p, u64p]),
+    "czk_vec_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_vec_sub": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_vec_mul": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_vec_scale": (C.c_int, [C.c_void_p, C.c_void_p, u64p, C.c_size_t]),
+    "czk_vec_distribute_powers": (C.c_int, [C.c_void_p, C.c_void_p, u64p, u64p, C.c_size_t]),
+    "czk_vec_divide_by_vanishing_on_coset": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint]),
+    "czk_msm_g1": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, u64p]),
+    "czk_msm_g2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, u64p]),
+    "czk_bases_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "czk_bases_free": (None, [C.c_void_p, C.c_void_p]),
+    "czk_bases_len": (C.c_size_t, [C.c_void_p]),
+    "czk_msm_bases": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_size_t, u64p]),
+    "czk_bases_synthetic": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p)]),
+    "czk_bases_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "czk_net_unique_id": (C.c_int, [C.c_void_p]),
+    "czk_net_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "czk_net_init_single": (C.c_int, [C.c_void_p]),
+    "czk_net_deinit": (None, [C.c_void_p]),
+    "czk_net_party_id": (C.c_int, [C.c_void_p]),
+    "czk_net_n_parties": (C.c_int, [C.c_void_p]),
+    "czk_net_allgather_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_net_allgather_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_net_bcast_from_king_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_net_stats": (C.c_int, [C.c_void_p, u64p]),
+    "czk_net_reset_stats": (None, [C.c_void_p]),
+    "czk_batch_open": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_beaver_batch_mul": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_microbench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+}
+
+# entry points added by later translation units (declared in include/czk_groth16.h)
+_OPTIONAL_SIGS = {}
+
+
+def exported_symbols():
+    """Every symbol include/czk.h declares (used by the CPU-tier load test)."""
+    return sorted(_SIGS)
+
+
+def load_library():
+    """Load libczk_b200.so.  Raises if it has not been built: there is no fallback implementation."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    so = library_path()
+    if not so.exists():
+        raise FileNotFoundError(
+            f"{so} is missing - build it with `python collaborative-zksnark_b200/build.py` "
+            "(__graft_entry__.build()); czk_b200 has no CPU fallback")
+    lib = C.CDLL(str(so))
+    for name, (res, args) in _SIGS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    for name, (res, args) in _OPTIONAL_SIGS.items():
+        if hasattr(lib, name):
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def _np_u64(a, shape_last=None):
+    a = np.ascontiguousarray(a, dtype=np.uint64)
+    if shape_last is not None:
+        a = a.reshape(-1, shape_last)
+    return a
+
+
+def domain_params(log_d: int):
+    lib = load_library()
+    outs = [np.zeros(4, np.uint64) for _ in range(4)]
+    rc = lib.czk_domain_params(log_d, *[o.ctypes.data_as(u64p) for o in outs])
+    if rc:
+        raise CzkError(rc, lib.czk_last_error(None).decode())
+    return dict(group_gen=outs[0], group_gen_inv=outs[1], size_inv=outs[2], generator_inv=outs[3])
+
+
+class DeviceVec:
+    """Device-resident Vec<Fr> (Montgomery limbs)."""
+
+    def __init__(self, ctx: "Context", n: int):
+        self.ctx = ctx
+        self.n = n
+        h = C.c_void_p()
+        ctx._chk(ctx.lib.czk_vec_alloc(ctx.h, n, C.byref(h)))
+        self.h = h
+
+    @classmethod
+    def from_numpy(cls, ctx, arr, n=None):
+        arr = _np_u64(arr, 4)
+        v = cls(ctx, n if n is not None else arr.shape[0])
+        v.upload(arr)
+        return v
+
+    def upload(self, arr, offset=0):
+        arr = _np_u64(arr, 4)
+        self.ctx._chk(self.ctx.lib.czk_vec_upload(self.ctx.h, self.h, offset, arr.ctypes.data, arr.shape[0]))
+
+    def numpy(self, offset=0, n=None):
+        n = self.n - offset if n is None else n
+        out = np.empty((n, 4), np.uint64)
+        self.ctx._chk(self.ctx.lib.czk_vec_download(self.ctx.h, self.h, offset, out.ctypes.data, n))
+        return out
+
+    def clone(self):
+        v = DeviceVec(self.ctx, self.n)
+        self.ctx._chk(self.ctx.lib.czk_vec_copy(self.ctx.h, v.h, 0, self.h, 0, self.n))
+        return v
+
+    @property
+    def device_ptr(self) -> int:
+        return self.ctx.lib.czk_vec_device_ptr(self.h)
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.czk_vec_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Bases:
+    """Device-resident affine bases (one CRS query)."""
+
+    def __init__(self, ctx, h, curve):
+        self.ctx, self.h, self.curve = ctx, h, curve
+
+    def __len__(self):
+        return self.ctx.lib.czk_bases_len(self.h)
+
+    def numpy(self, off=0, n=None):
+        n = len(self) - off if n is None else n
+        w = 12 if self.curve == 1 else 24
+        xy = np.empty((n, w), np.uint64)
+        inf = np.empty(n, np.uint8)
+        self.ctx._chk(self.ctx.lib.czk_bases_download(self.ctx.h, self.h, off, n, xy.ctypes.data, inf.ctypes.data))
+        return xy, inf
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.czk_bases_free(self.ctx.h, self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Context:
+    """One party pinned to one GPU."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.czk_ctx_create(device, C.byref(h))
+        if rc:
+            raise CzkError(rc, self.lib.czk_last_error(None).decode())
+        self.h = h
+        self.device = device
+
+    def _chk(self, rc):
+        if rc:
+            raise CzkError(rc, self.lib.czk_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.lib.czk_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        self._chk(self.lib.czk_ctx_sync(self.h))
+
+    @property
+    def stream(self) -> int:
+        return self.lib.czk_ctx_stream(self.h)
+
+    @property
+    def launches(self) -> int:
+        return self.lib.czk_ctx_launches(self.h)
+
+    # ------------------------------------------------------------------ vectors
+    def vec(self, n):
+        return DeviceVec(self, n)
+
+    def vec_from(self, arr, n=None):
+        return DeviceVec.from_numpy(self, arr, n)
+
+    # ------------------------------------------------------------------ EvaluationDomain (host buffers: e2e path)
+    def _ntt_host(self, data, inverse, coset):
+        a = np.array(data, dtype=np.uint64, order="C").reshape(-1, 4)
+        n = a.shape[0]
+        log_d = max(n - 1, 0).bit_length()
+        if (1 << log_d) != n:  # resize with zeros (radix2/mod.rs:100-101)
+            a = np.concatenate([a, np.zeros(((1 << log_d) - n, 4), np.uint64)])
+        self._chk(self.lib.czk_ntt_fr(self.h, a.ctypes.data, log_d, int(inverse), int(coset)))
+        return a
+
+    def fft(self, data):
+        return self._ntt_host(data, False, False)
+
+    def ifft(self, data):
+        return self._ntt_host(data, True, False)
+
+    def coset_fft(self, data):
+        return self._ntt_host(data, False, True)
+
+    def coset_ifft(self, data):
+        return self._ntt_host(data, True, True)
+
+    # device-resident, in place
+    def ntt_in_place(self, v: DeviceVec, log_d: int, inverse=False, coset=False):
+        self._chk(self.lib.czk_ntt_vec(self.h, v.h, log_d, int(inverse), int(coset)))
+
+    def vec_add(self, a, b, n=None):
+        self._chk(self.lib.czk_vec_add(self.h, a.h, b.h, a.n if n is None else n))
+
+    def vec_sub(self, a, b, n=None):
+        self._chk(self.lib.czk_vec_sub(self.h, a.h, b.h, a.n if n is None else n))
+
+    def vec_mul(self, a, b, n=None):
+        self._chk(self.lib.czk_vec_mul(self.h, a.h, b.h, a.n if n is None else n))
+
+    def vec_scale(self, a, c, n=None):
+        c = _np_u64(c)
+        self._chk(self.lib.czk_vec_scale(self.h, a.h, c.ctypes.data_as(u64p), a.n if n is None else n))
+
+    def distribute_powers(self, a, g, c, n=None):
+        g, c = _np_u64(g), _np_u64(c)
+        self._chk(self.lib.czk_vec_distribute_powers(self.h, a.h, g.ctypes.data_as(u64p), c.ctypes.data_as(u64p), a.n if n is None else n))
+
+    def divide_by_vanishing_on_coset(self, a, log_d):
+        self._chk(self.lib.czk_vec_divide_by_vanishing_on_coset(self.h, a.h, log_d))
+
+    # ------------------------------------------------------------------ MSM
+    def _msm_host(self, fn, w, bases_xy, inf, scalars, montgomery):
+        bases_xy = _np_u64(bases_xy, w)
+        scalars = _np_u64(scalars, 4)
+        n = min(bases_xy.shape[0], scalars.shape[0])  # variable_base.rs:16
+        infp = None
+        if inf is not None:
+            inf = np.ascontiguousarray(inf, dtype=np.uint8)
+            infp = inf.ctypes.data
+        out = np.zeros(3 * (w // 2), np.uint64)
+        self._chk(fn(self.h, bases_xy.ctypes.data, infp, scalars.ctypes.data, int(montgomery), n, out.ctypes.data_as(u64p)))
+        return out
+
+    def msm_g1(self, bases_xy, inf, scalars, montgomery=True):
+        """-> Jacobian (x, y, z) limbs, affine-normalised (z = 1) or (1, 1, 0)."""
+        return self._msm_host(self.lib.czk_msm_g1, 12, bases_xy, inf, scalars, montgomery)
+
+    def msm_g2(self, bases_xy, inf, scalars, montgomery=True):
+        return self._msm_host(self.lib.czk_msm_g2, 24, bases_xy, inf, scalars, montgomery)
+
+    def bases_upload(self, curve, bases_xy, inf=None):
+        w = 12 if curve == 1 else 24
+        bases_xy = _np_u64(bases_xy, w)
+        infp = None
+        if inf is not None:
+            inf = np.ascontiguousarray(inf, dtype=np.uint8)
+            infp = inf.ctypes.data
+        h = C.c_void_p()
+        self._chk(self.lib.czk_bases_upload(self.h, curve, bases_xy.ctypes.data, infp, bases_xy.shape[0], C.byref(h)))
+        return Bases(self, h, curve)
+
+    def bases_synthetic(self, curve, seed, n, inf_every=0):
+        h = C.c_void_p()
+        self._chk(self.lib.czk_bases_synthetic(self.h, curve, seed, n, inf_every, C.byref(h)))
+        return Bases(self, h, curve)
+
+    def msm_bases(self, bases: Bases, scalars: DeviceVec, n=None, base_off=0, sc_off=0, montgomery=True):
+        n = min(len(bases) - base_off, scalars.n - sc_off) if n is None else n
+        w = 12 if bases.curve == 1 else 24
+        out = np.zeros(3 * (w // 2), np.uint64)
+        self._chk(self.lib.czk_msm_bases(self.h, bases.h, base_off, scalars.h, sc_off, int(montgomery), n, out.ctypes.data_as(u64p)))
+        return out
+
+    # ------------------------------------------------------------------ MpcNet
+    def net_init(self, rank, nranks, unique_id: bytes | None):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id) if unique_id is not None else None
+        self._chk(self.lib.czk_net_init(self.h, rank, nranks, buf))
+
+    def net_unique_id(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        rc = self.lib.czk_net_unique_id(buf)
+        if rc:
+            raise CzkError(rc, self.lib.czk_last_error(None).decode())
+        return bytes(buf)
+
+    @property
+    def party_id(self):
+        return self.lib.czk_net_party_id(self.h)
+
+    @property
+    def n_parties(self):
+        return self.lib.czk_net_n_parties(self.h)
+
+    def am_king(self):
+        return self.party_id == 0
+
+    def broadcast_bytes(self, data: bytes):
+        """MpcNet::broadcast_bytes: every party's message, in party order."""
+        n = len(data)
+        send = np.frombuffer(data, dtype=np.uint8).copy()
+        recv = np.empty(n * self.n_parties, np.uint8)
+        self._chk(self.lib.czk_net_allgather_host(self.h, send.ctypes.data, recv.ctypes.data, n))
+        return [recv[i * n:(i + 1) * n].tobytes() for i in range(self.n_parties)]
+
+    def net_stats(self):
+        out = np.zeros(5, np.uint64)
+        self.lib.czk_net_stats(self.h, out.ctypes.data_as(u64p))
+        return dict(zip(("bytes_sent", "bytes_recv", "broadcasts", "to_king", "from_king"), (int(x) for x in out)))
+
+    def net_reset_stats(self):
+        self.lib.czk_net_reset_stats(self.h)
+
+    # ------------------------------------------------------------------ FieldShare
+    def batch_open(self, scheme, sh: DeviceVec, mac: DeviceVec | None = None, n=None):
+        n = sh.n if n is None else n
+        out = DeviceVec(self, n)
+        self._chk(self.lib.czk_batch_open(self.h, scheme, sh.h, mac.h if mac is not None else None, out.h, n))
+        return out
+
+    def batch_mul(self, scheme, x_sh, x_mac, y_sh, y_mac, n=None):
+        """x *= y on shares (Field::batch_product_in_place on MpcField, wire/field.rs:358-393)."""
+        n = x_sh.n if n is None else n
+        self._chk(self.lib.czk_beaver_batch_mul(self.h, scheme, x_sh.h, x_mac.h if x_mac is not None else None, y_sh.h,
+                                                y_mac.h if y_mac is not None else None, n))
+
+    # ------------------------------------------------------------------ diagnostics
+    def microbench(self, kind, blocks_per_sm=8, threads=128, iters=2000):
+        ops = C.c_double()
+        ms = C.c_double()
+        self._chk(self.lib.czk_microbench(self.h, kind, blocks_per_sm, threads, iters, C.byref(ops), C.byref(ms)))
+        return ops.value, ms.value

@@ -1,0 +1,802 @@
+// C ABI of libczk_b200.so (include/czk.h): context, device vectors, NTT / MSM orchestration,
+// NCCL-backed party network, share opening and Beaver multiplication.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/czk.h"
+#include "fr_ops.cuh"
+#include "host_field.hpp"
+#include "launch_count.hpp"
+#include "msm.cuh"
+#include "ntt.cuh"
+
+namespace czk {
+std::atomic<uint64_t> g_launch_count{0};
+cudaError_t microbench_run(int kind, int blocks, int threads, int iters, uint64_t* scratch, double* ops_per_launch,
+                           cudaStream_t st);
+}  // namespace czk
+
+using namespace czk;
+using namespace czk::host;
+
+static thread_local std::string g_tls_error;
+
+// ------------------------------------------------------------------------------------------ NCCL (resolved at run time)
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+static NcclApi& nccl_api() {
+    static NcclApi api;
+    if (api.handle || api.ok) return api;
+    // if torch already loaded its bundled libnccl.so.2 the loader hands back that copy
+    api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) return api;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+    api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
+    api.Broadcast = (decltype(api.Broadcast))dlsym(api.handle, "ncclBroadcast");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Broadcast && api.GetErrorString;
+    return api;
+}
+
+// ------------------------------------------------------------------------------------------ objects
+struct czk_vec {
+    uint64_t* d = nullptr;
+    size_t n = 0;
+};
+struct czk_bases {
+    int curve = 1;
+    uint32_t* xy = nullptr;  // n * (24 | 48) words
+    uint8_t* inf = nullptr;  // n bytes, or nullptr when no point is infinity
+    size_t n = 0;
+};
+struct Domain {
+    int log_d = 0;
+    uint32_t* tw = nullptr;
+    uint32_t *g_lo = nullptr, *g_hi = nullptr, *gi_lo = nullptr, *gi_hi = nullptr;
+    int lo_log = 0;
+    HFr size_inv, group_gen, group_gen_inv, generator_inv;
+};
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct czk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::map<int, Domain> domains;
+    MsmWorkspace ws;
+    void* pinned = nullptr;  // host staging for window sums
+    size_t pinned_cap = 0;
+    Scratch up_bases, up_inf, up_scalars, up_vec;  // staging for the host-pointer entry points
+    Scratch open_gather, open_sigma, open_sx, open_oy, open_d, open_dm;
+    uint32_t* flag = nullptr;
+    // network
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    uint64_t stats[5] = {0, 0, 0, 0, 0};
+};
+
+static int fail(czk_ctx* ctx, int code, const std::string& msg) {
+    g_tls_error = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+#define CUDA_TRY(ctx, expr)                                                                                  \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess)                                                                               \
+            return fail(ctx, CZK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+    } while (0)
+#define CZK_TRY(expr)            \
+    do {                         \
+        int _s = (expr);         \
+        if (_s != CZK_OK) return _s; \
+    } while (0)
+
+static int scratch_reserve(czk_ctx* ctx, Scratch& s, size_t bytes) {
+    if (bytes <= s.cap) return CZK_OK;
+    if (s.p) CUDA_TRY(ctx, cudaFree(s.p));
+    s.p = nullptr;
+    s.cap = 0;
+    size_t want = bytes + bytes / 8;
+    CUDA_TRY(ctx, cudaMalloc(&s.p, want));
+    s.cap = want;
+    return CZK_OK;
+}
+
+const char* czk_version(void) { return "czk-b200 0.1 (sm_100a)"; }
+
+const char* czk_last_error(const czk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_tls_error.c_str(); }
+
+int czk_ctx_create(int device, czk_ctx** out) {
+    if (!out) return fail(nullptr, CZK_ERR_ARG, "czk_ctx_create: out is null");
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, CZK_ERR_NO_DEVICE,
+                    std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                        "); libczk_b200 has no CPU fallback");
+    if (device < 0 || device >= count) return fail(nullptr, CZK_ERR_ARG, "czk_ctx_create: device index out of range");
+    czk_ctx* ctx = new czk_ctx();
+    ctx->device = device;
+    CUDA_TRY(ctx, cudaSetDevice(device));
+    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CUDA_TRY(ctx, cudaMalloc((void**)&ctx->flag, 4));
+    CUDA_TRY(ctx, cudaMemset(ctx->flag, 0, 4));
+    *out = ctx;
+    return CZK_OK;
+}
+
+static void free_ws(MsmWorkspace& ws) {
+    cudaFree(ws.scalars);
+    cudaFree(ws.hist);
+    cudaFree(ws.offsets);
+    cudaFree(ws.sorted);
+    cudaFree(ws.buckets);
+    cudaFree(ws.partial);
+    cudaFree(ws.winsum);
+    ws = MsmWorkspace();
+}
+
+void czk_ctx_destroy(czk_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    czk_net_deinit(ctx);
+    for (auto& kv : ctx->domains) {
+        Domain& d = kv.second;
+        cudaFree(d.tw);
+        cudaFree(d.g_lo);
+        cudaFree(d.g_hi);
+        cudaFree(d.gi_lo);
+        cudaFree(d.gi_hi);
+    }
+    free_ws(ctx->ws);
+    for (Scratch* s : {&ctx->up_bases, &ctx->up_inf, &ctx->up_scalars, &ctx->up_vec, &ctx->open_gather, &ctx->open_sigma,
+                       &ctx->open_sx, &ctx->open_oy, &ctx->open_d, &ctx->open_dm})
+        cudaFree(s->p);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cudaFree(ctx->flag);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int czk_ctx_sync(czk_ctx* ctx) {
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CZK_OK;
+}
+void* czk_ctx_stream(czk_ctx* ctx) { return (void*)ctx->stream; }
+uint64_t czk_ctx_launches(const czk_ctx*) { return g_launch_count.load(); }
+
+// ------------------------------------------------------------------------------------------ vectors
+int czk_vec_alloc(czk_ctx* ctx, size_t n, czk_vec** out) {
+    if (!ctx || !out) return fail(ctx, CZK_ERR_ARG, "czk_vec_alloc: null argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    czk_vec* v = new czk_vec();
+    v->n = n;
+    size_t bytes = (n ? n : 1) * 32;
+    cudaError_t e = cudaMalloc((void**)&v->d, bytes);
+    if (e != cudaSuccess) {
+        delete v;
+        return fail(ctx, CZK_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    CUDA_TRY(ctx, cudaMemsetAsync(v->d, 0, bytes, ctx->stream));
+    *out = v;
+    return CZK_OK;
+}
+void czk_vec_free(czk_ctx* ctx, czk_vec* v) {
+    if (!v) return;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    cudaFree(v->d);
+    delete v;
+}
+size_t czk_vec_len(const czk_vec* v) { return v ? v->n : 0; }
+uint64_t* czk_vec_device_ptr(czk_vec* v) { return v ? v->d : nullptr; }
+
+int czk_vec_upload(czk_ctx* ctx, czk_vec* v, size_t offset, const uint64_t* host, size_t n) {
+    if (!v || (!host && n) || offset + n > v->n) return fail(ctx, CZK_ERR_ARG, "czk_vec_upload: range");
+    CUDA_TRY(ctx, cudaMemcpyAsync(v->d + 4 * offset, host, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CZK_OK;
+}
+int czk_vec_download(czk_ctx* ctx, const czk_vec* v, size_t offset, uint64_t* host, size_t n) {
+    if (!v || (!host && n) || offset + n > v->n) return fail(ctx, CZK_ERR_ARG, "czk_vec_download: range");
+    CUDA_TRY(ctx, cudaMemcpyAsync(host, v->d + 4 * offset, n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CZK_OK;
+}
+int czk_vec_copy(czk_ctx* ctx, czk_vec* dst, size_t dst_off, const czk_vec* src, size_t src_off, size_t n) {
+    if (!dst || !src || dst_off + n > dst->n || src_off + n > src->n) return fail(ctx, CZK_ERR_ARG, "czk_vec_copy: range");
+    CUDA_TRY(ctx, cudaMemcpyAsync(dst->d + 4 * dst_off, src->d + 4 * src_off, n * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+    return CZK_OK;
+}
+int czk_vec_zero(czk_ctx* ctx, czk_vec* v, size_t offset, size_t n) {
+    if (!v || offset + n > v->n) return fail(ctx, CZK_ERR_ARG, "czk_vec_zero: range");
+    CUDA_TRY(ctx, cudaMemsetAsync(v->d + 4 * offset, 0, n * 32, ctx->stream));
+    return CZK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ NTT
+static HFr domain_root(unsigned log_d) {
+    HFr w = HFr::from_limbs(FrParams::ROOT_2_47_64);
+    for (unsigned i = log_d; i < FrParams::TWO_ADICITY; i++) w = HFr::sqr(w);
+    return w;
+}
+
+int czk_domain_params(unsigned log_d, uint64_t group_gen[4], uint64_t group_gen_inv[4], uint64_t size_inv[4],
+                      uint64_t generator_inv[4]) {
+    if (log_d > FrParams::TWO_ADICITY) return fail(nullptr, CZK_ERR_ARG, "domain larger than 2^47");
+    HFr w = domain_root(log_d);
+    w.to_limbs(group_gen);
+    HFr::inv(w).to_limbs(group_gen_inv);
+    HFr::inv(HFr::from_u64((uint64_t)1 << log_d)).to_limbs(size_inv);
+    HFr::inv(HFr::from_limbs(FrParams::GENERATOR_64)).to_limbs(generator_inv);
+    return CZK_OK;
+}
+
+static int get_domain(czk_ctx* ctx, int log_d, Domain** out) {
+    auto it = ctx->domains.find(log_d);
+    if (it != ctx->domains.end()) {
+        *out = &it->second;
+        return CZK_OK;
+    }
+    Domain d;
+    d.log_d = log_d;
+    d.group_gen = domain_root((unsigned)log_d);
+    d.group_gen_inv = HFr::inv(d.group_gen);
+    d.size_inv = HFr::inv(HFr::from_u64((uint64_t)1 << log_d));
+    HFr g = HFr::from_limbs(FrParams::GENERATOR_64);
+    d.generator_inv = HFr::inv(g);
+    d.lo_log = log_d < 10 ? log_d : 10;
+    size_t half = log_d ? ((size_t)1 << (log_d - 1)) : 1;
+    size_t nlo = (size_t)1 << d.lo_log, nhi = (size_t)1 << (log_d - d.lo_log);
+    CUDA_TRY(ctx, cudaMalloc((void**)&d.tw, half * 32));
+    CUDA_TRY(ctx, cudaMalloc((void**)&d.g_lo, nlo * 32));
+    CUDA_TRY(ctx, cudaMalloc((void**)&d.g_hi, nhi * 32));
+    CUDA_TRY(ctx, cudaMalloc((void**)&d.gi_lo, nlo * 32));
+    CUDA_TRY(ctx, cudaMalloc((void**)&d.gi_hi, nhi * 32));
+    HFr one = HFr::one();
+    CUDA_TRY(ctx, ntt_build_powers(d.tw, d.group_gen.l, one.l, half, ctx->stream));
+    CUDA_TRY(ctx, ntt_build_powers(d.g_lo, g.l, one.l, nlo, ctx->stream));
+    HFr g_hi = HFr::pow_u64(g, (uint64_t)nlo);
+    CUDA_TRY(ctx, ntt_build_powers(d.g_hi, g_hi.l, one.l, nhi, ctx->stream));
+    CUDA_TRY(ctx, ntt_build_powers(d.gi_lo, d.generator_inv.l, one.l, nlo, ctx->stream));
+    HFr gi_hi = HFr::pow_u64(d.generator_inv, (uint64_t)nlo);
+    CUDA_TRY(ctx, ntt_build_powers(d.gi_hi, gi_hi.l, d.size_inv.l, nhi, ctx->stream));
+    auto ins = ctx->domains.emplace(log_d, d);
+    *out = &ins.first->second;
+    return CZK_OK;
+}
+
+int czk_ntt_fr_dev(czk_ctx* ctx, uint64_t* dev_data, unsigned log_d, int inverse, int coset) {
+    if (!ctx || !dev_data) return fail(ctx, CZK_ERR_ARG, "czk_ntt_fr_dev: null argument");
+    if (log_d > 30) return fail(ctx, CZK_ERR_ARG, "czk_ntt_fr_dev: log_d > 30 unsupported");
+    if (log_d == 0) return CZK_OK;  // size-1 domain: every transform is the identity
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    Domain* d;
+    CZK_TRY(get_domain(ctx, (int)log_d, &d));
+    uint32_t* data = reinterpret_cast<uint32_t*>(dev_data);
+    if (!inverse && coset) CUDA_TRY(ctx, ntt_scale_by_powers(data, d->g_lo, d->g_hi, d->lo_log, (int)log_d, ctx->stream));
+    CUDA_TRY(ctx, ntt_run_passes(data, d->tw, (int)log_d, inverse != 0, ctx->stream));
+    if (!inverse) CUDA_TRY(ctx, ntt_bitrev_scale(data, (int)log_d, 0, nullptr, nullptr, nullptr, 0, ctx->stream));
+    else if (!coset) CUDA_TRY(ctx, ntt_bitrev_scale(data, (int)log_d, 1, d->size_inv.l, nullptr, nullptr, 0, ctx->stream));
+    else CUDA_TRY(ctx, ntt_bitrev_scale(data, (int)log_d, 2, nullptr, d->gi_lo, d->gi_hi, d->lo_log, ctx->stream));
+    return CZK_OK;
+}
+
+int czk_ntt_vec(czk_ctx* ctx, czk_vec* v, unsigned log_d, int inverse, int coset) {
+    if (!v || v->n < ((size_t)1 << log_d)) return fail(ctx, CZK_ERR_ARG, "czk_ntt_vec: vector shorter than the domain");
+    return czk_ntt_fr_dev(ctx, v->d, log_d, inverse, coset);
+}
+
+int czk_ntt_fr(czk_ctx* ctx, uint64_t* host_data, unsigned log_d, int inverse, int coset) {
+    if (!ctx || !host_data) return fail(ctx, CZK_ERR_ARG, "czk_ntt_fr: null argument");
+    if (log_d > 30) return fail(ctx, CZK_ERR_ARG, "czk_ntt_fr: log_d > 30 unsupported");
+    size_t bytes = ((size_t)1 << log_d) * 32;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CZK_TRY(scratch_reserve(ctx, ctx->up_vec, bytes));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->up_vec.p, host_data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CZK_TRY(czk_ntt_fr_dev(ctx, (uint64_t*)ctx->up_vec.p, log_d, inverse, coset));
+    CUDA_TRY(ctx, cudaMemcpyAsync(host_data, ctx->up_vec.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CZK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ pointwise
+#define VEC_CHECK2(a, b, n, name) \
+    if (!ctx || !(a) || !(b) || (n) > (a)->n || (n) > (b)->n) return fail(ctx, CZK_ERR_ARG, name ": range")
+int czk_vec_add(czk_ctx* ctx, czk_vec* a, const czk_vec* b, size_t n) {
+    VEC_CHECK2(a, b, n, "czk_vec_add");
+    CUDA_TRY(ctx, fr_binop((uint32_t*)a->d, (const uint32_t*)b->d, n, FR_ADD, ctx->stream));
+    return CZK_OK;
+}
+int czk_vec_sub(czk_ctx* ctx, czk_vec* a, const czk_vec* b, size_t n) {
+    VEC_CHECK2(a, b, n, "czk_vec_sub");
+    CUDA_TRY(ctx, fr_binop((uint32_t*)a->d, (const uint32_t*)b->d, n, FR_SUB, ctx->stream));
+    return CZK_OK;
+}
+int czk_vec_mul(czk_ctx* ctx, czk_vec* a, const czk_vec* b, size_t n) {
+    VEC_CHECK2(a, b, n, "czk_vec_mul");
+    CUDA_TRY(ctx, fr_binop((uint32_t*)a->d, (const uint32_t*)b->d, n, FR_MUL, ctx->stream));
+    return CZK_OK;
+}
+int czk_vec_scale(czk_ctx* ctx, czk_vec* a, const uint64_t c[4], size_t n) {
+    if (!ctx || !a || !c || n > a->n) return fail(ctx, CZK_ERR_ARG, "czk_vec_scale: range");
+    CUDA_TRY(ctx, fr_scale((uint32_t*)a->d, c, n, ctx->stream));
+    return CZK_OK;
+}
+int czk_vec_distribute_powers(czk_ctx* ctx, czk_vec* a, const uint64_t g[4], const uint64_t c[4], size_t n) {
+    if (!ctx || !a || !g || !c || n > a->n) return fail(ctx, CZK_ERR_ARG, "czk_vec_distribute_powers: range");
+    if (!n) return CZK_OK;
+    // a[i] *= c g^i with a two-level power table built on the fly
+    int lo_log = 10;
+    size_t nlo = (size_t)1 << lo_log, nhi = (n + nlo - 1) >> lo_log;
+    CZK_TRY(scratch_reserve(ctx, ctx->open_sigma, (nlo + nhi) * 32));
+    uint32_t* lo = (uint32_t*)ctx->open_sigma.p;
+    uint32_t* hi = lo + nlo * 8;
+    HFr gg = HFr::from_limbs(g), one = HFr::one();
+    CUDA_TRY(ctx, ntt_build_powers(lo, gg.l, one.l, nlo, ctx->stream));
+    HFr ghi = HFr::pow_u64(gg, (uint64_t)nlo);
+    CUDA_TRY(ctx, ntt_build_powers(hi, ghi.l, c, nhi, ctx->stream));
+    // reuse the NTT pre-scale kernel on the first n elements (n need not be a power of two)
+    CUDA_TRY(ctx, fr_scale_by_tables((uint32_t*)a->d, lo, hi, lo_log, n, ctx->stream));
+    return CZK_OK;
+}
+int czk_vec_divide_by_vanishing_on_coset(czk_ctx* ctx, czk_vec* a, unsigned log_d) {
+    size_t n = (size_t)1 << log_d;
+    if (!ctx || !a || n > a->n) return fail(ctx, CZK_ERR_ARG, "czk_vec_divide_by_vanishing_on_coset: range");
+    // 1 / (g^D - 1)   (radix2/mod.rs:191-193, domain/mod.rs:184-191)
+    HFr g = HFr::from_limbs(FrParams::GENERATOR_64);
+    HFr z = HFr::sub(HFr::pow_u64(g, (uint64_t)n), HFr::one());
+    HFr zi = HFr::inv(z);
+    CUDA_TRY(ctx, fr_scale((uint32_t*)a->d, zi.l, n, ctx->stream));
+    return CZK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ MSM
+static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
+    MsmWorkspace& ws = ctx->ws;
+    size_t total = (size_t)cfg.nwin * cfg.nb;
+    int pw = (int)msm_point_words(curve);
+    bool grow_n = n > ws.cap_n;
+    bool grow_b = total > ws.cap_buckets || pw > ws.point_words;
+    if (grow_n) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ws.scalars);
+        cudaFree(ws.sorted);
+        ws.scalars = ws.sorted = nullptr;
+        size_t cap = n + n / 16 + 64;
+        CUDA_TRY(ctx, cudaMalloc((void**)&ws.scalars, cap * 32));
+        // worst case windows for this n: ceil(254/2) covers every config
+        CUDA_TRY(ctx, cudaMalloc((void**)&ws.sorted, cap * 4 * 32));
+        ws.cap_n = cap;
+    }
+    // `sorted` holds n * nwin entries; the allocation above budgets 32 windows, small-c configs need more
+    if ((size_t)cfg.nwin > 32) {
+        size_t need = n * cfg.nwin * 4;
+        if (need > ws.cap_n * 4 * 32) {
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ws.sorted);
+            CUDA_TRY(ctx, cudaMalloc((void**)&ws.sorted, need));
+        }
+    }
+    if (grow_b) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ws.hist);
+        cudaFree(ws.offsets);
+        cudaFree(ws.buckets);
+        cudaFree(ws.partial);
+        cudaFree(ws.winsum);
+        ws.hist = ws.offsets = ws.buckets = ws.partial = ws.winsum = nullptr;
+        size_t cap = total > ws.cap_buckets ? total : ws.cap_buckets;
+        int pww = pw > ws.point_words ? pw : ws.point_words;
+        CUDA_TRY(ctx, cudaMalloc((void**)&ws.hist, cap * 4));
+        CUDA_TRY(ctx, cudaMalloc((void**)&ws.offsets, cap * 4));
+        CUDA_TRY(ctx, cudaMalloc((void**)&ws.buckets, cap * pww * 4));
+        CUDA_TRY(ctx, cudaMalloc((void**)&ws.partial, cap * pww * 4));  // >= nwin * nchunks points
+        CUDA_TRY(ctx, cudaMalloc((void**)&ws.winsum, 256 * (size_t)pww * 4));
+        ws.cap_buckets = cap;
+        ws.point_words = pww;
+    }
+    size_t pin = 256 * 96 * 4;
+    if (ctx->pinned_cap < pin) {
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        CUDA_TRY(ctx, cudaMallocHost(&ctx->pinned, pin));
+        ctx->pinned_cap = pin;
+    }
+    return CZK_OK;
+}
+
+template <class HF, int LIMBS>
+static void msm_host_tail(const uint32_t* winsums, const MsmConfig& cfg, uint64_t* out_xyz) {
+    typedef HPoint<HF> P;
+    const uint64_t* w64 = reinterpret_cast<const uint64_t*>(winsums);
+    auto load = [&](unsigned w) {
+        P p;
+        const uint64_t* b = w64 + (size_t)w * 4 * LIMBS;
+        p.x = HF::from_limbs(b);
+        p.y = HF::from_limbs(b + LIMBS);
+        p.zz = HF::from_limbs(b + 2 * LIMBS);
+        p.zzz = HF::from_limbs(b + 3 * LIMBS);
+        return p;
+    };
+    P total = P::infinity();
+    for (int w = (int)cfg.nwin - 1; w >= 0; w--) {
+        for (unsigned k = 0; k < cfg.c; k++) total = P::dbl(total);
+        total.add(load((unsigned)w));
+    }
+    HF ax, ay;
+    if (total.to_affine(ax, ay)) {
+        ax.to_limbs(out_xyz);
+        ay.to_limbs(out_xyz + LIMBS);
+        HF::one().to_limbs(out_xyz + 2 * LIMBS);
+    } else {
+        // GroupProjective::zero() = (1, 1, 0)
+        HF::one().to_limbs(out_xyz);
+        HF::one().to_limbs(out_xyz + LIMBS);
+        HF::zero().to_limbs(out_xyz + 2 * LIMBS);
+    }
+}
+
+static int msm_core(czk_ctx* ctx, int curve, const uint32_t* bases, const uint8_t* inf, const uint32_t* scalars, int mont,
+                    size_t n, uint64_t* out_xyz) {
+    if (n >= ((size_t)1 << 31)) return fail(ctx, CZK_ERR_ARG, "msm: more than 2^31 - 1 terms");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    MsmConfig cfg = msm_choose_config(n ? n : 1);
+    CZK_TRY(ws_reserve(ctx, curve, n, cfg));
+    CUDA_TRY(ctx, msm_run(curve, bases, inf, scalars, mont != 0, n, cfg, ctx->ws, ctx->stream));
+    size_t pw = msm_point_words(curve);
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, ctx->ws.winsum, cfg.nwin * pw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (curve == 1) msm_host_tail<HFq, 6>((const uint32_t*)ctx->pinned, cfg, out_xyz);
+    else msm_host_tail<HFq2, 12>((const uint32_t*)ctx->pinned, cfg, out_xyz);
+    return CZK_OK;
+}
+
+static int msm_host_entry(czk_ctx* ctx, int curve, const uint64_t* bases_xy, const uint8_t* inf, const uint64_t* scalars,
+                          int mont, size_t n, uint64_t* out_xyz) {
+    if (!ctx || !out_xyz || (n && (!bases_xy || !scalars))) return fail(ctx, CZK_ERR_ARG, "czk_msm: null argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    size_t pb = curve == 1 ? 96 : 192;
+    CZK_TRY(scratch_reserve(ctx, ctx->up_bases, (n ? n : 1) * pb));
+    CZK_TRY(scratch_reserve(ctx, ctx->up_scalars, (n ? n : 1) * 32));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->up_bases.p, bases_xy, n * pb, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->up_scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, ctx->stream));
+    const uint8_t* dinf = nullptr;
+    if (inf) {
+        CZK_TRY(scratch_reserve(ctx, ctx->up_inf, n ? n : 1));
+        CUDA_TRY(ctx, cudaMemcpyAsync(ctx->up_inf.p, inf, n, cudaMemcpyHostToDevice, ctx->stream));
+        dinf = (const uint8_t*)ctx->up_inf.p;
+    }
+    return msm_core(ctx, curve, (const uint32_t*)ctx->up_bases.p, dinf, (const uint32_t*)ctx->up_scalars.p, mont, n, out_xyz);
+}
+
+int czk_msm_g1(czk_ctx* ctx, const uint64_t* bases_xy, const uint8_t* inf, const uint64_t* scalars, int scalars_montgomery,
+               size_t n, uint64_t out_xyz[18]) {
+    return msm_host_entry(ctx, 1, bases_xy, inf, scalars, scalars_montgomery, n, out_xyz);
+}
+int czk_msm_g2(czk_ctx* ctx, const uint64_t* bases_xy, const uint8_t* inf, const uint64_t* scalars, int scalars_montgomery,
+               size_t n, uint64_t out_xyz[36]) {
+    return msm_host_entry(ctx, 2, bases_xy, inf, scalars, scalars_montgomery, n, out_xyz);
+}
+
+int czk_bases_upload(czk_ctx* ctx, int curve, const uint64_t* bases_xy, const uint8_t* inf, size_t n, czk_bases** out) {
+    if (!ctx || !out || (curve != 1 && curve != 2) || (n && !bases_xy)) return fail(ctx, CZK_ERR_ARG, "czk_bases_upload: argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    czk_bases* b = new czk_bases();
+    b->curve = curve;
+    b->n = n;
+    size_t pb = curve == 1 ? 96 : 192;
+    CUDA_TRY(ctx, cudaMalloc((void**)&b->xy, (n ? n : 1) * pb));
+    CUDA_TRY(ctx, cudaMemcpyAsync(b->xy, bases_xy, n * pb, cudaMemcpyHostToDevice, ctx->stream));
+    bool any = false;
+    if (inf)
+        for (size_t i = 0; i < n && !any; i++) any = inf[i] != 0;
+    if (any) {
+        CUDA_TRY(ctx, cudaMalloc((void**)&b->inf, n));
+        CUDA_TRY(ctx, cudaMemcpyAsync(b->inf, inf, n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = b;
+    return CZK_OK;
+}
+void czk_bases_free(czk_ctx* ctx, czk_bases* b) {
+    if (!b) return;
+    if (ctx) cudaStreamSynchronize(ctx->stream);
+    cudaFree(b->xy);
+    cudaFree(b->inf);
+    delete b;
+}
+size_t czk_bases_len(const czk_bases* b) { return b ? b->n : 0; }
+
+int czk_msm_bases(czk_ctx* ctx, const czk_bases* b, size_t base_off, const czk_vec* sc, size_t sc_off, int scalars_montgomery,
+                  size_t n, uint64_t* out_xyz) {
+    if (!ctx || !b || !sc || !out_xyz || base_off + n > b->n || sc_off + n > sc->n)
+        return fail(ctx, CZK_ERR_ARG, "czk_msm_bases: range");
+    size_t pw = b->curve == 1 ? 24 : 48;
+    return msm_core(ctx, b->curve, b->xy + base_off * pw, b->inf ? b->inf + base_off : nullptr,
+                    (const uint32_t*)(sc->d + 4 * sc_off), scalars_montgomery, n, out_xyz);
+}
+
+static uint64_t splitmix(uint64_t& x) {
+    x += 0x9E3779B97F4A7C15ull;
+    uint64_t z = x;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+int czk_bases_synthetic(czk_ctx* ctx, int curve, uint64_t seed, size_t n, size_t inf_every, czk_bases** out) {
+    if (!ctx || !out || (curve != 1 && curve != 2)) return fail(ctx, CZK_ERR_ARG, "czk_bases_synthetic: argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    uint64_t st = seed;
+    uint64_t k0[4], ks[4];
+    for (int i = 0; i < 4; i++) {
+        k0[i] = splitmix(st);
+        ks[i] = splitmix(st);
+    }
+    k0[3] &= (1ull << 56) - 1;  // < 2^248 < r
+    ks[3] &= (1ull << 56) - 1;
+    ks[0] |= 1;
+    czk_bases* b = new czk_bases();
+    b->curve = curve;
+    b->n = n;
+    size_t pb = curve == 1 ? 96 : 192;
+    CUDA_TRY(ctx, cudaMalloc((void**)&b->xy, (n ? n : 1) * pb + 2 * pb));
+    // generator and step point (kstep * G) on the host, staged after the output array
+    std::vector<uint64_t> gs(2 * pb / 8);
+    if (curve == 1) {
+        HG1 g = HG1::from_affine(HFq::from_limbs(CurveConsts::G1_GEN), HFq::from_limbs(CurveConsts::G1_GEN + 6));
+        HG1 s = HG1::mul(g, ks, 4);
+        HFq sx, sy;
+        s.to_affine(sx, sy);
+        std::memcpy(gs.data(), CurveConsts::G1_GEN, 96);
+        sx.to_limbs(gs.data() + 12);
+        sy.to_limbs(gs.data() + 18);
+    } else {
+        HG2 g = HG2::from_affine(HFq2::from_limbs(CurveConsts::G2_GEN), HFq2::from_limbs(CurveConsts::G2_GEN + 12));
+        HG2 s = HG2::mul(g, ks, 4);
+        HFq2 sx, sy;
+        s.to_affine(sx, sy);
+        std::memcpy(gs.data(), CurveConsts::G2_GEN, 192);
+        sx.to_limbs(gs.data() + 24);
+        sy.to_limbs(gs.data() + 36);
+    }
+    uint32_t* stage = b->xy + (n ? n : 1) * (pb / 4);
+    CUDA_TRY(ctx, cudaMemcpyAsync(stage, gs.data(), 2 * pb, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, ec_gen_progression_dev(curve, b->xy, stage, stage + pb / 4, k0, ks, n, ctx->stream));
+    if (inf_every && n) {
+        std::vector<uint8_t> flags(n, 0);
+        for (size_t i = inf_every - 1; i < n; i += inf_every) flags[i] = 1;
+        CUDA_TRY(ctx, cudaMalloc((void**)&b->inf, n));
+        CUDA_TRY(ctx, cudaMemcpyAsync(b->inf, flags.data(), n, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = b;
+    return CZK_OK;
+}
+
+int czk_bases_download(czk_ctx* ctx, const czk_bases* b, size_t off, size_t n, uint64_t* xy, uint8_t* inf) {
+    if (!ctx || !b || off + n > b->n || (n && !xy)) return fail(ctx, CZK_ERR_ARG, "czk_bases_download: range");
+    size_t pb = b->curve == 1 ? 96 : 192;
+    CUDA_TRY(ctx, cudaMemcpyAsync(xy, (const uint8_t*)b->xy + off * pb, n * pb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (inf) {
+        if (b->inf) CUDA_TRY(ctx, cudaMemcpyAsync(inf, b->inf + off, n, cudaMemcpyDeviceToHost, ctx->stream));
+        else std::memset(inf, 0, n);
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CZK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ network
+int czk_net_unique_id(uint8_t out[128]) {
+    NcclApi& api = nccl_api();
+    if (!api.ok) return fail(nullptr, CZK_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    ncclUniqueId id;
+    ncclResult_t r = api.GetUniqueId(&id);
+    if (r != ncclSuccess) return fail(nullptr, CZK_ERR_NCCL, std::string("ncclGetUniqueId: ") + api.GetErrorString(r));
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+    std::memcpy(out, &id, 128);
+    return CZK_OK;
+}
+int czk_net_init(czk_ctx* ctx, int rank, int nranks, const uint8_t nccl_unique_id[128]) {
+    if (!ctx || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, CZK_ERR_ARG, "czk_net_init: rank");
+    czk_net_deinit(ctx);
+    ctx->rank = rank;
+    ctx->nranks = nranks;
+    if (nranks == 1) return CZK_OK;
+    NcclApi& api = nccl_api();
+    if (!api.ok) return fail(ctx, CZK_ERR_NCCL, "libnccl.so.2 could not be loaded");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    ncclUniqueId id;
+    std::memcpy(&id, nccl_unique_id, 128);
+    ncclResult_t r = api.CommInitRank(&ctx->comm, nranks, id, rank);
+    if (r != ncclSuccess) return fail(ctx, CZK_ERR_NCCL, std::string("ncclCommInitRank: ") + api.GetErrorString(r));
+    return CZK_OK;
+}
+int czk_net_init_single(czk_ctx* ctx) { return czk_net_init(ctx, 0, 1, nullptr); }
+void czk_net_deinit(czk_ctx* ctx) {
+    if (ctx && ctx->comm) {
+        cudaStreamSynchronize(ctx->stream);
+        nccl_api().CommDestroy(ctx->comm);
+        ctx->comm = nullptr;
+    }
+    if (ctx) {
+        ctx->rank = 0;
+        ctx->nranks = 1;
+    }
+}
+int czk_net_party_id(const czk_ctx* ctx) { return ctx->rank; }
+int czk_net_n_parties(const czk_ctx* ctx) { return ctx->nranks; }
+
+int czk_net_allgather_dev(czk_ctx* ctx, const void* dev_send, void* dev_recv, size_t bytes) {
+    if (!ctx || !dev_send || !dev_recv) return fail(ctx, CZK_ERR_ARG, "czk_net_allgather_dev: null");
+    // mpc-net broadcast accounting (multi.rs:145-174): one message to, and one from, every other party
+    ctx->stats[0] += bytes * (uint64_t)(ctx->nranks - 1);
+    ctx->stats[1] += bytes * (uint64_t)(ctx->nranks - 1);
+    ctx->stats[2] += 1;
+    if (ctx->nranks == 1) {
+        if (dev_send != dev_recv) CUDA_TRY(ctx, cudaMemcpyAsync(dev_recv, dev_send, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        return CZK_OK;
+    }
+    ncclResult_t r = nccl_api().AllGather(dev_send, dev_recv, bytes, ncclUint8, ctx->comm, ctx->stream);
+    if (r != ncclSuccess) return fail(ctx, CZK_ERR_NCCL, std::string("ncclAllGather: ") + nccl_api().GetErrorString(r));
+    return CZK_OK;
+}
+int czk_net_allgather_host(czk_ctx* ctx, const void* host_send, void* host_recv, size_t bytes) {
+    if (!ctx || !host_send || !host_recv) return fail(ctx, CZK_ERR_ARG, "czk_net_allgather_host: null");
+    size_t total = bytes * (size_t)ctx->nranks;
+    CZK_TRY(scratch_reserve(ctx, ctx->open_d, bytes + total + 32));
+    uint8_t* send = (uint8_t*)ctx->open_d.p;
+    uint8_t* recv = send + ((bytes + 15) / 16) * 16;
+    CUDA_TRY(ctx, cudaMemcpyAsync(send, host_send, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CZK_TRY(czk_net_allgather_dev(ctx, send, recv, bytes));
+    CUDA_TRY(ctx, cudaMemcpyAsync(host_recv, recv, total, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CZK_OK;
+}
+int czk_net_bcast_from_king_dev(czk_ctx* ctx, void* dev_buf, size_t bytes) {
+    if (!ctx || !dev_buf) return fail(ctx, CZK_ERR_ARG, "czk_net_bcast_from_king_dev: null");
+    if (ctx->rank == 0) ctx->stats[0] += bytes * (uint64_t)(ctx->nranks - 1);
+    else ctx->stats[1] += bytes;
+    ctx->stats[4] += 1;
+    if (ctx->nranks == 1) return CZK_OK;
+    ncclResult_t r = nccl_api().Broadcast(dev_buf, dev_buf, bytes, ncclUint8, 0, ctx->comm, ctx->stream);
+    if (r != ncclSuccess) return fail(ctx, CZK_ERR_NCCL, std::string("ncclBroadcast: ") + nccl_api().GetErrorString(r));
+    return CZK_OK;
+}
+int czk_net_stats(const czk_ctx* ctx, uint64_t out[5]) {
+    for (int i = 0; i < 5; i++) out[i] = ctx->stats[i];
+    return CZK_OK;
+}
+void czk_net_reset_stats(czk_ctx* ctx) {
+    for (int i = 0; i < 5; i++) ctx->stats[i] = 0;
+}
+
+// ------------------------------------------------------------------------------------------ shares
+// out[i] = sum over parties of sh[i]; SPDZ additionally exchanges sigma = mac_share*x - mac and checks sum == 0
+static int open_raw(czk_ctx* ctx, int scheme, const uint32_t* sh, const uint32_t* mac, uint32_t* out, size_t n) {
+    if (scheme == CZK_SCHEME_PLAIN) {
+        if (out != sh) CUDA_TRY(ctx, cudaMemcpyAsync(out, sh, n * 32, cudaMemcpyDeviceToDevice, ctx->stream));
+        return CZK_OK;
+    }
+    size_t bytes = n * 32;
+    CZK_TRY(scratch_reserve(ctx, ctx->open_gather, bytes * (size_t)ctx->nranks));
+    uint32_t* gath = (uint32_t*)ctx->open_gather.p;
+    CZK_TRY(czk_net_allgather_dev(ctx, sh, gath, bytes));
+    CUDA_TRY(ctx, fr_sum_parties(out, gath, n, ctx->nranks, ctx->stream));
+    if (scheme == CZK_SCHEME_SPDZ) {
+        if (!mac) return fail(ctx, CZK_ERR_ARG, "SPDZ open needs the MAC share vector");
+        CZK_TRY(scratch_reserve(ctx, ctx->open_sigma, bytes));
+        HFr ms = ctx->rank == 0 ? HFr::one() : HFr::zero();  // spdz.rs:31-37 (global MAC key stubbed to 1)
+        CUDA_TRY(ctx, fr_spdz_sigma((uint32_t*)ctx->open_sigma.p, out, mac, ms.l, n, ctx->stream));
+        // atomic_broadcast (channel.rs:50-75): the data round; the SHA-256 commitment round of the reference
+        // is host-side bookkeeping between mutually distrusting machines and is not reproduced inside one box
+        CZK_TRY(czk_net_allgather_dev(ctx, ctx->open_sigma.p, gath, bytes));
+        CUDA_TRY(ctx, fr_check_zero_sum(gath, n, ctx->nranks, ctx->flag, ctx->stream));
+        uint32_t flag = 0;
+        CUDA_TRY(ctx, cudaMemcpyAsync(&flag, ctx->flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (flag) {
+            cudaMemsetAsync(ctx->flag, 0, 4, ctx->stream);
+            return fail(ctx, CZK_ERR_PROTOCOL, "SPDZ MAC check failed (spdz.rs:182 assert!(sum.is_zero()))");
+        }
+    }
+    return CZK_OK;
+}
+
+int czk_batch_open(czk_ctx* ctx, int scheme, const czk_vec* sh, const czk_vec* mac, czk_vec* out_pub, size_t n) {
+    if (!ctx || !sh || !out_pub || n > sh->n || n > out_pub->n || (mac && n > mac->n))
+        return fail(ctx, CZK_ERR_ARG, "czk_batch_open: range");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    return open_raw(ctx, scheme, (const uint32_t*)sh->d, mac ? (const uint32_t*)mac->d : nullptr, (uint32_t*)out_pub->d, n);
+}
+
+int czk_beaver_batch_mul(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac, const czk_vec* y_sh, const czk_vec* y_mac,
+                         size_t n) {
+    if (!ctx || !x_sh || !y_sh || n > x_sh->n || n > y_sh->n) return fail(ctx, CZK_ERR_ARG, "czk_beaver_batch_mul: range");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (scheme == CZK_SCHEME_PLAIN) return czk_vec_mul(ctx, x_sh, y_sh, n);
+    bool spdz = scheme == CZK_SCHEME_SPDZ;
+    if (spdz && (!x_mac || !y_mac || n > x_mac->n || n > y_mac->n)) return fail(ctx, CZK_ERR_ARG, "SPDZ product needs MAC vectors");
+    size_t bytes = n * 32;
+    CZK_TRY(scratch_reserve(ctx, ctx->open_sx, bytes));
+    CZK_TRY(scratch_reserve(ctx, ctx->open_oy, bytes));
+    CZK_TRY(scratch_reserve(ctx, ctx->open_d, bytes));
+    if (spdz) CZK_TRY(scratch_reserve(ctx, ctx->open_dm, bytes));
+    // stub triple (wire/field.rs:41-77): x = y = z = from_add_shared(1 at the king, 0 elsewhere);
+    // SPDZ from_add_shared(f) sets mac = f * mac() = f (spdz.rs:138-143)
+    HFr t = ctx->rank == 0 ? HFr::one() : HFr::zero();
+    HFr king = t;  // additive shift lands at the king; SPDZ MAC shift uses mac_share, same stub value
+    uint32_t* d = (uint32_t*)ctx->open_d.p;
+    uint32_t* dm = spdz ? (uint32_t*)ctx->open_dm.p : nullptr;
+    uint32_t* sx = (uint32_t*)ctx->open_sx.p;
+    uint32_t* oy = (uint32_t*)ctx->open_oy.p;
+    // sx = open(s + x)
+    CUDA_TRY(ctx, fr_add_const(d, (const uint32_t*)x_sh->d, t.l, n, ctx->stream));
+    if (spdz) CUDA_TRY(ctx, fr_add_const(dm, (const uint32_t*)x_mac->d, t.l, n, ctx->stream));
+    CZK_TRY(open_raw(ctx, scheme, d, dm, sx, n));
+    // oy = open(o + y)
+    CUDA_TRY(ctx, fr_add_const(d, (const uint32_t*)y_sh->d, t.l, n, ctx->stream));
+    if (spdz) CUDA_TRY(ctx, fr_add_const(dm, (const uint32_t*)y_mac->d, t.l, n, ctx->stream));
+    CZK_TRY(open_raw(ctx, scheme, d, dm, oy, n));
+    // z - sx*y - oy*x + shift(sx*oy)
+    CUDA_TRY(ctx, fr_beaver_finish((uint32_t*)x_sh->d, sx, oy, t.l, t.l, t.l, king.l, n, ctx->stream));
+    if (spdz) CUDA_TRY(ctx, fr_beaver_finish((uint32_t*)x_mac->d, sx, oy, t.l, t.l, t.l, king.l, n, ctx->stream));
+    return CZK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ diagnostics
+int czk_microbench(czk_ctx* ctx, int kind, int blocks_per_sm, int threads, int iters, double* ops_per_s, double* ms) {
+    if (!ctx || !ops_per_s || !ms) return fail(ctx, CZK_ERR_ARG, "czk_microbench: null");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    int blocks = prop.multiProcessorCount * blocks_per_sm;
+    CZK_TRY(scratch_reserve(ctx, ctx->up_vec, (size_t)blocks * threads * 8));
+    double ops = 0;
+    cudaEvent_t e0, e1;
+    CUDA_TRY(ctx, cudaEventCreate(&e0));
+    CUDA_TRY(ctx, cudaEventCreate(&e1));
+    CUDA_TRY(ctx, microbench_run(kind, blocks, threads, iters, (uint64_t*)ctx->up_vec.p, &ops, ctx->stream));  // warm-up
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        CUDA_TRY(ctx, cudaEventRecord(e0, ctx->stream));
+        CUDA_TRY(ctx, microbench_run(kind, blocks, threads, iters, (uint64_t*)ctx->up_vec.p, &ops, ctx->stream));
+        CUDA_TRY(ctx, cudaEventRecord(e1, ctx->stream));
+        CUDA_TRY(ctx, cudaEventSynchronize(e1));
+        float t;
+        CUDA_TRY(ctx, cudaEventElapsedTime(&t, e0, e1));
+        if (t < best) best = t;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *ms = best;
+    *ops_per_s = ops / (best * 1e-3);
+    return CZK_OK;
+}
+

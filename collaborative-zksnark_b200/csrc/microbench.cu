@@ -1,0 +1,93 @@
+// Integer-pipe microbenchmarks: the roofline denominators for the field kernels.  MEASURED_PEAKS.json
+// carries only HBM and bf16 peaks; these measure IMAD / IMAD.WIDE issue rates and the achieved field
+// multiplication and point addition rates at a chosen occupancy.
+#include <cuda_runtime.h>
+#include "ec.cuh"
+#include "launch_count.hpp"
+
+namespace czk {
+
+// kind 0: independent chains of 32x32+64 -> 64 multiply-adds (IMAD.WIDE.U32)
+__global__ void k_mb_wide(uint64_t* out, int iters, uint32_t seed) {
+    uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+    uint64_t c0 = a, c1 = b, c2 = a ^ b, c3 = a + b, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c0) : "r"(a), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c1) : "r"(a), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c2) : "r"(a), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c3) : "r"(a), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c4) : "r"(a), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c5) : "r"(a), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c6) : "r"(a), "r"(b));
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c7) : "r"(a), "r"(b));
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+}
+// kind 1: the same work as (mad.lo, mad.hi) pairs = 2 IMAD issue slots per product
+__global__ void k_mb_pair(uint64_t* out, int iters, uint32_t seed) {
+    uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+    uint32_t l0 = a, h0 = b, l1 = 1, h1 = 2, l2 = 3, h2 = 4, l3 = 5, h3 = 6;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 16; k++) {
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(l0) : "r"(a), "r"(b));
+            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(h0) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(l1) : "r"(a), "r"(b));
+            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(h1) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(l2) : "r"(a), "r"(b));
+            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(h2) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(l3) : "r"(a), "r"(b));
+            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(h3) : "r"(a), "r"(b));
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((uint64_t)(l0 ^ l1 ^ l2 ^ l3) << 32) | (h0 ^ h1 ^ h2 ^ h3);
+}
+template <class F>
+__global__ void k_mb_mul(uint64_t* out, int iters, uint32_t seed) {
+    F x = F::one(), y = F::r2();
+    x.l[0] ^= seed + threadIdx.x;
+    y.l[1] ^= blockIdx.x;
+    for (int i = 0; i < iters; i++) {
+        x = F::mul(x, y);
+        y = F::mul(y, x);
+    }
+    uint64_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < F::N; i++) acc ^= (uint64_t)(x.l[i] ^ y.l[i]) << (i & 31);
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+__global__ void k_mb_madd(uint64_t* out, int iters, uint32_t seed) {
+    XYZZ<Fq> acc = XYZZ<Fq>::from_affine(Fq::r2(), Fq::one());
+    Fq px = Fq::one(), py = Fq::r2();
+    px.l[0] ^= seed + threadIdx.x;
+    py.l[1] ^= blockIdx.x;
+    for (int i = 0; i < iters; i++) {
+        acc.add_affine(px, py);
+        px.l[2] += 1;
+    }
+    uint64_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r ^= (uint64_t)(acc.x.l[i] ^ acc.y.l[i] ^ acc.zz.l[i] ^ acc.zzz.l[i]) << (i & 31);
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
+cudaError_t microbench_run(int kind, int blocks, int threads, int iters, uint64_t* scratch, double* ops_per_launch,
+                           cudaStream_t st) {
+    double per_thread = 0;
+    switch (kind) {
+        case 0: k_mb_wide<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 64.0 * iters; break;
+        case 1: k_mb_pair<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 64.0 * iters; break;
+        case 2: k_mb_mul<Fr><<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 2.0 * iters; break;
+        case 3: k_mb_mul<Fq><<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 2.0 * iters; break;
+        case 4: k_mb_madd<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 1.0 * iters; break;
+        default: return cudaErrorInvalidValue;
+    }
+    CZK_LAUNCHED();
+    *ops_per_launch = per_thread * (double)blocks * (double)threads;
+    return cudaGetLastError();
+}
+
+}  // namespace czk

@@ -1,0 +1,326 @@
+// Device kernels of the bucket-method MSM (see msm.cuh for the pipeline and the reference lines replaced).
+#include "msm.cuh"
+
+#include "launch_count.hpp"
+
+namespace czk {
+
+// ------------------------------------------------------------------ element I/O (16-byte vector accesses)
+template <class F>
+struct FieldIO;
+template <>
+struct FieldIO<Fq> {
+    static constexpr int W = 12;
+    __device__ __forceinline__ static Fq load(const uint32_t* p) {
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+        uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
+        Fq r;
+        r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+        r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+        r.l[8] = c.x; r.l[9] = c.y; r.l[10] = c.z; r.l[11] = c.w;
+        return r;
+    }
+    __device__ __forceinline__ static Fq load_rw(const uint32_t* p) {
+        const uint4* q = reinterpret_cast<const uint4*>(p);
+        uint4 a = q[0], b = q[1], c = q[2];
+        Fq r;
+        r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+        r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+        r.l[8] = c.x; r.l[9] = c.y; r.l[10] = c.z; r.l[11] = c.w;
+        return r;
+    }
+    __device__ __forceinline__ static void store(uint32_t* p, const Fq& v) {
+        uint4* q = reinterpret_cast<uint4*>(p);
+        q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+        q[2] = make_uint4(v.l[8], v.l[9], v.l[10], v.l[11]);
+    }
+};
+template <>
+struct FieldIO<Fq2> {
+    static constexpr int W = 24;
+    __device__ __forceinline__ static Fq2 load(const uint32_t* p) { return Fq2{FieldIO<Fq>::load(p), FieldIO<Fq>::load(p + 12)}; }
+    __device__ __forceinline__ static Fq2 load_rw(const uint32_t* p) {
+        return Fq2{FieldIO<Fq>::load_rw(p), FieldIO<Fq>::load_rw(p + 12)};
+    }
+    __device__ __forceinline__ static void store(uint32_t* p, const Fq2& v) {
+        FieldIO<Fq>::store(p, v.c0);
+        FieldIO<Fq>::store(p + 12, v.c1);
+    }
+};
+template <class F>
+__device__ __forceinline__ XYZZ<F> load_point(const uint32_t* p) {
+    constexpr int W = FieldIO<F>::W;
+    XYZZ<F> r;
+    r.x = FieldIO<F>::load_rw(p);
+    r.y = FieldIO<F>::load_rw(p + W);
+    r.zz = FieldIO<F>::load_rw(p + 2 * W);
+    r.zzz = FieldIO<F>::load_rw(p + 3 * W);
+    return r;
+}
+template <class F>
+__device__ __forceinline__ void store_point(uint32_t* p, const XYZZ<F>& v) {
+    constexpr int W = FieldIO<F>::W;
+    FieldIO<F>::store(p, v.x);
+    FieldIO<F>::store(p + W, v.y);
+    FieldIO<F>::store(p + 2 * W, v.zz);
+    FieldIO<F>::store(p + 3 * W, v.zzz);
+}
+
+size_t msm_point_words(int curve) { return curve == 1 ? 48 : 96; }
+
+// ------------------------------------------------------------------ 1. prepare
+__global__ void k_msm_prepare(const uint32_t* __restrict__ scalars_in, const uint8_t* __restrict__ inf,
+                              uint32_t* __restrict__ scalars_out, uint32_t* __restrict__ hist, size_t n, unsigned c,
+                              unsigned nwin, unsigned nb, int mont) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* q = reinterpret_cast<const uint4*>(scalars_in) + 2 * i;
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    Fr s;
+    s.l[0] = a.x; s.l[1] = a.y; s.l[2] = a.z; s.l[3] = a.w;
+    s.l[4] = b.x; s.l[5] = b.y; s.l[6] = b.z; s.l[7] = b.w;
+    if (mont) s = Fr::from_mont(s);
+    if (inf && inf[i]) s = Fr::zero();
+    uint4* o = reinterpret_cast<uint4*>(scalars_out) + 2 * i;
+    o[0] = make_uint4(s.l[0], s.l[1], s.l[2], s.l[3]);
+    o[1] = make_uint4(s.l[4], s.l[5], s.l[6], s.l[7]);
+    uint32_t sl[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) sl[k] = s.l[k];
+    DigitCursor cur;
+    for (unsigned w = 0; w < nwin; w++) {
+        int32_t d = cur.next(sl, c, w);
+        if (d != 0) {
+            uint32_t mag = (uint32_t)(d < 0 ? -d : d);
+            atomicAdd(&hist[(size_t)w * nb + (mag - 1)], 1u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ 2. exclusive scan (one block)
+__global__ void __launch_bounds__(1024) k_exclusive_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n) {
+    __shared__ uint32_t sums[1024];
+    const unsigned tid = threadIdx.x;
+    size_t per = (n + 1023) / 1024;
+    size_t lo = (size_t)tid * per;
+    size_t hi = lo + per < n ? lo + per : n;
+    uint32_t s = 0;
+    for (size_t k = lo; k < hi; k++) s += in[k];
+    sums[tid] = s;
+    __syncthreads();
+    for (unsigned off = 1; off < 1024; off <<= 1) {
+        uint32_t v = tid >= off ? sums[tid - off] : 0u;
+        __syncthreads();
+        sums[tid] += v;
+        __syncthreads();
+    }
+    uint32_t base = tid ? sums[tid - 1] : 0u;
+    for (size_t k = lo; k < hi; k++) {
+        uint32_t v = in[k];
+        out[k] = base;
+        base += v;
+    }
+}
+
+// ------------------------------------------------------------------ 3. scatter
+__global__ void k_msm_scatter(const uint32_t* __restrict__ scalars, uint32_t* __restrict__ cursor,
+                              uint32_t* __restrict__ sorted, size_t n, unsigned c, unsigned nwin, unsigned nb) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4* q = reinterpret_cast<const uint4*>(scalars) + 2 * i;
+    uint4 a = q[0], b = q[1];
+    uint32_t sl[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    DigitCursor cur;
+    for (unsigned w = 0; w < nwin; w++) {
+        int32_t d = cur.next(sl, c, w);
+        if (d != 0) {
+            uint32_t mag = (uint32_t)(d < 0 ? -d : d);
+            uint32_t pos = atomicAdd(&cursor[(size_t)w * nb + (mag - 1)], 1u);
+            sorted[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ 4. accumulate: one thread per bucket
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                         const uint32_t* __restrict__ ends, const uint32_t* __restrict__ hist,
+                                                         uint32_t* __restrict__ buckets, size_t total) {
+    constexpr int W = FieldIO<F>::W;
+    size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    uint32_t cnt = hist[id];
+    uint32_t start = ends[id] - cnt;
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    for (uint32_t k = 0; k < cnt; k++) {
+        uint32_t e = sorted[start + k];
+        size_t idx = e & 0x7fffffffu;
+        const uint32_t* p = bases + idx * (2 * W);
+        F x = FieldIO<F>::load(p);
+        F y = FieldIO<F>::load(p + W);
+        if (e >> 31) y = F::neg(y);
+        acc.add_affine(x, y);
+    }
+    store_point<F>(buckets + id * (4 * W), acc);
+}
+
+// ------------------------------------------------------------------ 5a. chunked running sums
+// thread t of window w owns buckets [lo, lo+chunk): emits  sum_b (b+1) B_b  over its chunk
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_reduce_chunks(const uint32_t* __restrict__ buckets, uint32_t* __restrict__ partial,
+                                                            unsigned nb, unsigned chunk, unsigned nwin) {
+    constexpr int W = FieldIO<F>::W;
+    unsigned nchunks = nb / chunk;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (size_t)nwin * nchunks) return;
+    unsigned w = (unsigned)(t / nchunks), ci = (unsigned)(t % nchunks);
+    unsigned lo = ci * chunk;
+    XYZZ<F> S = XYZZ<F>::infinity(), T = XYZZ<F>::infinity();
+    for (unsigned k = chunk; k-- > 0;) {
+        XYZZ<F> B = load_point<F>(buckets + ((size_t)w * nb + lo + k) * (4 * W));
+        S.add(B);
+        T.add(S);
+    }
+    if (lo) {
+        // lo * S, MSB-first double and add
+        XYZZ<F> R = XYZZ<F>::infinity();
+        int top = 31 - __clz(lo);
+        for (int bit = top; bit >= 0; bit--) {
+            R = XYZZ<F>::dbl(R);
+            if ((lo >> bit) & 1) R.add(S);
+        }
+        T.add(R);
+    }
+    store_point<F>(partial + t * (4 * W), T);
+}
+
+// ------------------------------------------------------------------ 5b. per-window tree sum
+constexpr int WINSUM_THREADS = 64;
+template <class F>
+__global__ void __launch_bounds__(WINSUM_THREADS) k_msm_window_sum(const uint32_t* __restrict__ partial, uint32_t* __restrict__ winsum,
+                                                                    unsigned nchunks) {
+    constexpr int W = FieldIO<F>::W;
+    __shared__ XYZZ<F> sm[WINSUM_THREADS];
+    unsigned w = blockIdx.x, tid = threadIdx.x;
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    for (unsigned k = tid; k < nchunks; k += WINSUM_THREADS) acc.add(load_point<F>(partial + ((size_t)w * nchunks + k) * (4 * W)));
+    sm[tid] = acc;
+    __syncthreads();
+    for (unsigned s = WINSUM_THREADS / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            XYZZ<F> a = sm[tid];
+            a.add(sm[tid + s]);
+            sm[tid] = a;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) store_point<F>(winsum + (size_t)w * (4 * W), sm[0]);
+}
+
+template <class F>
+static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const uint32_t* scalars, bool mont, size_t n,
+                             const MsmConfig& cfg, MsmWorkspace& ws, cudaStream_t st) {
+    size_t total = (size_t)cfg.nwin * cfg.nb;
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(ws.hist, 0, total * sizeof(uint32_t), st)) != cudaSuccess) return e;
+    if (n) {
+        unsigned blocks = (unsigned)((n + 255) / 256);
+        k_msm_prepare<<<blocks, 256, 0, st>>>(scalars, inf, ws.scalars, ws.hist, n, cfg.c, cfg.nwin, cfg.nb, mont ? 1 : 0); CZK_LAUNCHED();
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    k_exclusive_scan<<<1, 1024, 0, st>>>(ws.hist, ws.offsets, total); CZK_LAUNCHED();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (n) {
+        unsigned blocks = (unsigned)((n + 255) / 256);
+        k_msm_scatter<<<blocks, 256, 0, st>>>(ws.scalars, ws.offsets, ws.sorted, n, cfg.c, cfg.nwin, cfg.nb); CZK_LAUNCHED();
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    }
+    k_msm_accumulate<F><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(bases, ws.sorted, ws.offsets, ws.hist, ws.buckets, total); CZK_LAUNCHED();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    unsigned nchunks = cfg.nb / cfg.chunk;
+    size_t rthreads = (size_t)cfg.nwin * nchunks;
+    k_msm_reduce_chunks<F><<<(unsigned)((rthreads + 127) / 128), 128, 0, st>>>(ws.buckets, ws.partial, cfg.nb, cfg.chunk, cfg.nwin); CZK_LAUNCHED();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    k_msm_window_sum<F><<<cfg.nwin, WINSUM_THREADS, 0, st>>>(ws.partial, ws.winsum, nchunks); CZK_LAUNCHED();
+    return cudaGetLastError();
+}
+
+cudaError_t msm_run(int curve, const uint32_t* bases, const uint8_t* inf, const uint32_t* scalars, bool scalars_mont,
+                    size_t n, const MsmConfig& cfg, MsmWorkspace& ws, cudaStream_t st) {
+    if (curve == 1) return msm_run_t<Fq>(bases, inf, scalars, scalars_mont, n, cfg, ws, st);
+    return msm_run_t<Fq2>(bases, inf, scalars, scalars_mont, n, cfg, ws, st);
+}
+
+// ------------------------------------------------------------------ synthetic / test input generator
+struct U256 {
+    uint64_t v[4];
+};
+constexpr int PROG_CHUNK = 64;
+template <class F>
+__global__ void __launch_bounds__(128) k_gen_progression(uint32_t* __restrict__ out_xy, const uint32_t* __restrict__ base_xy,
+                                                          const uint32_t* __restrict__ step_xy, U256 k0, U256 kstep, size_t n) {
+    constexpr int W = FieldIO<F>::W;
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t lo = t * PROG_CHUNK;
+    if (lo >= n) return;
+    // k = k0 + lo * kstep  (mod r), computed in Montgomery form then brought back
+    Fr k0m, ksm, lom = Fr::zero();
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        k0m.l[2 * i] = (uint32_t)k0.v[i];
+        k0m.l[2 * i + 1] = (uint32_t)(k0.v[i] >> 32);
+        ksm.l[2 * i] = (uint32_t)kstep.v[i];
+        ksm.l[2 * i + 1] = (uint32_t)(kstep.v[i] >> 32);
+    }
+    lom.l[0] = (uint32_t)lo;
+    lom.l[1] = (uint32_t)((uint64_t)lo >> 32);
+    Fr k = Fr::add(Fr::to_mont(k0m), Fr::mul(Fr::to_mont(lom), Fr::to_mont(ksm)));
+    k = Fr::from_mont(k);
+    uint32_t kb[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) kb[i] = k.l[i];
+    F bx = FieldIO<F>::load(base_xy), by = FieldIO<F>::load(base_xy + W);
+    F sx = FieldIO<F>::load(step_xy), sy = FieldIO<F>::load(step_xy + W);
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    for (int bit = 252; bit >= 0; bit--) {
+        acc = XYZZ<F>::dbl(acc);
+        if ((kb[bit >> 5] >> (bit & 31)) & 1) acc.add_affine(bx, by);
+    }
+    size_t hi = lo + PROG_CHUNK < n ? lo + PROG_CHUNK : n;
+    for (size_t i = lo; i < hi; i++) {
+        F ox, oy;
+        if (acc.is_inf()) {
+            ox = F::zero();
+            oy = F::one();
+        } else {
+            F inv = F::inv_fermat(F::mul(acc.zz, acc.zzz));
+            ox = F::mul(acc.x, F::mul(inv, acc.zzz));
+            oy = F::mul(acc.y, F::mul(inv, acc.zz));
+        }
+        FieldIO<F>::store(out_xy + i * (2 * W), ox);
+        FieldIO<F>::store(out_xy + i * (2 * W) + W, oy);
+        acc.add_affine(sx, sy);
+    }
+}
+
+cudaError_t ec_gen_progression_dev(int curve, uint32_t* out_xy, const uint32_t* base_xy, const uint32_t* step_xy,
+                                   const uint64_t k0_canon[4], const uint64_t kstep_canon[4], size_t n, cudaStream_t st) {
+    U256 a, b;
+    for (int i = 0; i < 4; i++) {
+        a.v[i] = k0_canon[i];
+        b.v[i] = kstep_canon[i];
+    }
+    size_t threads = (n + PROG_CHUNK - 1) / PROG_CHUNK;
+    unsigned blocks = (unsigned)((threads + 127) / 128);
+    if (!blocks) return cudaSuccess;
+    if (curve == 1) {
+        k_gen_progression<Fq><<<blocks, 128, 0, st>>>(out_xy, base_xy, step_xy, a, b, n);
+    } else {
+        k_gen_progression<Fq2><<<blocks, 128, 0, st>>>(out_xy, base_xy, step_xy, a, b, n);
+    }
+    CZK_LAUNCHED();
+    return cudaGetLastError();
+}
+
+}  // namespace czk

@@ -1,0 +1,72 @@
+// Variable-base multi-scalar multiplication on BLS12-377 G1 / G2.
+//
+// Replaces VariableBaseMSM::multi_scalar_mul (algebra/ec/src/msm/variable_base.rs:12-106) and its
+// wrapper AffineCurve::multi_scalar_mul (algebra/ec/src/lib.rs:302-311: Fr -> BigInt per scalar).
+// Same function - sum_i s_i P_i over min(len) terms, infinity bases and zero scalars contribute
+// nothing - computed by a device bucket method that shares nothing with the reference's loop
+// structure:
+//   1. prepare   : scalar from Montgomery form, balanced signed c-bit digits, per-bucket histogram
+//   2. scan      : exclusive prefix sum of the histogram -> bucket offsets
+//   3. scatter   : counting sort of (point index, sign) by (window, |digit|)
+//   4. accumulate: one thread per bucket, XYZZ mixed additions over its sorted run
+//   5. reduce    : per window sum_b b * B_b  by chunked running sums, then a block tree sum
+//   6. host tail : sum_w 2^(c w) W_w (c doublings per window, variable_base.rs:92-105) and one
+//                  affine normalisation, on the CPU - it is O(windows), strictly serial.
+// The window size c is chosen for the GPU, not by the reference's ln_without_floats heuristic;
+// the group element returned is the same, and it is returned in affine-normalised form.
+#pragma once
+#include <cuda_runtime.h>
+#include "ec.cuh"
+#include "msm_digits.cuh"
+
+namespace czk {
+
+struct MsmConfig {
+    unsigned c;        // window bits
+    unsigned nwin;     // windows
+    unsigned nb;       // buckets per window = 2^(c-1)
+    unsigned chunk;    // buckets per thread in the reduce kernel
+};
+
+inline MsmConfig msm_choose_config(size_t n) {
+    // c ~ log2(n) - 4, clamped; measured trade-off between N*W mixed adds and 2^c*W bucket work
+    unsigned lg = 0;
+    while (((size_t)1 << lg) < n) lg++;
+    unsigned c = lg > 6 ? lg - 4 : 2;
+    if (c < 2) c = 2;
+    if (c > 16) c = 16;
+    MsmConfig cfg;
+    cfg.c = c;
+    cfg.nwin = msm_num_windows(c);
+    cfg.nb = 1u << (c - 1);
+    cfg.chunk = cfg.nb >= 16 ? 16 : cfg.nb;
+    return cfg;
+}
+
+struct MsmWorkspace {
+    uint32_t* scalars = nullptr;   // n x 8 canonical
+    uint32_t* hist = nullptr;      // nwin*nb
+    uint32_t* offsets = nullptr;   // nwin*nb (exclusive scan, then advanced to bucket ends by the scatter)
+    uint32_t* sorted = nullptr;    // n*nwin entries: point index | sign << 31
+    uint32_t* buckets = nullptr;   // nwin*nb points, XYZZ
+    uint32_t* partial = nullptr;   // nwin*(nb/chunk) points
+    uint32_t* winsum = nullptr;    // nwin points
+    size_t cap_n = 0;
+    size_t cap_buckets = 0;
+    int point_words = 0;
+};
+
+// curve: 1 = G1 (Fq, 12 words per coordinate), 2 = G2 (Fq2, 24 words per coordinate)
+// bases: n affine points, x | y, Montgomery, 16-byte aligned; inf: n bytes or nullptr.
+// scalars: n x 8 words.  winsum_out: device buffer of cfg.nwin XYZZ points.
+cudaError_t msm_run(int curve, const uint32_t* bases, const uint8_t* inf, const uint32_t* scalars, bool scalars_mont,
+                    size_t n, const MsmConfig& cfg, MsmWorkspace& ws, cudaStream_t st);
+
+size_t msm_point_words(int curve);  // 4 coordinates
+
+// test / synthetic-input helper: out[i] = (k0 + i * kstep) * base as affine points (x | y)
+// (step_xy = kstep * base, affine, device memory)
+cudaError_t ec_gen_progression_dev(int curve, uint32_t* out_xy, const uint32_t* base_xy, const uint32_t* step_xy,
+                                   const uint64_t k0_canon[4], const uint64_t kstep_canon[4], size_t n, cudaStream_t st);
+
+}  // namespace czk

@@ -1,0 +1,150 @@
+/* czk.h - C ABI of libczk_b200.so: the B200 (sm_100a) hot path of collaborative-zksnark.
+ *
+ * Every entry point is what the reference's FFI for this path would bind (the Rust
+ * `-sys` stub is in INTEGRATION.md).  Plain pointers and sizes only.  All field
+ * elements cross the boundary in the reference's in-memory form: little-endian u64
+ * limbs in Montgomery representation (Fr = 4 limbs, R = 2^256; Fq = 6 limbs,
+ * R = 2^384; Fq2 = c0 | c1), see algebra/ff/src/fields/macros.rs:103-108.
+ * Affine points are x | y (12 limbs G1, 24 limbs G2) plus a separate infinity byte
+ * (the reference's GroupAffine is repr(Rust): x, y, infinity: bool -
+ * algebra/ec/src/models/short_weierstrass_jacobian.rs:43-49).
+ *
+ * Error behaviour: the reference's functions on this path return values and panic on
+ * misuse; here every function returns 0 on success and a non-zero czk_status
+ * otherwise, czk_last_error() gives the message, and the binding panics on non-zero.
+ * Calls are synchronous (they return when the result is in the caller's buffer),
+ * matching the reference's blocking calls from a single main thread per party.
+ */
+#ifndef CZK_H
+#define CZK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CZK_API __attribute__((visibility("default")))
+#else
+#define CZK_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum czk_status {
+    CZK_OK = 0,
+    CZK_ERR_CUDA = 1,       /* a CUDA runtime call or kernel failed */
+    CZK_ERR_ARG = 2,        /* invalid argument (size, null pointer, unsupported domain) */
+    CZK_ERR_NO_DEVICE = 3,  /* no usable CUDA device: the product path never falls back to the CPU */
+    CZK_ERR_NCCL = 4,
+    CZK_ERR_PROTOCOL = 5    /* MAC check / degree check / cross-party consistency failed (reference: assert!) */
+} czk_status;
+
+typedef struct czk_ctx czk_ctx;     /* one per party / GPU */
+typedef struct czk_vec czk_vec;     /* device-resident vector of Fr */
+typedef struct czk_bases czk_bases; /* device-resident affine bases (a CRS query) */
+
+/* ---- context ---------------------------------------------------------------------------- */
+CZK_API int czk_ctx_create(int device, czk_ctx** out);
+CZK_API void czk_ctx_destroy(czk_ctx* ctx);
+CZK_API const char* czk_last_error(const czk_ctx* ctx); /* ctx may be NULL: last error of the calling thread */
+CZK_API int czk_ctx_sync(czk_ctx* ctx);
+/* The CUDA stream every kernel of this context is launched on (a cudaStream_t). */
+CZK_API void* czk_ctx_stream(czk_ctx* ctx);
+/* Number of this library's kernel launches issued through ctx since creation. */
+CZK_API uint64_t czk_ctx_launches(const czk_ctx* ctx);
+CZK_API const char* czk_version(void);
+
+/* ---- device vectors of Fr ----------------------------------------------------------------- */
+CZK_API int czk_vec_alloc(czk_ctx* ctx, size_t n, czk_vec** out); /* zero filled */
+CZK_API void czk_vec_free(czk_ctx* ctx, czk_vec* v);
+CZK_API size_t czk_vec_len(const czk_vec* v);
+CZK_API uint64_t* czk_vec_device_ptr(czk_vec* v);
+CZK_API int czk_vec_upload(czk_ctx* ctx, czk_vec* v, size_t offset, const uint64_t* host, size_t n);
+CZK_API int czk_vec_download(czk_ctx* ctx, const czk_vec* v, size_t offset, uint64_t* host, size_t n);
+CZK_API int czk_vec_copy(czk_ctx* ctx, czk_vec* dst, size_t dst_off, const czk_vec* src, size_t src_off, size_t n);
+CZK_API int czk_vec_zero(czk_ctx* ctx, czk_vec* v, size_t offset, size_t n);
+
+/* ---- NTT: replaces Radix2EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place ------------
+ * algebra/poly/src/domain/radix2/mod.rs:99-117, radix2/fft.rs:22-260, domain/mod.rs:93-142.
+ * In place, natural order in and out, size 2^log_d (the caller zero-pads like mod.rs:100-101).
+ * inverse: 0 fft, 1 ifft.  coset: 0 subgroup, 1 coset of the multiplicative generator 22.      */
+CZK_API int czk_ntt_fr(czk_ctx* ctx, uint64_t* host_data, unsigned log_d, int inverse, int coset); /* host buffer in/out */
+CZK_API int czk_ntt_fr_dev(czk_ctx* ctx, uint64_t* dev_data, unsigned log_d, int inverse, int coset);
+CZK_API int czk_ntt_vec(czk_ctx* ctx, czk_vec* v, unsigned log_d, int inverse, int coset);
+/* Domain constants as Radix2EvaluationDomain::new computes them (radix2/mod.rs:51-82). */
+CZK_API int czk_domain_params(unsigned log_d, uint64_t group_gen[4], uint64_t group_gen_inv[4], uint64_t size_inv[4],
+                      uint64_t generator_inv[4]);
+
+/* ---- pointwise Fr helpers used between the transforms -------------------------------------------
+ * domain/mod.rs:93-126 (distribute_powers), :184-191 (divide_by_vanishing_poly_on_coset_in_place),
+ * mpc-snarks/src/groth/r1cs_to_qap.rs:92,105-109.                                                */
+CZK_API int czk_vec_add(czk_ctx* ctx, czk_vec* a, const czk_vec* b, size_t n);              /* a += b */
+CZK_API int czk_vec_sub(czk_ctx* ctx, czk_vec* a, const czk_vec* b, size_t n);              /* a -= b */
+CZK_API int czk_vec_mul(czk_ctx* ctx, czk_vec* a, const czk_vec* b, size_t n);              /* a *= b (plain field) */
+CZK_API int czk_vec_scale(czk_ctx* ctx, czk_vec* a, const uint64_t c[4], size_t n);         /* a *= c */
+CZK_API int czk_vec_distribute_powers(czk_ctx* ctx, czk_vec* a, const uint64_t g[4], const uint64_t c[4], size_t n); /* a[i] *= c g^i */
+CZK_API int czk_vec_divide_by_vanishing_on_coset(czk_ctx* ctx, czk_vec* a, unsigned log_d);
+
+/* ---- MSM: replaces VariableBaseMSM::multi_scalar_mul / AffineCurve::multi_scalar_mul / Msm::msm --
+ * algebra/ec/src/msm/variable_base.rs:12-106, algebra/ec/src/lib.rs:302-311,
+ * mpc-algebra/src/share/msm.rs:6-48.  Uses min(len) terms; infinity bases and zero scalars are
+ * skipped.  scalars_montgomery = 1: Fr in Montgomery form (what AffineCurve::multi_scalar_mul
+ * takes); 0: canonical BigInt256 (what VariableBaseMSM takes).  The result is written as a Jacobian
+ * triple x | y | z that is already affine-normalised: (x, y, 1), or (1, 1, 0) for infinity
+ * (short_weierstrass_jacobian.rs:440-448), i.e. `.into_affine()` is a no-op on it.               */
+CZK_API int czk_msm_g1(czk_ctx* ctx, const uint64_t* bases_xy, const uint8_t* inf, const uint64_t* scalars,
+               int scalars_montgomery, size_t n, uint64_t out_xyz[18]);
+CZK_API int czk_msm_g2(czk_ctx* ctx, const uint64_t* bases_xy, const uint8_t* inf, const uint64_t* scalars,
+               int scalars_montgomery, size_t n, uint64_t out_xyz[36]);
+/* Device-resident bases (the reference re-passes the same pk.*_query every proof). curve: 1 = G1, 2 = G2. */
+CZK_API int czk_bases_upload(czk_ctx* ctx, int curve, const uint64_t* bases_xy, const uint8_t* inf, size_t n, czk_bases** out);
+CZK_API void czk_bases_free(czk_ctx* ctx, czk_bases* b);
+CZK_API size_t czk_bases_len(const czk_bases* b);
+/* MSM of bases[base_off .. base_off+n) by the device scalars sc[sc_off .. sc_off+n). */
+CZK_API int czk_msm_bases(czk_ctx* ctx, const czk_bases* b, size_t base_off, const czk_vec* sc, size_t sc_off,
+                  int scalars_montgomery, size_t n, uint64_t* out_xyz);
+/* Synthetic bases for benchmarks: P_i = (k0 + i*kstep) * G (distinct points of the prime-order subgroup,
+ * generated on the device), every `inf_every`-th entry flagged infinity (0 = none).                */
+CZK_API int czk_bases_synthetic(czk_ctx* ctx, int curve, uint64_t seed, size_t n, size_t inf_every, czk_bases** out);
+CZK_API int czk_bases_download(czk_ctx* ctx, const czk_bases* b, size_t off, size_t n, uint64_t* xy, uint8_t* inf);
+
+/* ---- network: replaces mpc-net's MpcNet (mpc-net/src/lib.rs:28-70, multi.rs:145-242) ------------
+ * One rank = one party = one GPU; rank 0 is the king.  nccl_unique_id is the 128-byte ncclUniqueId
+ * produced by czk_net_unique_id on rank 0 and distributed by the launcher.                        */
+CZK_API int czk_net_unique_id(uint8_t out[128]);
+CZK_API int czk_net_init(czk_ctx* ctx, int rank, int nranks, const uint8_t nccl_unique_id[128]);
+CZK_API int czk_net_init_single(czk_ctx* ctx); /* 1 party, no communicator */
+CZK_API void czk_net_deinit(czk_ctx* ctx);
+CZK_API int czk_net_party_id(const czk_ctx* ctx);
+CZK_API int czk_net_n_parties(const czk_ctx* ctx);
+/* broadcast_bytes: every party contributes `bytes` bytes, receives all (nranks * bytes) in rank order. */
+CZK_API int czk_net_allgather_dev(czk_ctx* ctx, const void* dev_send, void* dev_recv, size_t bytes);
+CZK_API int czk_net_allgather_host(czk_ctx* ctx, const void* host_send, void* host_recv, size_t bytes);
+/* send_bytes_to_king / recv_bytes_from_king with equal slices for every party. */
+CZK_API int czk_net_bcast_from_king_dev(czk_ctx* ctx, void* dev_buf, size_t bytes);
+/* Stats (mpc-net/src/lib.rs:8-26): bytes_sent, bytes_recv, broadcasts, to_king, from_king. */
+CZK_API int czk_net_stats(const czk_ctx* ctx, uint64_t out[5]);
+CZK_API void czk_net_reset_stats(czk_ctx* ctx);
+
+/* ---- shares: replaces FieldShare::{batch_open,batch_mul} ------------------------------------------
+ * mpc-algebra/src/share/{field.rs:97-127, add.rs:121-125, spdz.rs:166-185}.
+ * scheme: 1 = additive (hbc), 2 = SPDZ.  For SPDZ a share vector is two czk_vec (sh, mac).         */
+#define CZK_SCHEME_PLAIN 0
+#define CZK_SCHEME_ADDITIVE 1
+#define CZK_SCHEME_SPDZ 2
+CZK_API int czk_batch_open(czk_ctx* ctx, int scheme, const czk_vec* sh, const czk_vec* mac, czk_vec* out_pub, size_t n);
+/* x *= y elementwise on shares with the reference's stub triple source (DummyFieldTripleSource,
+ * mpc-algebra/src/wire/field.rs:41-77): Beaver multiplication, two opens.                         */
+CZK_API int czk_beaver_batch_mul(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac, const czk_vec* y_sh,
+                         const czk_vec* y_mac, size_t n);
+
+/* ---- diagnostics --------------------------------------------------------------------------------- */
+/* Integer-pipe microbenchmarks; result = operations per second.  kind: 0 IMAD.WIDE.U32 chain,
+ * 1 IMAD lo/hi pair, 2 Fr mul, 3 Fq mul, 4 G1 mixed add. */
+CZK_API int czk_microbench(czk_ctx* ctx, int kind, int blocks_per_sm, int threads, int iters, double* ops_per_s, double* ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CZK_H */

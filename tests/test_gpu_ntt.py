@@ -1,0 +1,100 @@
+"""GPU parity: device NTT (czk_ntt_fr / czk_ntt_vec) vs the CPU oracle, bit-exact.
+
+Mirrors the reference's own NTT tests (algebra/poly/src/domain/radix2/mod.rs:320-360, :381-491):
+FFT == polynomial evaluation at w^i / g w^i, iFFT o FFT == id, and all four transform flavours.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("log_d", [0, 1, 2, 3, 5, 8, 10, 11, 12, 13, 16, 18])
+def test_ntt_matches_oracle_all_flavours(ctx, oracle, log_d):
+    n = 1 << log_d
+    v = oracle.random_fr_mont(0x47 + log_d, n)
+    for inverse in (False, True):
+        for coset in (False, True):
+            got = ctx._ntt_host(v, inverse, coset)
+            exp = oracle.ntt(v, inverse, coset, threads=8) if n > 1 else v.copy()
+            assert got.shape == exp.shape
+            assert (got == exp).all(), f"log_d={log_d} inverse={inverse} coset={coset}: first diff at {np.argwhere(got != exp)[:3]}"
+
+
+def test_ntt_zero_pads_short_input(ctx, oracle):
+    # radix2/mod.rs:100-101: coeffs.resize(size, zero)
+    v = oracle.random_fr_mont(9, 1000)
+    padded = np.concatenate([v, np.zeros((24, 4), np.uint64)])
+    assert (ctx.fft(v) == oracle.ntt(padded)).all()
+
+
+def test_fft_is_polynomial_evaluation(ctx, oracle, pymodel):
+    # radix2/mod.rs:320-360 test_fft_correctness, on BLS12-377 Fr
+    log_d = 6
+    n = 1 << log_d
+    coeffs = oracle.random_fr_mont(77, n)
+    d = oracle.domain_params(n)
+    evals = ctx.fft(coeffs)
+    cevals = ctx.coset_fft(coeffs)
+    g = oracle.fr_from_ints([pymodel.FR_GENERATOR])[0]
+    for i in (0, 1, 2, 17, n - 1):
+        wi = oracle.fr_pow_u64(d["group_gen"], i)
+        assert (evals[i] == oracle.poly_eval(coeffs, wi)).all()
+        assert (cevals[i] == oracle.poly_eval(coeffs, oracle.fr_mul(g[None, :], wi[None, :])[0])).all()
+
+
+@pytest.mark.parametrize("log_d", [20, 21, 22])
+def test_ntt_large_roundtrip_and_spot_parity(ctx, oracle, log_d):
+    """BASELINE sizes: bit-exact vs the oracle (multi-threaded) and the size-independent identities."""
+    n = 1 << log_d
+    v = oracle.random_fr_mont(0x47 + log_d, n)
+    dv = ctx.vec_from(v)
+    ctx.ntt_in_place(dv, log_d, inverse=False, coset=True)
+    fwd = dv.numpy()
+    assert (fwd == oracle.ntt(v, False, True, threads=oracle.cpu_threads())).all()
+    ctx.ntt_in_place(dv, log_d, inverse=True, coset=True)
+    assert (dv.numpy() == v).all()
+    # linearity: NTT(a + b) == NTT(a) + NTT(b)
+    w = oracle.random_fr_mont(0x1234 + log_d, n)
+    da, db = ctx.vec_from(v), ctx.vec_from(w)
+    ds = ctx.vec_from(oracle.fr_add(v, w))
+    for x in (da, db, ds):
+        ctx.ntt_in_place(x, log_d)
+    ctx.vec_add(da, db)
+    assert (da.numpy() == ds.numpy()).all()
+
+
+def test_domain_params_match_oracle(czk, oracle):
+    for log_d in (0, 1, 4, 11, 21, 24, 30):
+        a = czk.domain_params(log_d)
+        b = oracle.domain_params(1 << log_d)
+        for k in ("group_gen", "group_gen_inv", "size_inv", "generator_inv"):
+            assert (a[k] == b[k]).all(), (log_d, k)
+
+
+def test_pointwise_helpers(ctx, oracle, pymodel):
+    n = 5000
+    a = oracle.random_fr_mont(1, n)
+    b = oracle.random_fr_mont(2, n)
+    for name, ref in (("vec_add", oracle.fr_add), ("vec_sub", oracle.fr_sub), ("vec_mul", oracle.fr_mul)):
+        da, db = ctx.vec_from(a), ctx.vec_from(b)
+        getattr(ctx, name)(da, db)
+        assert (da.numpy() == ref(a, b)).all(), name
+    c = oracle.random_fr_mont(3, 1)[0]
+    da = ctx.vec_from(a)
+    ctx.vec_scale(da, c)
+    assert (da.numpy() == oracle.fr_mul(a, np.tile(c, (n, 1)))).all()
+    # distribute_powers (domain/mod.rs:93-104): a[i] *= c * g^i
+    g = oracle.fr_from_ints([pymodel.FR_GENERATOR])[0]
+    da = ctx.vec_from(a)
+    ctx.distribute_powers(da, g, c)
+    ai = oracle.fr_to_ints(a)
+    ci = oracle.fr_to_ints(c[None, :])[0]
+    exp = [x * ci * pow(pymodel.FR_GENERATOR, i, pymodel.R_MOD) % pymodel.R_MOD for i, x in enumerate(ai)]
+    assert oracle.fr_to_ints(da.numpy()) == exp
+    # divide_by_vanishing_poly_on_coset_in_place
+    log_d = 12
+    x = oracle.random_fr_mont(4, 1 << log_d)
+    dx = ctx.vec_from(x)
+    ctx.divide_by_vanishing_on_coset(dx, log_d)
+    assert (dx.numpy() == oracle.divide_by_vanishing_on_coset(x)).all()
