@@ -157,6 +157,9 @@ static void free_ws(MsmWorkspace& ws) {
     cudaFree(ws.buckets);
     cudaFree(ws.partial);
     cudaFree(ws.winsum);
+    cudaFree(ws.segcnt);
+    cudaFree(ws.segoff);
+    cudaFree(ws.segsum);
     ws = MsmWorkspace();
 }
 
@@ -409,7 +412,9 @@ static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
         cudaFree(ws.buckets);
         cudaFree(ws.partial);
         cudaFree(ws.winsum);
-        ws.hist = ws.offsets = ws.buckets = ws.partial = ws.winsum = nullptr;
+        cudaFree(ws.segcnt);
+        cudaFree(ws.segoff);
+        ws.hist = ws.offsets = ws.buckets = ws.partial = ws.winsum = ws.segcnt = ws.segoff = nullptr;
         size_t cap = total > ws.cap_buckets ? total : ws.cap_buckets;
         int pww = pw > ws.point_words ? pw : ws.point_words;
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.hist, cap * 4));
@@ -417,8 +422,24 @@ static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.buckets, cap * pww * 4));
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.partial, cap * pww * 4));  // >= nwin * nchunks points
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.winsum, 256 * (size_t)pww * 4));
+        CUDA_TRY(ctx, cudaMalloc((void**)&ws.segcnt, cap * 4));
+        CUDA_TRY(ctx, cudaMalloc((void**)&ws.segoff, cap * 4));
         ws.cap_buckets = cap;
         ws.point_words = pww;
+    }
+    {
+        // per-segment sums: one slot per bucket plus one per `seg` sorted entries (see msm_run)
+        size_t items = total + (n * cfg.nwin) / 128 + 64;
+        if (items > ws.cap_items || pw > ws.seg_point_words) {
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(ws.segsum);
+            ws.segsum = nullptr;
+            size_t cap = items + items / 8;
+            int pww = pw > ws.seg_point_words ? pw : ws.seg_point_words;
+            CUDA_TRY(ctx, cudaMalloc((void**)&ws.segsum, cap * (size_t)pww * 4));
+            ws.cap_items = cap;
+            ws.seg_point_words = pww;
+        }
     }
     size_t pin = 256 * 96 * 4;
     if (ctx->pinned_cap < pin) {

@@ -142,19 +142,46 @@ __global__ void k_msm_scatter(const uint32_t* __restrict__ scalars, uint32_t* __
     }
 }
 
-// ------------------------------------------------------------------ 4. accumulate: one thread per bucket
+// ------------------------------------------------------------------ 4. accumulate
+// A bucket's sorted run is cut into segments of at most `seg` points; one thread sums one segment.
+// With uniform digits every bucket is a single segment (seg >= the mean bucket load) and the result
+// goes straight to buckets[]; heavier buckets - a degenerate top window, repeated scalars - are split
+// so no thread ever walks more than `seg` points, and a second kernel folds the segment sums.
+__global__ void k_msm_seg_counts(const uint32_t* __restrict__ hist, uint32_t* __restrict__ segcnt, size_t total, uint32_t seg) {
+    size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= total) return;
+    uint32_t c = hist[id];
+    segcnt[id] = c ? (c + seg - 1) / seg : 1u;  // empty buckets keep one (empty) segment so they get zeroed
+}
+
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                          const uint32_t* __restrict__ ends, const uint32_t* __restrict__ hist,
-                                                         uint32_t* __restrict__ buckets, size_t total) {
+                                                         const uint32_t* __restrict__ segoff, const uint32_t* __restrict__ segcnt,
+                                                         uint32_t* __restrict__ buckets, uint32_t* __restrict__ segsum, size_t total,
+                                                         size_t max_items, uint32_t seg) {
     constexpr int W = FieldIO<F>::W;
     size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= total) return;
-    uint32_t cnt = hist[id];
-    uint32_t start = ends[id] - cnt;
+    if (id >= max_items) return;
+    size_t nitems = (size_t)segoff[total - 1] + segcnt[total - 1];
+    if (id >= nitems) return;
+    // bucket b with segoff[b] <= id < segoff[b] + segcnt[b]: last b with segoff[b] <= id
+    size_t lo = 0, hi = total - 1;
+    while (lo < hi) {
+        size_t mid = (lo + hi + 1) >> 1;
+        if (segoff[mid] <= id) lo = mid;
+        else hi = mid - 1;
+    }
+    const size_t b = lo;
+    const uint32_t k = (uint32_t)(id - segoff[b]);
+    const uint32_t cnt = hist[b];
+    const uint32_t start = ends[b] - cnt + k * seg;
+    uint32_t len = cnt - k * seg;
+    if (cnt < k * seg) len = 0;
+    if (len > seg) len = seg;
     XYZZ<F> acc = XYZZ<F>::infinity();
-    for (uint32_t k = 0; k < cnt; k++) {
-        uint32_t e = sorted[start + k];
+    for (uint32_t j = 0; j < len; j++) {
+        uint32_t e = sorted[start + j];
         size_t idx = e & 0x7fffffffu;
         const uint32_t* p = bases + idx * (2 * W);
         F x = FieldIO<F>::load(p);
@@ -162,7 +189,24 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restri
         if (e >> 31) y = F::neg(y);
         acc.add_affine(x, y);
     }
-    store_point<F>(buckets + id * (4 * W), acc);
+    if (segcnt[b] == 1) store_point<F>(buckets + b * (4 * W), acc);
+    else store_point<F>(segsum + id * (4 * W), acc);
+}
+
+// fold the segment sums of the (rare) multi-segment buckets
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_fold_segments(const uint32_t* __restrict__ segoff, const uint32_t* __restrict__ segcnt,
+                                                            const uint32_t* __restrict__ segsum, uint32_t* __restrict__ buckets,
+                                                            size_t total) {
+    constexpr int W = FieldIO<F>::W;
+    size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= total) return;
+    uint32_t n = segcnt[b];
+    if (n <= 1) return;
+    size_t off = segoff[b];
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    for (uint32_t k = 0; k < n; k++) acc.add(load_point<F>(segsum + (off + k) * (4 * W)));
+    store_point<F>(buckets + b * (4 * W), acc);
 }
 
 // ------------------------------------------------------------------ 5a. chunked running sums
@@ -236,7 +280,18 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
         k_msm_scatter<<<blocks, 256, 0, st>>>(ws.scalars, ws.offsets, ws.sorted, n, cfg.c, cfg.nwin, cfg.nb); CZK_LAUNCHED();
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    k_msm_accumulate<F><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(bases, ws.sorted, ws.offsets, ws.hist, ws.buckets, total); CZK_LAUNCHED();
+    // segment length: at least the mean load of a busy bucket, and ~sqrt(n) so that neither the per-segment
+    // walk nor the fold over segments can exceed O(sqrt(n)) serial additions whatever the digits are
+    uint32_t seg = 128;
+    while ((size_t)seg * seg < n) seg <<= 1;
+    size_t max_items = total + (n * cfg.nwin) / seg + 1;
+    if (max_items > ws.cap_items) return cudaErrorInvalidValue;
+    k_msm_seg_counts<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.hist, ws.segcnt, total, seg); CZK_LAUNCHED();
+    k_exclusive_scan<<<1, 1024, 0, st>>>(ws.segcnt, ws.segoff, total); CZK_LAUNCHED();
+    k_msm_accumulate<F><<<(unsigned)((max_items + 127) / 128), 128, 0, st>>>(bases, ws.sorted, ws.offsets, ws.hist, ws.segoff, ws.segcnt,
+                                                                          ws.buckets, ws.segsum, total, max_items, seg); CZK_LAUNCHED();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    k_msm_fold_segments<F><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(ws.segoff, ws.segcnt, ws.segsum, ws.buckets, total); CZK_LAUNCHED();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     unsigned nchunks = cfg.nb / cfg.chunk;
     size_t rthreads = (size_t)cfg.nwin * nchunks;

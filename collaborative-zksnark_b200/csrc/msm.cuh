@@ -35,6 +35,11 @@ inline MsmConfig msm_choose_config(size_t n) {
     unsigned c = lg > 6 ? lg - 4 : 2;
     if (c < 2) c = 2;
     if (c > 16) c = 16;
+    // avoid window sizes whose top window holds only a few bits of the 253-bit scalar: its few buckets
+    // would each receive n / 2^bits points.  (c = 16, 15, 11 and the small sizes are balanced.)
+    if (c == 14) c = 15;
+    if (c == 12 || c == 13) c = 11;
+    if (c == 10 || c == 9) c = 8;
     MsmConfig cfg;
     cfg.c = c;
     cfg.nwin = msm_num_windows(c);
@@ -51,6 +56,11 @@ struct MsmWorkspace {
     uint32_t* buckets = nullptr;   // nwin*nb points, XYZZ
     uint32_t* partial = nullptr;   // nwin*(nb/chunk) points
     uint32_t* winsum = nullptr;    // nwin points
+    uint32_t* segcnt = nullptr;    // nwin*nb: segments per bucket
+    uint32_t* segoff = nullptr;    // nwin*nb: exclusive scan of segcnt
+    uint32_t* segsum = nullptr;    // cap_items points: per-segment sums of multi-segment buckets
+    size_t cap_items = 0;
+    int seg_point_words = 0;
     size_t cap_n = 0;
     size_t cap_buckets = 0;
     int point_words = 0;

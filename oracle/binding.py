@@ -303,3 +303,94 @@ def random_fr_canonical(seed: int, n: int) -> np.ndarray:
 
 def random_fr_mont(seed: int, n: int) -> np.ndarray:
     return fr_from_repr(random_fr_canonical(seed, n))
+
+
+# ---------------------------------------------------------------- Groth16 (squaring circuit) + shares
+SCHEME_PLAIN, SCHEME_ADDITIVE, SCHEME_SPDZ = 0, 1, 2
+
+
+def generators():
+    g1 = np.zeros(12, np.uint64)
+    g2 = np.zeros(24, np.uint64)
+    lib().orc_generators(_p(g1), _p(g2))
+    return g1, g2
+
+
+def groth16_domain_size(n_sq: int) -> int:
+    f = lib().orc_groth16_domain_size
+    f.restype = C.c_size_t
+    return f(C.c_size_t(n_sq))
+
+
+def squaring_chain(start_mont, n_sq: int) -> np.ndarray:
+    out = np.zeros((n_sq + 1, 4), np.uint64)
+    lib().orc_squaring_chain(_p(out), _p(np.ascontiguousarray(start_mont, np.uint64)), C.c_size_t(n_sq))
+    return out
+
+
+def groth16_setup(n_sq: int, toxic_mont: np.ndarray, threads=1) -> dict:
+    """toxic_mont: (7,4) Montgomery Fr = alpha, beta, gamma, delta, tau, g1_scalar, g2_scalar."""
+    D = groth16_domain_size(n_sq)
+    nv = n_sq + 2
+    pk = dict(n_sq=n_sq, D=D,
+              a_query=np.zeros((nv, 12), np.uint64), a_inf=np.zeros(nv, np.uint8),
+              b_g1_query=np.zeros((nv, 12), np.uint64), b1_inf=np.zeros(nv, np.uint8),
+              b_g2_query=np.zeros((nv, 24), np.uint64), b2_inf=np.zeros(nv, np.uint8),
+              h_query=np.zeros((D - 1, 12), np.uint64), h_inf=np.zeros(D - 1, np.uint8),
+              l_query=np.zeros((n_sq, 12), np.uint64), l_inf=np.zeros(n_sq, np.uint8),
+              vk_g1=np.zeros((3, 12), np.uint64), vk_g2=np.zeros((3, 24), np.uint64),
+              gamma_abc_g1=np.zeros((2, 12), np.uint64))
+    toxic_mont = np.ascontiguousarray(toxic_mont, np.uint64).reshape(7, 4)
+    ok = lib().orc_groth16_setup(C.c_size_t(n_sq), _p(toxic_mont), _p(pk["a_query"]), _p8(pk["a_inf"]), _p(pk["b_g1_query"]),
+                                 _p8(pk["b1_inf"]), _p(pk["b_g2_query"]), _p8(pk["b2_inf"]), _p(pk["h_query"]), _p8(pk["h_inf"]),
+                                 _p(pk["l_query"]), _p8(pk["l_inf"]), _p(pk["vk_g1"]), _p(pk["vk_g2"]), _p(pk["gamma_abc_g1"]),
+                                 C.c_int(threads))
+    assert ok
+    return pk
+
+
+def king_share_batch(values_mont: np.ndarray, n_parties: int, seed: int):
+    """Additive shares in the shape of king_share_batch (add.rs:105-117 / spdz.rs:150-162): parties
+    0..n-2 get uniform values, party n-1 gets f - sum.  (The reference's ChaCha stream is not reproduced.)"""
+    values_mont = np.ascontiguousarray(values_mont, np.uint64).reshape(-1, 4)
+    k = values_mont.shape[0]
+    shares = [random_fr_mont(seed + 1000 * p, k) for p in range(n_parties - 1)]
+    last = values_mont.copy()
+    for s in shares:
+        last = fr_sub(last, s)
+    return shares + [last]
+
+
+def _chain_ptrs(chain_shares):
+    arrs = [np.ascontiguousarray(c, np.uint64).reshape(-1, 4) for c in chain_shares]
+    ptrs = (u64p * len(arrs))(*[_p(a) for a in arrs])
+    return arrs, ptrs
+
+
+def groth16_witness_map(scheme, n_sq, chain_shares, threads=1):
+    n = len(chain_shares)
+    D = groth16_domain_size(n_sq)
+    arrs, ptrs = _chain_ptrs(chain_shares)
+    h = np.zeros((n, D, 4), np.uint64)
+    ok = lib().orc_groth16_witness_map(C.c_int(scheme), C.c_int(n), C.c_size_t(n_sq), ptrs, _p(h), C.c_int(threads))
+    return h, bool(ok)
+
+
+def groth16_prove(scheme, n_sq, chain_shares, r_sh, s_sh, pk, threads=1, want_h=True):
+    n = len(chain_shares)
+    D = pk["D"]
+    arrs, ptrs = _chain_ptrs(chain_shares)
+    r_sh = np.ascontiguousarray(r_sh, np.uint64).reshape(n, 4)
+    s_sh = np.ascontiguousarray(s_sh, np.uint64).reshape(n, 4)
+    h = np.zeros((n, D, 4), np.uint64) if want_h else None
+    proof_sh = np.zeros((n, 48), np.uint64)
+    proof_sh_inf = np.zeros((n, 3), np.uint8)
+    proof = np.zeros(48, np.uint64)
+    proof_inf = np.zeros(3, np.uint8)
+    ok = lib().orc_groth16_prove(C.c_int(scheme), C.c_int(n), C.c_size_t(n_sq), ptrs, _p(r_sh), _p(s_sh),
+                                 _p(pk["a_query"]), _p8(pk["a_inf"]), _p(pk["b_g1_query"]), _p8(pk["b1_inf"]),
+                                 _p(pk["b_g2_query"]), _p8(pk["b2_inf"]), _p(pk["h_query"]), _p8(pk["h_inf"]),
+                                 _p(pk["l_query"]), _p8(pk["l_inf"]), _p(pk["vk_g1"]), _p(pk["vk_g2"]),
+                                 _p(h) if want_h else None, _p(proof_sh), _p8(proof_sh_inf), _p(proof), _p8(proof_inf),
+                                 C.c_int(threads))
+    return dict(ok=bool(ok), h=h, proof_sh=proof_sh, proof_sh_inf=proof_sh_inf, proof=proof, proof_inf=proof_inf)

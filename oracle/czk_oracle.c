@@ -160,11 +160,31 @@ static inline int fq2_inv(fq2_t *r, const fq2_t *a) {
 #undef BF
 #undef BFW
 
+
+/* curves/bls12_377/src/curves/g1.rs:46-51 and g2.rs:68-86: generators, canonical integers (converted to
+ * Montgomery form at init) */
+static const uint64_t G1_GEN_CANON[12] = {0xeab9b16eb21be9efull, 0xd5481512ffcd394eull, 0x188282c8bd37cb5cull, 0x85951e2caa9d41bbull, 0xc8fc6225bf87ff54ull, 0x008848defe740a67ull,
+                                          0xfd82de55559c8ea6ull, 0xc2fe3d3634a9591aull, 0x6d182ad44fb82305ull, 0xbd7fb348ca3e52d9ull, 0x1f674f5d30afeec4ull, 0x01914a69c5102effull};
+static const uint64_t G2_GEN_CANON[24] = {0x74e3e48f7c005196ull, 0x71889f52bb535402ull, 0x7ea501f557db6b9bull, 0xc565f071203e5031ull, 0xc89630a2a3841d01ull, 0x018480be71c785feull,
+                                          0xb26bfefa6ea16afeull, 0x5cf89984bff76fe6ull, 0xe7223ece0799c9deull, 0x532777ee6651cecbull, 0x70dc5a51b1b140d5ull, 0x00ea6040e7004031ull,
+                                          0xf094094409fd4ddfull, 0xf2cf88886d8c7c2eull, 0xe458c282f832d204ull, 0xde03ed7274b49a58ull, 0xd960736bcbb2efb4ull, 0x00690d665d446f7bull,
+                                          0xd9a1cdd185eb8f93ull, 0x4279b83f5e52270bull, 0x2463b01acee304c2ull, 0x61ef11ac3d591bf1ull, 0x9e549da3151a70aaull, 0x00f8169fd2835518ull};
+uint64_t ORC_G1_GEN[12], ORC_G2_GEN[24];
+static void orc_init_generators(void) {
+    for (int i = 0; i < 2; i++) fq_from_repr((fq_t *)(ORC_G1_GEN + 6 * i), G1_GEN_CANON + 6 * i);
+    for (int i = 0; i < 4; i++) fq_from_repr((fq_t *)(ORC_G2_GEN + 6 * i), G2_GEN_CANON + 6 * i);
+}
+EXPORT void orc_generators(uint64_t *g1, uint64_t *g2) {
+    memcpy(g1, ORC_G1_GEN, sizeof ORC_G1_GEN);
+    memcpy(g2, ORC_G2_GEN, sizeof ORC_G2_GEN);
+}
+
 static int g_inited = 0;
 EXPORT void orc_init(void) {
     if (g_inited) return;
     fr_init(FR_MODULUS);
     fq_init(FQ_MODULUS);
+    orc_init_generators();
     g_inited = 1;
 }
 __attribute__((constructor)) static void orc_ctor(void) { orc_init(); }

@@ -1,0 +1,107 @@
+"""The DEVICE field / curve headers (collaborative-zksnark_b200/csrc/{carry,fp,ec,msm_digits}.cuh),
+compiled for the host with the PTX carry flag emulated (tests/emu), against the oracle.  This checks the
+exact limb schedule the GPU executes without needing a GPU; the -m gpu tests check the kernels."""
+import ctypes as C
+import random
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.run(["make", "-C", str(ROOT / "tests/emu"), "-s"], check=True)
+    return C.CDLL(str(ROOT / "tests/emu/libczk_emu.so"))
+
+
+def P(a):
+    return a.ctypes.data_as(C.POINTER(C.c_uint64))
+
+
+def _edge(vals_list, mod):
+    for v in vals_list:
+        v[0:4] = [0, mod - 1, 1, mod - 1]
+    if len(vals_list) > 1:
+        vals_list[1][0:4] = [0, mod - 1, mod - 1, 1]
+        vals_list[0][5] = vals_list[1][5]  # a - a
+
+
+@pytest.mark.parametrize("name,nl,nargs", [
+    ("fr_mul", 4, 2), ("fr_add", 4, 2), ("fr_sub", 4, 2), ("fr_neg", 4, 1),
+    ("fq_mul", 6, 2), ("fq_add", 6, 2), ("fq_sub", 6, 2),
+])
+def test_prime_field_ops(emu, oracle, pymodel, name, nl, nargs):
+    rnd = random.Random(hash(name) & 0xffff)
+    mod = pymodel.R_MOD if nl == 4 else pymodel.Q_MOD
+    n = 3000
+    vals = [[rnd.randrange(mod) for _ in range(n)] for _ in range(nargs)]
+    _edge(vals, mod)
+    frm = oracle.fr_from_ints if nl == 4 else oracle.fq_from_ints
+    arrs = [frm(v) for v in vals]
+    out = np.zeros_like(arrs[0])
+    getattr(emu, "emu_" + name)(P(out), *[P(a) for a in arrs], C.c_size_t(n))
+    assert (out == getattr(oracle, name)(*arrs)).all()
+
+
+def test_fq2_and_inversions(emu, oracle, pymodel):
+    rnd = random.Random(7)
+    a = oracle.fq_from_ints([rnd.randrange(pymodel.Q_MOD) for _ in range(400)]).reshape(-1, 12)
+    b = oracle.fq_from_ints([rnd.randrange(pymodel.Q_MOD) for _ in range(400)]).reshape(-1, 12)
+    out = np.zeros_like(a)
+    emu.emu_fq2_mul(P(out), P(a), P(b), C.c_size_t(200))
+    assert (out == oracle.fq2_mul(a, b)).all()
+    emu.emu_fq2_sqr(P(out), P(a), C.c_size_t(200))
+    assert (out == oracle.fq2_sqr(a)).all()
+    emu.emu_fq2_inv(P(out[:10]), P(a[:10]), C.c_size_t(10))
+    assert (out[:10] == oracle.fq2_inv(a[:10])).all()
+    x = oracle.fq_from_ints([rnd.randrange(1, pymodel.Q_MOD) for _ in range(10)])
+    o6 = np.zeros_like(x)
+    emu.emu_fq_inv(P(o6), P(x), C.c_size_t(10))
+    assert (o6 == oracle.fq_inv(x)).all()
+    y = oracle.fr_from_ints([rnd.randrange(1, pymodel.R_MOD) for _ in range(10)])
+    o4 = np.zeros_like(y)
+    emu.emu_fr_inv(P(o4), P(y), C.c_size_t(10))
+    assert (o4 == oracle.fr_inv(y)).all()
+    emu.emu_fr_from_mont(P(o4), P(y), C.c_size_t(10))
+    assert (o4 == oracle.fr_into_repr(y)).all()
+
+
+@pytest.mark.parametrize("g", ["g1", "g2"])
+def test_xyzz_bucket_accumulation(emu, oracle, pymodel, g):
+    """Signed accumulation exactly like a device bucket, incl. P+P (doubling branch), P + -P, and the
+    XYZZ+XYZZ path used by the bucket reduction."""
+    G = oracle.G1 if g == "g1" else oracle.G2
+    gen = pymodel.G1_GEN if g == "g1" else pymodel.G2_GEN
+    mul, add, neg = (pymodel.g1_mul, pymodel.g1_add, pymodel.g1_neg) if g == "g1" else (pymodel.g2_mul, pymodel.g2_add, pymodel.g2_neg)
+    fn = emu.emu_g1_sum if g == "g1" else emu.emu_g2_sum
+    ks = [3, 3, 5, 7, 7, 7, 11, 13, 2, 9, 9, 4]
+    pts = [mul(gen, k) for k in ks]
+    sign = np.array([0, 0, 0, 0, 1, 0, 1, 0, 0, 1, 0, 0], np.uint8)
+    expect = None
+    for p, s in zip(pts, sign):
+        expect = add(expect, neg(p) if s else p)
+    xy, _ = G.affine_from_ints(pts)
+    out = np.zeros(G.w, np.uint64)
+    for tree in (0, 1):
+        isinf = fn(P(out), P(xy), sign.ctypes.data_as(C.POINTER(C.c_uint8)), C.c_size_t(len(pts)), C.c_int(tree))
+        assert not isinf and G.affine_to_ints(out)[0] == expect
+    xy, _ = G.affine_from_ints([mul(gen, 5), mul(gen, 5), neg(mul(gen, 10))])
+    for tree in (0, 1):
+        assert fn(P(out), P(xy), None, C.c_size_t(3), C.c_int(tree)) == 1
+
+
+@pytest.mark.parametrize("c", [2, 3, 8, 11, 13, 15, 16, 17, 23])
+def test_signed_digit_decomposition(emu, oracle, pymodel, c):
+    rnd = random.Random(c)
+    nwin = (254 + c - 1) // c
+    cases = [0, 1, pymodel.R_MOD - 1, (1 << 252) + 12345, 1 << (c - 1), (1 << c) - 1, (1 << (c - 1)) + 1]
+    cases += [rnd.randrange(pymodel.R_MOD) for _ in range(300)]
+    for s in cases:
+        out = np.zeros(nwin, np.int32)
+        emu.emu_signed_digits(out.ctypes.data_as(C.POINTER(C.c_int32)), P(oracle.ints_to_limbs([s], 4)), C.c_uint(c), C.c_uint(nwin))
+        assert sum(int(d) << (c * w) for w, d in enumerate(out)) == s
+        assert all(abs(int(d)) <= 1 << (c - 1) for d in out)
