@@ -1,0 +1,276 @@
+#!/usr/bin/env python3
+"""bench.py - Groth16 proof time at 2^20 R1CS constraints on BLS12-377, one MPC party per GPU.
+
+    python bench.py --gpus 1 --steps K --warmup W
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference ...       # the CPU path (oracle port of the reference) on the host cores
+
+A "step" is one proof: create_random_proof + reveal (mpc-snarks/src/proof.rs:130-139) of the repeated-squaring
+circuit with 2^20 squarings (D = 2^21) under SPDZ shares: 14 NTTs of 2^21, the Beaver product with its opens,
+MSMs of 2^21-1, 2^20, 2^20+1 (x2) G1 terms and 2^20+1 G2 terms, and the O(1) share/group tail.  Synthetic data:
+device-generated CRS bases of the reference's shapes (the proof does not verify; the work is identical), seeded
+witness chain shared additively by the king.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+LOG_N = 20
+METRIC = "groth16_proof_ms_2^20_r1cs_bls12_377"
+# BASELINE.md section 1 (reference's published figures, GCP n2-standard-2, 1 physical core per party)
+PUBLISHED_MS = {1: 127400.0, 2: 320400.0, 3: 323300.0}
+
+
+def ref_msm_adds(n: int) -> int:
+    """SURVEY.md 8(d) normaliser: N*W + 2(2^c - 1)W + 253 with the reference's c, W."""
+    def ark_log2(x):
+        return 0 if x == 0 else (x.bit_length() - 1 if x & (x - 1) == 0 else x.bit_length())
+    c = 3 if n < 32 else ark_log2(n) * 69 // 100 + 2
+    w = (253 + c - 1) // c
+    return n * w + 2 * ((1 << c) - 1) * w + 253
+
+
+class ClockSampler:
+    """nvidia-smi sampling DURING the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 9:
+                self.rows.append(parts)
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        pw = [float(r[3]) for r in self.rows if r[3].replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(self.rows), "reasons": sorted(reasons)}
+
+
+def cpu_reference_leg(steps: int, warmup: int, sample_log_n: int, scheme_name: str = "spdz"):
+    """Time the oracle (a C port of the reference's prover: `kind: port`) on the host cores, all threads,
+    on a bounded sample of the workload; scale linearly in the constraint count to 2^20."""
+    from oracle import binding as o
+
+    o.build()
+    threads = o.cpu_threads()
+    n_sq = 1 << sample_log_n
+    # synthetic key of the right shapes: points from an arithmetic progression (no setup cost)
+    import numpy as np
+
+    g1, g2 = o.generators()
+    ks = o.random_fr_mont(1, 2)
+    D = o.groth16_domain_size(n_sq)
+
+    def pts(G, g, n):
+        return G.gen_progression(g, ks[0], ks[1], n, threads=threads)
+
+    pk = dict(n_sq=n_sq, D=D, a_query=pts(o.G1, g1, n_sq + 2), a_inf=None, b_g1_query=pts(o.G1, g1, n_sq + 2), b1_inf=None,
+              b_g2_query=pts(o.G2, g2, n_sq + 2), b2_inf=None, h_query=pts(o.G1, g1, D - 1), h_inf=None,
+              l_query=pts(o.G1, g1, n_sq), l_inf=None, vk_g1=pts(o.G1, g1, 3), vk_g2=pts(o.G2, g2, 3))
+    chain = o.squaring_chain(o.random_fr_mont(2, 1)[0], n_sq)
+    r, s = o.random_fr_mont(3, 1), o.random_fr_mont(4, 1)
+    scheme = o.SCHEME_SPDZ if scheme_name == "spdz" else o.SCHEME_PLAIN
+    times = []
+    for i in range(warmup + steps):
+        t = time.perf_counter()
+        res = o.groth16_prove(scheme, n_sq, [chain], r, s, pk, threads=threads, want_h=False)
+        dt = time.perf_counter() - t
+        assert res["ok"]
+        if i >= warmup:
+            times.append(dt)
+    scale = float(1 << (LOG_N - sample_log_n))
+    ms_sample = 1e3 * sum(times) / len(times)
+    return dict(value=ms_sample * scale, unit="ms", cores=threads, kind="port",
+                sample=f"one party's Groth16 {scheme_name} proof at 2^{sample_log_n} constraints, {threads} host threads "
+                       f"(window-parallel MSM, chunk-parallel NTT), {ms_sample:.1f} ms measured x{int(scale)} (linear in constraints)",
+                ms_sample=ms_sample)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cb = cpu_reference_leg(max(1, args.steps), max(0, min(args.warmup, 1)), args.cpu_sample_log_n)
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": cb["value"], "higher_is_better": False, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64 limbs (Montgomery), integer", "data": "synthetic",
+            "config": {"workload": f"groth16 spdz 2^{LOG_N} constraints BLS12-377, one party's work on the host CPU (oracle port of the reference prover)",
+                       "parties": args.gpus},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="czk", choices=["czk", "reference"])
+    ap.add_argument("--log-n", type=int, default=LOG_N, help="log2 constraints (default 20 = the BASELINE config)")
+    ap.add_argument("--scheme", default="spdz", choices=["spdz", "additive", "plain"])
+    ap.add_argument("--cpu-sample-log-n", type=int, default=16)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+
+    import czk_b200
+    from czk_b200 import launch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the czk arm has no CPU fallback (use --impl reference for the CPU path)")
+    warmup = max(args.warmup, 3)
+    party = launch.Party()
+    ctx, rank, world = party.ctx, party.rank, party.world
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    scheme = {"spdz": czk_b200.SCHEME_SPDZ, "additive": czk_b200.SCHEME_ADDITIVE, "plain": czk_b200.SCHEME_PLAIN}[args.scheme]
+    n_sq = 1 << args.log_n
+
+    # ---- setup (untimed, like the reference: CRS + king_share_batch happen before start_timer!, proof.rs:113-129)
+    imad_peak, _ = ctx.microbench(0, 8, 256, 2000)  # measured IMAD.WIDE.U32 issue rate: the integer roofline denominator
+    pk = czk_b200.ProvingKey.synthetic(ctx, n_sq, seed=0x377)
+    D = pk.domain_size
+    chain = czk_b200.squaring_chain(np.array([0x1234567, 0x89abcdef, 0x55aa55aa, 0x0123], np.uint64), n_sq) if rank == 0 else None
+    mine = launch.king_share_scatter(chain, n_sq + 1, seed=0x5eed)
+    pinned = torch.from_numpy(mine.view(np.int64).copy()).pin_memory()
+    mine_pinned = pinned.numpy().view(np.uint64)
+    chain_dev = ctx.vec_from(mine)
+    rho = np.array([0x0123456789abcdef, 0x0fedcba987654321, 0x1111222233334444, 0x0000000055556666], np.uint64)
+    sig = np.array([0x0aaaaaaabbbbbbbb, 0x0ccccccccddddddd, 0x0eeeeeeeffffffff, 0x0000000012345678], np.uint64)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{ctx.device}")  # > 126 MB L2
+
+    def step(resident: bool):
+        flush.zero_()  # L2 flush between iterations (inputs per proof are also > L2: 64 MB vectors x 6, 100-200 MB bases)
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        res = czk_b200.groth16_prove(ctx, scheme, pk, chain_dev if resident else mine_pinned, rho, sig)
+        ctx.sync()
+        return (time.perf_counter() - t) * 1e3, res
+
+    for _ in range(warmup):
+        step(True)
+    step(False)
+
+    def timed(resident: bool, k: int):
+        launch.barrier()
+        torch.cuda.synchronize()
+        ctx.msm_stats(1, reset=True)
+        ctx.msm_stats(2, reset=True)
+        l0 = ctx.launches
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        times, phases = [], []
+        for _ in range(k):
+            ms, res = step(resident)
+            times.append(ms)
+            phases.append(res["phases_ms"])
+        launch.barrier()
+        torch.cuda.synchronize()
+        total = launch.max_over_ranks(sum(times))
+        return total / k, times, phases, ctx.launches - l0, ctx.msm_stats(1), ctx.msm_stats(2)
+
+    sampler = ClockSampler(ctx.device)
+    sampler.start()
+    ms_res, times_res, phases, launches, st1, st2 = timed(True, args.steps)
+    ms_e2e, times_e2e, phases_e2e, _, _, _ = timed(False, args.steps)
+    clocks = sampler.stop()
+
+    if rank != 0:
+        party.close()
+        return 0
+
+    avg = lambda key: sum(p[key] for p in phases) / len(phases)
+    n_h = D - 1
+    msm_h_ms = avg("msm_h")
+    # dominant kernel: k_msm_accumulate<Fq> (bucket accumulation), CUDA events on the launching stream
+    acc_ms = st1["accumulate_ms"] / max(st1["launches"], 1)
+    terms_per_launch = st1["terms"] / max(st1["launches"], 1)
+    peaks = {}
+    pf = ROOT / "MEASURED_PEAKS.json"
+    if pf.exists():
+        peaks = json.loads(pf.read_text())
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    alg_bytes = 128.0 * terms_per_launch  # 32 B scalar + 96 B affine base per G1 term
+    achieved_gbs = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms else 0.0
+    nwin = 16
+    wide_mads = terms_per_launch * nwin * 10 * 288  # N*W mixed additions x (8M + 2S) x 2*12^2 wide multiply-adds
+    int_rate = wide_mads / (acc_ms * 1e-3) if acc_ms else 0.0
+    line = {
+        "metric": METRIC, "value": ms_res, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms_res, "higher_is_better": False, "scaling": "weak",
+        "vs_baseline": (ms_res / PUBLISHED_MS[world]) if (args.log_n == LOG_N and world in PUBLISHED_MS) else None,
+        "dtype": "u32 limbs (Montgomery Fr/Fq), integer", "data": "synthetic",
+        "config": {"workload": f"groth16 {args.scheme} 2^{args.log_n} constraints (D=2^{D.bit_length() - 1}) BLS12-377, one party per GPU",
+                   "parties": world, "l2": "256 MiB flush write between iterations", "bases": "device-generated synthetic CRS of the reference's shapes",
+                   "published_reference_ms": PUBLISHED_MS.get(world)},
+        "clocks": clocks,
+        "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": int((n_sq + 1) * 32), "d2h_bytes_per_step": int(2 * 48 * 8 + 6 + 5 * 16 * 192)},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "k_msm_accumulate<Fq>", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved_gbs / hbm_peak, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                     "note": "bucket accumulation is bound by the INT32 multiply pipe, not HBM: see roofline_int",
+                     "launch_ms": acc_ms, "launches_per_step": st1["launches"] / args.steps, "share_of_step": st1["accumulate_ms"] / args.steps / ms_res},
+        "roofline_int": {"kernel": "k_msm_accumulate<Fq>", "bound": "imad", "achieved": int_rate, "peak": imad_peak, "unit": "IMAD.WIDE/s",
+                         "frac": int_rate / imad_peak if imad_peak else None,
+                         "peak_source": "czk_microbench kind 0 (independent mad.wide.u32 chains), measured at bench start"},
+        "g1_msm_adds_per_s": ref_msm_adds(n_h) / (msm_h_ms * 1e-3),
+        "g1_msm": {"n": n_h, "ms": msm_h_ms, "adds_ref": ref_msm_adds(n_h)},
+        "g2_msm_ms": avg("msm_b_g2"), "msm_device_ms_per_step": {"g1": st1["msm_ms"] / args.steps, "g2": st2["msm_ms"] / args.steps},
+        "phases_ms": {k: avg(k) for k in phases[0]},
+        "times_ms": {"resident": times_res, "e2e": times_e2e},
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference_leg(1, 0, args.cpu_sample_log_n)
+    print(json.dumps(line))
+    party.close()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -15,5 +15,10 @@ from .binding import (  # noqa: F401
     SCHEME_PLAIN,
     SCHEME_ADDITIVE,
     SCHEME_SPDZ,
+    ProvingKey,
+    groth16_witness_map,
+    groth16_prove,
+    squaring_chain,
+    king_share_batch,
 )
 from .build import build as build_library  # noqa: F401

@@ -81,11 +81,25 @@ _SIGS = {
     "czk_net_reset_stats": (None, [C.c_void_p]),
     "czk_batch_open": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "czk_beaver_batch_mul": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_msm_stats": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int]),
     "czk_microbench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
-# entry points added by later translation units (declared in include/czk_groth16.h)
-_OPTIONAL_SIGS = {}
+# include/czk_groth16.h
+_OPTIONAL_SIGS = {
+    "czk_groth16_pk_upload": (C.c_int, [C.c_void_p, C.c_size_t] + [C.c_void_p] * 12 + [C.POINTER(C.c_void_p)]),
+    "czk_groth16_pk_synthetic": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "czk_groth16_pk_free": (None, [C.c_void_p, C.c_void_p]),
+    "czk_groth16_pk_domain_size": (C.c_size_t, [C.c_void_p]),
+    "czk_groth16_pk_query": (C.c_void_p, [C.c_void_p, C.c_int]),
+    "czk_groth16_pk_vk": (C.c_int, [C.c_void_p, u64p, u64p]),
+    "czk_groth16_witness_map": (C.c_int, [C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p]),
+    "czk_groth16_prove": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, u64p, u64p, u64p, u8p, u64p, u8p]),
+    "czk_groth16_prove_vec": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, u64p, u64p, u64p, u8p, u64p, u8p]),
+    "czk_squaring_chain": (C.c_int, [u64p, C.c_size_t, C.c_void_p]),
+    "czk_king_share_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_void_p]),
+    "czk_groth16_last_phases": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+}
 
 
 def exported_symbols():
@@ -391,8 +405,119 @@ class Context:
                                                 y_mac.h if y_mac is not None else None, n))
 
     # ------------------------------------------------------------------ diagnostics
+    def msm_stats(self, curve=1, reset=False):
+        out = (C.c_double * 4)()
+        self._chk(self.lib.czk_msm_stats(self.h, curve, out, int(reset)))
+        return dict(accumulate_ms=out[0], launches=int(out[1]), terms=out[2], msm_ms=out[3])
+
     def microbench(self, kind, blocks_per_sm=8, threads=128, iters=2000):
         ops = C.c_double()
         ms = C.c_double()
         self._chk(self.lib.czk_microbench(self.h, kind, blocks_per_sm, threads, iters, C.byref(ops), C.byref(ms)))
         return ops.value, ms.value
+
+
+class ProvingKey:
+    """Device-resident groth16 ProvingKey for the squaring circuit (include/czk_groth16.h)."""
+
+    QUERIES = ("a_query", "b_g1_query", "b_g2_query", "h_query", "l_query")
+
+    def __init__(self, ctx: Context, h, n_sq: int):
+        self.ctx, self.h, self.n_sq = ctx, h, n_sq
+
+    @classmethod
+    def upload(cls, ctx: Context, pk: dict):
+        """pk: dict with the arrays of groth16 setup (a_query, a_inf, ..., vk_g1, vk_g2)."""
+        def p(a):
+            return np.ascontiguousarray(a).ctypes.data if a is not None else None
+        keep = [np.ascontiguousarray(pk[k]) for k in ("a_query", "a_inf", "b_g1_query", "b1_inf", "b_g2_query", "b2_inf",
+                                                       "h_query", "h_inf", "l_query", "l_inf", "vk_g1", "vk_g2")]
+        h = C.c_void_p()
+        ctx._chk(ctx.lib.czk_groth16_pk_upload(ctx.h, pk["n_sq"], *[k.ctypes.data for k in keep], C.byref(h)))
+        return cls(ctx, h, pk["n_sq"])
+
+    @classmethod
+    def synthetic(cls, ctx: Context, n_sq: int, seed: int = 1):
+        h = C.c_void_p()
+        ctx._chk(ctx.lib.czk_groth16_pk_synthetic(ctx.h, n_sq, seed, C.byref(h)))
+        return cls(ctx, h, n_sq)
+
+    @property
+    def domain_size(self):
+        return self.ctx.lib.czk_groth16_pk_domain_size(self.h)
+
+    def query(self, which: int) -> "Bases":
+        b = Bases(self.ctx, C.c_void_p(self.ctx.lib.czk_groth16_pk_query(self.h, which)), 2 if which == 2 else 1)
+        b.free = lambda: None  # owned by the key
+        return b
+
+    def to_host(self) -> dict:
+        """Download everything (for comparisons in tests)."""
+        out = dict(n_sq=self.n_sq, D=self.domain_size)
+        for i, (name, inf) in enumerate(zip(self.QUERIES, ("a_inf", "b1_inf", "b2_inf", "h_inf", "l_inf"))):
+            xy, f = self.query(i).numpy()
+            out[name], out[inf] = xy, f
+        v1 = np.zeros((3, 12), np.uint64)
+        v2 = np.zeros((3, 24), np.uint64)
+        self.ctx._chk(self.ctx.lib.czk_groth16_pk_vk(self.h, v1.ctypes.data_as(u64p), v2.ctypes.data_as(u64p)))
+        out["vk_g1"], out["vk_g2"] = v1, v2
+        return out
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.czk_groth16_pk_free(self.ctx.h, self.h)
+            self.h = None
+
+
+def groth16_witness_map(ctx: Context, scheme: int, n_sq: int, chain_sh) -> np.ndarray:
+    chain_sh = _np_u64(chain_sh, 4)
+    assert chain_sh.shape[0] == n_sq + 1
+    d = 1
+    while d < n_sq + 2:
+        d <<= 1
+    h = np.empty((d, 4), np.uint64)
+    ctx._chk(ctx.lib.czk_groth16_witness_map(ctx.h, scheme, n_sq, chain_sh.ctypes.data, h.ctypes.data))
+    return h
+
+
+def squaring_chain(start_mont, n_sq: int) -> np.ndarray:
+    lib = load_library()
+    out = np.empty((n_sq + 1, 4), np.uint64)
+    rc = lib.czk_squaring_chain(_np_u64(start_mont).ctypes.data_as(u64p), n_sq, out.ctypes.data)
+    if rc:
+        raise CzkError(rc, lib.czk_last_error(None).decode())
+    return out
+
+
+def king_share_batch(values_mont, n_parties: int, seed: int) -> np.ndarray:
+    """-> (n_parties, k, 4) additive shares (Reveal::king_share_batch)."""
+    lib = load_library()
+    values_mont = _np_u64(values_mont, 4)
+    k = values_mont.shape[0]
+    out = np.empty((n_parties, k, 4), np.uint64)
+    rc = lib.czk_king_share_batch(values_mont.ctypes.data, k, n_parties, seed, out.ctypes.data)
+    if rc:
+        raise CzkError(rc, lib.czk_last_error(None).decode())
+    return out
+
+
+def groth16_prove(ctx: Context, scheme: int, pk: ProvingKey, chain_sh, r_sh, s_sh) -> dict:
+    """create_random_proof + reveal for this party (mpc-snarks/src/proof.rs:130-139).
+    chain_sh: host array (n_sq + 1, 4) - copied to the device inside the call - or a DeviceVec."""
+    dev = isinstance(chain_sh, DeviceVec)
+    if not dev:
+        chain_sh = _np_u64(chain_sh, 4)
+        assert chain_sh.shape[0] == pk.n_sq + 1
+    r_sh, s_sh = _np_u64(r_sh), _np_u64(s_sh)
+    proof_sh = np.zeros(48, np.uint64)
+    proof = np.zeros(48, np.uint64)
+    sh_inf = np.zeros(3, np.uint8)
+    inf = np.zeros(3, np.uint8)
+    fn = ctx.lib.czk_groth16_prove_vec if dev else ctx.lib.czk_groth16_prove
+    ctx._chk(fn(ctx.h, scheme, pk.h, chain_sh.h if dev else chain_sh.ctypes.data, r_sh.ctypes.data_as(u64p),
+                s_sh.ctypes.data_as(u64p), proof_sh.ctypes.data_as(u64p), sh_inf.ctypes.data_as(u8p), proof.ctypes.data_as(u64p),
+                inf.ctypes.data_as(u8p)))
+    ph = (C.c_double * 8)()
+    ctx.lib.czk_groth16_last_phases(ctx.h, ph)
+    names = ("upload", "witness_map", "msm_h", "msm_l", "msm_a", "msm_b_g1", "msm_b_g2", "group_tail_reveal")
+    return dict(proof_sh=proof_sh, proof_sh_inf=sh_inf, proof=proof, proof_inf=inf, phases_ms=dict(zip(names, list(ph))))

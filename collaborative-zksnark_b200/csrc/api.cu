@@ -25,110 +25,11 @@ cudaError_t microbench_run(int kind, int blocks, int threads, int iters, uint64_
                            cudaStream_t st);
 }  // namespace czk
 
-using namespace czk;
-using namespace czk::host;
-
-static thread_local std::string g_tls_error;
-
-// ------------------------------------------------------------------------------------------ NCCL (resolved at run time)
-struct NcclApi {
-    void* handle = nullptr;
-    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
-    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
-    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
-    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
-    const char* (*GetErrorString)(ncclResult_t) = nullptr;
-    bool ok = false;
-};
-static NcclApi& nccl_api() {
-    static NcclApi api;
-    if (api.handle || api.ok) return api;
-    // if torch already loaded its bundled libnccl.so.2 the loader hands back that copy
-    api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-    if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-    if (!api.handle) return api;
-    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
-    api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
-    api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
-    api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
-    api.Broadcast = (decltype(api.Broadcast))dlsym(api.handle, "ncclBroadcast");
-    api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
-    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Broadcast && api.GetErrorString;
-    return api;
-}
-
-// ------------------------------------------------------------------------------------------ objects
-struct czk_vec {
-    uint64_t* d = nullptr;
-    size_t n = 0;
-};
-struct czk_bases {
-    int curve = 1;
-    uint32_t* xy = nullptr;  // n * (24 | 48) words
-    uint8_t* inf = nullptr;  // n bytes, or nullptr when no point is infinity
-    size_t n = 0;
-};
-struct Domain {
-    int log_d = 0;
-    uint32_t* tw = nullptr;
-    uint32_t *g_lo = nullptr, *g_hi = nullptr, *gi_lo = nullptr, *gi_hi = nullptr;
-    int lo_log = 0;
-    HFr size_inv, group_gen, group_gen_inv, generator_inv;
-};
-struct Scratch {
-    void* p = nullptr;
-    size_t cap = 0;
-};
-
-struct czk_ctx {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    std::string err;
-    std::map<int, Domain> domains;
-    MsmWorkspace ws;
-    void* pinned = nullptr;  // host staging for window sums
-    size_t pinned_cap = 0;
-    Scratch up_bases, up_inf, up_scalars, up_vec;  // staging for the host-pointer entry points
-    Scratch open_gather, open_sigma, open_sx, open_oy, open_d, open_dm;
-    uint32_t* flag = nullptr;
-    // network
-    int rank = 0, nranks = 1;
-    ncclComm_t comm = nullptr;
-    uint64_t stats[5] = {0, 0, 0, 0, 0};
-};
-
-static int fail(czk_ctx* ctx, int code, const std::string& msg) {
-    g_tls_error = msg;
-    if (ctx) ctx->err = msg;
-    return code;
-}
-#define CUDA_TRY(ctx, expr)                                                                                  \
-    do {                                                                                                     \
-        cudaError_t _e = (expr);                                                                             \
-        if (_e != cudaSuccess)                                                                               \
-            return fail(ctx, CZK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));              \
-    } while (0)
-#define CZK_TRY(expr)            \
-    do {                         \
-        int _s = (expr);         \
-        if (_s != CZK_OK) return _s; \
-    } while (0)
-
-static int scratch_reserve(czk_ctx* ctx, Scratch& s, size_t bytes) {
-    if (bytes <= s.cap) return CZK_OK;
-    if (s.p) CUDA_TRY(ctx, cudaFree(s.p));
-    s.p = nullptr;
-    s.cap = 0;
-    size_t want = bytes + bytes / 8;
-    CUDA_TRY(ctx, cudaMalloc(&s.p, want));
-    s.cap = want;
-    return CZK_OK;
-}
+#include "ctx.hpp"
 
 const char* czk_version(void) { return "czk-b200 0.1 (sm_100a)"; }
 
-const char* czk_last_error(const czk_ctx* ctx) { return ctx ? ctx->err.c_str() : g_tls_error.c_str(); }
+const char* czk_last_error(const czk_ctx* ctx) { return ctx ? ctx->err.c_str() : czk_tls_error().c_str(); }
 
 int czk_ctx_create(int device, czk_ctx** out) {
     if (!out) return fail(nullptr, CZK_ERR_ARG, "czk_ctx_create: out is null");
@@ -160,6 +61,8 @@ static void free_ws(MsmWorkspace& ws) {
     cudaFree(ws.segcnt);
     cudaFree(ws.segoff);
     cudaFree(ws.segsum);
+    for (int i = 0; i < 4; i++)
+        if (ws.ev[i]) cudaEventDestroy(ws.ev[i]);
     ws = MsmWorkspace();
 }
 
@@ -441,6 +344,8 @@ static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
             ws.seg_point_words = pww;
         }
     }
+    for (int i = 0; i < 4; i++)
+        if (!ws.ev[i]) CUDA_TRY(ctx, cudaEventCreate(&ws.ev[i]));
     size_t pin = 256 * 96 * 4;
     if (ctx->pinned_cap < pin) {
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -491,6 +396,17 @@ static int msm_core(czk_ctx* ctx, int curve, const uint32_t* bases, const uint8_
     size_t pw = msm_point_words(curve);
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, ctx->ws.winsum, cfg.nwin * pw * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    {
+        float a = 0, m = 0;
+        if (cudaEventElapsedTime(&a, ctx->ws.ev[0], ctx->ws.ev[1]) == cudaSuccess &&
+            cudaEventElapsedTime(&m, ctx->ws.ev[2], ctx->ws.ev[3]) == cudaSuccess) {
+            int k = curve == 1 ? 0 : 1;
+            ctx->acc_ms[k] += a;
+            ctx->msm_ms[k] += m;
+            ctx->acc_terms[k] += (double)n;
+            ctx->acc_launches[k] += 1;
+        }
+    }
     if (curve == 1) msm_host_tail<HFq, 6>((const uint32_t*)ctx->pinned, cfg, out_xyz);
     else msm_host_tail<HFq2, 12>((const uint32_t*)ctx->pinned, cfg, out_xyz);
     return CZK_OK;
@@ -791,6 +707,20 @@ int czk_beaver_batch_mul(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac
 }
 
 // ------------------------------------------------------------------------------------------ diagnostics
+int czk_msm_stats(czk_ctx* ctx, int curve, double out[4], int reset) {
+    if (!ctx || !out || (curve != 1 && curve != 2)) return fail(ctx, CZK_ERR_ARG, "czk_msm_stats: argument");
+    int k = curve - 1;
+    out[0] = ctx->acc_ms[k];
+    out[1] = (double)ctx->acc_launches[k];
+    out[2] = ctx->acc_terms[k];
+    out[3] = ctx->msm_ms[k];
+    if (reset) {
+        ctx->acc_ms[k] = ctx->msm_ms[k] = ctx->acc_terms[k] = 0;
+        ctx->acc_launches[k] = 0;
+    }
+    return CZK_OK;
+}
+
 int czk_microbench(czk_ctx* ctx, int kind, int blocks_per_sm, int threads, int iters, double* ops_per_s, double* ms) {
     if (!ctx || !ops_per_s || !ms) return fail(ctx, CZK_ERR_ARG, "czk_microbench: null");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));

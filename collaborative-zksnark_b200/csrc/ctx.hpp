@@ -1,0 +1,123 @@
+// Internal (not installed) definitions shared by the translation units of libczk_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/czk.h"
+#include "host_field.hpp"
+#include "msm.cuh"
+
+using namespace czk;
+using namespace czk::host;
+
+inline std::string& czk_tls_error() {
+    static thread_local std::string e;
+    return e;
+}
+
+// ------------------------------------------------------------------------------------------ NCCL (resolved at run time)
+struct NcclApi {
+    void* handle = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+    bool ok = false;
+};
+inline NcclApi& nccl_api() {
+    static NcclApi api;
+    if (api.handle || api.ok) return api;
+    // if torch already loaded its bundled libnccl.so.2 the loader hands back that copy
+    api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) api.handle = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) return api;
+    api.GetUniqueId = (decltype(api.GetUniqueId))dlsym(api.handle, "ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))dlsym(api.handle, "ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
+    api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
+    api.Broadcast = (decltype(api.Broadcast))dlsym(api.handle, "ncclBroadcast");
+    api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Broadcast && api.GetErrorString;
+    return api;
+}
+
+// ------------------------------------------------------------------------------------------ objects
+struct czk_vec {
+    uint64_t* d = nullptr;
+    size_t n = 0;
+};
+struct czk_bases {
+    int curve = 1;
+    uint32_t* xy = nullptr;  // n * (24 | 48) words
+    uint8_t* inf = nullptr;  // n bytes, or nullptr when no point is infinity
+    size_t n = 0;
+};
+struct Domain {
+    int log_d = 0;
+    uint32_t* tw = nullptr;
+    uint32_t *g_lo = nullptr, *g_hi = nullptr, *gi_lo = nullptr, *gi_hi = nullptr;
+    int lo_log = 0;
+    HFr size_inv, group_gen, group_gen_inv, generator_inv;
+};
+struct Scratch {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct czk_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    std::map<int, Domain> domains;
+    MsmWorkspace ws;
+    void* pinned = nullptr;  // host staging for window sums
+    size_t pinned_cap = 0;
+    Scratch up_bases, up_inf, up_scalars, up_vec;  // staging for the host-pointer entry points
+    Scratch open_gather, open_sigma, open_sx, open_oy, open_d, open_dm;
+    uint32_t* flag = nullptr;
+    // network
+    int rank = 0, nranks = 1;
+    ncclComm_t comm = nullptr;
+    uint64_t stats[5] = {0, 0, 0, 0, 0};
+    // kernel timing of the MSM (CUDA events on the launching stream), per curve: [0] G1, [1] G2
+    double acc_ms[2] = {0, 0}, msm_ms[2] = {0, 0}, acc_terms[2] = {0, 0};
+    uint64_t acc_launches[2] = {0, 0};
+};
+
+inline int fail(czk_ctx* ctx, int code, const std::string& msg) {
+    czk_tls_error() = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+#define CUDA_TRY(ctx, expr)                                                                                  \
+    do {                                                                                                     \
+        cudaError_t _e = (expr);                                                                             \
+        if (_e != cudaSuccess)                                                                               \
+            return fail(ctx, CZK_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+    } while (0)
+#define CZK_TRY(expr)            \
+    do {                         \
+        int _s = (expr);         \
+        if (_s != CZK_OK) return _s; \
+    } while (0)
+
+inline int scratch_reserve(czk_ctx* ctx, Scratch& s, size_t bytes) {
+    if (bytes <= s.cap) return CZK_OK;
+    if (s.p) CUDA_TRY(ctx, cudaFree(s.p));
+    s.p = nullptr;
+    s.cap = 0;
+    size_t want = bytes + bytes / 8;
+    CUDA_TRY(ctx, cudaMalloc(&s.p, want));
+    s.cap = want;
+    return CZK_OK;
+}
+

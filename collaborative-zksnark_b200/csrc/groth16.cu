@@ -1,0 +1,498 @@
+// Groth16 prover loop on shares (include/czk_groth16.h): host-side C++ orchestration of the device
+// kernels.  Mirrors mpc-snarks/src/groth/prover.rs:66-177 (create_proof), :216-232 (calculate_coeff) and
+// mpc-snarks/src/groth/r1cs_to_qap.rs:47-112 (witness_map) for the benchmark's squaring circuit
+// (mpc-snarks/src/proof.rs:304-344), with the share semantics of mpc-algebra/src/share/{add,spdz}.rs and the
+// Beaver-on-groups step of share/group.rs:70-109.  The O(1) group operations run on the host (host_field.hpp).
+#include <chrono>
+
+#include "../../include/czk_groth16.h"
+#include "ctx.hpp"
+#include "fr_ops.cuh"
+
+struct czk_pk {
+    size_t n_sq = 0, D = 0;
+    unsigned log_d = 0;
+    czk_bases* q[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // a, b_g1, b_g2, h, l
+    uint64_t vk_g1[36];
+    uint64_t vk_g2[72];
+    // first entries of the a / b queries (calculate_coeff adds query[0] on the host)
+    uint64_t a0[12], b10[12], b20[24];
+    uint8_t a0_inf = 0, b10_inf = 0, b20_inf = 0;
+};
+
+static double now_ms() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static thread_local double g_phases[8];
+
+static size_t domain_size_for(size_t n_sq, unsigned* log_d) {
+    size_t need = n_sq + 2, d = 1;  // num_constraints + num_instance_variables (r1cs_to_qap.rs:63-64)
+    unsigned l = 0;
+    while (d < need) {
+        d <<= 1;
+        l++;
+    }
+    *log_d = l;
+    return d;
+}
+
+static int pk_finish(czk_ctx* ctx, czk_pk* pk) {
+    uint8_t inf = 0;
+    CZK_TRY(czk_bases_download(ctx, pk->q[0], 0, 1, pk->a0, &inf));
+    pk->a0_inf = inf;
+    CZK_TRY(czk_bases_download(ctx, pk->q[1], 0, 1, pk->b10, &inf));
+    pk->b10_inf = inf;
+    CZK_TRY(czk_bases_download(ctx, pk->q[2], 0, 1, pk->b20, &inf));
+    pk->b20_inf = inf;
+    return CZK_OK;
+}
+
+int czk_groth16_pk_upload(czk_ctx* ctx, size_t n_sq, const uint64_t* a_query, const uint8_t* a_inf, const uint64_t* b_g1_query,
+                          const uint8_t* b1_inf, const uint64_t* b_g2_query, const uint8_t* b2_inf, const uint64_t* h_query,
+                          const uint8_t* h_inf, const uint64_t* l_query, const uint8_t* l_inf, const uint64_t vk_g1[36],
+                          const uint64_t vk_g2[72], czk_pk** out) {
+    if (!ctx || !out || !n_sq || !a_query || !b_g1_query || !b_g2_query || !h_query || !l_query || !vk_g1 || !vk_g2)
+        return fail(ctx, CZK_ERR_ARG, "czk_groth16_pk_upload: null argument");
+    czk_pk* pk = new czk_pk();
+    pk->n_sq = n_sq;
+    pk->D = domain_size_for(n_sq, &pk->log_d);
+    CZK_TRY(czk_bases_upload(ctx, 1, a_query, a_inf, n_sq + 2, &pk->q[0]));
+    CZK_TRY(czk_bases_upload(ctx, 1, b_g1_query, b1_inf, n_sq + 2, &pk->q[1]));
+    CZK_TRY(czk_bases_upload(ctx, 2, b_g2_query, b2_inf, n_sq + 2, &pk->q[2]));
+    CZK_TRY(czk_bases_upload(ctx, 1, h_query, h_inf, pk->D - 1, &pk->q[3]));
+    CZK_TRY(czk_bases_upload(ctx, 1, l_query, l_inf, n_sq, &pk->q[4]));
+    std::memcpy(pk->vk_g1, vk_g1, sizeof pk->vk_g1);
+    std::memcpy(pk->vk_g2, vk_g2, sizeof pk->vk_g2);
+    CZK_TRY(pk_finish(ctx, pk));
+    *out = pk;
+    return CZK_OK;
+}
+
+int czk_groth16_pk_synthetic(czk_ctx* ctx, size_t n_sq, uint64_t seed, czk_pk** out) {
+    if (!ctx || !out || !n_sq) return fail(ctx, CZK_ERR_ARG, "czk_groth16_pk_synthetic: argument");
+    czk_pk* pk = new czk_pk();
+    pk->n_sq = n_sq;
+    pk->D = domain_size_for(n_sq, &pk->log_d);
+    // Groth16 queries hold the point at infinity for variables absent from a matrix: flag every 1024th entry
+    CZK_TRY(czk_bases_synthetic(ctx, 1, seed * 8 + 1, n_sq + 2, 1024, &pk->q[0]));
+    CZK_TRY(czk_bases_synthetic(ctx, 1, seed * 8 + 2, n_sq + 2, 1024, &pk->q[1]));
+    CZK_TRY(czk_bases_synthetic(ctx, 2, seed * 8 + 3, n_sq + 2, 1024, &pk->q[2]));
+    CZK_TRY(czk_bases_synthetic(ctx, 1, seed * 8 + 4, pk->D - 1, 0, &pk->q[3]));
+    CZK_TRY(czk_bases_synthetic(ctx, 1, seed * 8 + 5, n_sq, 1024, &pk->q[4]));
+    // vk points: further synthetic points (downloaded from two tiny synthetic sets)
+    czk_bases *v1 = nullptr, *v2 = nullptr;
+    CZK_TRY(czk_bases_synthetic(ctx, 1, seed * 8 + 6, 3, 0, &v1));
+    CZK_TRY(czk_bases_synthetic(ctx, 2, seed * 8 + 7, 3, 0, &v2));
+    CZK_TRY(czk_bases_download(ctx, v1, 0, 3, pk->vk_g1, nullptr));
+    CZK_TRY(czk_bases_download(ctx, v2, 0, 3, pk->vk_g2, nullptr));
+    czk_bases_free(ctx, v1);
+    czk_bases_free(ctx, v2);
+    CZK_TRY(pk_finish(ctx, pk));
+    *out = pk;
+    return CZK_OK;
+}
+
+void czk_groth16_pk_free(czk_ctx* ctx, czk_pk* pk) {
+    if (!pk) return;
+    for (int i = 0; i < 5; i++) czk_bases_free(ctx, pk->q[i]);
+    delete pk;
+}
+size_t czk_groth16_pk_domain_size(const czk_pk* pk) { return pk ? pk->D : 0; }
+const czk_bases* czk_groth16_pk_query(const czk_pk* pk, int which) { return (pk && which >= 0 && which < 5) ? pk->q[which] : nullptr; }
+int czk_groth16_pk_vk(const czk_pk* pk, uint64_t vk_g1[36], uint64_t vk_g2[72]) {
+    if (!pk) return CZK_ERR_ARG;
+    std::memcpy(vk_g1, pk->vk_g1, sizeof pk->vk_g1);
+    std::memcpy(vk_g2, pk->vk_g2, sizeof pk->vk_g2);
+    return CZK_OK;
+}
+int czk_groth16_last_phases(const czk_ctx*, double out_ms[8]) {
+    for (int i = 0; i < 8; i++) out_ms[i] = g_phases[i];
+    return CZK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ witness map
+struct ShareVecs {
+    czk_vec *a = nullptr, *b = nullptr, *c = nullptr;       // value component
+    czk_vec *am = nullptr, *bm = nullptr, *cm = nullptr;    // SPDZ MAC component
+    czk_vec* chain = nullptr;                               // n_sq + 1 uploaded shares
+    czk_vec* assign = nullptr;                              // [out, w_0 .. w_{n-1}]
+};
+static void free_share_vecs(czk_ctx* ctx, ShareVecs& v) {
+    for (czk_vec* p : {v.a, v.b, v.c, v.am, v.bm, v.cm, v.chain, v.assign}) czk_vec_free(ctx, p);
+    v = ShareVecs();
+}
+
+// r1cs_to_qap.rs:66-110 on this party's shares.  On return v.a (and v.am) hold h; v.chain / v.assign are filled.
+static int witness_map_dev(czk_ctx* ctx, int scheme, size_t n_sq, unsigned log_d, const uint64_t* chain_sh,
+                           const czk_vec* chain_dev, ShareVecs& v) {
+    const size_t D = (size_t)1 << log_d;
+    const bool spdz = scheme == CZK_SCHEME_SPDZ;
+    double t0 = now_ms();
+    CZK_TRY(czk_vec_alloc(ctx, n_sq + 1, &v.chain));
+    CZK_TRY(czk_vec_alloc(ctx, n_sq + 1, &v.assign));
+    CZK_TRY(czk_vec_alloc(ctx, D, &v.a));
+    CZK_TRY(czk_vec_alloc(ctx, D, &v.b));
+    CZK_TRY(czk_vec_alloc(ctx, D, &v.c));
+    if (chain_dev) CZK_TRY(czk_vec_copy(ctx, v.chain, 0, chain_dev, 0, n_sq + 1));
+    else CUDA_TRY(ctx, cudaMemcpyAsync(czk_vec_device_ptr(v.chain), chain_sh, (n_sq + 1) * 32, cudaMemcpyHostToDevice, ctx->stream));
+    // full_assignment = [one, out] ++ witness;  assignment (prover.rs:118) = [out] ++ witness
+    CZK_TRY(czk_vec_copy(ctx, v.assign, 0, v.chain, n_sq, 1));
+    CZK_TRY(czk_vec_copy(ctx, v.assign, 1, v.chain, 0, n_sq));
+    // a[i] = b[i] = w_i, c[i] = w_{i+1} (c[n-1] = out);  a[n] = one, a[n+1] = out   (r1cs_to_qap.rs:70-83)
+    CZK_TRY(czk_vec_copy(ctx, v.a, 0, v.chain, 0, n_sq));
+    CZK_TRY(czk_vec_copy(ctx, v.b, 0, v.chain, 0, n_sq));
+    CZK_TRY(czk_vec_copy(ctx, v.c, 0, v.chain, 1, n_sq));
+    CZK_TRY(czk_vec_copy(ctx, v.a, n_sq + 1, v.chain, n_sq, 1));
+    // Public(1) lowered to share form: the king holds 1 (add.rs:88-92; SPDZ mac = 1 * mac_share, spdz.rs:132-137)
+    HFr one_val = (scheme == CZK_SCHEME_PLAIN || ctx->rank == 0) ? HFr::one() : HFr::zero();
+    CUDA_TRY(ctx, cudaMemcpyAsync(czk_vec_device_ptr(v.a) + 4 * n_sq, one_val.l, 32, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if (spdz) {
+        // from_add_shared: mac = share * mac() with the MAC key stubbed to 1 (spdz.rs:41-47,138-143); the MAC vectors
+        // then go through every linear map separately, as in spdz.rs:186-208
+        CZK_TRY(czk_vec_alloc(ctx, D, &v.am));
+        CZK_TRY(czk_vec_alloc(ctx, D, &v.bm));
+        CZK_TRY(czk_vec_alloc(ctx, D, &v.cm));
+        CZK_TRY(czk_vec_copy(ctx, v.am, 0, v.a, 0, D));
+        CZK_TRY(czk_vec_copy(ctx, v.bm, 0, v.b, 0, D));
+        CZK_TRY(czk_vec_copy(ctx, v.cm, 0, v.c, 0, D));
+    }
+    g_phases[0] = now_ms() - t0;
+    t0 = now_ms();
+    czk_vec* comps[2][3] = {{v.a, v.b, v.c}, {v.am, v.bm, v.cm}};
+    for (int k = 0; k < (spdz ? 2 : 1); k++) {
+        for (int j = 0; j < 2; j++) {  // a, b
+            CZK_TRY(czk_ntt_vec(ctx, comps[k][j], log_d, 1, 0));  // ifft_in_place
+            CZK_TRY(czk_ntt_vec(ctx, comps[k][j], log_d, 0, 1));  // coset_fft_in_place
+        }
+    }
+    CZK_TRY(czk_beaver_batch_mul(ctx, scheme, v.a, v.am, v.b, v.bm, D));  // F::batch_product_in_place(&mut ab, &b)
+    for (int k = 0; k < (spdz ? 2 : 1); k++) {
+        CZK_TRY(czk_ntt_vec(ctx, comps[k][2], log_d, 1, 0));
+        CZK_TRY(czk_ntt_vec(ctx, comps[k][2], log_d, 0, 1));
+        CZK_TRY(czk_vec_sub(ctx, comps[k][0], comps[k][2], D));                         // ab -= c
+        CZK_TRY(czk_vec_divide_by_vanishing_on_coset(ctx, comps[k][0], log_d));          // /= Z_H(g)
+        CZK_TRY(czk_ntt_vec(ctx, comps[k][0], log_d, 1, 1));                             // coset_ifft_in_place
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    g_phases[1] = now_ms() - t0;
+    return CZK_OK;
+}
+
+int czk_groth16_witness_map(czk_ctx* ctx, int scheme, size_t n_sq, const uint64_t* chain_sh, uint64_t* h_out) {
+    if (!ctx || !chain_sh || !h_out || !n_sq) return fail(ctx, CZK_ERR_ARG, "czk_groth16_witness_map: argument");
+    if (scheme == CZK_SCHEME_PLAIN && ctx->nranks != 1) return fail(ctx, CZK_ERR_ARG, "plain scheme needs a 1-party context");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    unsigned log_d;
+    size_t D = domain_size_for(n_sq, &log_d);
+    ShareVecs v;
+    int rc = witness_map_dev(ctx, scheme, n_sq, log_d, chain_sh, nullptr, v);
+    if (rc == CZK_OK) rc = czk_vec_download(ctx, v.a, 0, h_out, D);
+    free_share_vecs(ctx, v);
+    return rc;
+}
+
+// ------------------------------------------------------------------------------------------ group shares on the host
+template <class HF, int LIMBS>
+struct GShare {
+    typedef HPoint<HF> P;
+    P sh, mac;
+
+    static P from_jac_out(const uint64_t* xyz) {  // (x, y, 1) or (1, 1, 0) as written by the MSM entry points
+        HF z = HF::from_limbs(xyz + 2 * LIMBS);
+        if (z.is_zero()) return P::infinity();
+        return P::from_affine(HF::from_limbs(xyz), HF::from_limbs(xyz + LIMBS));
+    }
+    static P from_affine_limbs(const uint64_t* xy, int inf) {
+        if (inf) return P::infinity();
+        return P::from_affine(HF::from_limbs(xy), HF::from_limbs(xy + LIMBS));
+    }
+    static int to_affine_limbs(const P& p, uint64_t* xy) {  // returns the infinity flag; infinity is written as (0, 1)
+        HF ax, ay;
+        if (!p.to_affine(ax, ay)) {
+            HF::zero().to_limbs(xy);
+            HF::one().to_limbs(xy + LIMBS);
+            return 1;
+        }
+        ax.to_limbs(xy);
+        ay.to_limbs(xy + LIMBS);
+        return 0;
+    }
+};
+
+static void fr_canonical(const uint64_t mont[4], uint64_t out[4]) { HFr::from_limbs(mont).from_mont().to_limbs(out); }
+
+// open one shared group element (add.rs:178-180 / spdz.rs:262-275): returns the sum of all parties' sh
+template <class HF, int LIMBS>
+static int group_open(czk_ctx* ctx, int scheme, const GShare<HF, LIMBS>& s, HPoint<HF>* out) {
+    typedef GShare<HF, LIMBS> GS;
+    typedef HPoint<HF> P;
+    if (scheme == CZK_SCHEME_PLAIN) {
+        *out = s.sh;
+        return CZK_OK;
+    }
+    const int n = ctx->nranks;
+    const size_t rec = (2 * LIMBS + 1) * 8;  // x | y | inf word
+    std::vector<uint64_t> send(2 * LIMBS + 1), recv((size_t)n * (2 * LIMBS + 1));
+    send[2 * LIMBS] = (uint64_t)GS::to_affine_limbs(s.sh, send.data());
+    CZK_TRY(czk_net_allgather_host(ctx, send.data(), recv.data(), rec));
+    P x = P::infinity();
+    for (int p = 0; p < n; p++) {
+        const uint64_t* r = recv.data() + (size_t)p * (2 * LIMBS + 1);
+        x.add(GS::from_affine_limbs(r, (int)r[2 * LIMBS]));
+    }
+    if (scheme == CZK_SCHEME_SPDZ) {
+        // dx_t = x * mac_share - mac ; all dx_t must sum to zero (Pragmatic MPC 6.6.2)
+        P dx = ctx->rank == 0 ? x : P::infinity();
+        P m = s.mac;
+        m.negate();
+        dx.add(m);
+        send[2 * LIMBS] = (uint64_t)GS::to_affine_limbs(dx, send.data());
+        CZK_TRY(czk_net_allgather_host(ctx, send.data(), recv.data(), rec));
+        P sum = P::infinity();
+        for (int p = 0; p < n; p++) {
+            const uint64_t* r = recv.data() + (size_t)p * (2 * LIMBS + 1);
+            sum.add(GS::from_affine_limbs(r, (int)r[2 * LIMBS]));
+        }
+        if (!sum.is_inf()) return fail(ctx, CZK_ERR_PROTOCOL, "SPDZ group MAC check failed (spdz.rs:273 assert!(sum.is_zero()))");
+    }
+    *out = x;
+    return CZK_OK;
+}
+
+// open one shared field element given as (sh, mac)
+static int field_open1(czk_ctx* ctx, int scheme, const HFr& sh, const HFr& mac, HFr* out) {
+    if (scheme == CZK_SCHEME_PLAIN) {
+        *out = sh;
+        return CZK_OK;
+    }
+    const int n = ctx->nranks;
+    std::vector<uint64_t> recv((size_t)n * 4);
+    CZK_TRY(czk_net_allgather_host(ctx, sh.l, recv.data(), 32));
+    HFr x = HFr::zero();
+    for (int p = 0; p < n; p++) x = HFr::add(x, HFr::from_limbs(recv.data() + 4 * p));
+    if (scheme == CZK_SCHEME_SPDZ) {
+        HFr ms = ctx->rank == 0 ? HFr::one() : HFr::zero();
+        HFr dx = HFr::sub(HFr::mul(ms, x), mac);
+        CZK_TRY(czk_net_allgather_host(ctx, dx.l, recv.data(), 32));
+        HFr sum = HFr::zero();
+        for (int p = 0; p < n; p++) sum = HFr::add(sum, HFr::from_limbs(recv.data() + 4 * p));
+        if (!sum.is_zero()) return fail(ctx, CZK_ERR_PROTOCOL, "SPDZ MAC check failed (spdz.rs:129 assert!(sum.is_zero()))");
+    }
+    *out = x;
+    return CZK_OK;
+}
+
+// GroupShare::scale (share/group.rs:70-109) with DummyGroupTripleSource (wire/group.rs:37-75): x = 0, y = 1@king, z = 0
+template <class HF, int LIMBS>
+static int group_scale_shared(czk_ctx* ctx, int scheme, GShare<HF, LIMBS>& self, const HFr& o_sh, const HFr& o_mac) {
+    typedef HPoint<HF> P;
+    if (scheme == CZK_SCHEME_PLAIN) {
+        uint64_t k[4];
+        o_sh.from_mont().to_limbs(k);
+        self.sh = P::mul(self.sh, k, 4);
+        self.mac = self.sh;
+        return CZK_OK;
+    }
+    P sx;
+    CZK_TRY((group_open<HF, LIMBS>(ctx, scheme, self, &sx)));
+    HFr y = ctx->rank == 0 ? HFr::one() : HFr::zero();
+    HFr oy;
+    CZK_TRY(field_open1(ctx, scheme, HFr::add(o_sh, y), HFr::add(o_mac, y), &oy));
+    // out = z - scale_pub_group(sx, y) - x.scale_pub_scalar(oy) ; out.shift(sx * oy)
+    GShare<HF, LIMBS> out;
+    out.sh = P::infinity();
+    out.mac = P::infinity();
+    if (ctx->rank == 0) {  // y = (1, mac 1) at the king, (0, 0) elsewhere: sx * 0 is the identity
+        P neg = sx;
+        neg.negate();
+        out.sh.add(neg);
+        out.mac.add(neg);
+        uint64_t k[4];
+        oy.from_mont().to_limbs(k);
+        P sxoy = P::mul(sx, k, 4);
+        out.sh.add(sxoy);   // AdditiveGroupShare::shift: king only
+        out.mac.add(sxoy);  // mac += other * mac_share (1 at the king)
+    }
+    self = out;
+    return CZK_OK;
+}
+
+template <class HF, int LIMBS>
+static void shift_pub(const czk_ctx* ctx, int scheme, GShare<HF, LIMBS>& s, const HPoint<HF>& el) {
+    if (scheme == CZK_SCHEME_PLAIN || ctx->rank == 0) {
+        s.sh.add(el);
+        s.mac.add(el);
+    }
+}
+
+static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t* chain_sh, const czk_vec* chain_dev,
+                      const uint64_t r_sh[4], const uint64_t s_sh[4], uint64_t proof_sh[48], uint8_t proof_sh_inf[3],
+                      uint64_t proof[48], uint8_t proof_inf[3]);
+
+int czk_groth16_prove(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t* chain_sh, const uint64_t r_sh[4],
+                      const uint64_t s_sh[4], uint64_t proof_sh[48], uint8_t proof_sh_inf[3], uint64_t proof[48],
+                      uint8_t proof_inf[3]) {
+    if (!chain_sh) return fail(ctx, CZK_ERR_ARG, "czk_groth16_prove: null argument");
+    return prove_impl(ctx, scheme, pk, chain_sh, nullptr, r_sh, s_sh, proof_sh, proof_sh_inf, proof, proof_inf);
+}
+int czk_groth16_prove_vec(czk_ctx* ctx, int scheme, const czk_pk* pk, const czk_vec* chain_dev, const uint64_t r_sh[4],
+                          const uint64_t s_sh[4], uint64_t proof_sh[48], uint8_t proof_sh_inf[3], uint64_t proof[48],
+                          uint8_t proof_inf[3]) {
+    if (!chain_dev || !pk || chain_dev->n < pk->n_sq + 1) return fail(ctx, CZK_ERR_ARG, "czk_groth16_prove_vec: chain vector");
+    return prove_impl(ctx, scheme, pk, nullptr, chain_dev, r_sh, s_sh, proof_sh, proof_sh_inf, proof, proof_inf);
+}
+
+int czk_squaring_chain(const uint64_t start[4], size_t n_sq, uint64_t* out) {
+    if (!start || !out) return fail(nullptr, CZK_ERR_ARG, "czk_squaring_chain: null argument");
+    HFr x = HFr::from_limbs(start);
+    x.to_limbs(out);
+    for (size_t i = 1; i <= n_sq; i++) {
+        x = HFr::sqr(x);
+        x.to_limbs(out + 4 * i);
+    }
+    return CZK_OK;
+}
+
+int czk_king_share_batch(const uint64_t* values, size_t k, int n_parties, uint64_t seed, uint64_t* out) {
+    if (!values || !out || n_parties < 1) return fail(nullptr, CZK_ERR_ARG, "czk_king_share_batch: argument");
+    uint64_t st = seed ^ 0x5eedc0deull;
+    auto next = [&]() {
+        st += 0x9E3779B97F4A7C15ull;
+        uint64_t z = st;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    };
+    for (size_t i = 0; i < k; i++) {
+        HFr rest = HFr::from_limbs(values + 4 * i);
+        for (int p = 0; p + 1 < n_parties; p++) {
+            HFr r;
+            do {  // uniform in [0, r): 253-bit candidates, rejection
+                for (int j = 0; j < 4; j++) r.l[j] = next();
+                r.l[3] &= (1ull << 61) - 1;
+            } while (HFr::geq_mod(r.l));
+            r.to_limbs(out + ((size_t)p * k + i) * 4);
+            rest = HFr::sub(rest, r);
+        }
+        rest.to_limbs(out + ((size_t)(n_parties - 1) * k + i) * 4);
+    }
+    return CZK_OK;
+}
+
+static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t* chain_sh, const czk_vec* chain_dev,
+                      const uint64_t r_sh[4], const uint64_t s_sh[4], uint64_t proof_sh[48], uint8_t proof_sh_inf[3],
+                      uint64_t proof[48], uint8_t proof_inf[3]) {
+    if (!ctx || !pk || !r_sh || !s_sh || !proof_sh || !proof_sh_inf || !proof || !proof_inf)
+        return fail(ctx, CZK_ERR_ARG, "czk_groth16_prove: null argument");
+    if (scheme == CZK_SCHEME_PLAIN && ctx->nranks != 1) return fail(ctx, CZK_ERR_ARG, "plain scheme needs a 1-party context");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    typedef GShare<HFq, 6> S1;
+    typedef GShare<HFq2, 12> S2;
+    const size_t n_sq = pk->n_sq, D = pk->D;
+    for (int i = 0; i < 8; i++) g_phases[i] = 0;
+    ShareVecs v;
+    int rc = witness_map_dev(ctx, scheme, n_sq, pk->log_d, chain_sh, chain_dev, v);
+    if (rc != CZK_OK) {
+        free_share_vecs(ctx, v);
+        return rc;
+    }
+    // ---- the five MSMs (prover.rs:104,108,132,143,155); share-local, no communication.
+    // SPDZ computes sh and mac as the same MSM of the value shares (spdz.rs:440-446): done once, used twice.
+    uint64_t o1[18], o2[36];
+    S1 h_acc, l_acc, a_acc, b1_acc;
+    S2 b2_acc;
+    auto fin = [&](int c) {
+        free_share_vecs(ctx, v);
+        return c;
+    };
+    double t0 = now_ms();
+    if ((rc = czk_msm_bases(ctx, pk->q[3], 0, v.a, 0, 1, D - 1, o1)) != CZK_OK) return fin(rc);
+    h_acc.sh = h_acc.mac = S1::from_jac_out(o1);
+    g_phases[2] = now_ms() - t0;
+    t0 = now_ms();
+    if ((rc = czk_msm_bases(ctx, pk->q[4], 0, v.chain, 0, 1, n_sq, o1)) != CZK_OK) return fin(rc);
+    l_acc.sh = l_acc.mac = S1::from_jac_out(o1);
+    g_phases[3] = now_ms() - t0;
+    t0 = now_ms();
+    if ((rc = czk_msm_bases(ctx, pk->q[0], 1, v.assign, 0, 1, n_sq + 1, o1)) != CZK_OK) return fin(rc);
+    a_acc.sh = a_acc.mac = S1::from_jac_out(o1);
+    g_phases[4] = now_ms() - t0;
+    t0 = now_ms();
+    if ((rc = czk_msm_bases(ctx, pk->q[1], 1, v.assign, 0, 1, n_sq + 1, o1)) != CZK_OK) return fin(rc);
+    b1_acc.sh = b1_acc.mac = S1::from_jac_out(o1);
+    g_phases[5] = now_ms() - t0;
+    t0 = now_ms();
+    if ((rc = czk_msm_bases(ctx, pk->q[2], 1, v.assign, 0, 1, n_sq + 1, o2)) != CZK_OK) return fin(rc);
+    b2_acc.sh = b2_acc.mac = S2::from_jac_out(o2);
+    g_phases[6] = now_ms() - t0;
+    free_share_vecs(ctx, v);
+
+    // ---- O(1) group arithmetic on shares (prover.rs:110-177)
+    t0 = now_ms();
+    HG1 alpha_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1), HFq::from_limbs(pk->vk_g1 + 6));
+    HG1 beta_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1 + 12), HFq::from_limbs(pk->vk_g1 + 18));
+    HG1 delta_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1 + 24), HFq::from_limbs(pk->vk_g1 + 30));
+    HG2 beta_g2 = HG2::from_affine(HFq2::from_limbs(pk->vk_g2), HFq2::from_limbs(pk->vk_g2 + 12));
+    HG2 delta_g2 = HG2::from_affine(HFq2::from_limbs(pk->vk_g2 + 48), HFq2::from_limbs(pk->vk_g2 + 60));
+    HFr r = HFr::from_limbs(r_sh), s = HFr::from_limbs(s_sh);
+    uint64_t rk[4], sk[4];
+    fr_canonical(r_sh, rk);
+    fr_canonical(s_sh, sk);
+    // from_add_shared scalars: mac = share (key 1), so scale_pub_group gives sh == mac (spdz.rs:419-423)
+    S1 rsd;
+    rsd.sh = rsd.mac = HG1::mul(delta_g1, rk, 4);  // delta_g1 * r
+    CZK_TRY((group_scale_shared<HFq, 6>(ctx, scheme, rsd, s, s)));  // ... * s
+    // A = r*delta + a_query[0] + MSM + alpha   (calculate_coeff, prover.rs:216-232)
+    S1 g_a;
+    g_a.sh = g_a.mac = HG1::mul(delta_g1, rk, 4);
+    shift_pub(ctx, scheme, g_a, S1::from_affine_limbs(pk->a0, pk->a0_inf));
+    g_a.sh.add(a_acc.sh);
+    g_a.mac.add(a_acc.mac);
+    shift_pub(ctx, scheme, g_a, alpha_g1);
+    S1 s_g_a = g_a;
+    CZK_TRY((group_scale_shared<HFq, 6>(ctx, scheme, s_g_a, s, s)));
+    S1 g1_b;
+    g1_b.sh = g1_b.mac = HG1::mul(delta_g1, sk, 4);
+    shift_pub(ctx, scheme, g1_b, S1::from_affine_limbs(pk->b10, pk->b10_inf));
+    g1_b.sh.add(b1_acc.sh);
+    g1_b.mac.add(b1_acc.mac);
+    shift_pub(ctx, scheme, g1_b, beta_g1);
+    S2 g2_b;
+    g2_b.sh = g2_b.mac = HG2::mul(delta_g2, sk, 4);
+    shift_pub(ctx, scheme, g2_b, S2::from_affine_limbs(pk->b20, pk->b20_inf));
+    g2_b.sh.add(b2_acc.sh);
+    g2_b.mac.add(b2_acc.mac);
+    shift_pub(ctx, scheme, g2_b, beta_g2);
+    S1 r_g1_b = g1_b;
+    CZK_TRY((group_scale_shared<HFq, 6>(ctx, scheme, r_g1_b, r, r)));
+    // C = s*A + r*B1 - r*s*delta + L + H
+    S1 g_c = s_g_a;
+    g_c.sh.add(r_g1_b.sh);
+    g_c.mac.add(r_g1_b.mac);
+    {
+        HG1 t = rsd.sh, u = rsd.mac;
+        t.negate();
+        u.negate();
+        g_c.sh.add(t);
+        g_c.mac.add(u);
+    }
+    g_c.sh.add(l_acc.sh);
+    g_c.mac.add(l_acc.mac);
+    g_c.sh.add(h_acc.sh);
+    g_c.mac.add(h_acc.mac);
+    proof_sh_inf[0] = (uint8_t)S1::to_affine_limbs(g_a.sh, proof_sh);
+    proof_sh_inf[1] = (uint8_t)S2::to_affine_limbs(g2_b.sh, proof_sh + 12);
+    proof_sh_inf[2] = (uint8_t)S1::to_affine_limbs(g_c.sh, proof_sh + 36);
+    // pf.reveal() (groth16/src/reveal.rs:7-12)
+    HG1 A, Cc;
+    HG2 B;
+    CZK_TRY((group_open<HFq, 6>(ctx, scheme, g_a, &A)));
+    CZK_TRY((group_open<HFq2, 12>(ctx, scheme, g2_b, &B)));
+    CZK_TRY((group_open<HFq, 6>(ctx, scheme, g_c, &Cc)));
+    proof_inf[0] = (uint8_t)S1::to_affine_limbs(A, proof);
+    proof_inf[1] = (uint8_t)S2::to_affine_limbs(B, proof + 12);
+    proof_inf[2] = (uint8_t)S1::to_affine_limbs(Cc, proof + 36);
+    g_phases[7] = now_ms() - t0;
+    return CZK_OK;
+}

@@ -267,6 +267,7 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
                              const MsmConfig& cfg, MsmWorkspace& ws, cudaStream_t st) {
     size_t total = (size_t)cfg.nwin * cfg.nb;
     cudaError_t e;
+    if (ws.ev[2]) cudaEventRecord(ws.ev[2], st);
     if ((e = cudaMemsetAsync(ws.hist, 0, total * sizeof(uint32_t), st)) != cudaSuccess) return e;
     if (n) {
         unsigned blocks = (unsigned)((n + 255) / 256);
@@ -288,8 +289,10 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
     if (max_items > ws.cap_items) return cudaErrorInvalidValue;
     k_msm_seg_counts<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.hist, ws.segcnt, total, seg); CZK_LAUNCHED();
     k_exclusive_scan<<<1, 1024, 0, st>>>(ws.segcnt, ws.segoff, total); CZK_LAUNCHED();
+    if (ws.ev[0]) cudaEventRecord(ws.ev[0], st);
     k_msm_accumulate<F><<<(unsigned)((max_items + 127) / 128), 128, 0, st>>>(bases, ws.sorted, ws.offsets, ws.hist, ws.segoff, ws.segcnt,
                                                                           ws.buckets, ws.segsum, total, max_items, seg); CZK_LAUNCHED();
+    if (ws.ev[1]) cudaEventRecord(ws.ev[1], st);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     k_msm_fold_segments<F><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(ws.segoff, ws.segcnt, ws.segsum, ws.buckets, total); CZK_LAUNCHED();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -298,6 +301,7 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
     k_msm_reduce_chunks<F><<<(unsigned)((rthreads + 127) / 128), 128, 0, st>>>(ws.buckets, ws.partial, cfg.nb, cfg.chunk, cfg.nwin); CZK_LAUNCHED();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     k_msm_window_sum<F><<<cfg.nwin, WINSUM_THREADS, 0, st>>>(ws.partial, ws.winsum, nchunks); CZK_LAUNCHED();
+    if (ws.ev[3]) cudaEventRecord(ws.ev[3], st);
     return cudaGetLastError();
 }
 

@@ -61,6 +61,7 @@ struct MsmWorkspace {
     uint32_t* segsum = nullptr;    // cap_items points: per-segment sums of multi-segment buckets
     size_t cap_items = 0;
     int seg_point_words = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // accumulate start/stop, whole MSM start/stop
     size_t cap_n = 0;
     size_t cap_buckets = 0;
     int point_words = 0;

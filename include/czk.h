@@ -140,6 +140,9 @@ CZK_API int czk_beaver_batch_mul(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_ve
                          const czk_vec* y_mac, size_t n);
 
 /* ---- diagnostics --------------------------------------------------------------------------------- */
+/* Device timing (CUDA events on the context's stream) of the MSMs run so far on this context, per curve:
+ * out = { bucket-accumulation kernel ms (sum), its launch count, terms processed (sum of n), whole-MSM device ms (sum) }. */
+CZK_API int czk_msm_stats(czk_ctx* ctx, int curve, double out[4], int reset);
 /* Integer-pipe microbenchmarks; result = operations per second.  kind: 0 IMAD.WIDE.U32 chain,
  * 1 IMAD lo/hi pair, 2 Fr mul, 3 Fq mul, 4 G1 mixed add. */
 CZK_API int czk_microbench(czk_ctx* ctx, int kind, int blocks_per_sm, int threads, int iters, double* ops_per_s, double* ms);

@@ -1,0 +1,64 @@
+/* czk_groth16.h - the Groth16 prover loop of collaborative-zksnark on top of czk.h.
+ *
+ * Host-side orchestration in C++ (the reference's is Rust: mpc-snarks/src/groth/prover.rs:66-177,
+ * mpc-snarks/src/groth/r1cs_to_qap.rs:47-112), specialised like the reference's benchmark to the
+ * repeated-squaring circuit (mpc-snarks/src/proof.rs:304-344).  One call = one party's share of the
+ * proof plus the revealed proof (`create_random_proof` + `pf.reveal()`, proof.rs:130-139): every NTT,
+ * MSM, share product and opening runs on this party's GPU; the parties meet only in the NCCL
+ * collectives of czk_net_*.
+ */
+#ifndef CZK_GROTH16_H
+#define CZK_GROTH16_H
+#include "czk.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct czk_pk czk_pk; /* device-resident ProvingKey (groth16 ProvingKey<E>: a/b_g1/b_g2/h/l queries + vk points) */
+
+/* Upload a proving key for n_sq squarings.  Shapes (groth16/src/generator.rs:109-221): a_query, b_g1_query,
+ * b_g2_query: n_sq + 2 points; h_query: D - 1 points with D = next_pow2(n_sq + 2); l_query: n_sq points;
+ * vk_g1 = alpha_g1 | beta_g1 | delta_g1 ; vk_g2 = beta_g2 | gamma_g2 | delta_g2.  inf arrays may be NULL. */
+CZK_API int czk_groth16_pk_upload(czk_ctx* ctx, size_t n_sq, const uint64_t* a_query, const uint8_t* a_inf,
+                                  const uint64_t* b_g1_query, const uint8_t* b1_inf, const uint64_t* b_g2_query,
+                                  const uint8_t* b2_inf, const uint64_t* h_query, const uint8_t* h_inf,
+                                  const uint64_t* l_query, const uint8_t* l_inf, const uint64_t vk_g1[36],
+                                  const uint64_t vk_g2[72], czk_pk** out);
+/* A proving key of the same shapes filled with synthetic device-generated bases (benchmarks: the proof does not
+ * verify, the work is identical).  Same seed => same key on every rank. */
+CZK_API int czk_groth16_pk_synthetic(czk_ctx* ctx, size_t n_sq, uint64_t seed, czk_pk** out);
+CZK_API void czk_groth16_pk_free(czk_ctx* ctx, czk_pk* pk);
+CZK_API size_t czk_groth16_pk_domain_size(const czk_pk* pk);
+/* which: 0 a_query, 1 b_g1_query, 2 b_g2_query, 3 h_query, 4 l_query */
+CZK_API const czk_bases* czk_groth16_pk_query(const czk_pk* pk, int which);
+CZK_API int czk_groth16_pk_vk(const czk_pk* pk, uint64_t vk_g1[36], uint64_t vk_g2[72]);
+
+/* R1CStoQAP::witness_map on this party's shares: chain_sh = n_sq + 1 Montgomery Fr (shares of w_0..w_{n-1}, out)
+ * in host memory; h_out = D Fr (this party's share of the quotient coefficients), host memory. */
+CZK_API int czk_groth16_witness_map(czk_ctx* ctx, int scheme, size_t n_sq, const uint64_t* chain_sh, uint64_t* h_out);
+
+/* create_proof on shares followed by reveal.  r_sh / s_sh: this party's shares of the prover randomness.
+ * proof_sh: this party's share A | B | C as affine x|y (12 + 24 + 12 limbs), proof_sh_inf: 3 infinity bytes;
+ * proof / proof_inf: the revealed proof (identical on every party).  scheme PLAIN requires a 1-party context. */
+CZK_API int czk_groth16_prove(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t* chain_sh, const uint64_t r_sh[4],
+                              const uint64_t s_sh[4], uint64_t proof_sh[48], uint8_t proof_sh_inf[3], uint64_t proof[48],
+                              uint8_t proof_inf[3]);
+/* Same, with this party's chain shares already resident on the device (n_sq + 1 elements). */
+CZK_API int czk_groth16_prove_vec(czk_ctx* ctx, int scheme, const czk_pk* pk, const czk_vec* chain_dev, const uint64_t r_sh[4],
+                                  const uint64_t s_sh[4], uint64_t proof_sh[48], uint8_t proof_sh_inf[3], uint64_t proof[48],
+                                  uint8_t proof_inf[3]);
+/* Witness generation of the benchmark circuit (mpc-snarks/src/proof.rs:308-310): out[i] = start^(2^i), i <= n_sq.
+ * Host-side, serial by nature, outside the reference's timed section. */
+CZK_API int czk_squaring_chain(const uint64_t start[4], size_t n_sq, uint64_t* out);
+/* Reveal::king_share_batch (share/add.rs:105-117, spdz.rs:150-162): additive shares of k values for n parties,
+ * parties 0..n-2 uniform, party n-1 the remainder; out = n_parties * k Fr, party-major.  Host-side. */
+CZK_API int czk_king_share_batch(const uint64_t* values, size_t k, int n_parties, uint64_t seed, uint64_t* out);
+/* Per-phase device/host milliseconds of the last czk_groth16_prove on this context:
+ * 0 upload, 1 witness map (NTTs + product), 2 MSM h, 3 MSM l, 4 MSM a, 5 MSM b_g1, 6 MSM b_g2, 7 group tail + reveal. */
+CZK_API int czk_groth16_last_phases(const czk_ctx* ctx, double out_ms[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

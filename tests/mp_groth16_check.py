@@ -1,0 +1,63 @@
+#!/usr/bin/env python3
+"""Multi-party parity run: `torchrun --nproc-per-node N tests/mp_groth16_check.py [--scheme spdz] [--log-n 10]`.
+Each rank is one party on its own GPU (NCCL opens through libczk_b200); rank p compares ITS h share, proof share
+and the revealed proof with the oracle's in-process simulation of all N parties on the same shares.
+Exit code 0 on parity.  (Test infrastructure: uses oracle/.)"""
+import argparse
+import random
+import sys
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import numpy as np
+
+import czk_b200
+from czk_b200 import launch
+from oracle import binding as o
+from oracle import pymodel as m
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scheme", default="spdz", choices=["additive", "spdz"])
+    ap.add_argument("--log-n", type=int, default=10)
+    ap.add_argument("--n", type=int, default=0, help="exact number of squarings (overrides --log-n)")
+    args = ap.parse_args()
+    party = launch.Party()
+    ctx, rank, world = party.ctx, party.rank, party.world
+    scheme = czk_b200.SCHEME_SPDZ if args.scheme == "spdz" else czk_b200.SCHEME_ADDITIVE
+    n_sq = args.n or (1 << args.log_n)
+    rnd = random.Random(1234 + n_sq)
+    toxic = [rnd.randrange(1, m.R_MOD) for _ in range(7)]
+    pk = o.groth16_setup(n_sq, o.fr_from_ints(toxic), threads=max(1, o.cpu_threads() // world))
+    chain = o.squaring_chain(o.fr_from_ints([rnd.randrange(m.R_MOD)])[0], n_sq)
+    # every rank derives the same sharing (the king's scatter is exercised separately below)
+    shares = czk_b200.king_share_batch(chain, world, seed=99)
+    mine = launch.king_share_scatter(chain if rank == 0 else None, n_sq + 1, seed=99)
+    assert (mine == shares[rank]).all(), "king scatter delivered the wrong slice"
+    rho, sigma = 1234567, 7654321  # MpcField::rand: same seeded value at every party
+    r_sh = o.fr_from_ints([rho] * world)
+    s_sh = o.fr_from_ints([sigma] * world)
+    exp = o.groth16_prove(scheme, n_sq, list(shares), r_sh, s_sh, pk, threads=max(1, o.cpu_threads() // world))
+    assert exp["ok"]
+    dpk = czk_b200.ProvingKey.upload(ctx, pk)
+    h = czk_b200.groth16_witness_map(ctx, scheme, n_sq, mine)
+    assert (h == exp["h"][rank]).all(), f"rank {rank}: h share differs"
+    got = czk_b200.groth16_prove(ctx, scheme, dpk, mine, r_sh[rank], s_sh[rank])
+    assert (got["proof"] == exp["proof"]).all() and (got["proof_inf"] == exp["proof_inf"]).all(), f"rank {rank}: revealed proof differs"
+    assert (got["proof_sh"] == exp["proof_sh"][rank]).all(), f"rank {rank}: proof share differs"
+    st = ctx.net_stats()
+    assert st["broadcasts"] > 0 and st["bytes_sent"] > 0
+    # batch_open parity on a random shared vector
+    x = o.random_fr_mont(5, 1000)
+    xs = czk_b200.king_share_batch(x, world, seed=3)
+    opened = ctx.batch_open(scheme, ctx.vec_from(xs[rank]), ctx.vec_from(xs[rank]) if scheme == czk_b200.SCHEME_SPDZ else None)
+    assert (opened.numpy() == x).all()
+    launch.barrier()
+    print(f"[rank {rank}/{world}] groth16 {args.scheme} n={n_sq}: parity ok; net {st}", flush=True)
+    party.close()
+
+
+if __name__ == "__main__":
+    main()
