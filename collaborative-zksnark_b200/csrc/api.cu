@@ -44,6 +44,12 @@ int czk_ctx_create(int device, czk_ctx** out) {
     ctx->device = device;
     CUDA_TRY(ctx, cudaSetDevice(device));
     CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+        cudaMemPool_t pool;
+        CUDA_TRY(ctx, cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = ~0ull;
+        CUDA_TRY(ctx, cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     CUDA_TRY(ctx, cudaMalloc((void**)&ctx->flag, 4));
     CUDA_TRY(ctx, cudaMemset(ctx->flag, 0, 4));
     *out = ctx;
@@ -61,6 +67,8 @@ static void free_ws(MsmWorkspace& ws) {
     cudaFree(ws.segcnt);
     cudaFree(ws.segoff);
     cudaFree(ws.segsum);
+    cudaFree(ws.items);
+    cudaFree(ws.queue);
     for (int i = 0; i < 4; i++)
         if (ws.ev[i]) cudaEventDestroy(ws.ev[i]);
     ws = MsmWorkspace();
@@ -103,10 +111,12 @@ int czk_vec_alloc(czk_ctx* ctx, size_t n, czk_vec** out) {
     czk_vec* v = new czk_vec();
     v->n = n;
     size_t bytes = (n ? n : 1) * 32;
-    cudaError_t e = cudaMalloc((void**)&v->d, bytes);
+    // stream-ordered allocation from the device's default pool (kept, never trimmed: see czk_ctx_create), so the
+    // per-proof witness vectors cost no cudaMalloc / cudaFree round trips
+    cudaError_t e = cudaMallocAsync((void**)&v->d, bytes, ctx->stream);
     if (e != cudaSuccess) {
         delete v;
-        return fail(ctx, CZK_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        return fail(ctx, CZK_ERR_CUDA, std::string("cudaMallocAsync: ") + cudaGetErrorString(e));
     }
     CUDA_TRY(ctx, cudaMemsetAsync(v->d, 0, bytes, ctx->stream));
     *out = v;
@@ -114,8 +124,8 @@ int czk_vec_alloc(czk_ctx* ctx, size_t n, czk_vec** out) {
 }
 void czk_vec_free(czk_ctx* ctx, czk_vec* v) {
     if (!v) return;
-    if (ctx) cudaStreamSynchronize(ctx->stream);
-    cudaFree(v->d);
+    if (ctx) cudaFreeAsync(v->d, ctx->stream);
+    else cudaFree(v->d);
     delete v;
 }
 size_t czk_vec_len(const czk_vec* v) { return v ? v->n : 0; }
@@ -336,10 +346,18 @@ static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
         if (items > ws.cap_items || pw > ws.seg_point_words) {
             CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
             cudaFree(ws.segsum);
-            ws.segsum = nullptr;
+            cudaFree(ws.items);
+            ws.segsum = ws.items = nullptr;
             size_t cap = items + items / 8;
             int pww = pw > ws.seg_point_words ? pw : ws.seg_point_words;
             CUDA_TRY(ctx, cudaMalloc((void**)&ws.segsum, cap * (size_t)pww * 4));
+            CUDA_TRY(ctx, cudaMalloc((void**)&ws.items, cap * 16));
+            if (!ws.queue) {
+                CUDA_TRY(ctx, cudaMalloc((void**)&ws.queue, 16));
+                cudaDeviceProp prop;
+                CUDA_TRY(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+                ws.sm_count = prop.multiProcessorCount;
+            }
             ws.cap_items = cap;
             ws.seg_point_words = pww;
         }

@@ -146,7 +146,6 @@ static int witness_map_dev(czk_ctx* ctx, int scheme, size_t n_sq, unsigned log_d
     // Public(1) lowered to share form: the king holds 1 (add.rs:88-92; SPDZ mac = 1 * mac_share, spdz.rs:132-137)
     HFr one_val = (scheme == CZK_SCHEME_PLAIN || ctx->rank == 0) ? HFr::one() : HFr::zero();
     CUDA_TRY(ctx, cudaMemcpyAsync(czk_vec_device_ptr(v.a) + 4 * n_sq, one_val.l, 32, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     if (spdz) {
         // from_add_shared: mac = share * mac() with the MAC key stubbed to 1 (spdz.rs:41-47,138-143); the MAC vectors
         // then go through every linear map separately, as in spdz.rs:186-208

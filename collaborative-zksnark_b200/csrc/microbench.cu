@@ -45,6 +45,93 @@ __global__ void k_mb_pair(uint64_t* out, int iters, uint32_t seed) {
     }
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((uint64_t)(l0 ^ l1 ^ l2 ^ l3) << 32) | (h0 ^ h1 ^ h2 ^ h3);
 }
+// kind 5: carry-chained wide multiply-adds (IMAD.WIDE.U32.X), the form the Montgomery rows issue
+__global__ void k_mb_wide_carry(uint64_t* out, int iters, uint32_t seed) {
+    uint32_t a[12], acc0[12], acc1[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        a[i] = seed * (i + 1) + threadIdx.x;
+        acc0[i] = i;
+        acc1[i] = blockIdx.x + i;
+    }
+    uint32_t b0 = seed ^ threadIdx.x, b1 = b0 * 3 + 1, b2 = b0 * 5 + 7, b3 = b0 * 7 + 11;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+        chain_mad<12>(acc0, a, b0);
+        chain_mad<12>(acc1, a, b1);
+        chain_mad<12>(acc0, a, b2);
+        chain_mad<12>(acc1, a, b3);
+    }
+    uint64_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r ^= ((uint64_t)acc0[i] << 32) | acc1[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+// kind 6: carry-chained 32-bit adds (IADD3.X)
+__global__ void k_mb_addc(uint64_t* out, int iters, uint32_t seed) {
+    uint32_t x[12], y[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        x[i] = seed * (i + 1) + threadIdx.x;
+        y[i] = blockIdx.x + i * 77;
+    }
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            x[0] = add_cc(x[0], y[0]);
+#pragma unroll
+            for (int j = 1; j < 11; j++) x[j] = addc_cc(x[j], y[j]);
+            x[11] = addc(x[11], y[11]);
+            y[0] = add_cc(y[0], x[0]);
+#pragma unroll
+            for (int j = 1; j < 11; j++) y[j] = addc_cc(y[j], x[j]);
+            y[11] = addc(y[11], x[11]);
+        }
+    }
+    uint64_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r ^= ((uint64_t)x[i] << 32) | y[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+// kind 7: independent 32-bit IMAD (lo) chains
+__global__ void k_mb_imad(uint64_t* out, int iters, uint32_t seed) {
+    uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+    uint32_t c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c0) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c1) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c2) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c3) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c4) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c5) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c6) : "r"(a), "r"(b));
+            asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(c7) : "r"(a), "r"(b));
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+}
+// kind 8: independent mad.hi chains
+__global__ void k_mb_imad_hi(uint64_t* out, int iters, uint32_t seed) {
+    uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+    uint32_t c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(c0) : "r"(a), "r"(b));
+            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(c1) : "r"(a), "r"(b));
+            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(c2) : "r"(a), "r"(b));
+            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(c3) : "r"(a), "r"(b));
+            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(c4) : "r"(a), "r"(b));
+            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(c5) : "r"(a), "r"(b));
+            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(c6) : "r"(a), "r"(b));
+            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(c7) : "r"(a), "r"(b));
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
+}
+
 template <class F>
 __global__ void k_mb_mul(uint64_t* out, int iters, uint32_t seed) {
     F x = F::one(), y = F::r2();
@@ -83,6 +170,10 @@ cudaError_t microbench_run(int kind, int blocks, int threads, int iters, uint64_
         case 2: k_mb_mul<Fr><<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 2.0 * iters; break;
         case 3: k_mb_mul<Fq><<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 2.0 * iters; break;
         case 4: k_mb_madd<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 1.0 * iters; break;
+        case 5: k_mb_wide_carry<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 24.0 * iters; break;
+        case 6: k_mb_addc<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 96.0 * iters; break;
+        case 7: k_mb_imad<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 64.0 * iters; break;
+        case 8: k_mb_imad_hi<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 64.0 * iters; break;
         default: return cudaErrorInvalidValue;
     }
     CZK_LAUNCHED();

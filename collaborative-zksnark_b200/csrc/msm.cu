@@ -98,28 +98,47 @@ __global__ void k_msm_prepare(const uint32_t* __restrict__ scalars_in, const uin
     }
 }
 
-// ------------------------------------------------------------------ 2. exclusive scan (one block)
+// ------------------------------------------------------------------ 2. exclusive scan (one block, coalesced tiles)
 __global__ void __launch_bounds__(1024) k_exclusive_scan(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n) {
-    __shared__ uint32_t sums[1024];
-    const unsigned tid = threadIdx.x;
-    size_t per = (n + 1023) / 1024;
-    size_t lo = (size_t)tid * per;
-    size_t hi = lo + per < n ? lo + per : n;
-    uint32_t s = 0;
-    for (size_t k = lo; k < hi; k++) s += in[k];
-    sums[tid] = s;
+    __shared__ uint32_t warp_sums[32];
+    __shared__ uint32_t carry_s;
+    const unsigned tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry_s = 0;
     __syncthreads();
-    for (unsigned off = 1; off < 1024; off <<= 1) {
-        uint32_t v = tid >= off ? sums[tid - off] : 0u;
+    for (size_t tile = 0; tile < n; tile += 4096) {
+        size_t i0 = tile + (size_t)tid * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) v[k] = (i0 + k < n) ? in[i0 + k] : 0u;
+        uint32_t tsum = v[0] + v[1] + v[2] + v[3];
+        uint32_t inc = tsum;  // inclusive scan of the per-thread sums within the warp
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += t;
+        }
+        if (lane == 31) warp_sums[wid] = inc;
         __syncthreads();
-        sums[tid] += v;
+        if (wid == 0) {
+            uint32_t w = warp_sums[lane];
+            uint32_t winc = w;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                uint32_t t = __shfl_up_sync(0xffffffffu, winc, off);
+                if (lane >= off) winc += t;
+            }
+            warp_sums[lane] = winc - w;  // exclusive prefix of the warp totals
+        }
         __syncthreads();
-    }
-    uint32_t base = tid ? sums[tid - 1] : 0u;
-    for (size_t k = lo; k < hi; k++) {
-        uint32_t v = in[k];
-        out[k] = base;
-        base += v;
+        uint32_t base = carry_s + warp_sums[wid] + (inc - tsum);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (i0 + k < n) out[i0 + k] = base;
+            base += v[k];
+        }
+        __syncthreads();
+        if (tid == 1023) carry_s = base;
+        __syncthreads();
     }
 }
 
@@ -154,43 +173,98 @@ __global__ void k_msm_seg_counts(const uint32_t* __restrict__ hist, uint32_t* __
     segcnt[id] = c ? (c + seg - 1) / seg : 1u;  // empty buckets keep one (empty) segment so they get zeroed
 }
 
-template <class F>
-__global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                                         const uint32_t* __restrict__ ends, const uint32_t* __restrict__ hist,
-                                                         const uint32_t* __restrict__ segoff, const uint32_t* __restrict__ segcnt,
-                                                         uint32_t* __restrict__ buckets, uint32_t* __restrict__ segsum, size_t total,
-                                                         size_t max_items, uint32_t seg) {
-    constexpr int W = FieldIO<F>::W;
+// item descriptors: one per segment, found by binary search once (fully parallel) so the accumulation loop
+// never searches.  desc = {first sorted entry, length, bucket, 1 if the bucket has several segments}
+__global__ void k_msm_build_items(const uint32_t* __restrict__ ends, const uint32_t* __restrict__ hist,
+                                  const uint32_t* __restrict__ segoff, const uint32_t* __restrict__ segcnt,
+                                  uint4* __restrict__ items, uint32_t* __restrict__ nitems_out, size_t total, size_t max_items,
+                                  uint32_t seg) {
     size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= max_items) return;
     size_t nitems = (size_t)segoff[total - 1] + segcnt[total - 1];
-    if (id >= nitems) return;
-    // bucket b with segoff[b] <= id < segoff[b] + segcnt[b]: last b with segoff[b] <= id
+    if (id == 0) {
+        nitems_out[0] = (uint32_t)nitems;
+        nitems_out[1] = 0;  // work-queue head
+    }
+    if (id >= max_items || id >= nitems) return;
     size_t lo = 0, hi = total - 1;
-    while (lo < hi) {
+    while (lo < hi) {  // last bucket b with segoff[b] <= id
         size_t mid = (lo + hi + 1) >> 1;
         if (segoff[mid] <= id) lo = mid;
         else hi = mid - 1;
     }
-    const size_t b = lo;
+    const uint32_t b = (uint32_t)lo;
     const uint32_t k = (uint32_t)(id - segoff[b]);
     const uint32_t cnt = hist[b];
-    const uint32_t start = ends[b] - cnt + k * seg;
-    uint32_t len = cnt - k * seg;
-    if (cnt < k * seg) len = 0;
+    uint32_t len = cnt > k * seg ? cnt - k * seg : 0;
     if (len > seg) len = seg;
+    items[id] = make_uint4(ends[b] - cnt + k * seg, len, b, segcnt[b] > 1 ? 1u : 0u);
+}
+
+// Lane-level dynamic scheduling: every lane of a resident warp owns one item at a time and adds ONE point per
+// loop trip; a lane whose item is exhausted stores its sum and pulls the next item from a global queue inside
+// the same trip.  Bucket loads differ (Poisson around N/2^(c-1)), but no lane waits for a longer neighbour:
+// the warp only idles at the very end of the kernel.  The next point is fetched while the current one is added.
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                                         const uint4* __restrict__ items, uint32_t* __restrict__ queue,
+                                                         uint32_t* __restrict__ buckets, uint32_t* __restrict__ segsum) {
+    constexpr int W = FieldIO<F>::W;
+    const uint32_t nitems = queue[0];
+    const unsigned lane = threadIdx.x & 31;
     XYZZ<F> acc = XYZZ<F>::infinity();
-    for (uint32_t j = 0; j < len; j++) {
-        uint32_t e = sorted[start + j];
-        size_t idx = e & 0x7fffffffu;
-        const uint32_t* p = bases + idx * (2 * W);
-        F x = FieldIO<F>::load(p);
-        F y = FieldIO<F>::load(p + W);
-        if (e >> 31) y = F::neg(y);
-        acc.add_affine(x, y);
+    uint32_t pos = 0, remaining = 0, item = 0xffffffffu, bucket = 0, multi = 0;
+    bool alive = true;
+    F nx, ny;            // prefetched point of the current trip
+    uint32_t nsign = 0;
+    while (true) {
+        if (remaining == 0 && alive) {
+            if (item != 0xffffffffu) {
+                if (multi) store_point<F>(segsum + (size_t)item * (4 * W), acc);
+                else store_point<F>(buckets + (size_t)bucket * (4 * W), acc);
+            }
+            // warp-aggregated fetch: one atomic for all lanes that need work
+            unsigned need = __activemask();
+            unsigned leader = __ffs(need) - 1;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(&queue[1], (uint32_t)__popc(need));
+            base = __shfl_sync(need, base, leader);
+            item = base + __popc(need & ((1u << lane) - 1));
+            if (item < nitems) {
+                uint4 d = items[item];
+                pos = d.x;
+                remaining = d.y;
+                bucket = d.z;
+                multi = d.w;
+                acc = XYZZ<F>::infinity();
+                if (remaining) {
+                    uint32_t e = sorted[pos];
+                    const uint32_t* p = bases + (size_t)(e & 0x7fffffffu) * (2 * W);
+                    nx = FieldIO<F>::load(p);
+                    ny = FieldIO<F>::load(p + W);
+                    nsign = e >> 31;
+                }
+            } else {
+                alive = false;
+                item = 0xffffffffu;
+            }
+        }
+        if (!__any_sync(0xffffffffu, alive)) break;
+        if (alive && remaining) {
+            F x = nx, y = ny;
+            uint32_t sg = nsign;
+            remaining--;
+            pos++;
+            if (remaining) {  // issue the next point's loads before the long addition
+                uint32_t e = sorted[pos];
+                const uint32_t* p = bases + (size_t)(e & 0x7fffffffu) * (2 * W);
+                nx = FieldIO<F>::load(p);
+                ny = FieldIO<F>::load(p + W);
+                nsign = e >> 31;
+            }
+            if (sg) y = F::neg(y);
+            acc.add_affine(x, y);
+        }
     }
-    if (segcnt[b] == 1) store_point<F>(buckets + b * (4 * W), acc);
-    else store_point<F>(segsum + id * (4 * W), acc);
 }
 
 // fold the segment sums of the (rare) multi-segment buckets
@@ -289,9 +363,17 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
     if (max_items > ws.cap_items) return cudaErrorInvalidValue;
     k_msm_seg_counts<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.hist, ws.segcnt, total, seg); CZK_LAUNCHED();
     k_exclusive_scan<<<1, 1024, 0, st>>>(ws.segcnt, ws.segoff, total); CZK_LAUNCHED();
+    k_msm_build_items<<<(unsigned)((max_items + 255) / 256), 256, 0, st>>>(ws.offsets, ws.hist, ws.segoff, ws.segcnt, (uint4*)ws.items,
+                                                                            ws.queue, total, max_items, seg); CZK_LAUNCHED();
     if (ws.ev[0]) cudaEventRecord(ws.ev[0], st);
-    k_msm_accumulate<F><<<(unsigned)((max_items + 127) / 128), 128, 0, st>>>(bases, ws.sorted, ws.offsets, ws.hist, ws.segoff, ws.segcnt,
-                                                                          ws.buckets, ws.segsum, total, max_items, seg); CZK_LAUNCHED();
+    {
+        // resident grid: the queue feeds lanes, so launch what the machine holds (2 blocks of 128 per SM at this
+        // register budget) and no more; small problems launch fewer blocks
+        size_t want = (max_items + 127) / 128;
+        size_t cap = (size_t)ws.sm_count * 2;
+        unsigned blocks = (unsigned)(want < cap ? want : cap);
+        k_msm_accumulate<F><<<blocks, 128, 0, st>>>(bases, ws.sorted, (const uint4*)ws.items, ws.queue, ws.buckets, ws.segsum); CZK_LAUNCHED();
+    }
     if (ws.ev[1]) cudaEventRecord(ws.ev[1], st);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     k_msm_fold_segments<F><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(ws.segoff, ws.segcnt, ws.segsum, ws.buckets, total); CZK_LAUNCHED();

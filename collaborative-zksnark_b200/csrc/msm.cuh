@@ -60,6 +60,9 @@ struct MsmWorkspace {
     uint32_t* segoff = nullptr;    // nwin*nb: exclusive scan of segcnt
     uint32_t* segsum = nullptr;    // cap_items points: per-segment sums of multi-segment buckets
     size_t cap_items = 0;
+    uint32_t* items = nullptr;     // cap_items x uint4 item descriptors
+    uint32_t* queue = nullptr;     // {item count, queue head}
+    int sm_count = 148;
     int seg_point_words = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // accumulate start/stop, whole MSM start/stop
     size_t cap_n = 0;
