@@ -242,28 +242,28 @@ struct Fq2 {
         return Fq::neg(Fq::add(x4, x));
     }
     // Karatsuba, 3 base-field products (quadratic_extension.rs:569-583)
-    CZK_HD static Fq2 mul(const Fq2& a, const Fq2& b) {
-        Fq v0 = Fq::mul_ni(a.c0, b.c0);
-        Fq v1 = Fq::mul_ni(a.c1, b.c1);
-        Fq t = Fq::mul_ni(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
+    CZK_HD_NOINLINE static Fq2 mul(const Fq2& a, const Fq2& b) {
+        Fq v0 = Fq::mul(a.c0, b.c0);
+        Fq v1 = Fq::mul(a.c1, b.c1);
+        Fq t = Fq::mul(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
         t = Fq::sub(Fq::sub(t, v0), v1);
         return Fq2{Fq::add(v0, mul_by_nonresidue(v1)), t};
     }
     // (c0^2 - 5 c1^2, 2 c0 c1) with 2 base-field products (quadratic_extension.rs:257-306)
-    CZK_HD static Fq2 sqr(const Fq2& a) {
+    CZK_HD_NOINLINE static Fq2 sqr(const Fq2& a) {
         Fq v0 = Fq::sub(a.c0, a.c1);
         Fq v3 = Fq::sub(a.c0, mul_by_nonresidue(a.c1));
-        Fq v2 = Fq::mul_ni(a.c0, a.c1);
-        v0 = Fq::mul_ni(v0, v3);
+        Fq v2 = Fq::mul(a.c0, a.c1);
+        v0 = Fq::mul(v0, v3);
         Fq c1 = Fq::dbl(v2);
         Fq c0 = Fq::add(Fq::add(v0, v2), mul_by_nonresidue(v2));
         return Fq2{c0, c1};
     }
-    CZK_HD static Fq2 inv_fermat(const Fq2& a) {
+    CZK_HD_NOINLINE static Fq2 inv_fermat(const Fq2& a) {
         // 1/(c0 + c1 u) = (c0 - c1 u) / (c0^2 + 5 c1^2)
-        Fq norm = Fq::sub(Fq::sqr_ni(a.c0), mul_by_nonresidue(Fq::sqr_ni(a.c1)));
+        Fq norm = Fq::sub(Fq::sqr(a.c0), mul_by_nonresidue(Fq::sqr(a.c1)));
         Fq ni = Fq::inv_fermat(norm);
-        return Fq2{Fq::mul_ni(a.c0, ni), Fq::neg(Fq::mul_ni(a.c1, ni))};
+        return Fq2{Fq::mul(a.c0, ni), Fq::neg(Fq::mul(a.c1, ni))};
     }
 };
 

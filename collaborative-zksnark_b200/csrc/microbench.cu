@@ -3,6 +3,7 @@
 // multiplication and point addition rates at a chosen occupancy.
 #include <cuda_runtime.h>
 #include "ec.cuh"
+#include "fq13.cuh"
 #include "launch_count.hpp"
 
 namespace czk {
@@ -161,6 +162,34 @@ __global__ void k_mb_madd(uint64_t* out, int iters, uint32_t seed) {
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+__global__ void k_mb_mul13(uint64_t* out, int iters, uint32_t seed) {
+    Fq13 x = Fq13::one(), y = Fq13::one();
+    x.d[0] ^= (seed + threadIdx.x) & 0xffff;
+    y.d[1] ^= blockIdx.x & 0xffff;
+    for (int i = 0; i < iters; i++) {
+        x = Fq13::mul(x, y);
+        y = Fq13::mul(y, x);
+    }
+    uint64_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 13; i++) acc ^= (uint64_t)(x.d[i] ^ y.d[i]) << (i & 31);
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
+__global__ void k_mb_madd13(uint64_t* out, int iters, uint32_t seed) {
+    XYZZ<Fq13> acc = XYZZ<Fq13>::from_affine(Fq13::one(), Fq13::one());
+    Fq13 px = Fq13::one(), py = Fq13::one();
+    px.d[0] ^= (seed + threadIdx.x) & 0xffff;
+    py.d[1] ^= blockIdx.x & 0xffff;
+    for (int i = 0; i < iters; i++) {
+        acc.add_affine(px, py);
+        px.d[2] = (px.d[2] + 1) & Fq13::MASK;
+    }
+    uint64_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 13; i++) r ^= (uint64_t)(acc.x.d[i] ^ acc.y.d[i] ^ acc.zz.d[i] ^ acc.zzz.d[i]) << (i & 31);
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 cudaError_t microbench_run(int kind, int blocks, int threads, int iters, uint64_t* scratch, double* ops_per_launch,
                            cudaStream_t st) {
     double per_thread = 0;
@@ -174,6 +203,8 @@ cudaError_t microbench_run(int kind, int blocks, int threads, int iters, uint64_
         case 6: k_mb_addc<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 96.0 * iters; break;
         case 7: k_mb_imad<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 64.0 * iters; break;
         case 8: k_mb_imad_hi<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 64.0 * iters; break;
+        case 9: k_mb_mul13<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 2.0 * iters; break;
+        case 10: k_mb_madd13<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 1.0 * iters; break;
         default: return cudaErrorInvalidValue;
     }
     CZK_LAUNCHED();

@@ -204,7 +204,7 @@ __global__ void k_msm_build_items(const uint32_t* __restrict__ ends, const uint3
 // loop trip; a lane whose item is exhausted stores its sum and pulls the next item from a global queue inside
 // the same trip.  Bucket loads differ (Poisson around N/2^(c-1)), but no lane waits for a longer neighbour:
 // the warp only idles at the very end of the kernel.  The next point is fetched while the current one is added.
-template <class F>
+template <class F, bool PREFETCH>
 __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                          const uint4* __restrict__ items, uint32_t* __restrict__ queue,
                                                          uint32_t* __restrict__ buckets, uint32_t* __restrict__ segsum) {
@@ -230,13 +230,16 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restri
             base = __shfl_sync(need, base, leader);
             item = base + __popc(need & ((1u << lane) - 1));
             if (item < nitems) {
+                // heaviest first: the top window covers only 253 - c*(W-1) bits, so its 2^bits buckets each hold
+                // N / 2^bits points; it is last in bucket order, hence served first (LPT scheduling)
+                item = nitems - 1 - item;
                 uint4 d = items[item];
                 pos = d.x;
                 remaining = d.y;
                 bucket = d.z;
                 multi = d.w;
                 acc = XYZZ<F>::infinity();
-                if (remaining) {
+                if (PREFETCH && remaining) {
                     uint32_t e = sorted[pos];
                     const uint32_t* p = bases + (size_t)(e & 0x7fffffffu) * (2 * W);
                     nx = FieldIO<F>::load(p);
@@ -250,11 +253,22 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restri
         }
         if (!__any_sync(0xffffffffu, alive)) break;
         if (alive && remaining) {
-            F x = nx, y = ny;
-            uint32_t sg = nsign;
+            F x, y;
+            uint32_t sg;
+            if (PREFETCH) {
+                x = nx;
+                y = ny;
+                sg = nsign;
+            } else {  // G2: the prefetch registers would spill; load in place
+                uint32_t e = sorted[pos];
+                const uint32_t* p = bases + (size_t)(e & 0x7fffffffu) * (2 * W);
+                x = FieldIO<F>::load(p);
+                y = FieldIO<F>::load(p + W);
+                sg = e >> 31;
+            }
             remaining--;
             pos++;
-            if (remaining) {  // issue the next point's loads before the long addition
+            if (PREFETCH && remaining) {  // issue the next point's loads before the long addition
                 uint32_t e = sorted[pos];
                 const uint32_t* p = bases + (size_t)(e & 0x7fffffffu) * (2 * W);
                 nx = FieldIO<F>::load(p);
@@ -313,16 +327,19 @@ __global__ void __launch_bounds__(128) k_msm_reduce_chunks(const uint32_t* __res
     store_point<F>(partial + t * (4 * W), T);
 }
 
-// ------------------------------------------------------------------ 5b. per-window tree sum
+// ------------------------------------------------------------------ 5b. tree sums of the chunk results
+// block b sums in[b*count .. (b+1)*count) -> out[b]; run twice (chunks -> groups -> window) so that the first
+// level has windows*groups blocks instead of one block per window
 constexpr int WINSUM_THREADS = 64;
+constexpr int WINSUM_GROUPS = 32;
 template <class F>
-__global__ void __launch_bounds__(WINSUM_THREADS) k_msm_window_sum(const uint32_t* __restrict__ partial, uint32_t* __restrict__ winsum,
-                                                                    unsigned nchunks) {
+__global__ void __launch_bounds__(WINSUM_THREADS) k_msm_block_sum(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                                                   unsigned count) {
     constexpr int W = FieldIO<F>::W;
     __shared__ XYZZ<F> sm[WINSUM_THREADS];
-    unsigned w = blockIdx.x, tid = threadIdx.x;
+    unsigned b = blockIdx.x, tid = threadIdx.x;
     XYZZ<F> acc = XYZZ<F>::infinity();
-    for (unsigned k = tid; k < nchunks; k += WINSUM_THREADS) acc.add(load_point<F>(partial + ((size_t)w * nchunks + k) * (4 * W)));
+    for (unsigned k = tid; k < count; k += WINSUM_THREADS) acc.add(load_point<F>(in + ((size_t)b * count + k) * (4 * W)));
     sm[tid] = acc;
     __syncthreads();
     for (unsigned s = WINSUM_THREADS / 2; s > 0; s >>= 1) {
@@ -333,7 +350,7 @@ __global__ void __launch_bounds__(WINSUM_THREADS) k_msm_window_sum(const uint32_
         }
         __syncthreads();
     }
-    if (tid == 0) store_point<F>(winsum + (size_t)w * (4 * W), sm[0]);
+    if (tid == 0) store_point<F>(out + (size_t)b * (4 * W), sm[0]);
 }
 
 template <class F>
@@ -372,7 +389,7 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
         size_t want = (max_items + 127) / 128;
         size_t cap = (size_t)ws.sm_count * 2;
         unsigned blocks = (unsigned)(want < cap ? want : cap);
-        k_msm_accumulate<F><<<blocks, 128, 0, st>>>(bases, ws.sorted, (const uint4*)ws.items, ws.queue, ws.buckets, ws.segsum); CZK_LAUNCHED();
+        k_msm_accumulate<F, (FieldIO<F>::W == 12)><<<blocks, 128, 0, st>>>(bases, ws.sorted, (const uint4*)ws.items, ws.queue, ws.buckets, ws.segsum); CZK_LAUNCHED();
     }
     if (ws.ev[1]) cudaEventRecord(ws.ev[1], st);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -382,7 +399,14 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
     size_t rthreads = (size_t)cfg.nwin * nchunks;
     k_msm_reduce_chunks<F><<<(unsigned)((rthreads + 127) / 128), 128, 0, st>>>(ws.buckets, ws.partial, cfg.nb, cfg.chunk, cfg.nwin); CZK_LAUNCHED();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    k_msm_window_sum<F><<<cfg.nwin, WINSUM_THREADS, 0, st>>>(ws.partial, ws.winsum, nchunks); CZK_LAUNCHED();
+    if (nchunks >= 2 * WINSUM_GROUPS) {
+        // partial[nwin*nchunks] -> segsum scratch [nwin*GROUPS] -> winsum[nwin]   (segsum is free again after the fold)
+        uint32_t* mid = ws.partial + rthreads * msm_point_words(FieldIO<F>::W == 12 ? 1 : 2);
+        k_msm_block_sum<F><<<cfg.nwin * WINSUM_GROUPS, WINSUM_THREADS, 0, st>>>(ws.partial, mid, nchunks / WINSUM_GROUPS); CZK_LAUNCHED();
+        k_msm_block_sum<F><<<cfg.nwin, WINSUM_THREADS, 0, st>>>(mid, ws.winsum, WINSUM_GROUPS); CZK_LAUNCHED();
+    } else {
+        k_msm_block_sum<F><<<cfg.nwin, WINSUM_THREADS, 0, st>>>(ws.partial, ws.winsum, nchunks); CZK_LAUNCHED();
+    }
     if (ws.ev[3]) cudaEventRecord(ws.ev[3], st);
     return cudaGetLastError();
 }

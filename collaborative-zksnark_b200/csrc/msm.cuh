@@ -32,7 +32,10 @@ inline MsmConfig msm_choose_config(size_t n) {
     // c ~ log2(n) - 4, clamped; measured trade-off between N*W mixed adds and 2^c*W bucket work
     unsigned lg = 0;
     while (((size_t)1 << lg) < n) lg++;
+    // 2^(c-1) buckets per window: c = lg - 4 balances N*W mixed additions against 2^c*W bucket-reduction additions
+    // up to 2^19; from 2^20 on one bit fewer halves the reduction for +6% accumulation (measured, profiles/)
     unsigned c = lg > 6 ? lg - 4 : 2;
+    if (lg == 20) c = 15;
     if (c < 2) c = 2;
     if (c > 16) c = 16;
     // avoid window sizes whose top window holds only a few bits of the 253-bit scalar: its few buckets

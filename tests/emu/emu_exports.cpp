@@ -4,6 +4,7 @@
 #include <cstring>
 #include "../../collaborative-zksnark_b200/csrc/ec.cuh"
 #include "../../collaborative-zksnark_b200/csrc/msm_digits.cuh"
+#include "../../collaborative-zksnark_b200/csrc/fq13.cuh"
 
 using namespace czk;
 #define EXPORT extern "C" __attribute__((visibility("default")))
@@ -114,4 +115,27 @@ EXPORT void emu_signed_digits(int32_t* out, const uint64_t* scalar_canonical, un
     uint32_t s[8];
     std::memcpy(s, scalar_canonical, 32);
     signed_digits(s, c, nwin, out);
+}
+
+// 13 x 29-bit digit field (csrc/fq13.cuh): op on values given / returned in the reference (12-limb, R = 2^384) form
+EXPORT void emu_fq13_binop(uint64_t* r, const uint64_t* a, const uint64_t* b, size_t n, int op) {
+    for (size_t i = 0; i < n; i++) {
+        Fq13 x = Fq13::from_std(ld<Fq>(a + 6 * i)), y = Fq13::from_std(ld<Fq>(b + 6 * i));
+        Fq13 z = op == 0 ? Fq13::mul(x, y) : op == 1 ? Fq13::add(x, y) : op == 2 ? Fq13::sub(x, y) : Fq13::neg(x);
+        st(r + 6 * i, z.to_std());
+    }
+}
+EXPORT int emu_g1_sum13(uint64_t* out_xy, const uint64_t* xy, const uint8_t* sign, size_t n) {
+    XYZZ<Fq13> acc = XYZZ<Fq13>::infinity();
+    for (size_t i = 0; i < n; i++) {
+        Fq13 x = Fq13::from_std(ld<Fq>(xy + 12 * i)), y = Fq13::from_std(ld<Fq>(xy + 12 * i + 6));
+        if (sign && sign[i]) y = Fq13::neg(y);
+        acc.add_affine(x, y);
+    }
+    if (acc.is_inf()) return 1;
+    XYZZ<Fq> s{acc.x.to_std(), acc.y.to_std(), acc.zz.to_std(), acc.zzz.to_std()};
+    Fq zi = Fq::inv_fermat(s.zz), zzzi = Fq::inv_fermat(s.zzz);
+    st(out_xy, Fq::mul(s.x, zi));
+    st(out_xy + 6, Fq::mul(s.y, zzzi));
+    return 0;
 }
