@@ -47,7 +47,8 @@ inline MsmConfig msm_choose_config(size_t n) {
     cfg.c = c;
     cfg.nwin = msm_num_windows(c);
     cfg.nb = 1u << (c - 1);
-    cfg.chunk = cfg.nb >= 16 ? 16 : cfg.nb;
+    // buckets per thread in the chunked running sums: small chunks = more threads, shorter serial chains
+    cfg.chunk = cfg.nb >= 4096 ? 4 : (cfg.nb >= 16 ? 16 : cfg.nb);
     return cfg;
 }
 

@@ -1,0 +1,63 @@
+#!/usr/bin/env python3
+"""Stand-in for the reference's `proof` binary (mpc-snarks/src/proof.rs:464-508) on the GPU path.
+
+    python tools/proof.py -p groth16 -c squaring --computation-size N local
+    torchrun --nproc-per-node P tools/proof.py -p groth16 -c squaring --computation-size N mpc --alg spdz
+
+`mpc --hosts F --party I` of the reference becomes one rank per party (RANK / WORLD_SIZE / LOCAL_RANK from
+torchrun); everything else keeps its meaning.  Prints the `End: ... timed section ...` line that
+mpc-snarks/scripts/bench.zsh:55 parses, and the mpc-net Stats line (proof.rs:367,443).
+"""
+import argparse
+import sys
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import numpy as np
+
+import czk_b200
+from czk_b200 import launch
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("-p", "--proof-system", default="groth16", choices=["groth16"])
+    ap.add_argument("-c", "--computation", default="squaring", choices=["squaring"])
+    ap.add_argument("--computation-size", type=int, default=10)
+    sub = ap.add_subparsers(dest="mode", required=True)
+    m = sub.add_parser("mpc")
+    m.add_argument("--alg", default="spdz", choices=["spdz", "hbc"])
+    m.add_argument("--hosts", default=None, help="ignored: parties are torchrun ranks")
+    m.add_argument("--party", type=int, default=None, help="ignored: party id = RANK")
+    sub.add_parser("local")
+    sub.add_parser("ark-local")
+    args = ap.parse_args()
+    party = launch.Party()
+    ctx, rank, world = party.ctx, party.rank, party.world
+    n_sq = args.computation_size
+    if args.mode == "mpc":
+        scheme = czk_b200.SCHEME_SPDZ if args.alg == "spdz" else czk_b200.SCHEME_ADDITIVE
+    else:
+        assert world == 1, "local proving is a single process"
+        scheme = czk_b200.SCHEME_PLAIN
+    pk = czk_b200.ProvingKey.synthetic(ctx, n_sq, seed=1)  # generate_random_parameters stand-in (untimed)
+    chain = czk_b200.squaring_chain(np.array([3, 1, 4, 1], np.uint64), n_sq) if rank == 0 else None
+    mine = launch.king_share_scatter(chain, n_sq + 1, seed=2)  # "do the mpc (cheat)" (untimed)
+    r = np.array([5, 9, 2, 6], np.uint64)
+    s = np.array([5, 3, 5, 8], np.uint64)
+    ctx.net_reset_stats()
+    launch.barrier()
+    t = time.perf_counter()
+    czk_b200.groth16_prove(ctx, scheme, pk, mine, r, s)
+    dt = launch.max_over_ranks(time.perf_counter() - t)
+    if rank == 0:
+        unit = f"{dt:.3f}s" if dt >= 1 else (f"{dt * 1e3:.3f}ms" if dt >= 1e-3 else f"{dt * 1e6:.3f}µs")
+        print(f"End:     timed section ............................................................{unit}")
+    print(f"Stats: {ctx.net_stats()}")
+    party.close()
+
+
+if __name__ == "__main__":
+    main()
