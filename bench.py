@@ -166,7 +166,19 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the czk arm has no CPU fallback (use --impl reference for the CPU path)")
     warmup = max(args.warmup, 3)
-    party = launch.Party()
+    # NCCL prints its version banner on stdout when NCCL_DEBUG is set in the environment; stdout must carry exactly
+    # one JSON line, so fd 1 points at stderr while the communicator comes up
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        party = launch.Party()
+        party.ctx.batch_open(czk_b200.SCHEME_ADDITIVE, party.ctx.vec(4))  # first collective: forces the lazy NCCL init now
+        party.ctx.sync()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
     ctx, rank, world = party.ctx, party.rank, party.world
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     scheme = {"spdz": czk_b200.SCHEME_SPDZ, "additive": czk_b200.SCHEME_ADDITIVE, "plain": czk_b200.SCHEME_PLAIN}[args.scheme]

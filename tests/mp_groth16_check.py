@@ -22,12 +22,12 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--scheme", default="spdz", choices=["additive", "spdz"])
     ap.add_argument("--log-n", type=int, default=10)
-    ap.add_argument("--n", type=int, default=0, help="exact number of squarings (overrides --log-n)")
+    ap.add_argument("--squarings", type=int, default=0, help="exact number of squarings (overrides --log-n)")
     args = ap.parse_args()
     party = launch.Party()
     ctx, rank, world = party.ctx, party.rank, party.world
     scheme = czk_b200.SCHEME_SPDZ if args.scheme == "spdz" else czk_b200.SCHEME_ADDITIVE
-    n_sq = args.n or (1 << args.log_n)
+    n_sq = args.squarings or (1 << args.log_n)
     rnd = random.Random(1234 + n_sq)
     toxic = [rnd.randrange(1, m.R_MOD) for _ in range(7)]
     pk = o.groth16_setup(n_sq, o.fr_from_ints(toxic), threads=max(1, o.cpu_threads() // world))
