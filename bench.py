@@ -249,8 +249,8 @@ def main():
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     alg_bytes = 128.0 * terms_per_launch  # 32 B scalar + 96 B affine base per G1 term
     achieved_gbs = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms else 0.0
-    nwin = 16
-    wide_mads = terms_per_launch * nwin * 10 * 288  # N*W mixed additions x (8M + 2S) x 2*12^2 wide multiply-adds
+    entries_per_launch = st1["entries"] / max(st1["launches"], 1)
+    wide_mads = entries_per_launch * 10 * 288  # N*W mixed additions x (8M + 2S) x 2*12^2 wide multiply-adds
     int_rate = wide_mads / (acc_ms * 1e-3) if acc_ms else 0.0
     line = {
         "metric": METRIC, "value": ms_res, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": warmup,

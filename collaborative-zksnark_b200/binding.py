@@ -65,6 +65,7 @@ _SIGS = {
     "czk_bases_upload": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_void_p)]),
     "czk_bases_free": (None, [C.c_void_p, C.c_void_p]),
     "czk_bases_len": (C.c_size_t, [C.c_void_p]),
+    "czk_bases_precompute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint]),
     "czk_msm_bases": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_size_t, u64p]),
     "czk_bases_synthetic": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p)]),
     "czk_bases_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
@@ -211,6 +212,11 @@ class Bases:
         inf = np.empty(n, np.uint8)
         self.ctx._chk(self.ctx.lib.czk_bases_download(self.ctx.h, self.h, off, n, xy.ctypes.data, inf.ctypes.data))
         return xy, inf
+
+    def precompute(self, c: int = 0):
+        """Build the merged-window table (2^(c w) * P_i); later msm_bases calls use it."""
+        self.ctx._chk(self.ctx.lib.czk_bases_precompute(self.ctx.h, self.h, c))
+        return self
 
     def free(self):
         if self.h:
@@ -406,9 +412,9 @@ class Context:
 
     # ------------------------------------------------------------------ diagnostics
     def msm_stats(self, curve=1, reset=False):
-        out = (C.c_double * 4)()
+        out = (C.c_double * 5)()
         self._chk(self.lib.czk_msm_stats(self.h, curve, out, int(reset)))
-        return dict(accumulate_ms=out[0], launches=int(out[1]), terms=out[2], msm_ms=out[3])
+        return dict(accumulate_ms=out[0], launches=int(out[1]), terms=out[2], msm_ms=out[3], entries=out[4])
 
     def microbench(self, kind, blocks_per_sm=8, threads=128, iters=2000):
         ops = C.c_double()

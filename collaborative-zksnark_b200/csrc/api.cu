@@ -68,6 +68,7 @@ static void free_ws(MsmWorkspace& ws) {
     cudaFree(ws.segoff);
     cudaFree(ws.segsum);
     cudaFree(ws.items);
+    cudaFree(ws.heavy);
     cudaFree(ws.queue);
     for (int i = 0; i < 4; i++)
         if (ws.ev[i]) cudaEventDestroy(ws.ev[i]);
@@ -294,7 +295,7 @@ int czk_vec_divide_by_vanishing_on_coset(czk_ctx* ctx, czk_vec* a, unsigned log_
 // ------------------------------------------------------------------------------------------ MSM
 static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
     MsmWorkspace& ws = ctx->ws;
-    size_t total = (size_t)cfg.nwin * cfg.nb;
+    size_t total = (size_t)cfg.bwin * cfg.nb;
     int pw = (int)msm_point_words(curve);
     bool grow_n = n > ws.cap_n;
     bool grow_b = total > ws.cap_buckets || pw > ws.point_words;
@@ -342,16 +343,18 @@ static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
     }
     {
         // per-segment sums: one slot per bucket plus one per `seg` sorted entries (see msm_run)
-        size_t items = total + (n * cfg.nwin) / 128 + 64;
+        size_t items = total + (n * cfg.nwin) / 32 + 64;
         if (items > ws.cap_items || pw > ws.seg_point_words) {
             CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
             cudaFree(ws.segsum);
             cudaFree(ws.items);
-            ws.segsum = ws.items = nullptr;
+            cudaFree(ws.heavy);
+            ws.segsum = ws.items = ws.heavy = nullptr;
             size_t cap = items + items / 8;
             int pww = pw > ws.seg_point_words ? pw : ws.seg_point_words;
             CUDA_TRY(ctx, cudaMalloc((void**)&ws.segsum, cap * (size_t)pww * 4));
             CUDA_TRY(ctx, cudaMalloc((void**)&ws.items, cap * 16));
+            CUDA_TRY(ctx, cudaMalloc((void**)&ws.heavy, cap * 4));
             if (!ws.queue) {
                 CUDA_TRY(ctx, cudaMalloc((void**)&ws.queue, 16));
                 cudaDeviceProp prop;
@@ -387,7 +390,7 @@ static void msm_host_tail(const uint32_t* winsums, const MsmConfig& cfg, uint64_
         return p;
     };
     P total = P::infinity();
-    for (int w = (int)cfg.nwin - 1; w >= 0; w--) {
+    for (int w = (int)cfg.bwin - 1; w >= 0; w--) {
         for (unsigned k = 0; k < cfg.c; k++) total = P::dbl(total);
         total.add(load((unsigned)w));
     }
@@ -405,14 +408,14 @@ static void msm_host_tail(const uint32_t* winsums, const MsmConfig& cfg, uint64_
 }
 
 static int msm_core(czk_ctx* ctx, int curve, const uint32_t* bases, const uint8_t* inf, const uint32_t* scalars, int mont,
-                    size_t n, uint64_t* out_xyz) {
+                    size_t n, uint64_t* out_xyz, const MsmConfig* merged_cfg = nullptr) {
     if (n >= ((size_t)1 << 31)) return fail(ctx, CZK_ERR_ARG, "msm: more than 2^31 - 1 terms");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    MsmConfig cfg = msm_choose_config(n ? n : 1);
+    MsmConfig cfg = merged_cfg ? *merged_cfg : msm_choose_config(n ? n : 1);
     CZK_TRY(ws_reserve(ctx, curve, n, cfg));
     CUDA_TRY(ctx, msm_run(curve, bases, inf, scalars, mont != 0, n, cfg, ctx->ws, ctx->stream));
     size_t pw = msm_point_words(curve);
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, ctx->ws.winsum, cfg.nwin * pw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, ctx->ws.winsum, cfg.bwin * pw * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     {
         float a = 0, m = 0;
@@ -422,6 +425,7 @@ static int msm_core(czk_ctx* ctx, int curve, const uint32_t* bases, const uint8_
             ctx->acc_ms[k] += a;
             ctx->msm_ms[k] += m;
             ctx->acc_terms[k] += (double)n;
+            ctx->acc_entries[k] += (double)n * cfg.nwin;
             ctx->acc_launches[k] += 1;
         }
     }
@@ -482,15 +486,44 @@ void czk_bases_free(czk_ctx* ctx, czk_bases* b) {
     if (ctx) cudaStreamSynchronize(ctx->stream);
     cudaFree(b->xy);
     cudaFree(b->inf);
+    cudaFree(b->table);
     delete b;
 }
 size_t czk_bases_len(const czk_bases* b) { return b ? b->n : 0; }
+
+int czk_bases_precompute(czk_ctx* ctx, czk_bases* b, unsigned c) {
+    if (!ctx || !b) return fail(ctx, CZK_ERR_ARG, "czk_bases_precompute: null argument");
+    if (b->n < 1024) return CZK_OK;  // small MSMs keep the windowed form
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    if (c == 0) c = msm_merged_window(b->n);
+    if (c < 4 || c > 24) return fail(ctx, CZK_ERR_ARG, "czk_bases_precompute: window size out of range");
+    unsigned nwin = msm_num_windows(c);
+    if ((size_t)nwin * b->n >= ((size_t)1 << 31)) return fail(ctx, CZK_ERR_ARG, "czk_bases_precompute: table too large to index");
+    if (b->table) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(b->table);
+        b->table = nullptr;
+    }
+    size_t pb = b->curve == 1 ? 96 : 192;
+    CUDA_TRY(ctx, cudaMalloc((void**)&b->table, (size_t)nwin * b->n * pb));
+    // infinity bases must read as (0, 0) so the doubling chain leaves them alone; their scalars are zeroed anyway
+    CUDA_TRY(ctx, msm_precompute_table(b->curve, b->table, b->xy, b->n, c, nwin, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    b->pre_c = c;
+    b->pre_w = nwin;
+    return CZK_OK;
+}
 
 int czk_msm_bases(czk_ctx* ctx, const czk_bases* b, size_t base_off, const czk_vec* sc, size_t sc_off, int scalars_montgomery,
                   size_t n, uint64_t* out_xyz) {
     if (!ctx || !b || !sc || !out_xyz || base_off + n > b->n || sc_off + n > sc->n)
         return fail(ctx, CZK_ERR_ARG, "czk_msm_bases: range");
     size_t pw = b->curve == 1 ? 24 : 48;
+    if (b->table && n >= 1024) {
+        MsmConfig cfg = msm_merged_config(b->pre_c, b->n, base_off);
+        return msm_core(ctx, b->curve, b->table, b->inf ? b->inf + base_off : nullptr, (const uint32_t*)(sc->d + 4 * sc_off),
+                        scalars_montgomery, n, out_xyz, &cfg);
+    }
     return msm_core(ctx, b->curve, b->xy + base_off * pw, b->inf ? b->inf + base_off : nullptr,
                     (const uint32_t*)(sc->d + 4 * sc_off), scalars_montgomery, n, out_xyz);
 }
@@ -725,15 +758,16 @@ int czk_beaver_batch_mul(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac
 }
 
 // ------------------------------------------------------------------------------------------ diagnostics
-int czk_msm_stats(czk_ctx* ctx, int curve, double out[4], int reset) {
+int czk_msm_stats(czk_ctx* ctx, int curve, double out[5], int reset) {
     if (!ctx || !out || (curve != 1 && curve != 2)) return fail(ctx, CZK_ERR_ARG, "czk_msm_stats: argument");
     int k = curve - 1;
     out[0] = ctx->acc_ms[k];
     out[1] = (double)ctx->acc_launches[k];
     out[2] = ctx->acc_terms[k];
     out[3] = ctx->msm_ms[k];
+    out[4] = ctx->acc_entries[k];
     if (reset) {
-        ctx->acc_ms[k] = ctx->msm_ms[k] = ctx->acc_terms[k] = 0;
+        ctx->acc_ms[k] = ctx->msm_ms[k] = ctx->acc_terms[k] = ctx->acc_entries[k] = 0;
         ctx->acc_launches[k] = 0;
     }
     return CZK_OK;

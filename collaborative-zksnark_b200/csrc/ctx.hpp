@@ -60,6 +60,8 @@ struct czk_bases {
     uint32_t* xy = nullptr;  // n * (24 | 48) words
     uint8_t* inf = nullptr;  // n bytes, or nullptr when no point is infinity
     size_t n = 0;
+    uint32_t* table = nullptr;  // merged-window table: pre_w slabs of n affine points, slab w = 2^(pre_c w) * xy
+    unsigned pre_c = 0, pre_w = 0;
 };
 struct Domain {
     int log_d = 0;
@@ -89,7 +91,7 @@ struct czk_ctx {
     ncclComm_t comm = nullptr;
     uint64_t stats[5] = {0, 0, 0, 0, 0};
     // kernel timing of the MSM (CUDA events on the launching stream), per curve: [0] G1, [1] G2
-    double acc_ms[2] = {0, 0}, msm_ms[2] = {0, 0}, acc_terms[2] = {0, 0};
+    double acc_ms[2] = {0, 0}, msm_ms[2] = {0, 0}, acc_terms[2] = {0, 0}, acc_entries[2] = {0, 0};
     uint64_t acc_launches[2] = {0, 0};
 };
 

@@ -4,6 +4,7 @@
 // (mpc-snarks/src/proof.rs:304-344), with the share semantics of mpc-algebra/src/share/{add,spdz}.rs and the
 // Beaver-on-groups step of share/group.rs:70-109.  The O(1) group operations run on the host (host_field.hpp).
 #include <chrono>
+#include <cstdlib>
 
 #include "../../include/czk_groth16.h"
 #include "ctx.hpp"
@@ -38,6 +39,10 @@ static size_t domain_size_for(size_t n_sq, unsigned* log_d) {
 
 static int pk_finish(czk_ctx* ctx, czk_pk* pk) {
     uint8_t inf = 0;
+    // merged-window tables for the five queries (one-off per key); CZK_PRECOMPUTE=0 keeps the windowed MSM
+    const char* env = getenv("CZK_PRECOMPUTE");
+    if (!env || atoi(env) != 0)
+        for (int i = 0; i < 5; i++) CZK_TRY(czk_bases_precompute(ctx, pk->q[i], 0));
     CZK_TRY(czk_bases_download(ctx, pk->q[0], 0, 1, pk->a0, &inf));
     pk->a0_inf = inf;
     CZK_TRY(czk_bases_download(ctx, pk->q[1], 0, 1, pk->b10, &inf));

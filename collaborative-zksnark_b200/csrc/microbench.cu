@@ -162,6 +162,21 @@ __global__ void k_mb_madd(uint64_t* out, int iters, uint32_t seed) {
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+__device__ uint32_t g_mb_zero = 0;
+__global__ void k_mb_mul_split(uint64_t* out, int iters, uint32_t seed) {
+    Fq x = Fq::one(), y = Fq::r2();
+    x.l[0] ^= seed + threadIdx.x;
+    y.l[1] ^= blockIdx.x;
+    const uint32_t z = *(volatile uint32_t*)&g_mb_zero;
+    for (int i = 0; i < iters; i++) {
+        x = Fq::mul_split(x, y, z);
+        y = Fq::mul_split(y, x, z);
+    }
+    uint64_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) acc ^= (uint64_t)(x.l[i] ^ y.l[i]) << (i & 31);
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
 __global__ void k_mb_mul13(uint64_t* out, int iters, uint32_t seed) {
     Fq13 x = Fq13::one(), y = Fq13::one();
     x.d[0] ^= (seed + threadIdx.x) & 0xffff;
@@ -203,6 +218,7 @@ cudaError_t microbench_run(int kind, int blocks, int threads, int iters, uint64_
         case 6: k_mb_addc<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 96.0 * iters; break;
         case 7: k_mb_imad<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 64.0 * iters; break;
         case 8: k_mb_imad_hi<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 64.0 * iters; break;
+        case 11: k_mb_mul_split<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 2.0 * iters; break;
         case 9: k_mb_mul13<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 2.0 * iters; break;
         case 10: k_mb_madd13<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 1.0 * iters; break;
         default: return cudaErrorInvalidValue;

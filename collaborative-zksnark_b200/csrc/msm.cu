@@ -1,6 +1,8 @@
 // Device kernels of the bucket-method MSM (see msm.cuh for the pipeline and the reference lines replaced).
 #include "msm.cuh"
 
+#include <cstdlib>
+
 #include "launch_count.hpp"
 
 namespace czk {
@@ -35,6 +37,13 @@ struct FieldIO<Fq> {
         q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
         q[2] = make_uint4(v.l[8], v.l[9], v.l[10], v.l[11]);
     }
+};
+template <>
+struct FieldIO<FqCall> {
+    static constexpr int W = 12;
+    __device__ __forceinline__ static FqCall load(const uint32_t* p) { return FqCall(FieldIO<Fq>::load(p)); }
+    __device__ __forceinline__ static FqCall load_rw(const uint32_t* p) { return FqCall(FieldIO<Fq>::load_rw(p)); }
+    __device__ __forceinline__ static void store(uint32_t* p, const FqCall& v) { FieldIO<Fq>::store(p, v); }
 };
 template <>
 struct FieldIO<Fq2> {
@@ -72,7 +81,7 @@ size_t msm_point_words(int curve) { return curve == 1 ? 48 : 96; }
 // ------------------------------------------------------------------ 1. prepare
 __global__ void k_msm_prepare(const uint32_t* __restrict__ scalars_in, const uint8_t* __restrict__ inf,
                               uint32_t* __restrict__ scalars_out, uint32_t* __restrict__ hist, size_t n, unsigned c,
-                              unsigned nwin, unsigned nb, int mont) {
+                              unsigned nwin, unsigned nb, int mont, int merged) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint4* q = reinterpret_cast<const uint4*>(scalars_in) + 2 * i;
@@ -93,7 +102,7 @@ __global__ void k_msm_prepare(const uint32_t* __restrict__ scalars_in, const uin
         int32_t d = cur.next(sl, c, w);
         if (d != 0) {
             uint32_t mag = (uint32_t)(d < 0 ? -d : d);
-            atomicAdd(&hist[(size_t)w * nb + (mag - 1)], 1u);
+            atomicAdd(&hist[(merged ? 0 : (size_t)w * nb) + (mag - 1)], 1u);
         }
     }
 }
@@ -144,7 +153,8 @@ __global__ void __launch_bounds__(1024) k_exclusive_scan(const uint32_t* __restr
 
 // ------------------------------------------------------------------ 3. scatter
 __global__ void k_msm_scatter(const uint32_t* __restrict__ scalars, uint32_t* __restrict__ cursor,
-                              uint32_t* __restrict__ sorted, size_t n, unsigned c, unsigned nwin, unsigned nb) {
+                              uint32_t* __restrict__ sorted, size_t n, unsigned c, unsigned nwin, unsigned nb, int merged,
+                              size_t stride, size_t off) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint4* q = reinterpret_cast<const uint4*>(scalars) + 2 * i;
@@ -155,8 +165,10 @@ __global__ void k_msm_scatter(const uint32_t* __restrict__ scalars, uint32_t* __
         int32_t d = cur.next(sl, c, w);
         if (d != 0) {
             uint32_t mag = (uint32_t)(d < 0 ? -d : d);
-            uint32_t pos = atomicAdd(&cursor[(size_t)w * nb + (mag - 1)], 1u);
-            sorted[pos] = (uint32_t)i | (d < 0 ? 0x80000000u : 0u);
+            uint32_t pos = atomicAdd(&cursor[(merged ? 0 : (size_t)w * nb) + (mag - 1)], 1u);
+            // merged: the entry addresses slab w of the precomputed table, 2^(c w) * P_i
+            uint32_t idx = merged ? (uint32_t)((size_t)w * stride + off + i) : (uint32_t)i;
+            sorted[pos] = idx | (d < 0 ? 0x80000000u : 0u);
         }
     }
 }
@@ -177,13 +189,13 @@ __global__ void k_msm_seg_counts(const uint32_t* __restrict__ hist, uint32_t* __
 // never searches.  desc = {first sorted entry, length, bucket, 1 if the bucket has several segments}
 __global__ void k_msm_build_items(const uint32_t* __restrict__ ends, const uint32_t* __restrict__ hist,
                                   const uint32_t* __restrict__ segoff, const uint32_t* __restrict__ segcnt,
-                                  uint4* __restrict__ items, uint32_t* __restrict__ nitems_out, size_t total, size_t max_items,
-                                  uint32_t seg) {
+                                  uint4* __restrict__ items, uint32_t* __restrict__ nitems_out, uint32_t* __restrict__ heavy,
+                                  size_t total, size_t max_items, uint32_t seg, uint32_t heavy_len) {
     size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t nitems = (size_t)segoff[total - 1] + segcnt[total - 1];
     if (id == 0) {
         nitems_out[0] = (uint32_t)nitems;
-        nitems_out[1] = 0;  // work-queue head
+        nitems_out[1] = 0;  // work-queue head   ([2] = heavy count, zeroed by the host before this launch)
     }
     if (id >= max_items || id >= nitems) return;
     size_t lo = 0, hi = total - 1;
@@ -197,19 +209,25 @@ __global__ void k_msm_build_items(const uint32_t* __restrict__ ends, const uint3
     const uint32_t cnt = hist[b];
     uint32_t len = cnt > k * seg ? cnt - k * seg : 0;
     if (len > seg) len = seg;
-    items[id] = make_uint4(ends[b] - cnt + k * seg, len, b, segcnt[b] > 1 ? 1u : 0u);
+    // items much longer than the mean are listed separately and served first (longest-processing-time-first):
+    // wherever they sit in bucket order - the windowed form's sparse top window, the merged form's low buckets -
+    // they must not be the last thing a lane picks up
+    uint32_t is_heavy = len >= heavy_len ? 2u : 0u;
+    if (is_heavy) heavy[atomicAdd(&nitems_out[2], 1u)] = (uint32_t)id;
+    items[id] = make_uint4(ends[b] - cnt + k * seg, len, b, (segcnt[b] > 1 ? 1u : 0u) | is_heavy);
 }
 
 // Lane-level dynamic scheduling: every lane of a resident warp owns one item at a time and adds ONE point per
 // loop trip; a lane whose item is exhausted stores its sum and pulls the next item from a global queue inside
 // the same trip.  Bucket loads differ (Poisson around N/2^(c-1)), but no lane waits for a longer neighbour:
 // the warp only idles at the very end of the kernel.  The next point is fetched while the current one is added.
-template <class F, bool PREFETCH>
-__global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
+template <class F, bool PREFETCH, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                          const uint4* __restrict__ items, uint32_t* __restrict__ queue,
-                                                         uint32_t* __restrict__ buckets, uint32_t* __restrict__ segsum) {
+                                                         const uint32_t* __restrict__ heavy, uint32_t* __restrict__ buckets,
+                                                         uint32_t* __restrict__ segsum) {
     constexpr int W = FieldIO<F>::W;
-    const uint32_t nitems = queue[0];
+    const uint32_t nitems = queue[0], nheavy = queue[2];
     const unsigned lane = threadIdx.x & 31;
     XYZZ<F> acc = XYZZ<F>::infinity();
     uint32_t pos = 0, remaining = 0, item = 0xffffffffu, bucket = 0, multi = 0;
@@ -228,17 +246,21 @@ __global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* __restri
             uint32_t base = 0;
             if (lane == leader) base = atomicAdd(&queue[1], (uint32_t)__popc(need));
             base = __shfl_sync(need, base, leader);
-            item = base + __popc(need & ((1u << lane) - 1));
-            if (item < nitems) {
-                // heaviest first: the top window covers only 253 - c*(W-1) bits, so its 2^bits buckets each hold
-                // N / 2^bits points; it is last in bucket order, hence served first (LPT scheduling)
-                item = nitems - 1 - item;
+            uint32_t q = base + __popc(need & ((1u << lane) - 1));
+            if (q < nheavy + nitems) {
+                // queue = the heavy items first, then every item in bucket order (heavy ones skipped there)
+                bool from_heavy = q < nheavy;
+                item = from_heavy ? heavy[q] : q - nheavy;
                 uint4 d = items[item];
                 pos = d.x;
                 remaining = d.y;
                 bucket = d.z;
-                multi = d.w;
+                multi = d.w & 1u;
                 acc = XYZZ<F>::infinity();
+                if (!from_heavy && (d.w & 2u)) {  // already taken from the heavy list: nothing to do, nothing to store
+                    remaining = 0;
+                    item = 0xffffffffu;
+                }
                 if (PREFETCH && remaining) {
                     uint32_t e = sorted[pos];
                     const uint32_t* p = bases + (size_t)(e & 0x7fffffffu) * (2 * W);
@@ -356,56 +378,72 @@ __global__ void __launch_bounds__(WINSUM_THREADS) k_msm_block_sum(const uint32_t
 template <class F>
 static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const uint32_t* scalars, bool mont, size_t n,
                              const MsmConfig& cfg, MsmWorkspace& ws, cudaStream_t st) {
-    size_t total = (size_t)cfg.nwin * cfg.nb;
+    size_t total = (size_t)cfg.bwin * cfg.nb;
     cudaError_t e;
     if (ws.ev[2]) cudaEventRecord(ws.ev[2], st);
     if ((e = cudaMemsetAsync(ws.hist, 0, total * sizeof(uint32_t), st)) != cudaSuccess) return e;
     if (n) {
         unsigned blocks = (unsigned)((n + 255) / 256);
-        k_msm_prepare<<<blocks, 256, 0, st>>>(scalars, inf, ws.scalars, ws.hist, n, cfg.c, cfg.nwin, cfg.nb, mont ? 1 : 0); CZK_LAUNCHED();
+        k_msm_prepare<<<blocks, 256, 0, st>>>(scalars, inf, ws.scalars, ws.hist, n, cfg.c, cfg.nwin, cfg.nb, mont ? 1 : 0, (int)cfg.merged); CZK_LAUNCHED();
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     k_exclusive_scan<<<1, 1024, 0, st>>>(ws.hist, ws.offsets, total); CZK_LAUNCHED();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (n) {
         unsigned blocks = (unsigned)((n + 255) / 256);
-        k_msm_scatter<<<blocks, 256, 0, st>>>(ws.scalars, ws.offsets, ws.sorted, n, cfg.c, cfg.nwin, cfg.nb); CZK_LAUNCHED();
+        k_msm_scatter<<<blocks, 256, 0, st>>>(ws.scalars, ws.offsets, ws.sorted, n, cfg.c, cfg.nwin, cfg.nb, (int)cfg.merged, cfg.table_stride,
+                                                cfg.table_off); CZK_LAUNCHED();
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
     // segment length: at least the mean load of a busy bucket, and ~sqrt(n) so that neither the per-segment
     // walk nor the fold over segments can exceed O(sqrt(n)) serial additions whatever the digits are
+    // item length: (a) at most ~sqrt(n), so neither a segment walk nor the fold over a bucket's segments can exceed
+    // O(sqrt n) serial additions whatever the digits are; (b) short enough that every lane of the resident grid gets
+    // several items (>= 8), or the last items of the queue run on a mostly idle machine
     uint32_t seg = 128;
     while ((size_t)seg * seg < n) seg <<= 1;
+    {
+        size_t lanes = (size_t)ws.sm_count * 256;
+        size_t fine = (n * cfg.nwin) / (lanes * 8);
+        if (fine < 32) fine = 32;
+        if (fine < seg) seg = (uint32_t)fine;
+    }
     size_t max_items = total + (n * cfg.nwin) / seg + 1;
     if (max_items > ws.cap_items) return cudaErrorInvalidValue;
     k_msm_seg_counts<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.hist, ws.segcnt, total, seg); CZK_LAUNCHED();
     k_exclusive_scan<<<1, 1024, 0, st>>>(ws.segcnt, ws.segoff, total); CZK_LAUNCHED();
+    if ((e = cudaMemsetAsync(ws.queue, 0, 16, st)) != cudaSuccess) return e;
+    uint32_t heavy_len = (uint32_t)(2 * ((n * cfg.nwin) / total + 1) + 16);
     k_msm_build_items<<<(unsigned)((max_items + 255) / 256), 256, 0, st>>>(ws.offsets, ws.hist, ws.segoff, ws.segcnt, (uint4*)ws.items,
-                                                                            ws.queue, total, max_items, seg); CZK_LAUNCHED();
+                                                                            ws.queue, ws.heavy, total, max_items, seg, heavy_len); CZK_LAUNCHED();
     if (ws.ev[0]) cudaEventRecord(ws.ev[0], st);
     {
         // resident grid: the queue feeds lanes, so launch what the machine holds (2 blocks of 128 per SM at this
         // register budget) and no more; small problems launch fewer blocks
         size_t want = (max_items + 127) / 128;
+        // resident grid: 2 blocks of 128 per SM is what the register budget allows; more (with fewer registers or
+        // out-of-line products) measured 3-8 % slower
         size_t cap = (size_t)ws.sm_count * 2;
         unsigned blocks = (unsigned)(want < cap ? want : cap);
-        k_msm_accumulate<F, (FieldIO<F>::W == 12)><<<blocks, 128, 0, st>>>(bases, ws.sorted, (const uint4*)ws.items, ws.queue, ws.buckets, ws.segsum); CZK_LAUNCHED();
+        k_msm_accumulate<F, (FieldIO<F>::W == 12), 2><<<blocks, 128, 0, st>>>(bases, ws.sorted, (const uint4*)ws.items, ws.queue, ws.heavy,
+                                                                               ws.buckets, ws.segsum);
+        CZK_LAUNCHED();
     }
     if (ws.ev[1]) cudaEventRecord(ws.ev[1], st);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     k_msm_fold_segments<F><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(ws.segoff, ws.segcnt, ws.segsum, ws.buckets, total); CZK_LAUNCHED();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     unsigned nchunks = cfg.nb / cfg.chunk;
-    size_t rthreads = (size_t)cfg.nwin * nchunks;
-    k_msm_reduce_chunks<F><<<(unsigned)((rthreads + 127) / 128), 128, 0, st>>>(ws.buckets, ws.partial, cfg.nb, cfg.chunk, cfg.nwin); CZK_LAUNCHED();
+    size_t rthreads = (size_t)cfg.bwin * nchunks;
+    k_msm_reduce_chunks<F><<<(unsigned)((rthreads + 127) / 128), 128, 0, st>>>(ws.buckets, ws.partial, cfg.nb, cfg.chunk, cfg.bwin); CZK_LAUNCHED();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (nchunks >= 2 * WINSUM_GROUPS) {
         // partial[nwin*nchunks] -> segsum scratch [nwin*GROUPS] -> winsum[nwin]   (segsum is free again after the fold)
         uint32_t* mid = ws.partial + rthreads * msm_point_words(FieldIO<F>::W == 12 ? 1 : 2);
-        k_msm_block_sum<F><<<cfg.nwin * WINSUM_GROUPS, WINSUM_THREADS, 0, st>>>(ws.partial, mid, nchunks / WINSUM_GROUPS); CZK_LAUNCHED();
-        k_msm_block_sum<F><<<cfg.nwin, WINSUM_THREADS, 0, st>>>(mid, ws.winsum, WINSUM_GROUPS); CZK_LAUNCHED();
+        k_msm_block_sum<F><<<cfg.bwin * WINSUM_GROUPS, WINSUM_THREADS, 0, st>>>(ws.partial, mid, nchunks / WINSUM_GROUPS); CZK_LAUNCHED();
+        k_msm_block_sum<F><<<cfg.bwin, WINSUM_THREADS, 0, st>>>(mid, ws.winsum, WINSUM_GROUPS); CZK_LAUNCHED();
     } else {
-        k_msm_block_sum<F><<<cfg.nwin, WINSUM_THREADS, 0, st>>>(ws.partial, ws.winsum, nchunks); CZK_LAUNCHED();
+        k_msm_block_sum<F><<<cfg.bwin, WINSUM_THREADS, 0, st>>>(ws.partial, ws.winsum, nchunks); CZK_LAUNCHED();
     }
     if (ws.ev[3]) cudaEventRecord(ws.ev[3], st);
     return cudaGetLastError();
@@ -415,6 +453,46 @@ cudaError_t msm_run(int curve, const uint32_t* bases, const uint8_t* inf, const 
                     size_t n, const MsmConfig& cfg, MsmWorkspace& ws, cudaStream_t st) {
     if (curve == 1) return msm_run_t<Fq>(bases, inf, scalars, scalars_mont, n, cfg, ws, st);
     return msm_run_t<Fq2>(bases, inf, scalars, scalars_mont, n, cfg, ws, st);
+}
+
+// ------------------------------------------------------------------ merged-window table
+// thread i: slab w holds 2^(c w) * P_i.  One doubling chain per base; every slab entry is normalised to affine
+// (Fermat inversion): a one-off cost per CRS query, amortised over every proof made with the key.
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_precompute(uint32_t* __restrict__ table, const uint32_t* __restrict__ bases, size_t n,
+                                                         unsigned c, unsigned nwin) {
+    constexpr int W = FieldIO<F>::W;
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    F x = FieldIO<F>::load(bases + i * (2 * W)), y = FieldIO<F>::load(bases + i * (2 * W) + W);
+    FieldIO<F>::store(table + i * (2 * W), x);
+    FieldIO<F>::store(table + i * (2 * W) + W, y);
+    XYZZ<F> acc = XYZZ<F>::from_affine(x, y);
+    if (x.is_zero() && y.is_zero()) acc = XYZZ<F>::infinity();  // infinity placeholder: never addressed (scalar zeroed)
+    for (unsigned w = 1; w < nwin; w++) {
+        for (unsigned k = 0; k < c; k++) acc = XYZZ<F>::dbl(acc);
+        F ox = F::zero(), oy = F::zero();
+        if (!acc.is_inf()) {
+            F inv = F::inv_fermat(F::mul(acc.zz, acc.zzz));
+            ox = F::mul(acc.x, F::mul(inv, acc.zzz));
+            oy = F::mul(acc.y, F::mul(inv, acc.zz));
+            acc = XYZZ<F>::from_affine(ox, oy);
+        }
+        FieldIO<F>::store(table + ((size_t)w * n + i) * (2 * W), ox);
+        FieldIO<F>::store(table + ((size_t)w * n + i) * (2 * W) + W, oy);
+    }
+}
+cudaError_t msm_precompute_table(int curve, uint32_t* table, const uint32_t* bases, size_t n, unsigned c, unsigned nwin,
+                                 cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    unsigned blocks = (unsigned)((n + 127) / 128);
+    if (curve == 1) {
+        k_msm_precompute<Fq><<<blocks, 128, 0, st>>>(table, bases, n, c, nwin);
+    } else {
+        k_msm_precompute<Fq2><<<blocks, 128, 0, st>>>(table, bases, n, c, nwin);
+    }
+    CZK_LAUNCHED();
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ synthetic / test input generator

@@ -23,10 +23,44 @@ namespace czk {
 
 struct MsmConfig {
     unsigned c;        // window bits
-    unsigned nwin;     // windows
-    unsigned nb;       // buckets per window = 2^(c-1)
+    unsigned nwin;     // digit windows W = ceil(254 / c)
+    unsigned nb;       // buckets per bucket-window = 2^(c-1)
     unsigned chunk;    // buckets per thread in the reduce kernel
+    // Merged windows: with the multiples 2^(c w) P_i precomputed (czk_bases_precompute) every digit of every window
+    // feeds ONE set of 2^(c-1) buckets - the (point, window) pair just selects a different table entry - so the
+    // bucket reduction runs once instead of W times, larger c (fewer additions) becomes affordable, and the host
+    // tail needs no doublings.  bwin = number of bucket sets (1 when merged, W otherwise).
+    unsigned merged = 0;
+    unsigned bwin = 0;
+    size_t table_stride = 0;  // merged: points per window slab of the table (= length of the uploaded base array)
+    size_t table_off = 0;     // merged: index of the first base of this MSM inside a slab
 };
+
+// window size for the merged form: accumulation is n * ceil(254/c) additions, reduction ~3.3 * 2^(c-1)
+inline unsigned msm_merged_window(size_t n) {
+    unsigned lg = 0;
+    while (((size_t)1 << lg) < n) lg++;
+    // only sizes whose top window is (nearly) full: its digits land in the low buckets, and a window holding b bits
+    // puts n / 2^b extra points into each of them (c = 18, 19, 21 leave 1, 6 and 1 bits)
+    unsigned c = lg >= 23 ? 20 : (lg >= 18 ? 17 : (lg >= 14 ? 16 : (lg > 10 ? lg - 2 : 8)));
+    return c;
+}
+inline MsmConfig msm_merged_config(unsigned c, size_t stride, size_t off) {
+    MsmConfig cfg;
+    cfg.c = c;
+    cfg.nwin = msm_num_windows(c);
+    cfg.nb = 1u << (c - 1);
+    // one bucket set only: the chunked running sums are latency-bound (few threads, ~30 us per addition with one warp
+    // per scheduler), so use small chunks here - ~16K threads - unlike the W-window form where chunk 4 doubles the work
+    cfg.chunk = 4;
+    while (cfg.nb / cfg.chunk > 16384 && cfg.chunk < 32) cfg.chunk <<= 1;
+    if (cfg.chunk > cfg.nb) cfg.chunk = cfg.nb;
+    cfg.merged = 1;
+    cfg.bwin = 1;
+    cfg.table_stride = stride;
+    cfg.table_off = off;
+    return cfg;
+}
 
 inline MsmConfig msm_choose_config(size_t n) {
     // c ~ log2(n) - 4, clamped; measured trade-off between N*W mixed adds and 2^c*W bucket work
@@ -50,6 +84,8 @@ inline MsmConfig msm_choose_config(size_t n) {
     // buckets per thread in the chunked running sums.  Each chunk pays a ~1.5 log2(nb)-addition scalar multiple for
     // its offset, so small chunks double the work (measured: chunk 4 is 3.7 ms slower per 2^20 MSM than 16)
     cfg.chunk = cfg.nb >= 16 ? 16 : cfg.nb;
+    cfg.merged = 0;
+    cfg.bwin = cfg.nwin;
     return cfg;
 }
 
@@ -66,7 +102,8 @@ struct MsmWorkspace {
     uint32_t* segsum = nullptr;    // cap_items points: per-segment sums of multi-segment buckets
     size_t cap_items = 0;
     uint32_t* items = nullptr;     // cap_items x uint4 item descriptors
-    uint32_t* queue = nullptr;     // {item count, queue head}
+    uint32_t* queue = nullptr;     // {item count, queue head, heavy count}
+    uint32_t* heavy = nullptr;     // cap_items item ids served first
     int sm_count = 148;
     int seg_point_words = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // accumulate start/stop, whole MSM start/stop
@@ -82,6 +119,10 @@ cudaError_t msm_run(int curve, const uint32_t* bases, const uint8_t* inf, const 
                     size_t n, const MsmConfig& cfg, MsmWorkspace& ws, cudaStream_t st);
 
 size_t msm_point_words(int curve);  // 4 coordinates
+
+// table[w * n + i] = 2^(c w) * bases[i] as affine points, w < nwin (slab 0 is a copy of the input)
+cudaError_t msm_precompute_table(int curve, uint32_t* table, const uint32_t* bases, size_t n, unsigned c, unsigned nwin,
+                                 cudaStream_t st);
 
 // test / synthetic-input helper: out[i] = (k0 + i * kstep) * base as affine points (x | y)
 // (step_xy = kstep * base, affine, device memory)

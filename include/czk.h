@@ -101,6 +101,9 @@ CZK_API int czk_msm_g2(czk_ctx* ctx, const uint64_t* bases_xy, const uint8_t* in
 CZK_API int czk_bases_upload(czk_ctx* ctx, int curve, const uint64_t* bases_xy, const uint8_t* inf, size_t n, czk_bases** out);
 CZK_API void czk_bases_free(czk_ctx* ctx, czk_bases* b);
 CZK_API size_t czk_bases_len(const czk_bases* b);
+/* Precompute the merged-window table 2^(c w) * P_i for a resident base set (c = 0: chosen from its length).  One-off
+ * cost per CRS query; afterwards czk_msm_bases uses one bucket set for all windows.  Same results. */
+CZK_API int czk_bases_precompute(czk_ctx* ctx, czk_bases* b, unsigned c);
 /* MSM of bases[base_off .. base_off+n) by the device scalars sc[sc_off .. sc_off+n). */
 CZK_API int czk_msm_bases(czk_ctx* ctx, const czk_bases* b, size_t base_off, const czk_vec* sc, size_t sc_off,
                   int scalars_montgomery, size_t n, uint64_t* out_xyz);
@@ -141,8 +144,9 @@ CZK_API int czk_beaver_batch_mul(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_ve
 
 /* ---- diagnostics --------------------------------------------------------------------------------- */
 /* Device timing (CUDA events on the context's stream) of the MSMs run so far on this context, per curve:
- * out = { bucket-accumulation kernel ms (sum), its launch count, terms processed (sum of n), whole-MSM device ms (sum) }. */
-CZK_API int czk_msm_stats(czk_ctx* ctx, int curve, double out[4], int reset);
+ * out = { bucket-accumulation kernel ms (sum), its launch count, terms processed (sum of n), whole-MSM device ms (sum),
+ *         (point, window) pairs = upper bound on mixed additions (sum of n * windows) }. */
+CZK_API int czk_msm_stats(czk_ctx* ctx, int curve, double out[5], int reset);
 /* Integer-pipe microbenchmarks; result = operations per second.  kind: 0 IMAD.WIDE.U32 chain,
  * 1 IMAD lo/hi pair, 2 Fr mul, 3 Fq mul, 4 G1 mixed add. */
 CZK_API int czk_microbench(czk_ctx* ctx, int kind, int blocks_per_sm, int threads, int iters, double* ops_per_s, double* ms);

@@ -148,3 +148,36 @@ def test_msm_linearity_at_2_20(ctx, oracle, pymodel):
     pst = jac_to_affine_ints(G, ctx.msm_bases(b, dst))
     assert pymodel.g1_add(ps, pt) == pst
     assert pymodel.g1_on_curve(pst)
+
+
+@pytest.mark.parametrize("g", ["g1", "g2"])
+def test_msm_merged_window_table_matches_oracle(ctx, oracle, g):
+    """czk_bases_precompute: merged-window MSM over the table 2^(c w) P_i must give the same group element,
+    including infinity bases, sub-ranges (query[1..]), edge scalars and several window sizes."""
+    G = oracle.G1 if g == "g1" else oracle.G2
+    n = 1 << 12
+    xy = make_points(G, n, seed=61)
+    inf = np.zeros(n, np.uint8)
+    inf[5::97] = 1
+    sc = oracle.random_fr_mont(62, n)
+    sc[7] = 0
+    sc[8] = oracle.fr_from_ints([1])[0]
+    dsc = ctx.vec_from(sc)
+    for c in (0, 8, 11, 13):
+        b = ctx.bases_upload(1 if g == "g1" else 2, xy, inf).precompute(c)
+        assert jac_to_affine_ints(G, ctx.msm_bases(b, dsc)) == _oracle_msm(G, xy, inf, sc)
+        got = jac_to_affine_ints(G, ctx.msm_bases(b, dsc, n=n - 3, base_off=3, sc_off=1))
+        assert got == _oracle_msm(G, xy[3:], inf[3:], sc[1:n - 2])
+        b.free()
+
+
+def test_msm_merged_large_and_linear(ctx, oracle, pymodel):
+    n = 1 << 18
+    b = ctx.bases_synthetic(1, seed=71, n=n, inf_every=1024)
+    xy, inf = b.numpy()
+    sc = oracle.random_fr_mont(72, n)
+    dsc = ctx.vec_from(sc)
+    plain = jac_to_affine_ints(oracle.G1, ctx.msm_bases(b, dsc))
+    b.precompute()
+    merged = jac_to_affine_ints(oracle.G1, ctx.msm_bases(b, dsc))
+    assert merged == plain == _oracle_msm(oracle.G1, xy, inf, sc, threads=oracle.cpu_threads())
