@@ -394,3 +394,41 @@ def groth16_prove(scheme, n_sq, chain_shares, r_sh, s_sh, pk, threads=1, want_h=
                                  _p(h) if want_h else None, _p(proof_sh), _p8(proof_sh_inf), _p(proof), _p8(proof_inf),
                                  C.c_int(threads))
     return dict(ok=bool(ok), h=h, proof_sh=proof_sh, proof_sh_inf=proof_sh_inf, proof=proof, proof_inf=proof_inf)
+
+
+SCHEME_GSZ = 3
+
+
+def groth16_prove_gsz(n_parties, n_sq, chain_mont, r_val, s_val, pk, threads=1):
+    """Groth16 under GSZ20 shares with the reference's stubbed preprocessing (every party holds the plaintext)."""
+    D = pk["D"]
+    chain_mont = np.ascontiguousarray(chain_mont, np.uint64).reshape(n_sq + 1, 4)
+    h = np.zeros((D, 4), np.uint64)
+    proof = np.zeros(48, np.uint64)
+    proof_inf = np.zeros(3, np.uint8)
+    check = np.zeros(16, np.uint64)
+    check_g1 = np.zeros(24, np.uint64)
+    check_g1_inf = np.zeros(2, np.uint8)
+    counts = np.zeros(2, np.uint64)
+    ok = lib().orc_groth16_prove_gsz(C.c_int(n_parties), C.c_size_t(n_sq), _p(chain_mont), _p(np.ascontiguousarray(r_val, np.uint64)),
+                                     _p(np.ascontiguousarray(s_val, np.uint64)), _p(pk["a_query"]), _p8(pk["a_inf"]),
+                                     _p(pk["b_g1_query"]), _p8(pk["b1_inf"]), _p(pk["b_g2_query"]), _p8(pk["b2_inf"]),
+                                     _p(pk["h_query"]), _p8(pk["h_inf"]), _p(pk["l_query"]), _p8(pk["l_inf"]), _p(pk["vk_g1"]),
+                                     _p(pk["vk_g2"]), _p(h), _p(proof), _p8(proof_inf), _p(check), _p(check_g1), _p8(check_g1_inf),
+                                     _p(counts), C.c_int(threads))
+    return dict(ok=bool(ok), h=h, proof=proof, proof_inf=proof_inf, field_check=check[:12].reshape(3, 4), group_check_x=check[12:16],
+                group_check_yz=check_g1.reshape(2, 12), group_check_inf=check_g1_inf, king_computes=int(counts[0]), opens=int(counts[1]))
+
+
+def gsz_share(n_parties, coeffs_mont):
+    coeffs_mont = np.ascontiguousarray(coeffs_mont, np.uint64).reshape(-1, 4)
+    out = np.zeros((n_parties, 4), np.uint64)
+    assert lib().orc_gsz_share(C.c_int(n_parties), _p(coeffs_mont), C.c_int(coeffs_mont.shape[0]), _p(out))
+    return out
+
+
+def gsz_open(shares_mont, degree):
+    shares_mont = np.ascontiguousarray(shares_mont, np.uint64).reshape(-1, 4)
+    out = np.zeros(4, np.uint64)
+    ok = lib().orc_gsz_open(C.c_int(shares_mont.shape[0]), _p(shares_mont), C.c_int(degree), _p(out))
+    return out, ok
