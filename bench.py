@@ -30,6 +30,8 @@ LOG_N = 20
 METRIC = "groth16_proof_ms_2^20_r1cs_bls12_377"
 # BASELINE.md section 1 (reference's published figures, GCP n2-standard-2, 1 physical core per party)
 PUBLISHED_MS = {1: 127400.0, 2: 320400.0, 3: 323300.0}
+# ncu --set full capture of the dominant kernel (profiles/r1_summary.md), DRAM bytes per launch averaged over a step
+NCU_TRAFFIC_BYTES_PER_LAUNCH = (6.215e9 + 3 * 3.110e9) / 4
 
 
 def ref_msm_adds(n: int) -> int:
@@ -264,7 +266,10 @@ def main():
         "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": int((n_sq + 1) * 32), "d2h_bytes_per_step": int(2 * 48 * 8 + 6 + 5 * 16 * 192)},
         "gpu_launches": int(launches),
         "roofline": {"kernel": "k_msm_accumulate<Fq>", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm_peak, "traffic": None,
+                     "frac": achieved_gbs / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
+                     "traffic_source": "profiles/r1_summary.md: ncu --set full dram__bytes_read+write of k_msm_accumulate<Fq>, 6.21 GB (2^21-1 terms) "
+                                       "and 3.11 GB (2^20 terms) per launch -> mean over the step's 4 launches; the bucket method gathers each "
+                                       "base once per window (15 x 96 B) from the precomputed table, so traffic >> the 128 B/term algorithmic figure",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                      "note": "bucket accumulation is bound by the INT32 multiply pipe, not HBM: see roofline_int",
                      "launch_ms": acc_ms, "launches_per_step": st1["launches"] / args.steps, "share_of_step": st1["accumulate_ms"] / args.steps / ms_res},
