@@ -40,6 +40,23 @@ CZK_HD void chain_mad(uint32_t* acc, const uint32_t* a, uint32_t bi) {
     chain_mad<N>(acc, a, bi, bi);
 }
 
+#ifdef __CUDACC__
+// 0xffffffff from constant memory: a value ptxas cannot see.  Both BLS12-377 moduli are 1 mod 2^32, so the Montgomery
+// factor m = -t0 mod 2^32; written as a visible negation ptxas refuses to fuse the (mad.lo.cc, madc.hi.cc) pairs
+// that multiply by it into IMAD.WIDE.U32.X and emits IMAD.X + IMAD.HI.U32.X instead (twice the multiply-pipe
+// slots for the whole reduction half of the product).  (t0 ^ ones) + 1 is the same value, opaque.
+static __device__ __constant__ uint32_t FP_ALL_ONES_C = 0xffffffffu;
+#endif
+template <class P>
+CZK_HD uint32_t mont_factor(uint32_t t0) {
+    static_assert(P::INV32 == 0xffffffffu, "both moduli are 1 mod 2^32");
+#ifdef __CUDA_ARCH__
+    return (t0 ^ FP_ALL_ONES_C) + 1u;
+#else
+    return t0 * P::INV32;
+#endif
+}
+
 // One row of the product: add a*bi and the Montgomery multiple of p that clears column 0.
 //   E holds columns 0..N-1 (pairs at even columns), O holds columns 1..N (pairs at odd columns).
 // On entry (not first) a division by 2^32 from the previous row is still pending, which is why
@@ -73,9 +90,17 @@ CZK_HD void mont_row(uint32_t* E, uint32_t* O, const uint32_t* a, uint32_t bi, c
         chain_mad<N>(E, a, bi, bi2);
         O[N - 1] = addc(O[N - 1], 0);
     }
-    uint32_t mi = E[0] * P::INV32;
+    uint32_t mi = mont_factor<P>(E[0]);
     chain_mad<N>(O, m + 1, mi);
-    chain_mad<N>(E, m, mi);
+    // E += mi * (p0, p2, p4, ...): p0 = 1, so the first product is mi itself (no multiply): E[0] + mi = 0 mod 2^32
+    static_assert(P::mod(0) == 1u, "both moduli are 1 mod 2^32");
+    E[0] = add_cc(E[0], mi);
+    E[1] = addc_cc(E[1], 0);
+#pragma unroll
+    for (int j = 2; j < N; j += 2) {
+        E[j] = madc_lo_cc(m[j], mi, E[j]);
+        E[j + 1] = madc_hi_cc(m[j], mi, E[j + 1]);
+    }
     O[N - 1] = addc(O[N - 1], 0);
 }
 
@@ -161,9 +186,15 @@ struct Fp {
         return r;
     }
     CZK_HD static Fp mul(const Fp& a, const Fp& b) {
-        uint32_t even[N], odd[N], m[N];
+        uint32_t m[N];
 #pragma unroll
         for (int i = 0; i < N; i++) m[i] = P::modc(i);
+        return mul_m(a, b, m);
+    }
+    // the product with the modulus limbs supplied by the caller (kernels that keep p in registers, loaded from
+    // memory the compiler cannot see through, get every reduction row fused into IMAD.WIDE.U32.X)
+    CZK_HD static Fp mul_m(const Fp& a, const Fp& b, const uint32_t* m) {
+        uint32_t even[N], odd[N];
 #pragma unroll
         for (int i = 0; i < N; i += 2) {
             mont_row<P>(even, odd, a.l, b.l[i], m, i == 0);

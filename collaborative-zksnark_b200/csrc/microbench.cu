@@ -68,6 +68,63 @@ __global__ void k_mb_wide_carry(uint64_t* out, int iters, uint32_t seed) {
     for (int i = 0; i < 12; i++) r ^= ((uint64_t)acc0[i] << 32) | acc1[i];
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
+__device__ uint32_t g_mb_in[64];
+__device__ uint32_t g_mb_lane_zero[32];
+// kind 13: carry-chained wide multiply-adds, accumulators updated in place (operands loaded from memory so that the
+// register allocation matches the field kernels': the loop is IMAD.WIDE.U32[.X] + one IADD3.X per chain)
+__global__ void k_mb_wide_carry_clean(uint64_t* out, int iters, uint32_t seed) {
+    uint32_t a[12], acc[12], acc2[12], b[4];
+    int z = g_mb_lane_zero[threadIdx.x & 31];
+#pragma unroll
+    for (int i = 0; i < 12; i++) a[i] = g_mb_in[i + z], acc[i] = g_mb_in[12 + i + z], acc2[i] = g_mb_in[24 + i + z];
+#pragma unroll
+    for (int i = 0; i < 4; i++) b[i] = g_mb_in[40 + i + z] + seed;
+#pragma unroll 1
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int r = 0; r < 4; r += 2) {
+            chain_mad<12>(acc, a, b[r]);
+            acc[11] = addc(acc[11], 0);
+            chain_mad<12>(acc2, a, b[r + 1]);
+            acc2[11] = addc(acc2[11], 0);
+        }
+    }
+    uint64_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) r ^= ((uint64_t)acc[i] << 32) | acc2[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+// kind 14: wide multiply-adds (multiply pipe) interleaved 1:1 with carry-chained adds (ALU pipe): do the pipes overlap?
+__global__ void k_mb_wide_plus_add(uint64_t* out, int iters, uint32_t seed) {
+    int z = g_mb_lane_zero[threadIdx.x & 31];
+    uint32_t a[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = g_mb_in[i + z] + threadIdx.x;
+    uint32_t b = g_mb_in[z + 17] + seed;
+    uint64_t c0 = a[0], c1 = b, c2 = a[1] ^ b, c3 = a[2] + b;
+    uint32_t x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = g_mb_in[20 + i + z];
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c0) : "r"(a[4 * k]), "r"(b));
+            x[0] = add_cc(x[0], x[4]);
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c1) : "r"(a[4 * k + 1]), "r"(b));
+            x[1] = addc_cc(x[1], x[5]);
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c2) : "r"(a[4 * k + 2]), "r"(b));
+            x[2] = addc_cc(x[2], x[6]);
+            asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(c3) : "r"(a[4 * k + 3]), "r"(b));
+            x[3] = addc(x[3], x[7]);
+        }
+        b += (uint32_t)c3;
+    }
+    uint64_t r = c0 ^ c1 ^ c2 ^ c3;
+#pragma unroll
+    for (int i = 0; i < 4; i++) r ^= x[i];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
 // kind 6: carry-chained 32-bit adds (IADD3.X)
 __global__ void k_mb_addc(uint64_t* out, int iters, uint32_t seed) {
     uint32_t x[12], y[12];
@@ -162,6 +219,25 @@ __global__ void k_mb_madd(uint64_t* out, int iters, uint32_t seed) {
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
 }
 
+__device__ uint32_t g_mb_mod[12] = {0x00000001u, 0x8508c000u, 0x30000000u, 0x170b5d44u, 0xba094800u, 0x1ef3622fu,
+                                    0x00f5138fu, 0x1a22d9f3u, 0x6ca1493bu, 0xc63b05c0u, 0x17c510eau, 0x01ae3a46u};
+// kind 12: Fq product with the modulus in registers (opaque to ptxas)
+__global__ void k_mb_mul_regmod(uint64_t* out, int iters, uint32_t seed) {
+    Fq x = Fq::one(), y = Fq::r2();
+    x.l[0] ^= seed + threadIdx.x;
+    y.l[1] ^= blockIdx.x;
+    uint32_t m[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) m[i] = ((volatile uint32_t*)g_mb_mod)[i + g_mb_lane_zero[threadIdx.x & 31]];
+    for (int i = 0; i < iters; i++) {
+        x = Fq::mul_m(x, y, m);
+        y = Fq::mul_m(y, x, m);
+    }
+    uint64_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) acc ^= (uint64_t)(x.l[i] ^ y.l[i]) << (i & 31);
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
 __device__ uint32_t g_mb_zero = 0;
 __global__ void k_mb_mul_split(uint64_t* out, int iters, uint32_t seed) {
     Fq x = Fq::one(), y = Fq::r2();
@@ -219,6 +295,9 @@ cudaError_t microbench_run(int kind, int blocks, int threads, int iters, uint64_
         case 7: k_mb_imad<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 64.0 * iters; break;
         case 8: k_mb_imad_hi<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 64.0 * iters; break;
         case 11: k_mb_mul_split<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 2.0 * iters; break;
+        case 12: k_mb_mul_regmod<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 2.0 * iters; break;
+        case 13: k_mb_wide_carry_clean<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 24.0 * iters; break;
+        case 14: k_mb_wide_plus_add<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 16.0 * iters; break;
         case 9: k_mb_mul13<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 2.0 * iters; break;
         case 10: k_mb_madd13<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 1.0 * iters; break;
         default: return cudaErrorInvalidValue;
