@@ -15,6 +15,7 @@ from .binding import (  # noqa: F401
     SCHEME_PLAIN,
     SCHEME_ADDITIVE,
     SCHEME_SPDZ,
+    SCHEME_GSZ,
     ProvingKey,
     groth16_witness_map,
     groth16_prove,

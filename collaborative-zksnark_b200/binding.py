@@ -18,7 +18,7 @@ import numpy as np
 _HERE = Path(__file__).resolve().parent
 _LIB = None
 
-SCHEME_PLAIN, SCHEME_ADDITIVE, SCHEME_SPDZ = 0, 1, 2
+SCHEME_PLAIN, SCHEME_ADDITIVE, SCHEME_SPDZ, SCHEME_GSZ = 0, 1, 2, 3
 
 u64p = C.POINTER(C.c_uint64)
 u8p = C.POINTER(C.c_uint8)
@@ -78,10 +78,16 @@ _SIGS = {
     "czk_net_allgather_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "czk_net_allgather_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "czk_net_bcast_from_king_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_net_gather_to_king_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "czk_net_stats": (C.c_int, [C.c_void_p, u64p]),
     "czk_net_reset_stats": (None, [C.c_void_p]),
     "czk_batch_open": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "czk_beaver_batch_mul": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_gsz_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_size_t]),
+    "czk_gsz_king_compute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t]),
+    "czk_gsz_batch_mul": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
+    "czk_gsz_check_products": (C.c_int, [C.c_void_p, u64p]),
+    "czk_gsz_stats": (C.c_int, [C.c_void_p, u64p]),
     "czk_msm_stats": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int]),
     "czk_microbench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
@@ -100,6 +106,7 @@ _OPTIONAL_SIGS = {
     "czk_squaring_chain": (C.c_int, [u64p, C.c_size_t, C.c_void_p]),
     "czk_king_share_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_void_p]),
     "czk_groth16_last_phases": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "czk_groth16_gsz_last_checks": (C.c_int, [C.c_void_p, u64p, u64p, u64p, u8p, u64p]),
 }
 
 
@@ -410,6 +417,30 @@ class Context:
         self._chk(self.lib.czk_beaver_batch_mul(self.h, scheme, x_sh.h, x_mac.h if x_mac is not None else None, y_sh.h,
                                                 y_mac.h if y_mac is not None else None, n))
 
+    # ------------------------------------------------------------------ GSZ20 shares (share/gsz20/mod.rs)
+    def gsz_open(self, sh: DeviceVec, degree: int, n=None):
+        n = sh.n if n is None else n
+        out = DeviceVec(self, n)
+        self._chk(self.lib.czk_gsz_open(self.h, sh.h, degree, out.h, n))
+        return out
+
+    def gsz_king_compute(self, v: DeviceVec, degree: int, n=None):
+        self._chk(self.lib.czk_gsz_king_compute(self.h, v.h, degree, v.n if n is None else n))
+
+    def gsz_batch_mul(self, x: DeviceVec, y: DeviceVec, n=None, queue_check=True):
+        self._chk(self.lib.czk_gsz_batch_mul(self.h, x.h, y.h, x.n if n is None else n, int(queue_check)))
+
+    def gsz_check_products(self):
+        """hadamard_check -> ip_check over the queued triples; returns the opened (x, y, z) of the last step."""
+        out = np.zeros(12, np.uint64)
+        self._chk(self.lib.czk_gsz_check_products(self.h, out.ctypes.data_as(u64p)))
+        return out.reshape(3, 4)
+
+    def gsz_stats(self):
+        out = np.zeros(2, np.uint64)
+        self._chk(self.lib.czk_gsz_stats(self.h, out.ctypes.data_as(u64p)))
+        return dict(king_computes=int(out[0]), opens=int(out[1]))
+
     # ------------------------------------------------------------------ diagnostics
     def msm_stats(self, curve=1, reset=False):
         out = (C.c_double * 5)()
@@ -526,4 +557,12 @@ def groth16_prove(ctx: Context, scheme: int, pk: ProvingKey, chain_sh, r_sh, s_s
     ph = (C.c_double * 8)()
     ctx.lib.czk_groth16_last_phases(ctx.h, ph)
     names = ("upload", "witness_map", "msm_h", "msm_l", "msm_a", "msm_b_g1", "msm_b_g2", "group_tail_reveal")
-    return dict(proof_sh=proof_sh, proof_sh_inf=sh_inf, proof=proof, proof_inf=inf, phases_ms=dict(zip(names, list(ph))))
+    res = dict(proof_sh=proof_sh, proof_sh_inf=sh_inf, proof=proof, proof_inf=inf, phases_ms=dict(zip(names, list(ph))))
+    if scheme == SCHEME_GSZ:
+        f3, gx, gyz = np.zeros(12, np.uint64), np.zeros(4, np.uint64), np.zeros(24, np.uint64)
+        ginf, cnt = np.zeros(2, np.uint8), np.zeros(2, np.uint64)
+        ctx._chk(ctx.lib.czk_groth16_gsz_last_checks(ctx.h, f3.ctypes.data_as(u64p), gx.ctypes.data_as(u64p), gyz.ctypes.data_as(u64p),
+                                                     ginf.ctypes.data_as(u8p), cnt.ctypes.data_as(u64p)))
+        res.update(field_check=f3.reshape(3, 4), group_check_x=gx, group_check_yz=gyz.reshape(2, 12), group_check_inf=ginf,
+                   king_computes=int(cnt[0]), opens=int(cnt[1]))
+    return res

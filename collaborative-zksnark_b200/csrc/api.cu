@@ -27,6 +27,7 @@ cudaError_t microbench_run(int kind, int blocks, int threads, int iters, uint64_
 
 #include "ctx.hpp"
 
+void gsz_release(czk_ctx* ctx);
 const char* czk_version(void) { return "czk-b200 0.1 (sm_100a)"; }
 
 const char* czk_last_error(const czk_ctx* ctx) { return ctx ? ctx->err.c_str() : czk_tls_error().c_str(); }
@@ -89,6 +90,7 @@ void czk_ctx_destroy(czk_ctx* ctx) {
         cudaFree(d.gi_hi);
     }
     free_ws(ctx->ws);
+    gsz_release(ctx);
     for (Scratch* s : {&ctx->up_bases, &ctx->up_inf, &ctx->up_scalars, &ctx->up_vec, &ctx->open_gather, &ctx->open_sigma,
                        &ctx->open_sx, &ctx->open_oy, &ctx->open_d, &ctx->open_dm})
         cudaFree(s->p);
@@ -599,6 +601,7 @@ int czk_bases_download(czk_ctx* ctx, const czk_bases* b, size_t off, size_t n, u
     return CZK_OK;
 }
 
+void gsz_release(czk_ctx* ctx);
 // ------------------------------------------------------------------------------------------ network
 int czk_net_unique_id(uint8_t out[128]) {
     NcclApi& api = nccl_api();
@@ -728,6 +731,8 @@ int czk_beaver_batch_mul(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac
     if (!ctx || !x_sh || !y_sh || n > x_sh->n || n > y_sh->n) return fail(ctx, CZK_ERR_ARG, "czk_beaver_batch_mul: range");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     if (scheme == CZK_SCHEME_PLAIN) return czk_vec_mul(ctx, x_sh, y_sh, n);
+    // GszFieldShare::batch_mul (gsz20/mod.rs:309-315): king degree reduction, triple queued for the product check
+    if (scheme == CZK_SCHEME_GSZ) return czk_gsz_batch_mul(ctx, x_sh, y_sh, n, 1);
     bool spdz = scheme == CZK_SCHEME_SPDZ;
     if (spdz && (!x_mac || !y_mac || n > x_mac->n || n > y_mac->n)) return fail(ctx, CZK_ERR_ARG, "SPDZ product needs MAC vectors");
     size_t bytes = n * 32;

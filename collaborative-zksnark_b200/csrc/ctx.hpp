@@ -30,6 +30,10 @@ struct NcclApi {
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(ncclResult_t) = nullptr;
     bool ok = false;
 };
@@ -46,7 +50,12 @@ inline NcclApi& nccl_api() {
     api.AllGather = (decltype(api.AllGather))dlsym(api.handle, "ncclAllGather");
     api.Broadcast = (decltype(api.Broadcast))dlsym(api.handle, "ncclBroadcast");
     api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
-    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Broadcast && api.GetErrorString;
+    api.Send = (decltype(api.Send))dlsym(api.handle, "ncclSend");
+    api.Recv = (decltype(api.Recv))dlsym(api.handle, "ncclRecv");
+    api.GroupStart = (decltype(api.GroupStart))dlsym(api.handle, "ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.handle, "ncclGroupEnd");
+    api.ok = api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.AllGather && api.Broadcast && api.GetErrorString &&
+             api.Send && api.Recv && api.GroupStart && api.GroupEnd;
     return api;
 }
 
@@ -75,6 +84,21 @@ struct Scratch {
     size_t cap = 0;
 };
 
+// GSZ20 (honest-majority Shamir) state of one party: the share domain of n parties and the queued product triples
+struct GszTriple {
+    uint64_t *x = nullptr, *y = nullptr, *z = nullptr;  // device copies, n elements each
+    size_t n = 0;
+};
+struct GszState {
+    int n = 0, t = 0;              // parties the tables below were built for, t = (n - 1) / 2
+    uint32_t* winv_dev = nullptr;  // n Montgomery Fr: w^-k, w = get_root_of_unity(n)
+    HFr n_inv;
+    std::vector<GszTriple> queue;  // field triples awaiting hadamard_check
+    uint64_t king_computes = 0, opens = 0;
+    uint64_t last_check[12] = {0};  // opened x, y, z of the last field product check
+    Scratch dot_partial, one_elem, pad_x, pad_y, gather;
+};
+
 struct czk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -90,6 +114,7 @@ struct czk_ctx {
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
     uint64_t stats[5] = {0, 0, 0, 0, 0};
+    GszState gsz;
     // kernel timing of the MSM (CUDA events on the launching stream), per curve: [0] G1, [1] G2
     double acc_ms[2] = {0, 0}, msm_ms[2] = {0, 0}, acc_terms[2] = {0, 0}, acc_entries[2] = {0, 0};
     uint64_t acc_launches[2] = {0, 0};

@@ -149,7 +149,8 @@ static int witness_map_dev(czk_ctx* ctx, int scheme, size_t n_sq, unsigned log_d
     CZK_TRY(czk_vec_copy(ctx, v.c, 0, v.chain, 1, n_sq));
     CZK_TRY(czk_vec_copy(ctx, v.a, n_sq + 1, v.chain, n_sq, 1));
     // Public(1) lowered to share form: the king holds 1 (add.rs:88-92; SPDZ mac = 1 * mac_share, spdz.rs:132-137)
-    HFr one_val = (scheme == CZK_SCHEME_PLAIN || ctx->rank == 0) ? HFr::one() : HFr::zero();
+    // GSZ: shift adds the public value at EVERY party (gsz20/mod.rs:270-273)
+    HFr one_val = (scheme == CZK_SCHEME_PLAIN || scheme == CZK_SCHEME_GSZ || ctx->rank == 0) ? HFr::one() : HFr::zero();
     CUDA_TRY(ctx, cudaMemcpyAsync(czk_vec_device_ptr(v.a) + 4 * n_sq, one_val.l, 32, cudaMemcpyHostToDevice, ctx->stream));
     if (spdz) {
         // from_add_shared: mac = share * mac() with the MAC key stubbed to 1 (spdz.rs:41-47,138-143); the MAC vectors
@@ -384,6 +385,243 @@ int czk_king_share_batch(const uint64_t* values, size_t k, int n_parties, uint64
     return CZK_OK;
 }
 
+// ------------------------------------------------------------------------------------------ GSZ20 group shares (host)
+// gsz20/mod.rs:942-1000, :1043-1130 (scale_pub_group, shift, open, king_compute, mult) and :1135-1400 (the group
+// ip_compute / ip_compress / ip_check / hadamard_check), for the three shared-scalar x shared-point products of
+// create_proof.  O(1) points: host arithmetic, the exchanges are host-staged NCCL all-gathers of single points.
+int gsz_coin(czk_ctx* ctx, HFr* out);
+int gsz_mult1(czk_ctx* ctx, const HFr& x, const HFr& y, HFr* out);
+int czk_gsz_open_scalar_internal(czk_ctx* ctx, const HFr& v, HFr* out);
+
+struct GszCheckOut {
+    uint64_t group_x[4];
+    uint64_t group_yz[24];
+    uint8_t group_inf[2];
+};
+static thread_local GszCheckOut g_gsz_check;
+
+template <class HF>
+static HPoint<HF> pt_scale(const HPoint<HF>& p, const HFr& s) {
+    uint64_t k[4];
+    s.from_mont().to_limbs(k);
+    return HPoint<HF>::mul(p, k, 4);
+}
+template <class HF>
+static void pt_sub(HPoint<HF>& a, const HPoint<HF>& b) {
+    HPoint<HF> t = b;
+    t.negate();
+    a.add(t);
+}
+// open_degree_vec on group shares with the reference's shares[i] indexing (:1056-1068):
+//   coeff_i = sum_j shares[i] * (w^-ij / n) = shares[i] * (n^-1 sum_j w^-ij)
+// so the value is the king's share and every higher coefficient is the identity.  Used by open (all-gather, every party
+// interpolates) and king_compute (gather to the king, king returns the value): the same points move either way.
+template <class HF, int LIMBS>
+static int gsz_group_open(czk_ctx* ctx, const HPoint<HF>& share, int degree, HPoint<HF>* out) {
+    typedef GShare<HF, LIMBS> GS;
+    typedef HPoint<HF> P;
+    const int n = ctx->nranks;
+    const size_t rec = (2 * LIMBS + 1) * 8;
+    std::vector<uint64_t> send(2 * LIMBS + 1), recv((size_t)n * (2 * LIMBS + 1));
+    send[2 * LIMBS] = (uint64_t)GS::to_affine_limbs(share, send.data());
+    CZK_TRY(czk_net_allgather_host(ctx, send.data(), recv.data(), rec));
+    HFr w = HFr::one(), n_inv = ctx->gsz.n_inv;
+    // w^-1 of the share domain: recomputed from the table constants kept by the field side
+    std::vector<HFr> winv((size_t)n);
+    {
+        std::vector<uint64_t> tab((size_t)n * 4);
+        CUDA_TRY(ctx, cudaMemcpy(tab.data(), ctx->gsz.winv_dev, (size_t)n * 32, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < n; k++) winv[k] = HFr::from_limbs(tab.data() + 4 * k);
+    }
+    (void)w;
+    for (int i = 0; i < n; i++) {
+        HFr sc = HFr::zero();
+        for (int j = 0; j < n; j++) sc = HFr::add(sc, winv[(size_t)((i * j) % n)]);
+        sc = HFr::mul(sc, n_inv);
+        const uint64_t* r = recv.data() + (size_t)i * (2 * LIMBS + 1);
+        P sh = GS::from_affine_limbs(r, (int)r[2 * LIMBS]);
+        P coeff = sc.is_zero() ? P::infinity() : (sc == HFr::one() ? sh : pt_scale(sh, sc));
+        if (i == 0) *out = coeff;
+        else if (i > degree && !coeff.is_inf())
+            return fail(ctx, CZK_ERR_PROTOCOL, "GSZ group degree check failed (gsz20/mod.rs:1070 assert)");
+    }
+    return CZK_OK;
+}
+// mult (:1112-1130): z = king_compute(y * x + r2) - r with r = r2 = identity
+static int gsz_g1_mult(czk_ctx* ctx, const HFr& x, const HG1& y, HG1* z) {
+    HG1 t = pt_scale(y, x);
+    ctx->gsz.king_computes++;
+    return gsz_group_open<HFq, 6>(ctx, t, 2 * ctx->gsz.t, z);
+}
+static int gsz_g1_ip_compute(czk_ctx* ctx, const HFr* xs, const HG1* ys, size_t k, HG1* out) {
+    HG1 acc = HG1::infinity();
+    for (size_t i = 0; i < k; i++) acc.add(pt_scale(ys[i], xs[i]));
+    ctx->gsz.king_computes++;
+    return gsz_group_open<HFq, 6>(ctx, acc, 2 * ctx->gsz.t, out);
+}
+// hadamard_check (:1330-1349) + ip_check (:1262-1328) on (field, group) triples
+static int gsz_g1_product_check(czk_ctx* ctx, std::vector<HFr> x, std::vector<HG1> y, std::vector<HG1> z) {
+    const size_t k = x.size();
+    if (!k) return CZK_OK;
+    HFr r, r_i = HFr::one();
+    CZK_TRY(gsz_coin(ctx, &r));
+    HG1 ip = HG1::infinity();
+    for (size_t i = 0; i < k; i++) {
+        x[i] = HFr::mul(x[i], r_i);
+        z[i] = pt_scale(z[i], r_i);
+        ip.add(z[i]);
+        r_i = HFr::mul(r_i, r);
+    }
+    size_t len = k;
+    std::vector<HFr> xm(k + 2), x3(k + 2);
+    std::vector<HG1> ym(k + 2), y3(k + 2);
+    x.resize(k + 2);
+    y.resize(k + 2);
+    while (len > 1) {
+        if (len & 1) {
+            x[len] = HFr::zero();
+            y[len] = HG1::infinity();
+            len++;
+        }
+        const size_t h = len / 2;
+        HG1 ip_l, ip_r, ip3;
+        CZK_TRY(gsz_g1_ip_compute(ctx, x.data(), y.data(), h, &ip_l));
+        ip_r = ip;
+        pt_sub(ip_r, ip_l);
+        for (size_t i = 0; i < h; i++) {
+            xm[i] = HFr::sub(x[h + i], x[i]);
+            x3[i] = HFr::add(x[h + i], xm[i]);
+            ym[i] = y[h + i];
+            pt_sub(ym[i], y[i]);
+            y3[i] = y[h + i];
+            y3[i].add(ym[i]);
+        }
+        CZK_TRY(gsz_g1_ip_compute(ctx, x3.data(), y3.data(), h, &ip3));
+        HFr rr;
+        CZK_TRY(gsz_coin(ctx, &rr));
+        for (size_t i = 0; i < h; i++) {
+            x[i] = HFr::add(HFr::mul(xm[i], rr), HFr::sub(x[i], xm[i]));
+            HG1 yb = y[i];
+            pt_sub(yb, ym[i]);
+            HG1 ymr = pt_scale(ym[i], rr);
+            ymr.add(yb);
+            y[i] = ymr;
+        }
+        {
+            HFr one = HFr::one(), two = HFr::from_u64(2), three = HFr::from_u64(3), inv2 = HFr::inv(two);
+            HFr a = HFr::sub(rr, two), b = HFr::sub(rr, three), c = HFr::sub(rr, one);
+            HFr f1 = HFr::mul(HFr::mul(a, b), inv2), f2 = HFr::neg(HFr::mul(c, b)), f3 = HFr::mul(HFr::mul(c, a), inv2);
+            HG1 s1 = pt_scale(ip_l, f1);
+            s1.add(pt_scale(ip_r, f2));
+            s1.add(pt_scale(ip3, f3));
+            ip = s1;
+        }
+        len = h;
+    }
+    HFr one = HFr::one(), ipr, xb, fx;
+    CZK_TRY(gsz_mult1(ctx, one, one, &ipr));
+    CZK_TRY(gsz_mult1(ctx, x[0], one, &xb));
+    HG1 yb, ib, fy, fz;
+    CZK_TRY(gsz_g1_mult(ctx, one, y[0], &yb));
+    CZK_TRY(gsz_g1_mult(ctx, ipr, ip, &ib));
+    CZK_TRY(czk_gsz_open_scalar_internal(ctx, xb, &fx));
+    ctx->gsz.opens += 2;
+    CZK_TRY((gsz_group_open<HFq, 6>(ctx, yb, ctx->gsz.t, &fy)));
+    CZK_TRY((gsz_group_open<HFq, 6>(ctx, ib, ctx->gsz.t, &fz)));
+    fx.to_limbs(g_gsz_check.group_x);
+    g_gsz_check.group_inf[0] = (uint8_t)GShare<HFq, 6>::to_affine_limbs(fy, g_gsz_check.group_yz);
+    g_gsz_check.group_inf[1] = (uint8_t)GShare<HFq, 6>::to_affine_limbs(fz, g_gsz_check.group_yz + 12);
+    uint64_t chk[12];
+    int chk_inf = GShare<HFq, 6>::to_affine_limbs(pt_scale(fy, fx), chk);
+    if (chk_inf != (int)g_gsz_check.group_inf[1] || std::memcmp(chk, g_gsz_check.group_yz + 12, sizeof chk) != 0)
+        return fail(ctx, CZK_ERR_PROTOCOL, "GSZ group product check failed (gsz20/mod.rs:1326 assert_eq!)");
+    return CZK_OK;
+}
+
+// create_proof's group arithmetic on GSZ shares + pf.reveal(); the first group reveal runs every queued product check
+// (:900-905, :1700-1711).  r, s: the value every party holds (the reference's rand() stub gives 1).
+static int prove_tail_gsz(czk_ctx* ctx, const czk_pk* pk, const uint64_t r_sh[4], const uint64_t s_sh[4], const HG1& h_acc,
+                          const HG1& l_acc, const HG1& a_acc, const HG1& b1_acc, const HG2& b2_acc, uint64_t proof_sh[48],
+                          uint8_t proof_sh_inf[3], uint64_t proof[48], uint8_t proof_inf[3]) {
+    typedef GShare<HFq, 6> S1;
+    typedef GShare<HFq2, 12> S2;
+    double t0 = now_ms();
+    HG1 alpha_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1), HFq::from_limbs(pk->vk_g1 + 6));
+    HG1 beta_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1 + 12), HFq::from_limbs(pk->vk_g1 + 18));
+    HG1 delta_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1 + 24), HFq::from_limbs(pk->vk_g1 + 30));
+    HG2 beta_g2 = HG2::from_affine(HFq2::from_limbs(pk->vk_g2), HFq2::from_limbs(pk->vk_g2 + 12));
+    HG2 delta_g2 = HG2::from_affine(HFq2::from_limbs(pk->vk_g2 + 48), HFq2::from_limbs(pk->vk_g2 + 60));
+    const HFr r = HFr::from_limbs(r_sh), s = HFr::from_limbs(s_sh);
+    std::vector<HFr> gx;
+    std::vector<HG1> gy, gz;
+    // r_s_delta_g1 = (delta * r) * s
+    HG1 rsd = pt_scale(delta_g1, r), t;
+    gx.push_back(s);
+    gy.push_back(rsd);
+    CZK_TRY(gsz_g1_mult(ctx, s, rsd, &t));
+    rsd = t;
+    gz.push_back(rsd);
+    // g_a = r*delta + a_query[0] + MSM + alpha   (shift adds public points at every party, :971-974)
+    HG1 g_a = pt_scale(delta_g1, r);
+    g_a.add(S1::from_affine_limbs(pk->a0, pk->a0_inf));
+    g_a.add(a_acc);
+    g_a.add(alpha_g1);
+    HG1 s_g_a;
+    gx.push_back(s);
+    gy.push_back(g_a);
+    CZK_TRY(gsz_g1_mult(ctx, s, g_a, &s_g_a));
+    gz.push_back(s_g_a);
+    HG1 g1_b = pt_scale(delta_g1, s);
+    g1_b.add(S1::from_affine_limbs(pk->b10, pk->b10_inf));
+    g1_b.add(b1_acc);
+    g1_b.add(beta_g1);
+    HG2 g2_b = pt_scale(delta_g2, s);
+    g2_b.add(S2::from_affine_limbs(pk->b20, pk->b20_inf));
+    g2_b.add(b2_acc);
+    g2_b.add(beta_g2);
+    HG1 r_g1_b;
+    gx.push_back(r);
+    gy.push_back(g1_b);
+    CZK_TRY(gsz_g1_mult(ctx, r, g1_b, &r_g1_b));
+    gz.push_back(r_g1_b);
+    HG1 g_c = s_g_a;
+    g_c.add(r_g1_b);
+    pt_sub(g_c, rsd);
+    g_c.add(l_acc);
+    g_c.add(h_acc);
+    proof_sh_inf[0] = (uint8_t)S1::to_affine_limbs(g_a, proof_sh);
+    proof_sh_inf[1] = (uint8_t)S2::to_affine_limbs(g2_b, proof_sh + 12);
+    proof_sh_inf[2] = (uint8_t)S1::to_affine_limbs(g_c, proof_sh + 36);
+    // pf.reveal(): queued field products first, then the group products, then the three opens
+    CZK_TRY(czk_gsz_check_products(ctx, nullptr));
+    CZK_TRY(gsz_g1_product_check(ctx, gx, gy, gz));
+    HG1 A, Cc;
+    HG2 B;
+    ctx->gsz.opens += 3;
+    CZK_TRY((gsz_group_open<HFq, 6>(ctx, g_a, ctx->gsz.t, &A)));
+    CZK_TRY((gsz_group_open<HFq2, 12>(ctx, g2_b, ctx->gsz.t, &B)));
+    CZK_TRY((gsz_group_open<HFq, 6>(ctx, g_c, ctx->gsz.t, &Cc)));
+    proof_inf[0] = (uint8_t)S1::to_affine_limbs(A, proof);
+    proof_inf[1] = (uint8_t)S2::to_affine_limbs(B, proof + 12);
+    proof_inf[2] = (uint8_t)S1::to_affine_limbs(Cc, proof + 36);
+    g_phases[7] = now_ms() - t0;
+    return CZK_OK;
+}
+
+int czk_groth16_gsz_last_checks(const czk_ctx* ctx, uint64_t field_xyz[12], uint64_t group_x[4], uint64_t group_yz[24],
+                                uint8_t group_inf[2], uint64_t counts[2]) {
+    if (!ctx) return CZK_ERR_ARG;
+    if (field_xyz) std::memcpy(field_xyz, ctx->gsz.last_check, sizeof ctx->gsz.last_check);
+    if (group_x) std::memcpy(group_x, g_gsz_check.group_x, sizeof g_gsz_check.group_x);
+    if (group_yz) std::memcpy(group_yz, g_gsz_check.group_yz, sizeof g_gsz_check.group_yz);
+    if (group_inf) std::memcpy(group_inf, g_gsz_check.group_inf, 2);
+    if (counts) {
+        counts[0] = ctx->gsz.king_computes;
+        counts[1] = ctx->gsz.opens;
+    }
+    return CZK_OK;
+}
+
 static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t* chain_sh, const czk_vec* chain_dev,
                       const uint64_t r_sh[4], const uint64_t s_sh[4], uint64_t proof_sh[48], uint8_t proof_sh_inf[3],
                       uint64_t proof[48], uint8_t proof_inf[3]) {
@@ -432,6 +670,8 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     g_phases[6] = now_ms() - t0;
     free_share_vecs(ctx, v);
 
+    if (scheme == CZK_SCHEME_GSZ)
+        return prove_tail_gsz(ctx, pk, r_sh, s_sh, h_acc.sh, l_acc.sh, a_acc.sh, b1_acc.sh, b2_acc.sh, proof_sh, proof_sh_inf, proof, proof_inf);
     // ---- O(1) group arithmetic on shares (prover.rs:110-177)
     t0 = now_ms();
     HG1 alpha_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1), HFq::from_limbs(pk->vk_g1 + 6));

@@ -126,13 +126,16 @@ CZK_API int czk_net_allgather_dev(czk_ctx* ctx, const void* dev_send, void* dev_
 CZK_API int czk_net_allgather_host(czk_ctx* ctx, const void* host_send, void* host_recv, size_t bytes);
 /* send_bytes_to_king / recv_bytes_from_king with equal slices for every party. */
 CZK_API int czk_net_bcast_from_king_dev(czk_ctx* ctx, void* dev_buf, size_t bytes);
+/* send_bytes_to_king (mpc-net/src/multi.rs:176-209): rank 0 receives every party's `bytes` bytes at
+ * dev_recv_king[p * bytes] (its own slice is copied); dev_recv_king is ignored on the other ranks. */
+CZK_API int czk_net_gather_to_king_dev(czk_ctx* ctx, const void* dev_send, void* dev_recv_king, size_t bytes);
 /* Stats (mpc-net/src/lib.rs:8-26): bytes_sent, bytes_recv, broadcasts, to_king, from_king. */
 CZK_API int czk_net_stats(const czk_ctx* ctx, uint64_t out[5]);
 CZK_API void czk_net_reset_stats(czk_ctx* ctx);
 
 /* ---- shares: replaces FieldShare::{batch_open,batch_mul} ------------------------------------------
  * mpc-algebra/src/share/{field.rs:97-127, add.rs:121-125, spdz.rs:166-185}.
- * scheme: 1 = additive (hbc), 2 = SPDZ.  For SPDZ a share vector is two czk_vec (sh, mac).         */
+ * scheme: 1 = additive (hbc), 2 = SPDZ, 3 = GSZ (see below).  For SPDZ a share vector is two czk_vec (sh, mac). */
 #define CZK_SCHEME_PLAIN 0
 #define CZK_SCHEME_ADDITIVE 1
 #define CZK_SCHEME_SPDZ 2
@@ -141,6 +144,25 @@ CZK_API int czk_batch_open(czk_ctx* ctx, int scheme, const czk_vec* sh, const cz
  * mpc-algebra/src/wire/field.rs:41-77): Beaver multiplication, two opens.                         */
 CZK_API int czk_beaver_batch_mul(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac, const czk_vec* y_sh,
                          const czk_vec* y_mac, size_t n);
+
+/* ---- GSZ20 honest-majority shares: replaces mpc-algebra/src/share/gsz20/mod.rs on the Groth16 path -------
+ * n parties, t = (n-1)/2, party j holds p(w^j) over the mixed-radix share domain of size n (n = 2^a or 3*2^a;
+ * :94-105).  A share vector is one czk_vec.  The reference's preprocessing stubs are kept (rand() = 1,
+ * double_rand() = (1, 1), the king returns the opened value to every party: :378-410, :468-486).
+ * A failed degree check or product check returns CZK_ERR_PROTOCOL (the reference assert!s).              */
+#define CZK_SCHEME_GSZ 3
+/* batch_open / open_degree_vec (:286-299, :434-459): all-gather, interpolate, degree <= `degree`, value at 0. */
+CZK_API int czk_gsz_open(czk_ctx* ctx, const czk_vec* sh, unsigned degree, czk_vec* out_pub, size_t n);
+/* batch_king_compute with f = identity (:488-524): v <- the value the king opens at `degree`, returned to everyone. */
+CZK_API int czk_gsz_king_compute(czk_ctx* ctx, czk_vec* v, unsigned degree, size_t n);
+/* batch_mult (:559-594): x <- x * y (local product + mask, king degree reduction 2t -> t); queue_check != 0 keeps
+ * the triple for czk_gsz_check_products.  czk_beaver_batch_mul(scheme GSZ) is this with queue_check = 1.   */
+CZK_API int czk_gsz_batch_mul(czk_ctx* ctx, czk_vec* x, const czk_vec* y, size_t n, int queue_check);
+/* check_accumulated_field_products: hadamard_check -> ip_check over every queued triple (:412-431, :599-808).
+ * final_xyz (may be NULL): the three values opened by the last step (x * y == z).                          */
+CZK_API int czk_gsz_check_products(czk_ctx* ctx, uint64_t final_xyz[12]);
+/* out = { king computations, opens } since context creation. */
+CZK_API int czk_gsz_stats(const czk_ctx* ctx, uint64_t out[2]);
 
 /* ---- diagnostics --------------------------------------------------------------------------------- */
 /* Device timing (CUDA events on the context's stream) of the MSMs run so far on this context, per curve:

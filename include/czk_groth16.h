@@ -44,6 +44,12 @@ CZK_API int czk_groth16_witness_map(czk_ctx* ctx, int scheme, size_t n_sq, const
 CZK_API int czk_groth16_prove(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t* chain_sh, const uint64_t r_sh[4],
                               const uint64_t s_sh[4], uint64_t proof_sh[48], uint8_t proof_sh_inf[3], uint64_t proof[48],
                               uint8_t proof_inf[3]);
+/* scheme CZK_SCHEME_GSZ: chain_sh / r_sh / s_sh are the values every party holds (king_share_batch hands the plaintext to
+ * every party at degree t, gsz20/mod.rs:202-212); the first group reveal runs the queued field and group product checks.
+ * After such a proof: the values those checks opened (field x | y | z; group x, then y | z affine + 2 infinity bytes)
+ * and counts = { king computations, opens } of the context. */
+CZK_API int czk_groth16_gsz_last_checks(const czk_ctx* ctx, uint64_t field_xyz[12], uint64_t group_x[4], uint64_t group_yz[24],
+                                        uint8_t group_inf[2], uint64_t counts[2]);
 /* Same, with this party's chain shares already resident on the device (n_sq + 1 elements). */
 CZK_API int czk_groth16_prove_vec(czk_ctx* ctx, int scheme, const czk_pk* pk, const czk_vec* chain_dev, const uint64_t r_sh[4],
                                   const uint64_t s_sh[4], uint64_t proof_sh[48], uint8_t proof_sh_inf[3], uint64_t proof[48],

@@ -20,7 +20,7 @@ from oracle import pymodel as m
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--scheme", default="spdz", choices=["additive", "spdz"])
+    ap.add_argument("--scheme", default="spdz", choices=["additive", "spdz", "gsz"])
     ap.add_argument("--log-n", type=int, default=10)
     ap.add_argument("--squarings", type=int, default=0, help="exact number of squarings (overrides --log-n)")
     args = ap.parse_args()
@@ -28,6 +28,8 @@ def main():
     ctx, rank, world = party.ctx, party.rank, party.world
     scheme = czk_b200.SCHEME_SPDZ if args.scheme == "spdz" else czk_b200.SCHEME_ADDITIVE
     n_sq = args.squarings or (1 << args.log_n)
+    if args.scheme == "gsz":
+        return main_gsz(party, n_sq)
     rnd = random.Random(1234 + n_sq)
     toxic = [rnd.randrange(1, m.R_MOD) for _ in range(7)]
     pk = o.groth16_setup(n_sq, o.fr_from_ints(toxic), threads=max(1, o.cpu_threads() // world))
@@ -56,6 +58,52 @@ def main():
     assert (opened.numpy() == x).all()
     launch.barrier()
     print(f"[rank {rank}/{world}] groth16 {args.scheme} n={n_sq}: parity ok; net {st}", flush=True)
+    party.close()
+
+
+def main_gsz(party, n_sq):
+    """GSZ20: every party holds the plaintext under the reference's stubs; real Shamir shares are exercised on
+    czk_gsz_open / czk_gsz_king_compute (open, degree check, failing degree check)."""
+    ctx, rank, world = party.ctx, party.rank, party.world
+    rnd = random.Random(4321 + n_sq)
+    toxic = [rnd.randrange(1, m.R_MOD) for _ in range(7)]
+    threads = max(1, o.cpu_threads() // world)
+    pk = o.groth16_setup(n_sq, o.fr_from_ints(toxic), threads=threads)
+    chain = o.squaring_chain(o.fr_from_ints([rnd.randrange(m.R_MOD)])[0], n_sq)
+    r, s = o.fr_from_ints([rnd.randrange(m.R_MOD)]), o.fr_from_ints([rnd.randrange(m.R_MOD)])
+    exp = o.groth16_prove_gsz(world, n_sq, chain, r[0], s[0], pk, threads=threads)
+    assert exp["ok"]
+    dpk = czk_b200.ProvingKey.upload(ctx, pk)
+    before = ctx.gsz_stats()
+    got = czk_b200.groth16_prove(ctx, czk_b200.SCHEME_GSZ, dpk, chain, r[0], s[0])
+    assert (got["proof"] == exp["proof"]).all() and (got["proof_inf"] == exp["proof_inf"]).all(), f"rank {rank}: proof differs"
+    assert (got["field_check"] == exp["field_check"]).all(), f"rank {rank}: field product check values differ"
+    assert (got["group_check_x"] == exp["group_check_x"]).all() and (got["group_check_yz"] == exp["group_check_yz"]).all()
+    assert got["king_computes"] - before["king_computes"] == exp["king_computes"] and got["opens"] - before["opens"] == exp["opens"]
+    # real Shamir shares: k random degree-t polynomials, party j holds p_i(w^j)
+    t = (world - 1) // 2
+    k = 257
+    coeffs = [o.random_fr_mont(900 + i, t + 1) for i in range(k)]
+    shares = np.stack([o.gsz_share(world, c) for c in coeffs], axis=1)  # (world, k, 4)
+    secrets = np.stack([c[0] for c in coeffs])
+    opened = ctx.gsz_open(ctx.vec_from(shares[rank]), t)
+    assert (opened.numpy() == secrets).all(), f"rank {rank}: Shamir open differs"
+    v = ctx.vec_from(shares[rank])
+    ctx.gsz_king_compute(v, t)
+    assert (v.numpy() == secrets).all()
+    if t >= 1:
+        # a product of two degree-t sharings has degree 2t: opens at 2t, must FAIL the degree-t check
+        prod = o.fr_mul(shares[rank], shares[rank])
+        assert (ctx.gsz_open(ctx.vec_from(prod), 2 * t).numpy() == o.fr_mul(secrets, secrets)).all()
+        try:
+            ctx.gsz_open(ctx.vec_from(prod), t)
+            raise AssertionError("degree check did not fire")
+        except czk_b200.CzkError as e:
+            assert e.code == 5
+    st = ctx.net_stats()
+    assert world == 1 or (st["to_king"] > 0 and st["from_king"] > 0)
+    launch.barrier()
+    print(f"[rank {rank}/{world}] groth16 gsz n={n_sq} t={t}: parity ok; {ctx.gsz_stats()} net {st}", flush=True)
     party.close()
 
 
