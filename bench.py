@@ -152,7 +152,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="czk", choices=["czk", "reference"])
     ap.add_argument("--log-n", type=int, default=LOG_N, help="log2 constraints (default 20 = the BASELINE config)")
-    ap.add_argument("--scheme", default="spdz", choices=["spdz", "additive", "plain"])
+    ap.add_argument("--scheme", default="spdz", choices=["spdz", "additive", "plain", "gsz"])
     ap.add_argument("--cpu-sample-log-n", type=int, default=16)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -183,15 +183,21 @@ def main():
         os.close(saved_stdout)
     ctx, rank, world = party.ctx, party.rank, party.world
     assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
-    scheme = {"spdz": czk_b200.SCHEME_SPDZ, "additive": czk_b200.SCHEME_ADDITIVE, "plain": czk_b200.SCHEME_PLAIN}[args.scheme]
+    scheme = {"spdz": czk_b200.SCHEME_SPDZ, "additive": czk_b200.SCHEME_ADDITIVE, "plain": czk_b200.SCHEME_PLAIN,
+              "gsz": czk_b200.SCHEME_GSZ}[args.scheme]
     n_sq = 1 << args.log_n
 
     # ---- setup (untimed, like the reference: CRS + king_share_batch happen before start_timer!, proof.rs:113-129)
     imad_peak, _ = ctx.microbench(0, 8, 256, 2000)  # measured IMAD.WIDE.U32 issue rate: the integer roofline denominator
     pk = czk_b200.ProvingKey.synthetic(ctx, n_sq, seed=0x377)
     D = pk.domain_size
-    chain = czk_b200.squaring_chain(np.array([0x1234567, 0x89abcdef, 0x55aa55aa, 0x0123], np.uint64), n_sq) if rank == 0 else None
-    mine = launch.king_share_scatter(chain, n_sq + 1, seed=0x5eed)
+    start = np.array([0x1234567, 0x89abcdef, 0x55aa55aa, 0x0123], np.uint64)
+    if args.scheme == "gsz":
+        # king_share_batch under GSZ hands the plaintext to every party (gsz20/mod.rs:202-212): each rank derives it
+        mine = czk_b200.squaring_chain(start, n_sq)
+    else:
+        chain = czk_b200.squaring_chain(start, n_sq) if rank == 0 else None
+        mine = launch.king_share_scatter(chain, n_sq + 1, seed=0x5eed)
     pinned = torch.from_numpy(mine.view(np.int64).copy()).pin_memory()
     mine_pinned = pinned.numpy().view(np.uint64)
     chain_dev = ctx.vec_from(mine)

@@ -88,6 +88,8 @@ _SIGS = {
     "czk_gsz_batch_mul": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "czk_gsz_check_products": (C.c_int, [C.c_void_p, u64p]),
     "czk_gsz_stats": (C.c_int, [C.c_void_p, u64p]),
+    "czk_msm_set_batched": (C.c_int, [C.c_void_p, C.c_int]),
+    "czk_fq_inverse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "czk_msm_stats": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int]),
     "czk_microbench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
@@ -442,6 +444,15 @@ class Context:
         return dict(king_computes=int(out[0]), opens=int(out[1]))
 
     # ------------------------------------------------------------------ diagnostics
+    def msm_set_batched(self, enabled: bool):
+        self._chk(self.lib.czk_msm_set_batched(self.h, int(enabled)))
+
+    def fq_inverse(self, a):
+        a = _np_u64(a, 6)
+        out = np.zeros_like(a)
+        self._chk(self.lib.czk_fq_inverse(self.h, a.ctypes.data, out.ctypes.data, a.shape[0]))
+        return out
+
     def msm_stats(self, curve=1, reset=False):
         out = (C.c_double * 5)()
         self._chk(self.lib.czk_msm_stats(self.h, curve, out, int(reset)))

@@ -58,6 +58,10 @@ int czk_ctx_create(int device, czk_ctx** out) {
 }
 
 static void free_ws(MsmWorkspace& ws) {
+    cudaFree(ws.bat_a);
+    cudaFree(ws.bat_b);
+    cudaFree(ws.bat_prefix);
+    if (ws.host_word) cudaFreeHost(ws.host_word);
     cudaFree(ws.scalars);
     cudaFree(ws.hist);
     cudaFree(ws.offsets);
@@ -358,13 +362,32 @@ static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
             CUDA_TRY(ctx, cudaMalloc((void**)&ws.items, cap * 16));
             CUDA_TRY(ctx, cudaMalloc((void**)&ws.heavy, cap * 4));
             if (!ws.queue) {
-                CUDA_TRY(ctx, cudaMalloc((void**)&ws.queue, 16));
+                CUDA_TRY(ctx, cudaMalloc((void**)&ws.queue, 64));
+                CUDA_TRY(ctx, cudaMallocHost((void**)&ws.host_word, 64));
+                const char* env = getenv("CZK_BATCHED");
+                if (!ws.batched_forced) ws.batched = !(env && atoi(env) == 0);
                 cudaDeviceProp prop;
                 CUDA_TRY(ctx, cudaGetDeviceProperties(&prop, ctx->device));
                 ws.sm_count = prop.multiProcessorCount;
             }
             ws.cap_items = cap;
             ws.seg_point_words = pww;
+        }
+    }
+    if (ws.batched) {
+        size_t pa, pb, pre;
+        msm_batched_bytes(curve, n * cfg.nwin, total, &pa, &pb, &pre);
+        struct { uint32_t** p; size_t* cap; size_t need; } bufs[3] = {{&ws.bat_a, &ws.cap_bat_a, pa}, {&ws.bat_b, &ws.cap_bat_b, pb},
+                                                                      {&ws.bat_prefix, &ws.cap_bat_prefix, pre}};
+        for (auto& b : bufs) {
+            if (b.need <= *b.cap) continue;
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            cudaFree(*b.p);
+            *b.p = nullptr;
+            *b.cap = 0;
+            size_t want = b.need + b.need / 16;
+            CUDA_TRY(ctx, cudaMalloc((void**)b.p, want));
+            *b.cap = want;
         }
     }
     for (int i = 0; i < 4; i++)
@@ -542,24 +565,28 @@ int czk_bases_synthetic(czk_ctx* ctx, int curve, uint64_t seed, size_t n, size_t
     if (!ctx || !out || (curve != 1 && curve != 2)) return fail(ctx, CZK_ERR_ARG, "czk_bases_synthetic: argument");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     uint64_t st = seed;
-    uint64_t k0[4], ks[4];
+    uint64_t k0[4], ks[4], kq[4], kq2[4];
     for (int i = 0; i < 4; i++) {
         k0[i] = splitmix(st);
         ks[i] = splitmix(st);
     }
+    for (int i = 0; i < 4; i++) kq[i] = splitmix(st);
     k0[3] &= (1ull << 56) - 1;  // < 2^248 < r
     ks[3] &= (1ull << 56) - 1;
+    kq[3] &= (1ull << 56) - 1;
     ks[0] |= 1;
+    kq[0] |= 1;
+    for (int i = 0; i < 4; i++) kq2[i] = (kq[i] << 1) | (i ? kq[i - 1] >> 63 : 0);  // 2 kq < 2^249
     czk_bases* b = new czk_bases();
     b->curve = curve;
     b->n = n;
     size_t pb = curve == 1 ? 96 : 192;
     CUDA_TRY(ctx, cudaMalloc((void**)&b->xy, (n ? n : 1) * pb + 2 * pb));
-    // generator and step point (kstep * G) on the host, staged after the output array
+    // generator and second-difference point (2 kquad * G) on the host, staged after the output array
     std::vector<uint64_t> gs(2 * pb / 8);
     if (curve == 1) {
         HG1 g = HG1::from_affine(HFq::from_limbs(CurveConsts::G1_GEN), HFq::from_limbs(CurveConsts::G1_GEN + 6));
-        HG1 s = HG1::mul(g, ks, 4);
+        HG1 s = HG1::mul(g, kq2, 4);
         HFq sx, sy;
         s.to_affine(sx, sy);
         std::memcpy(gs.data(), CurveConsts::G1_GEN, 96);
@@ -567,7 +594,7 @@ int czk_bases_synthetic(czk_ctx* ctx, int curve, uint64_t seed, size_t n, size_t
         sy.to_limbs(gs.data() + 18);
     } else {
         HG2 g = HG2::from_affine(HFq2::from_limbs(CurveConsts::G2_GEN), HFq2::from_limbs(CurveConsts::G2_GEN + 12));
-        HG2 s = HG2::mul(g, ks, 4);
+        HG2 s = HG2::mul(g, kq2, 4);
         HFq2 sx, sy;
         s.to_affine(sx, sy);
         std::memcpy(gs.data(), CurveConsts::G2_GEN, 192);
@@ -576,7 +603,7 @@ int czk_bases_synthetic(czk_ctx* ctx, int curve, uint64_t seed, size_t n, size_t
     }
     uint32_t* stage = b->xy + (n ? n : 1) * (pb / 4);
     CUDA_TRY(ctx, cudaMemcpyAsync(stage, gs.data(), 2 * pb, cudaMemcpyHostToDevice, ctx->stream));
-    CUDA_TRY(ctx, ec_gen_progression_dev(curve, b->xy, stage, stage + pb / 4, k0, ks, n, ctx->stream));
+    CUDA_TRY(ctx, ec_gen_progression_dev(curve, b->xy, stage, stage + pb / 4, k0, ks, kq, n, ctx->stream));
     if (inf_every && n) {
         std::vector<uint8_t> flags(n, 0);
         for (size_t i = inf_every - 1; i < n; i += inf_every) flags[i] = 1;
@@ -763,6 +790,24 @@ int czk_beaver_batch_mul(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac
 }
 
 // ------------------------------------------------------------------------------------------ diagnostics
+int czk_msm_set_batched(czk_ctx* ctx, int enabled) {
+    if (!ctx) return CZK_ERR_ARG;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->ws.batched = enabled != 0;
+    ctx->ws.batched_forced = true;
+    return CZK_OK;
+}
+int czk_fq_inverse(czk_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n) {
+    if (!ctx || !in || !out) return fail(ctx, CZK_ERR_ARG, "czk_fq_inverse: null");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CZK_TRY(scratch_reserve(ctx, ctx->up_bases, n * 96));
+    uint32_t* d = (uint32_t*)ctx->up_bases.p;
+    CUDA_TRY(ctx, cudaMemcpyAsync(d, in, n * 48, cudaMemcpyHostToDevice, ctx->stream));
+    CUDA_TRY(ctx, fq_inverse_batch(d, d + n * 12, n, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(out, d + n * 12, n * 48, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CZK_OK;
+}
 int czk_msm_stats(czk_ctx* ctx, int curve, double out[5], int reset) {
     if (!ctx || !out || (curve != 1 && curve != 2)) return fail(ctx, CZK_ERR_ARG, "czk_msm_stats: argument");
     int k = curve - 1;

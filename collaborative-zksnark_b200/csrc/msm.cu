@@ -4,77 +4,9 @@
 #include <cstdlib>
 
 #include "launch_count.hpp"
+#include "msm_io.cuh"
 
 namespace czk {
-
-// ------------------------------------------------------------------ element I/O (16-byte vector accesses)
-template <class F>
-struct FieldIO;
-template <>
-struct FieldIO<Fq> {
-    static constexpr int W = 12;
-    __device__ __forceinline__ static Fq load(const uint32_t* p) {
-        const uint4* q = reinterpret_cast<const uint4*>(p);
-        uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2);
-        Fq r;
-        r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
-        r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
-        r.l[8] = c.x; r.l[9] = c.y; r.l[10] = c.z; r.l[11] = c.w;
-        return r;
-    }
-    __device__ __forceinline__ static Fq load_rw(const uint32_t* p) {
-        const uint4* q = reinterpret_cast<const uint4*>(p);
-        uint4 a = q[0], b = q[1], c = q[2];
-        Fq r;
-        r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
-        r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
-        r.l[8] = c.x; r.l[9] = c.y; r.l[10] = c.z; r.l[11] = c.w;
-        return r;
-    }
-    __device__ __forceinline__ static void store(uint32_t* p, const Fq& v) {
-        uint4* q = reinterpret_cast<uint4*>(p);
-        q[0] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
-        q[1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
-        q[2] = make_uint4(v.l[8], v.l[9], v.l[10], v.l[11]);
-    }
-};
-template <>
-struct FieldIO<FqCall> {
-    static constexpr int W = 12;
-    __device__ __forceinline__ static FqCall load(const uint32_t* p) { return FqCall(FieldIO<Fq>::load(p)); }
-    __device__ __forceinline__ static FqCall load_rw(const uint32_t* p) { return FqCall(FieldIO<Fq>::load_rw(p)); }
-    __device__ __forceinline__ static void store(uint32_t* p, const FqCall& v) { FieldIO<Fq>::store(p, v); }
-};
-template <>
-struct FieldIO<Fq2> {
-    static constexpr int W = 24;
-    __device__ __forceinline__ static Fq2 load(const uint32_t* p) { return Fq2{FieldIO<Fq>::load(p), FieldIO<Fq>::load(p + 12)}; }
-    __device__ __forceinline__ static Fq2 load_rw(const uint32_t* p) {
-        return Fq2{FieldIO<Fq>::load_rw(p), FieldIO<Fq>::load_rw(p + 12)};
-    }
-    __device__ __forceinline__ static void store(uint32_t* p, const Fq2& v) {
-        FieldIO<Fq>::store(p, v.c0);
-        FieldIO<Fq>::store(p + 12, v.c1);
-    }
-};
-template <class F>
-__device__ __forceinline__ XYZZ<F> load_point(const uint32_t* p) {
-    constexpr int W = FieldIO<F>::W;
-    XYZZ<F> r;
-    r.x = FieldIO<F>::load_rw(p);
-    r.y = FieldIO<F>::load_rw(p + W);
-    r.zz = FieldIO<F>::load_rw(p + 2 * W);
-    r.zzz = FieldIO<F>::load_rw(p + 3 * W);
-    return r;
-}
-template <class F>
-__device__ __forceinline__ void store_point(uint32_t* p, const XYZZ<F>& v) {
-    constexpr int W = FieldIO<F>::W;
-    FieldIO<F>::store(p, v.x);
-    FieldIO<F>::store(p + W, v.y);
-    FieldIO<F>::store(p + 2 * W, v.zz);
-    FieldIO<F>::store(p + 3 * W, v.zzz);
-}
 
 size_t msm_point_words(int curve) { return curve == 1 ? 48 : 96; }
 
@@ -178,11 +110,14 @@ __global__ void k_msm_scatter(const uint32_t* __restrict__ scalars, uint32_t* __
 // With uniform digits every bucket is a single segment (seg >= the mean bucket load) and the result
 // goes straight to buckets[]; heavier buckets - a degenerate top window, repeated scalars - are split
 // so no thread ever walks more than `seg` points, and a second kernel folds the segment sums.
-__global__ void k_msm_seg_counts(const uint32_t* __restrict__ hist, uint32_t* __restrict__ segcnt, size_t total, uint32_t seg) {
+__global__ void k_msm_seg_counts(const uint32_t* __restrict__ hist, uint32_t* __restrict__ segcnt, size_t total, uint32_t seg,
+                                 uint32_t* __restrict__ maxlen) {
     size_t id = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (id >= total) return;
-    uint32_t c = hist[id];
-    segcnt[id] = c ? (c + seg - 1) / seg : 1u;  // empty buckets keep one (empty) segment so they get zeroed
+    uint32_t c = id < total ? hist[id] : 0u;
+    if (id < total) segcnt[id] = c ? (c + seg - 1) / seg : 1u;  // empty buckets keep one (empty) segment so they get zeroed
+    // longest bucket: the number of halving rounds of the batched-affine path
+    uint32_t m = __reduce_max_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(maxlen, m);
 }
 
 // item descriptors: one per segment, found by binary search once (fully parallel) so the accumulation loop
@@ -225,8 +160,9 @@ template <class F, bool PREFETCH, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                          const uint4* __restrict__ items, uint32_t* __restrict__ queue,
                                                          const uint32_t* __restrict__ heavy, uint32_t* __restrict__ buckets,
-                                                         uint32_t* __restrict__ segsum) {
+                                                         uint32_t* __restrict__ segsum, const uint32_t* __restrict__ gate) {
     constexpr int W = FieldIO<F>::W;
+    if (gate && *gate == 0) return;  // the batched-affine path already produced the buckets
     const uint32_t nitems = queue[0], nheavy = queue[2];
     const unsigned lane = threadIdx.x & 31;
     XYZZ<F> acc = XYZZ<F>::infinity();
@@ -307,10 +243,10 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* __
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_fold_segments(const uint32_t* __restrict__ segoff, const uint32_t* __restrict__ segcnt,
                                                             const uint32_t* __restrict__ segsum, uint32_t* __restrict__ buckets,
-                                                            size_t total) {
+                                                            size_t total, const uint32_t* __restrict__ gate) {
     constexpr int W = FieldIO<F>::W;
     size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= total) return;
+    if (b >= total || (gate && *gate == 0)) return;
     uint32_t n = segcnt[b];
     if (n <= 1) return;
     size_t off = segoff[b];
@@ -410,13 +346,27 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
     }
     size_t max_items = total + (n * cfg.nwin) / seg + 1;
     if (max_items > ws.cap_items) return cudaErrorInvalidValue;
-    k_msm_seg_counts<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.hist, ws.segcnt, total, seg); CZK_LAUNCHED();
+    // queue words: 0 item count, 1 queue head, 2 heavy count, 3 "affine path gave up" flag, 4 longest bucket
+    if ((e = cudaMemsetAsync(ws.queue, 0, 32, st)) != cudaSuccess) return e;
+    k_msm_seg_counts<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.hist, ws.segcnt, total, seg, ws.queue + 4); CZK_LAUNCHED();
     k_exclusive_scan<<<1, 1024, 0, st>>>(ws.segcnt, ws.segoff, total); CZK_LAUNCHED();
-    if ((e = cudaMemsetAsync(ws.queue, 0, 16, st)) != cudaSuccess) return e;
     uint32_t heavy_len = (uint32_t)(2 * ((n * cfg.nwin) / total + 1) + 16);
     k_msm_build_items<<<(unsigned)((max_items + 255) / 256), 256, 0, st>>>(ws.offsets, ws.hist, ws.segoff, ws.segcnt, (uint4*)ws.items,
                                                                             ws.queue, ws.heavy, total, max_items, seg, heavy_len); CZK_LAUNCHED();
     if (ws.ev[0]) cudaEventRecord(ws.ev[0], st);
+    const uint32_t* gate = nullptr;
+    // worth it only when buckets are long (merged windows over a large base set): below ~2^18 terms the rounds' fixed
+    // latencies (one block-wide inversion each) cost more than the multiplications they save
+    if (ws.batched && n * cfg.nwin >= ((size_t)1 << 22) && n * cfg.nwin >= total * 64) {
+        // tree of batched affine additions (msm_batched.cu); needs the longest bucket to know the number of rounds
+        if ((e = cudaMemcpyAsync(ws.host_word, ws.queue + 4, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+        const uint32_t maxlen = *ws.host_word;
+        if ((e = msm_batched_accumulate(FieldIO<F>::W == 12 ? 1 : 2, bases, ws.sorted, ws.offsets, ws.hist, total, n * cfg.nwin, maxlen,
+                                        ws.bat_a, ws.bat_b, ws.bat_prefix, ws.buckets, ws.queue + 3, ws.sm_count, st)) != cudaSuccess)
+            return e;
+        gate = ws.queue + 3;
+    }
     {
         // resident grid: the queue feeds lanes, so launch what the machine holds (2 blocks of 128 per SM at this
         // register budget) and no more; small problems launch fewer blocks
@@ -426,12 +376,12 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
         size_t cap = (size_t)ws.sm_count * 2;
         unsigned blocks = (unsigned)(want < cap ? want : cap);
         k_msm_accumulate<F, (FieldIO<F>::W == 12), 2><<<blocks, 128, 0, st>>>(bases, ws.sorted, (const uint4*)ws.items, ws.queue, ws.heavy,
-                                                                               ws.buckets, ws.segsum);
+                                                                               ws.buckets, ws.segsum, gate);
         CZK_LAUNCHED();
     }
     if (ws.ev[1]) cudaEventRecord(ws.ev[1], st);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    k_msm_fold_segments<F><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(ws.segoff, ws.segcnt, ws.segsum, ws.buckets, total); CZK_LAUNCHED();
+    k_msm_fold_segments<F><<<(unsigned)((total + 127) / 128), 128, 0, st>>>(ws.segoff, ws.segcnt, ws.segsum, ws.buckets, total, gate); CZK_LAUNCHED();
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     unsigned nchunks = cfg.nb / cfg.chunk;
     size_t rthreads = (size_t)cfg.bwin * nchunks;
@@ -501,35 +451,50 @@ struct U256 {
 };
 constexpr int PROG_CHUNK = 64;
 template <class F>
+__device__ __forceinline__ XYZZ<F> scalar_mul_affine(const uint32_t* kb, const F& bx, const F& by) {
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    for (int bit = 252; bit >= 0; bit--) {
+        acc = XYZZ<F>::dbl(acc);
+        if ((kb[bit >> 5] >> (bit & 31)) & 1) acc.add_affine(bx, by);
+    }
+    return acc;
+}
+// out[i] = (k0 + i kstep + i^2 kquad) * base.  A thread computes its chunk's first point and first difference by
+// double-and-add, then runs the two finite differences: P_{i+1} = P_i + D_i, D_{i+1} = D_i + 2 kquad base.
+template <class F>
 __global__ void __launch_bounds__(128) k_gen_progression(uint32_t* __restrict__ out_xy, const uint32_t* __restrict__ base_xy,
-                                                          const uint32_t* __restrict__ step_xy, U256 k0, U256 kstep, size_t n) {
+                                                          const uint32_t* __restrict__ quad2_xy, U256 k0, U256 kstep, U256 kquad,
+                                                          size_t n) {
     constexpr int W = FieldIO<F>::W;
     size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     size_t lo = t * PROG_CHUNK;
     if (lo >= n) return;
-    // k = k0 + lo * kstep  (mod r), computed in Montgomery form then brought back
-    Fr k0m, ksm, lom = Fr::zero();
+    Fr k0m, ksm, kqm, lom = Fr::zero();
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         k0m.l[2 * i] = (uint32_t)k0.v[i];
         k0m.l[2 * i + 1] = (uint32_t)(k0.v[i] >> 32);
         ksm.l[2 * i] = (uint32_t)kstep.v[i];
         ksm.l[2 * i + 1] = (uint32_t)(kstep.v[i] >> 32);
+        kqm.l[2 * i] = (uint32_t)kquad.v[i];
+        kqm.l[2 * i + 1] = (uint32_t)(kquad.v[i] >> 32);
     }
     lom.l[0] = (uint32_t)lo;
     lom.l[1] = (uint32_t)((uint64_t)lo >> 32);
-    Fr k = Fr::add(Fr::to_mont(k0m), Fr::mul(Fr::to_mont(lom), Fr::to_mont(ksm)));
-    k = Fr::from_mont(k);
-    uint32_t kb[8];
+    k0m = Fr::to_mont(k0m);
+    ksm = Fr::to_mont(ksm);
+    kqm = Fr::to_mont(kqm);
+    lom = Fr::to_mont(lom);
+    // k = k0 + lo ks + lo^2 kq ;  dk = ks + (2 lo + 1) kq
+    Fr k = Fr::from_mont(Fr::add(k0m, Fr::mul(lom, Fr::add(ksm, Fr::mul(lom, kqm)))));
+    Fr dk = Fr::from_mont(Fr::add(ksm, Fr::mul(Fr::add(Fr::dbl(lom), Fr::one()), kqm)));
+    uint32_t kb[8], db[8];
 #pragma unroll
-    for (int i = 0; i < 8; i++) kb[i] = k.l[i];
+    for (int i = 0; i < 8; i++) kb[i] = k.l[i], db[i] = dk.l[i];
     F bx = FieldIO<F>::load(base_xy), by = FieldIO<F>::load(base_xy + W);
-    F sx = FieldIO<F>::load(step_xy), sy = FieldIO<F>::load(step_xy + W);
-    XYZZ<F> acc = XYZZ<F>::infinity();
-    for (int bit = 252; bit >= 0; bit--) {
-        acc = XYZZ<F>::dbl(acc);
-        if ((kb[bit >> 5] >> (bit & 31)) & 1) acc.add_affine(bx, by);
-    }
+    F qx = FieldIO<F>::load(quad2_xy), qy = FieldIO<F>::load(quad2_xy + W);
+    XYZZ<F> acc = scalar_mul_affine<F>(kb, bx, by);
+    XYZZ<F> dif = scalar_mul_affine<F>(db, bx, by);
     size_t hi = lo + PROG_CHUNK < n ? lo + PROG_CHUNK : n;
     for (size_t i = lo; i < hi; i++) {
         F ox, oy;
@@ -543,24 +508,27 @@ __global__ void __launch_bounds__(128) k_gen_progression(uint32_t* __restrict__ 
         }
         FieldIO<F>::store(out_xy + i * (2 * W), ox);
         FieldIO<F>::store(out_xy + i * (2 * W) + W, oy);
-        acc.add_affine(sx, sy);
+        acc.add(dif);
+        dif.add_affine(qx, qy);
     }
 }
 
-cudaError_t ec_gen_progression_dev(int curve, uint32_t* out_xy, const uint32_t* base_xy, const uint32_t* step_xy,
-                                   const uint64_t k0_canon[4], const uint64_t kstep_canon[4], size_t n, cudaStream_t st) {
-    U256 a, b;
+cudaError_t ec_gen_progression_dev(int curve, uint32_t* out_xy, const uint32_t* base_xy, const uint32_t* quad2_xy,
+                                   const uint64_t k0_canon[4], const uint64_t kstep_canon[4], const uint64_t kquad_canon[4],
+                                   size_t n, cudaStream_t st) {
+    U256 a, b, q;
     for (int i = 0; i < 4; i++) {
         a.v[i] = k0_canon[i];
         b.v[i] = kstep_canon[i];
+        q.v[i] = kquad_canon[i];
     }
     size_t threads = (n + PROG_CHUNK - 1) / PROG_CHUNK;
     unsigned blocks = (unsigned)((threads + 127) / 128);
     if (!blocks) return cudaSuccess;
     if (curve == 1) {
-        k_gen_progression<Fq><<<blocks, 128, 0, st>>>(out_xy, base_xy, step_xy, a, b, n);
+        k_gen_progression<Fq><<<blocks, 128, 0, st>>>(out_xy, base_xy, quad2_xy, a, b, q, n);
     } else {
-        k_gen_progression<Fq2><<<blocks, 128, 0, st>>>(out_xy, base_xy, step_xy, a, b, n);
+        k_gen_progression<Fq2><<<blocks, 128, 0, st>>>(out_xy, base_xy, quad2_xy, a, b, q, n);
     }
     CZK_LAUNCHED();
     return cudaGetLastError();

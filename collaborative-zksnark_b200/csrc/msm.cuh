@@ -104,6 +104,12 @@ struct MsmWorkspace {
     uint32_t* items = nullptr;     // cap_items x uint4 item descriptors
     uint32_t* queue = nullptr;     // {item count, queue head, heavy count}
     uint32_t* heavy = nullptr;     // cap_items item ids served first
+    // batched-affine accumulation (msm_batched.cu): ping-pong point arrays, prefix-product scratch
+    uint32_t *bat_a = nullptr, *bat_b = nullptr, *bat_prefix = nullptr;
+    size_t cap_bat_a = 0, cap_bat_b = 0, cap_bat_prefix = 0;  // bytes
+    uint32_t* host_word = nullptr;                             // pinned: the longest-bucket readback
+    bool batched = true;                                       // CZK_BATCHED=0 keeps the XYZZ walk
+    bool batched_forced = false;                               // set by czk_msm_set_batched
     int sm_count = 148;
     int seg_point_words = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // accumulate start/stop, whole MSM start/stop
@@ -120,13 +126,27 @@ cudaError_t msm_run(int curve, const uint32_t* bases, const uint8_t* inf, const 
 
 size_t msm_point_words(int curve);  // 4 coordinates
 
+// Batched-affine bucket accumulation (msm_batched.cu).  ends / hist: the counting sort's bucket ends and lengths;
+// entries: an upper bound on the sorted entries (n * windows); maxlen: the longest bucket.  Writes `buckets` (XYZZ)
+// unless an addition without an affine formula was met, in which case *flag becomes non-zero and the caller's XYZZ
+// kernel must run.  pa / pb / prefix: scratch of the sizes msm_batched_bytes reports.
+size_t msm_batched_bytes(int curve, size_t entries, size_t nb, size_t* pa, size_t* pb, size_t* pre);
+cudaError_t msm_batched_accumulate(int curve, const uint32_t* bases, const uint32_t* sorted, const uint32_t* ends,
+                                   const uint32_t* hist, size_t nb, size_t entries, uint32_t maxlen, uint32_t* pa, uint32_t* pb,
+                                   uint32_t* prefix, uint32_t* buckets, uint32_t* flag, int sm_count, cudaStream_t st);
+// out[i] = 1 / in[i] in Fq (Montgomery), 0 -> 0: the block inversion of the batched path, exposed for its parity test
+cudaError_t fq_inverse_batch(const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st);
+
 // table[w * n + i] = 2^(c w) * bases[i] as affine points, w < nwin (slab 0 is a copy of the input)
 cudaError_t msm_precompute_table(int curve, uint32_t* table, const uint32_t* bases, size_t n, unsigned c, unsigned nwin,
                                  cudaStream_t st);
 
-// test / synthetic-input helper: out[i] = (k0 + i * kstep) * base as affine points (x | y)
-// (step_xy = kstep * base, affine, device memory)
-cudaError_t ec_gen_progression_dev(int curve, uint32_t* out_xy, const uint32_t* base_xy, const uint32_t* step_xy,
-                                   const uint64_t k0_canon[4], const uint64_t kstep_canon[4], size_t n, cudaStream_t st);
+// synthetic-input helper: out[i] = (k0 + i kstep + i^2 kquad) * base as affine points (x | y); quad2_xy = the affine
+// point 2 kquad * base (device memory).  The quadratic term matters: with a plain arithmetic progression every
+// difference P_i - P_j = (i - j) kstep base repeats, so partial bucket sums coincide far more often than between the
+// independent-looking points of a real CRS.
+cudaError_t ec_gen_progression_dev(int curve, uint32_t* out_xy, const uint32_t* base_xy, const uint32_t* quad2_xy,
+                                   const uint64_t k0_canon[4], const uint64_t kstep_canon[4], const uint64_t kquad_canon[4],
+                                   size_t n, cudaStream_t st);
 
 }  // namespace czk

@@ -1,0 +1,446 @@
+// Bucket accumulation by batched affine additions (the fast path of step 4 in msm.cuh).
+//
+// The reference adds every point of a bucket into a Jacobian accumulator (variable_base.rs:66-78, madd-2007-bl,
+// 7M + 4S per point); the XYZZ kernel in msm.cu does the same walk at 8M + 2S.  Here a bucket is summed as a binary
+// tree of AFFINE additions instead: round r halves every bucket's run (pairs are added, an odd leftover is copied),
+// and all the additions of a round - tens of millions, all independent - share inversions through Montgomery's
+// trick, so one addition costs 6 field products (1 for the running product, 2 to peel its inverse back off, 3 for
+// lambda, lambda^2 and y3) instead of 10.  log2(longest bucket) rounds; the work halves every round.
+//
+// Layout: round r's points are an array in which bucket b owns the slots [S_r(b), S_r(b) + L_r(b)) with
+//     L_r(b) = ceil(L_0(b) / 2^r),   S_{r+1}(b) = floor(S_r(b) / 2) + b,   S_0 / L_0 = the counting sort's runs,
+// which never overlap (the + b pays for the rounding) and need no per-round scan: a thread finds its bucket with one
+// binary search over the closed form and then walks.  Round 0 reads the bases through the sorted (index | sign) list.
+//
+// One thread owns B consecutive output slots: it multiplies up the B differences x2 - x1 (prefix products to a
+// scratch array), the block multiplies the 128 thread products up a tree in shared memory, ONE thread inverts the
+// root (binary extended Euclid, the reference's own inversion algorithm, macros.rs:368-422), the inverses flow back
+// down the tree, and each thread peels its B inverses off backwards while it forms the sums.
+//
+// Affine addition has no formula for P + P or P + (-P) (x2 == x1).  Those cannot occur between distinct CRS points
+// and random partial sums, but they do occur in adversarial inputs (a repeated base, P and -P in one bucket): the
+// kernel then raises a flag, and the XYZZ kernel - which handles every case the reference does - recomputes the
+// buckets.  Both kernels are always enqueued; the one that is not needed returns at once (no host round trip).
+#include "msm.cuh"
+#include <cstdlib>
+
+#include "launch_count.hpp"
+#include "msm_io.cuh"
+
+namespace czk {
+
+struct BatGeom {
+    const uint32_t* ends;  // bucket end offsets in the sorted list (after the scatter)
+    const uint32_t* hist;  // bucket lengths L_0
+    uint32_t nb;           // buckets (all windows)
+    int r;                 // the round whose array is the INPUT
+};
+__device__ __forceinline__ uint32_t bat_start(const BatGeom& g, uint32_t b, int r) {
+    uint32_t s = g.ends[b] - g.hist[b];
+    for (int i = 0; i < r; i++) s = (s >> 1) + b;
+    return s;
+}
+__device__ __forceinline__ uint32_t bat_len(const BatGeom& g, uint32_t b, int r) {
+    return (uint32_t)(((uint64_t)g.hist[b] + ((1ull << r) - 1)) >> r);
+}
+
+// ------------------------------------------------------------------ inversion (one thread per block)
+// a^-1 for a != 0, Montgomery form in and out: the binary extended Euclidean algorithm of the reference
+// (algebra/ff/src/fields/macros.rs:368-422) on 32-bit limbs; b starts at R^2 so the result is already in Montgomery form.
+__device__ __noinline__ Fq fq_inverse_binary(const Fq& a) {
+    constexpr int N = 12;
+    uint32_t u[N], v[N], b[N], c[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+        u[i] = a.l[i];
+        v[i] = FqParams::mod(i);
+        b[i] = FqParams::r2(i);
+        c[i] = 0;
+    }
+    auto is_one = [](const uint32_t* x) {
+        uint32_t o = x[0] ^ 1u;
+#pragma unroll
+        for (int i = 1; i < N; i++) o |= x[i];
+        return o == 0;
+    };
+    auto halve = [](uint32_t* x, uint32_t* y) {  // x >>= 1 ; y = y / 2 mod p
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) x[i] = __funnelshift_r(x[i], x[i + 1], 1);
+        x[N - 1] >>= 1;
+        if (y[0] & 1u) {  // y + p < 2^378: no carry out of the top limb
+            y[0] = add_cc(y[0], FqParams::mod(0));
+#pragma unroll
+            for (int i = 1; i < N - 1; i++) y[i] = addc_cc(y[i], FqParams::mod(i));
+            y[N - 1] = addc(y[N - 1], FqParams::mod(N - 1));
+        }
+#pragma unroll
+        for (int i = 0; i < N - 1; i++) y[i] = __funnelshift_r(y[i], y[i + 1], 1);
+        y[N - 1] >>= 1;
+    };
+    auto sub_pair = [](uint32_t* x, const uint32_t* y, uint32_t* s, const uint32_t* t) {  // x -= y ; s = s - t mod p
+        x[0] = sub_cc(x[0], y[0]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) x[i] = subc_cc(x[i], y[i]);
+        x[N - 1] = subc(x[N - 1], y[N - 1]);
+        s[0] = sub_cc(s[0], t[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) s[i] = subc_cc(s[i], t[i]);
+        uint32_t borrow = subc(0, 0);
+        s[0] = add_cc(s[0], FqParams::mod(0) & borrow);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) s[i] = addc_cc(s[i], FqParams::mod(i) & borrow);
+        s[N - 1] = addc(s[N - 1], FqParams::mod(N - 1) & borrow);
+    };
+    auto less = [](const uint32_t* x, const uint32_t* y) {  // x < y
+        uint32_t t = sub_cc(x[0], y[0]);
+#pragma unroll
+        for (int i = 1; i < N; i++) t = subc_cc(x[i], y[i]);
+        (void)t;
+        return subc(0, 0) != 0;
+    };
+#pragma unroll 1
+    while (!is_one(u) && !is_one(v)) {
+#pragma unroll 1
+        while ((u[0] & 1u) == 0) halve(u, b);
+#pragma unroll 1
+        while ((v[0] & 1u) == 0) halve(v, c);
+        if (less(v, u)) sub_pair(u, v, b, c);
+        else sub_pair(v, u, c, b);
+    }
+    Fq r;
+    const bool first = is_one(u);
+#pragma unroll
+    for (int i = 0; i < N; i++) r.l[i] = first ? b[i] : c[i];
+    return r;
+}
+__device__ __forceinline__ Fq field_inverse(const Fq& a) { return fq_inverse_binary(a); }
+// 1 / (c0 + c1 u) = (c0 - c1 u) / (c0^2 + 5 c1^2)   (quadratic_extension.rs:308-324)
+__device__ __forceinline__ Fq2 field_inverse(const Fq2& a) {
+    Fq norm = Fq::sub(Fq::mul_ni(a.c0, a.c0), Fq2::mul_by_nonresidue(Fq::mul_ni(a.c1, a.c1)));
+    Fq ni = fq_inverse_binary(norm);
+    return Fq2{Fq::mul_ni(a.c0, ni), Fq::neg(Fq::mul_ni(a.c1, ni))};
+}
+// exported for the parity test of the inversion itself
+__global__ void k_fq_inverse(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fq a = FieldIO<Fq>::load(in + i * 12);
+    FieldIO<Fq>::store(out + i * 12, a.is_zero() ? a : fq_inverse_binary(a));
+}
+cudaError_t fq_inverse_batch(const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    k_fq_inverse<<<(unsigned)((n + 31) / 32), 32, 0, st>>>(in, out, n); CZK_LAUNCHED();
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------ shared-memory product tree (limb-major)
+template <class F>
+struct TreeIO;
+template <>
+struct TreeIO<Fq> {
+    __device__ __forceinline__ static Fq ld(const uint32_t* t, unsigned i) {
+        Fq r;
+#pragma unroll
+        for (int w = 0; w < 12; w++) r.l[w] = t[w * 256 + i];
+        return r;
+    }
+    __device__ __forceinline__ static void st(uint32_t* t, unsigned i, const Fq& v) {
+#pragma unroll
+        for (int w = 0; w < 12; w++) t[w * 256 + i] = v.l[w];
+    }
+};
+template <>
+struct TreeIO<Fq2> {
+    __device__ __forceinline__ static Fq2 ld(const uint32_t* t, unsigned i) {
+        return Fq2{TreeIO<Fq>::ld(t, i), TreeIO<Fq>::ld(t + 12 * 256, i)};
+    }
+    __device__ __forceinline__ static void st(uint32_t* t, unsigned i, const Fq2& v) {
+        TreeIO<Fq>::st(t, i, v.c0);
+        TreeIO<Fq>::st(t + 12 * 256, i, v.c1);
+    }
+};
+// products outside the two hot loops go through out-of-line bodies (code size)
+__device__ __forceinline__ Fq cold_mul(const Fq& a, const Fq& b) { return Fq::mul_ni(a, b); }
+__device__ __forceinline__ Fq2 cold_mul(const Fq2& a, const Fq2& b) { return Fq2::mul(a, b); }
+
+// ------------------------------------------------------------------ one round
+struct BatCursor {
+    uint32_t b, s_in, len_in, s_out, len_out, next_s_out;
+};
+__device__ __forceinline__ void bat_seek(const BatGeom& g, BatCursor& c, uint32_t b) {
+    c.b = b;
+    c.s_in = bat_start(g, b, g.r);
+    c.len_in = bat_len(g, b, g.r);
+    c.s_out = (c.s_in >> 1) + b;
+    c.len_out = (c.len_in + 1) >> 1;
+    c.next_s_out = b + 1 < g.nb ? (bat_start(g, b + 1, g.r) >> 1) + b + 1 : 0xffffffffu;
+}
+
+template <class F, bool FIRST>
+__device__ __forceinline__ void bat_load_x(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                           const uint32_t* __restrict__ in, uint32_t pos, F& x) {
+    constexpr int W = FieldIO<F>::W;
+    if (FIRST) {
+        uint32_t e = sorted[pos];
+        x = FieldIO<F>::load(bases + (size_t)(e & 0x7fffffffu) * (2 * W));
+    } else {
+        x = FieldIO<F>::load_rw(in + (size_t)pos * (2 * W));
+    }
+}
+// round 0: the point named by a sorted entry (index | sign << 31); later rounds: slot `pos` of the point array
+template <class F, bool FIRST>
+__device__ __forceinline__ void bat_load_xy(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ in, uint32_t pos,
+                                            uint32_t entry, F& x, F& y) {
+    constexpr int W = FieldIO<F>::W;
+    if (FIRST) {
+        const uint32_t* p = bases + (size_t)(entry & 0x7fffffffu) * (2 * W);
+        x = FieldIO<F>::load(p);
+        y = FieldIO<F>::load(p + W);
+        if (entry >> 31) y = F::neg(y);
+    } else {
+        const uint32_t* p = in + (size_t)pos * (2 * W);
+        x = FieldIO<F>::load_rw(p);
+        y = FieldIO<F>::load_rw(p + W);
+    }
+}
+
+constexpr int BAT_THREADS = 128;
+template <class F, bool FIRST, int MINB>
+__global__ void __launch_bounds__(BAT_THREADS, MINB)
+    k_bat_round(BatGeom g, const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ in,
+                uint32_t* __restrict__ out, uint32_t* __restrict__ prefix, uint32_t* __restrict__ flag, const int B) {
+    constexpr int W = FieldIO<F>::W;
+    __shared__ uint32_t tree[W * 256];
+    const unsigned tid = threadIdx.x;
+    // slots actually in use this round: block-uniform early exit before any barrier
+    const uint32_t used = (bat_start(g, g.nb - 1, g.r) >> 1) + (g.nb - 1) + ((bat_len(g, g.nb - 1, g.r) + 1) >> 1);
+    const size_t block_first = (size_t)blockIdx.x * BAT_THREADS * B;
+    if (block_first >= used) return;
+    const size_t o0 = block_first + (size_t)tid * B;
+    // prefix scratch: element j of thread tid of this block, coalesced across the block
+    uint32_t* const pre = prefix + ((size_t)blockIdx.x * B * BAT_THREADS + tid) * W;
+    constexpr size_t PRE_STRIDE = (size_t)BAT_THREADS * W;
+
+    BatCursor c;
+    {
+        // largest b with S_{r+1}(b) <= o0   (S_{r+1} is strictly increasing and S_{r+1}(0) = 0)
+        uint32_t lo = 0, hi = g.nb - 1;
+        const uint32_t target = o0 > 0xfffffffeull ? 0xfffffffeu : (uint32_t)o0;
+        while (lo < hi) {
+            uint32_t mid = lo + (hi - lo + 1) / 2;
+            uint32_t s = (bat_start(g, mid, g.r) >> 1) + mid;
+            if (s <= target) lo = mid;
+            else hi = mid - 1;
+        }
+        bat_seek(g, c, lo);
+    }
+    const F one = F::one();
+    // ---- phase 1: running product of the differences (the next pair's x coordinates are fetched while the current
+    // product is formed: the gathers of round 0 are random 48-byte reads of a multi-GB table)
+    F acc = one;
+    F nx1, nx2;
+    bool npair;
+    {
+        while (o0 >= c.next_s_out) bat_seek(g, c, c.b + 1);
+        const uint32_t k = (uint32_t)(o0 - c.s_out);
+        npair = k < c.len_out && 2 * k + 1 < c.len_in;
+        if (npair) {
+            bat_load_x<F, FIRST>(bases, sorted, in, c.s_in + 2 * k, nx1);
+            bat_load_x<F, FIRST>(bases, sorted, in, c.s_in + 2 * k + 1, nx2);
+        }
+    }
+#pragma unroll 1
+    for (int j = 0; j < B; j++) {
+        const bool pair = npair;
+        F x1 = nx1, x2 = nx2;
+        if (j + 1 < B) {
+            const size_t o = o0 + j + 1;
+            while (o >= c.next_s_out) bat_seek(g, c, c.b + 1);
+            const uint32_t k = (uint32_t)(o - c.s_out);
+            npair = k < c.len_out && 2 * k + 1 < c.len_in;
+            if (npair) {
+                bat_load_x<F, FIRST>(bases, sorted, in, c.s_in + 2 * k, nx1);
+                bat_load_x<F, FIRST>(bases, sorted, in, c.s_in + 2 * k + 1, nx2);
+            }
+        }
+        F d = one;
+        if (pair) {
+            d = F::sub(x2, x1);
+            if (d.is_zero()) {  // P + P or P + (-P): no affine formula; the XYZZ kernel will redo the buckets
+                atomicOr(flag, 1u);
+                d = one;
+            }
+        }
+        acc = j == 0 ? d : F::mul(acc, d);
+        FieldIO<F>::store(pre + (size_t)j * PRE_STRIDE, acc);
+    }
+    // ---- phase 2: one inversion for the block
+    TreeIO<F>::st(tree, 128 + tid, acc);
+    __syncthreads();
+#pragma unroll 1
+    for (unsigned width = 64; width >= 1; width >>= 1) {
+        if (tid < width) {
+            unsigned i = width + tid;
+            TreeIO<F>::st(tree, i, cold_mul(TreeIO<F>::ld(tree, 2 * i), TreeIO<F>::ld(tree, 2 * i + 1)));
+        }
+        __syncthreads();
+    }
+    if (tid == 0) TreeIO<F>::st(tree, 1, field_inverse(TreeIO<F>::ld(tree, 1)));
+    __syncthreads();
+#pragma unroll 1
+    for (unsigned width = 1; width <= 64; width <<= 1) {
+        if (tid < width) {
+            unsigned i = width + tid;
+            F inv_i = TreeIO<F>::ld(tree, i), l = TreeIO<F>::ld(tree, 2 * i), r = TreeIO<F>::ld(tree, 2 * i + 1);
+            TreeIO<F>::st(tree, 2 * i, cold_mul(inv_i, r));
+            TreeIO<F>::st(tree, 2 * i + 1, cold_mul(inv_i, l));
+        }
+        __syncthreads();
+    }
+    F inv = TreeIO<F>::ld(tree, 128 + tid);  // 1 / (this thread's product)
+    // ---- phase 3: peel the inverses off backwards and form the sums
+    // the cursor (and in round 0 the sorted entries) run one slot ahead of the arithmetic: when a slot's turn comes its
+    // gather addresses are already known, so only ONE memory latency is exposed per slot instead of two dependent ones
+    uint32_t n_pos = 0, n_e1 = 0, n_e2 = 0;
+    bool n_live = false, n_pair = false;
+    {
+        const size_t o = o0 + B - 1;
+        while (o < c.s_out) bat_seek(g, c, c.b - 1);
+        const uint32_t k = (uint32_t)(o - c.s_out);
+        n_live = k < c.len_out;
+        n_pair = n_live && 2 * k + 1 < c.len_in;
+        n_pos = c.s_in + 2 * k;
+        if (FIRST && n_live) n_e1 = sorted[n_pos];
+        if (FIRST && n_pair) n_e2 = sorted[n_pos + 1];
+    }
+#pragma unroll 1
+    for (int j = B - 1; j >= 0; j--) {
+        const size_t o = o0 + j;
+        const bool live = n_live, pair = n_pair;
+        const uint32_t pos = n_pos, e1 = n_e1, e2 = n_e2;
+        F x1, y1, x2, y2, d = one;
+        if (live) bat_load_xy<F, FIRST>(bases, in, pos, e1, x1, y1);
+        if (pair) bat_load_xy<F, FIRST>(bases, in, pos + 1, e2, x2, y2);
+        if (j > 0) {
+            const size_t on = o - 1;
+            while (on < c.s_out) bat_seek(g, c, c.b - 1);
+            const uint32_t k = (uint32_t)(on - c.s_out);
+            n_live = k < c.len_out;
+            n_pair = n_live && 2 * k + 1 < c.len_in;
+            n_pos = c.s_in + 2 * k;
+            if (FIRST && n_live) n_e1 = sorted[n_pos];
+            if (FIRST && n_pair) n_e2 = sorted[n_pos + 1];
+        }
+        // 1 / d_j = inv * prefix_{j-1}: independent of the points just requested, so it runs under their latency
+        F dinv = inv;
+        if (j > 0) dinv = F::mul(inv, FieldIO<F>::load_rw(pre + (size_t)(j - 1) * PRE_STRIDE));
+        if (pair) {
+            d = F::sub(x2, x1);
+            if (d.is_zero()) d = one;
+        }
+        if (j > 0) inv = F::mul(inv, d);
+        uint32_t* dst = out + o * (2 * W);
+        if (pair) {
+            F lam = F::mul(F::sub(y2, y1), dinv);
+            F x3 = F::sub(F::sub(F::sqr(lam), x1), x2);
+            F y3 = F::sub(F::mul(lam, F::sub(x1, x3)), y1);
+            FieldIO<F>::store(dst, x3);
+            FieldIO<F>::store(dst + W, y3);
+        } else if (live) {  // odd leftover: carried to the next round unchanged
+            FieldIO<F>::store(dst, x1);
+            FieldIO<F>::store(dst + W, y1);
+        }
+    }
+}
+
+// buckets[b] = sum of the (few) points left in bucket b after the halving rounds, as XYZZ for the reduction kernels.
+// The late rounds of the tree hold little work but each still costs a block-wide inversion; once every bucket is
+// down to BAT_WALK points or fewer, a plain mixed-addition walk (one thread per bucket, every special case of the
+// reference's add_assign_mixed handled by XYZZ::add_affine) finishes them in one launch.
+constexpr uint32_t BAT_WALK = 24;
+template <class F>
+__global__ void __launch_bounds__(128) k_bat_finish(BatGeom g, const uint32_t* __restrict__ in, uint32_t* __restrict__ buckets,
+                                                     const uint32_t* __restrict__ flag) {
+    constexpr int W = FieldIO<F>::W;
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= g.nb || *flag) return;
+    XYZZ<F> p = XYZZ<F>::infinity();
+    const uint32_t len = bat_len(g, b, g.r);
+    const uint32_t* src = in + (size_t)bat_start(g, b, g.r) * (2 * W);
+    for (uint32_t i = 0; i < len; i++, src += 2 * W) p.add_affine(FieldIO<F>::load_rw(src), FieldIO<F>::load_rw(src + W));
+    store_point<F>(buckets + (size_t)b * (4 * W), p);
+}
+
+// slots of the array produced by round r (an upper bound the host can compute): E / 2^(r+1) + 2 nb
+static size_t bat_bound(size_t entries, size_t nb, int r_out) { return (entries >> r_out) + 2 * nb + 2; }
+
+// slots per thread: 32 while a round has enough slots to fill the machine, fewer in the short late rounds so that
+// their serial per-thread chain (and with it the latency floor of a round) shrinks
+constexpr int BAT_B_MAX = 128, BAT_B_MIN = 4;
+static int bat_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+template <class F>
+struct BatTuning;
+template <>
+struct BatTuning<Fq> {
+    static constexpr int MINB = 3;
+};
+template <>
+struct BatTuning<Fq2> {
+    static constexpr int MINB = 2;
+};
+static int bat_pick_b(size_t slots, int sm_count, int minb) {
+    size_t want_blocks = (size_t)sm_count * minb * 2;
+    static const int bmax = bat_env("CZK_BAT_BMAX", 64);
+    int b = bmax < BAT_B_MIN ? BAT_B_MIN : (bmax > BAT_B_MAX ? BAT_B_MAX : bmax);
+    while (b > BAT_B_MIN && slots / ((size_t)BAT_THREADS * b) < want_blocks) b >>= 1;
+    return b;
+}
+
+size_t msm_batched_bytes(int curve, size_t entries, size_t nb, size_t* pa, size_t* pb, size_t* pre) {
+    const size_t pt = (curve == 1 ? 24 : 48) * 4, el = pt / 2;
+    *pa = bat_bound(entries, nb, 1) * pt;
+    *pb = bat_bound(entries, nb, 2) * pt;
+    size_t slots = bat_bound(entries, nb, 1), per_block = (size_t)BAT_THREADS * BAT_B_MAX;
+    *pre = ((slots + per_block - 1) / per_block) * per_block * el;
+    return *pa + *pb + *pre;
+}
+
+template <class F>
+static cudaError_t msm_batched_t(const uint32_t* bases, const uint32_t* sorted, const uint32_t* ends, const uint32_t* hist,
+                                 size_t nb, size_t entries, uint32_t maxlen, uint32_t* pa, uint32_t* pb, uint32_t* prefix,
+                                 uint32_t* buckets, uint32_t* flag, int sm_count, cudaStream_t st) {
+    constexpr int MINB = BatTuning<F>::MINB;
+    int rounds = 1;  // at least one: round 0 turns (index | sign) entries into points
+    while (rounds < 32 && (((uint64_t)maxlen + ((1ull << rounds) - 1)) >> rounds) > BAT_WALK) rounds++;
+    BatGeom g{ends, hist, (uint32_t)nb, 0};
+    uint32_t* bufs[2] = {pa, pb};
+    for (int r = 0; r < rounds; r++) {
+        g.r = r;
+        size_t slots = bat_bound(entries, nb, r + 1);
+        const int B = bat_pick_b(slots, sm_count, MINB);
+        const size_t per_block = (size_t)BAT_THREADS * B;
+        unsigned blocks = (unsigned)((slots + per_block - 1) / per_block);
+        uint32_t* dst = bufs[r & 1];
+        const uint32_t* src = r ? bufs[(r - 1) & 1] : nullptr;
+        if (r == 0) k_bat_round<F, true, MINB><<<blocks, BAT_THREADS, 0, st>>>(g, bases, sorted, nullptr, dst, prefix, flag, B);
+        else k_bat_round<F, false, MINB><<<blocks, BAT_THREADS, 0, st>>>(g, nullptr, nullptr, src, dst, prefix, flag, B);
+        CZK_LAUNCHED();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    g.r = rounds;
+    k_bat_finish<F><<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(g, bufs[(rounds - 1) & 1], buckets, flag); CZK_LAUNCHED();
+    return cudaGetLastError();
+}
+
+cudaError_t msm_batched_accumulate(int curve, const uint32_t* bases, const uint32_t* sorted, const uint32_t* ends,
+                                   const uint32_t* hist, size_t nb, size_t entries, uint32_t maxlen, uint32_t* pa, uint32_t* pb,
+                                   uint32_t* prefix, uint32_t* buckets, uint32_t* flag, int sm_count, cudaStream_t st) {
+    if (curve == 1) return msm_batched_t<Fq>(bases, sorted, ends, hist, nb, entries, maxlen, pa, pb, prefix, buckets, flag, sm_count, st);
+    return msm_batched_t<Fq2>(bases, sorted, ends, hist, nb, entries, maxlen, pa, pb, prefix, buckets, flag, sm_count, st);
+}
+
+}  // namespace czk

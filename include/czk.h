@@ -107,8 +107,8 @@ CZK_API int czk_bases_precompute(czk_ctx* ctx, czk_bases* b, unsigned c);
 /* MSM of bases[base_off .. base_off+n) by the device scalars sc[sc_off .. sc_off+n). */
 CZK_API int czk_msm_bases(czk_ctx* ctx, const czk_bases* b, size_t base_off, const czk_vec* sc, size_t sc_off,
                   int scalars_montgomery, size_t n, uint64_t* out_xyz);
-/* Synthetic bases for benchmarks: P_i = (k0 + i*kstep) * G (distinct points of the prime-order subgroup,
- * generated on the device), every `inf_every`-th entry flagged infinity (0 = none).                */
+/* Synthetic bases for benchmarks: P_i = (k0 + i*k1 + i^2*k2) * G with seeded 248-bit k0, k1, k2 (distinct points of
+ * the prime-order subgroup, generated on the device), every `inf_every`-th entry flagged infinity (0 = none). */
 CZK_API int czk_bases_synthetic(czk_ctx* ctx, int curve, uint64_t seed, size_t n, size_t inf_every, czk_bases** out);
 CZK_API int czk_bases_download(czk_ctx* ctx, const czk_bases* b, size_t off, size_t n, uint64_t* xy, uint8_t* inf);
 
@@ -169,6 +169,12 @@ CZK_API int czk_gsz_stats(const czk_ctx* ctx, uint64_t out[2]);
  * out = { bucket-accumulation kernel ms (sum), its launch count, terms processed (sum of n), whole-MSM device ms (sum),
  *         (point, window) pairs = upper bound on mixed additions (sum of n * windows) }. */
 CZK_API int czk_msm_stats(czk_ctx* ctx, int curve, double out[5], int reset);
+/* Bucket accumulation algorithm: 1 (default) = tree of batched affine additions with the XYZZ walk as the fallback for
+ * inputs that need P + P / P + (-P); 0 = the XYZZ walk only.  Same results; for A/B measurements and tests. */
+CZK_API int czk_msm_set_batched(czk_ctx* ctx, int enabled);
+/* out[i] = in[i]^-1 in Fq (n x 6 limbs, Montgomery; 0 -> 0) with the device's binary-Euclid inversion (the one inversion
+ * per block of the batched-affine path; algebra/ff/src/fields/macros.rs:368-422).  Host buffers. */
+CZK_API int czk_fq_inverse(czk_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n);
 /* Integer-pipe microbenchmarks; result = operations per second.  kind: 0 IMAD.WIDE.U32 chain,
  * 1 IMAD lo/hi pair, 2 Fr mul, 3 Fq mul, 4 G1 mixed add. */
 CZK_API int czk_microbench(czk_ctx* ctx, int kind, int blocks_per_sm, int threads, int iters, double* ops_per_s, double* ms);

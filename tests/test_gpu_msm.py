@@ -181,3 +181,39 @@ def test_msm_merged_large_and_linear(ctx, oracle, pymodel):
     b.precompute()
     merged = jac_to_affine_ints(oracle.G1, ctx.msm_bases(b, dsc))
     assert merged == plain == _oracle_msm(oracle.G1, xy, inf, sc, threads=oracle.cpu_threads())
+
+
+def test_fq_inverse_device_matches_oracle(ctx, oracle, pymodel):
+    """The one inversion per block of the batched-affine accumulation: binary extended Euclid on the device
+    (algebra/ff/src/fields/macros.rs:368-422) vs the oracle's restatement, edge values included."""
+    q = pymodel.Q_MOD
+    vals = [1, 2, q - 1, q - 2, (q + 1) // 2, 3, 1 << 376, (1 << 376) + 1] + [pow(7, 1000 + i, q) for i in range(120)]
+    a = oracle.fq_from_ints(vals)
+    assert (ctx.fq_inverse(a) == oracle.fq_inv(a)).all()
+    z = oracle.fq_from_ints([0])
+    assert (ctx.fq_inverse(z) == z).all()
+
+
+@pytest.mark.parametrize("g", ["g1", "g2"])
+def test_msm_batched_affine_equals_xyzz_walk(ctx, oracle, g):
+    """Both accumulation algorithms give the same group element (and both match the oracle): random scalars (the
+    affine tree runs to the end), a repeated base and cancelling pairs (it must raise its flag and hand over)."""
+    G = _groups(oracle)[g]
+    n = 3000
+    xy = make_points(G, n, seed=71)
+    sc = oracle.random_fr_mont(72, n)
+    exp = _oracle_msm(G, xy, None, sc)
+    try:
+        ctx.msm_set_batched(False)
+        walk = _msm(ctx, G, xy, None, sc)
+        ctx.msm_set_batched(True)
+        tree = _msm(ctx, G, xy, None, sc)
+        assert walk == exp and tree == exp
+        rep = np.repeat(xy[:1], 700, axis=0)
+        sc7 = oracle.random_fr_mont(73, 700)
+        assert _msm(ctx, G, rep, None, sc7) == _oracle_msm(G, rep, None, sc7)
+        # skewed bucket loads: few distinct scalars => some very long buckets next to empty ones (many rounds)
+        few = np.tile(oracle.random_fr_mont(74, 3), (1000, 1))
+        assert _msm(ctx, G, xy, None, few) == _oracle_msm(G, xy, None, few)
+    finally:
+        ctx.msm_set_batched(True)
