@@ -30,8 +30,13 @@ LOG_N = 20
 METRIC = "groth16_proof_ms_2^20_r1cs_bls12_377"
 # BASELINE.md section 1 (reference's published figures, GCP n2-standard-2, 1 physical core per party)
 PUBLISHED_MS = {1: 127400.0, 2: 320400.0, 3: 323300.0}
-# ncu --set full capture of the dominant kernel (profiles/r1_summary.md), DRAM bytes per launch averaged over a step
-NCU_TRAFFIC_BYTES_PER_LAUNCH = (6.215e9 + 3 * 3.110e9) / 4
+# The dominant "kernel" is the bucket accumulation of one G1 MSM: 5 launches of k_bat_round<Fq> (halving rounds of the
+# batched-affine tree) + k_bat_finish<Fq>; it is timed as one unit by CUDA events on the launching stream.
+ACC_KERNEL = "k_bat_round<Fq> x5 + k_bat_finish<Fq> (bucket accumulation of one G1 MSM)"
+# ncu --set full capture of those launches (profiles/r1_summary.md): dram__bytes_read + write summed over the rounds of
+# the 2^21-1 term MSM; the 2^20 term MSMs move half of it -> mean over the step's 4 G1 MSMs
+NCU_TRAFFIC_BYTES_2_21 = 22.8e9
+NCU_TRAFFIC_BYTES_PER_LAUNCH = NCU_TRAFFIC_BYTES_2_21 * (1 + 3 * 0.5) / 4
 
 
 def ref_msm_adds(n: int) -> int:
@@ -258,7 +263,9 @@ def main():
     alg_bytes = 128.0 * terms_per_launch  # 32 B scalar + 96 B affine base per G1 term
     achieved_gbs = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms else 0.0
     entries_per_launch = st1["entries"] / max(st1["launches"], 1)
-    wide_mads = entries_per_launch * 10 * 288  # N*W mixed additions x (8M + 2S) x 2*12^2 wide multiply-adds
+    # N*W bucket additions; the batched-affine tree spends 6 products per addition + ~0.5 for the block-wide inversion
+    # trees (the XYZZ walk: 8M + 2S = 10); one product = 276 wide multiply-adds (2*12^2 - 12: p0 = 1 rows need none)
+    wide_mads = entries_per_launch * 6.5 * 276
     int_rate = wide_mads / (acc_ms * 1e-3) if acc_ms else 0.0
     line = {
         "metric": METRIC, "value": ms_res, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": warmup,
@@ -271,15 +278,16 @@ def main():
         "clocks": clocks,
         "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": int((n_sq + 1) * 32), "d2h_bytes_per_step": int(2 * 48 * 8 + 6 + 5 * 16 * 192)},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "k_msm_accumulate<Fq>", "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
+        "roofline": {"kernel": ACC_KERNEL, "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved_gbs / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
-                     "traffic_source": "profiles/r1_summary.md: ncu --set full dram__bytes_read+write of k_msm_accumulate<Fq>, 6.21 GB (2^21-1 terms) "
-                                       "and 3.11 GB (2^20 terms) per launch -> mean over the step's 4 launches; the bucket method gathers each "
-                                       "base once per window (15 x 96 B) from the precomputed table, so traffic >> the 128 B/term algorithmic figure",
+                     "traffic_source": "profiles/r1_summary.md: ncu --set full dram__bytes_read+write summed over the rounds of one 2^21-1 term "
+                                       "accumulation, halved for the 2^20 term MSMs, mean over the step's 4 G1 MSMs; round 0 gathers each base "
+                                       "once per window from the precomputed table and every round streams points + prefix products, so "
+                                       "traffic >> the 128 B/term algorithmic figure",
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                     "note": "bucket accumulation is bound by the INT32 multiply pipe, not HBM: see roofline_int",
+                     "note": "bucket accumulation is bound by integer-instruction dispatch (IMAD.WIDE pipe), not HBM: see roofline_int",
                      "launch_ms": acc_ms, "launches_per_step": st1["launches"] / args.steps, "share_of_step": st1["accumulate_ms"] / args.steps / ms_res},
-        "roofline_int": {"kernel": "k_msm_accumulate<Fq>", "bound": "imad", "achieved": int_rate, "peak": imad_peak, "unit": "IMAD.WIDE/s",
+        "roofline_int": {"kernel": ACC_KERNEL, "bound": "imad", "achieved": int_rate, "peak": imad_peak, "unit": "IMAD.WIDE/s",
                          "frac": int_rate / imad_peak if imad_peak else None,
                          "peak_source": "czk_microbench kind 0 (independent mad.wide.u32 chains), measured at bench start"},
         "g1_msm_adds_per_s": ref_msm_adds(n_h) / (msm_h_ms * 1e-3),

@@ -316,7 +316,7 @@ struct Fq2 {
         return Fq::neg(Fq::add(x4, x));
     }
     // Karatsuba, 3 base-field products (quadratic_extension.rs:569-583)
-    CZK_HD_NOINLINE static Fq2 mul(const Fq2& a, const Fq2& b) {
+    CZK_HD static Fq2 mul_inl(const Fq2& a, const Fq2& b) {
         Fq v0 = Fq::mul(a.c0, b.c0);
         Fq v1 = Fq::mul(a.c1, b.c1);
         Fq t = Fq::mul(Fq::add(a.c0, a.c1), Fq::add(b.c0, b.c1));
@@ -324,7 +324,7 @@ struct Fq2 {
         return Fq2{Fq::add(v0, mul_by_nonresidue(v1)), t};
     }
     // (c0^2 - 5 c1^2, 2 c0 c1) with 2 base-field products (quadratic_extension.rs:257-306)
-    CZK_HD_NOINLINE static Fq2 sqr(const Fq2& a) {
+    CZK_HD static Fq2 sqr_inl(const Fq2& a) {
         Fq v0 = Fq::sub(a.c0, a.c1);
         Fq v3 = Fq::sub(a.c0, mul_by_nonresidue(a.c1));
         Fq v2 = Fq::mul(a.c0, a.c1);
@@ -333,6 +333,9 @@ struct Fq2 {
         Fq c0 = Fq::add(Fq::add(v0, v2), mul_by_nonresidue(v2));
         return Fq2{c0, c1};
     }
+    // out-of-line bodies: what the long point-addition formulas call (operands and result travel through local memory)
+    CZK_HD_NOINLINE static Fq2 mul(const Fq2& a, const Fq2& b) { return mul_inl(a, b); }
+    CZK_HD_NOINLINE static Fq2 sqr(const Fq2& a) { return sqr_inl(a); }
     CZK_HD_NOINLINE static Fq2 inv_fermat(const Fq2& a) {
         // 1/(c0 + c1 u) = (c0 - c1 u) / (c0^2 + 5 c1^2)
         Fq norm = Fq::sub(Fq::sqr(a.c0), mul_by_nonresidue(Fq::sqr(a.c1)));

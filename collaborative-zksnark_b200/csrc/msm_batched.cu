@@ -159,6 +159,16 @@ struct TreeIO<Fq2> {
         TreeIO<Fq>::st(t + 12 * 256, i, v.c1);
     }
 };
+// products inside the two hot loops: inlined (for Fq2 the out-of-line bodies cost a round trip through local memory per
+// operand; measured below)
+template <int INL>
+__device__ __forceinline__ Fq hot_mul(const Fq& a, const Fq& b) { return Fq::mul(a, b); }
+template <int INL>
+__device__ __forceinline__ Fq hot_sqr(const Fq& a) { return Fq::sqr(a); }
+template <int INL>
+__device__ __forceinline__ Fq2 hot_mul(const Fq2& a, const Fq2& b) { return INL ? Fq2::mul_inl(a, b) : Fq2::mul(a, b); }
+template <int INL>
+__device__ __forceinline__ Fq2 hot_sqr(const Fq2& a) { return INL ? Fq2::sqr_inl(a) : Fq2::sqr(a); }
 // products outside the two hot loops go through out-of-line bodies (code size)
 __device__ __forceinline__ Fq cold_mul(const Fq& a, const Fq& b) { return Fq::mul_ni(a, b); }
 __device__ __forceinline__ Fq2 cold_mul(const Fq2& a, const Fq2& b) { return Fq2::mul(a, b); }
@@ -205,6 +215,9 @@ __device__ __forceinline__ void bat_load_xy(const uint32_t* __restrict__ bases, 
 }
 
 constexpr int BAT_THREADS = 128;
+#ifndef BAT_INLINE_FQ2
+#define BAT_INLINE_FQ2 1
+#endif
 template <class F, bool FIRST, int MINB>
 __global__ void __launch_bounds__(BAT_THREADS, MINB)
     k_bat_round(BatGeom g, const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ in,
@@ -271,7 +284,7 @@ __global__ void __launch_bounds__(BAT_THREADS, MINB)
                 d = one;
             }
         }
-        acc = j == 0 ? d : F::mul(acc, d);
+        acc = j == 0 ? d : hot_mul<BAT_INLINE_FQ2>(acc, d);
         FieldIO<F>::store(pre + (size_t)j * PRE_STRIDE, acc);
     }
     // ---- phase 2: one inversion for the block
@@ -333,17 +346,17 @@ __global__ void __launch_bounds__(BAT_THREADS, MINB)
         }
         // 1 / d_j = inv * prefix_{j-1}: independent of the points just requested, so it runs under their latency
         F dinv = inv;
-        if (j > 0) dinv = F::mul(inv, FieldIO<F>::load_rw(pre + (size_t)(j - 1) * PRE_STRIDE));
+        if (j > 0) dinv = hot_mul<BAT_INLINE_FQ2>(inv, FieldIO<F>::load_rw(pre + (size_t)(j - 1) * PRE_STRIDE));
         if (pair) {
             d = F::sub(x2, x1);
             if (d.is_zero()) d = one;
         }
-        if (j > 0) inv = F::mul(inv, d);
+        if (j > 0) inv = hot_mul<BAT_INLINE_FQ2>(inv, d);
         uint32_t* dst = out + o * (2 * W);
         if (pair) {
-            F lam = F::mul(F::sub(y2, y1), dinv);
-            F x3 = F::sub(F::sub(F::sqr(lam), x1), x2);
-            F y3 = F::sub(F::mul(lam, F::sub(x1, x3)), y1);
+            F lam = hot_mul<BAT_INLINE_FQ2>(F::sub(y2, y1), dinv);
+            F x3 = F::sub(F::sub(hot_sqr<BAT_INLINE_FQ2>(lam), x1), x2);
+            F y3 = F::sub(hot_mul<BAT_INLINE_FQ2>(lam, F::sub(x1, x3)), y1);
             FieldIO<F>::store(dst, x3);
             FieldIO<F>::store(dst + W, y3);
         } else if (live) {  // odd leftover: carried to the next round unchanged

@@ -28,7 +28,7 @@ def main():
     ap.add_argument("--computation-size", type=int, default=10)
     sub = ap.add_subparsers(dest="mode", required=True)
     m = sub.add_parser("mpc")
-    m.add_argument("--alg", default="spdz", choices=["spdz", "hbc"])
+    m.add_argument("--alg", default="spdz", choices=["spdz", "hbc", "gsz"])
     m.add_argument("--hosts", default=None, help="ignored: parties are torchrun ranks")
     m.add_argument("--party", type=int, default=None, help="ignored: party id = RANK")
     sub.add_parser("local")
@@ -38,13 +38,17 @@ def main():
     ctx, rank, world = party.ctx, party.rank, party.world
     n_sq = args.computation_size
     if args.mode == "mpc":
-        scheme = czk_b200.SCHEME_SPDZ if args.alg == "spdz" else czk_b200.SCHEME_ADDITIVE
+        scheme = {"spdz": czk_b200.SCHEME_SPDZ, "hbc": czk_b200.SCHEME_ADDITIVE, "gsz": czk_b200.SCHEME_GSZ}[args.alg]
     else:
         assert world == 1, "local proving is a single process"
         scheme = czk_b200.SCHEME_PLAIN
     pk = czk_b200.ProvingKey.synthetic(ctx, n_sq, seed=1)  # generate_random_parameters stand-in (untimed)
-    chain = czk_b200.squaring_chain(np.array([3, 1, 4, 1], np.uint64), n_sq) if rank == 0 else None
-    mine = launch.king_share_scatter(chain, n_sq + 1, seed=2)  # "do the mpc (cheat)" (untimed)
+    if args.mode == "mpc" and args.alg == "gsz":
+        # king_share_batch under GSZ hands every party the value itself (gsz20/mod.rs:202-212)
+        mine = czk_b200.squaring_chain(np.array([3, 1, 4, 1], np.uint64), n_sq)
+    else:
+        chain = czk_b200.squaring_chain(np.array([3, 1, 4, 1], np.uint64), n_sq) if rank == 0 else None
+        mine = launch.king_share_scatter(chain, n_sq + 1, seed=2)  # "do the mpc (cheat)" (untimed)
     r = np.array([5, 9, 2, 6], np.uint64)
     s = np.array([5, 3, 5, 8], np.uint64)
     ctx.net_reset_stats()
