@@ -83,6 +83,13 @@ _SIGS = {
     "czk_net_reset_stats": (None, [C.c_void_p]),
     "czk_batch_open": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "czk_beaver_batch_mul": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_vec_prefix_products": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_vec_batch_inverse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_poly_div_linear": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, u64p, C.c_void_p, u64p]),
+    "czk_share_batch_inv": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_share_batch_div": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_share_partial_products": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_kzg_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, u64p, u64p, u64p]),
     "czk_gsz_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_size_t]),
     "czk_gsz_king_compute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t]),
     "czk_gsz_batch_mul": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
@@ -418,6 +425,41 @@ class Context:
         n = x_sh.n if n is None else n
         self._chk(self.lib.czk_beaver_batch_mul(self.h, scheme, x_sh.h, x_mac.h if x_mac is not None else None, y_sh.h,
                                                 y_mac.h if y_mac is not None else None, n))
+
+    # ------------------------------------------------------------------ Plonk / KZG10 leaves
+    def prefix_products(self, v: DeviceVec, n=None):
+        self._chk(self.lib.czk_vec_prefix_products(self.h, v.h, v.n if n is None else n))
+
+    def batch_inverse(self, v: DeviceVec, n=None):
+        self._chk(self.lib.czk_vec_batch_inverse(self.h, v.h, v.n if n is None else n))
+
+    def poly_div_linear(self, p: DeviceVec, z, n=None):
+        """(q, rem) = p / (X - z): q a DeviceVec of n - 1 coefficients, rem = p(z) as 4 limbs."""
+        n = p.n if n is None else n
+        q = DeviceVec(self, max(n - 1, 1))
+        rem = np.zeros(4, np.uint64)
+        self._chk(self.lib.czk_poly_div_linear(self.h, p.h, n, _np_u64(z).ctypes.data_as(u64p), q.h, rem.ctypes.data_as(u64p)))
+        return q, rem
+
+    def share_batch_inv(self, scheme, x_sh, x_mac=None, n=None):
+        self._chk(self.lib.czk_share_batch_inv(self.h, scheme, x_sh.h, x_mac.h if x_mac is not None else None, x_sh.n if n is None else n))
+
+    def share_batch_div(self, scheme, x_sh, x_mac, y_sh, y_mac, n=None):
+        self._chk(self.lib.czk_share_batch_div(self.h, scheme, x_sh.h, x_mac.h if x_mac is not None else None, y_sh.h,
+                                               y_mac.h if y_mac is not None else None, x_sh.n if n is None else n))
+
+    def share_partial_products(self, scheme, x_sh, x_mac=None, n=None):
+        self._chk(self.lib.czk_share_partial_products(self.h, scheme, x_sh.h, x_mac.h if x_mac is not None else None,
+                                                      x_sh.n if n is None else n))
+
+    def kzg_open(self, powers: "Bases", p: DeviceVec, z, n=None):
+        """KZG10::open without hiding on one coefficient vector: (w as Jacobian limbs, eval)."""
+        n = p.n if n is None else n
+        w = np.zeros(18, np.uint64)
+        ev = np.zeros(4, np.uint64)
+        self._chk(self.lib.czk_kzg_open(self.h, powers.h, p.h, n, _np_u64(z).ctypes.data_as(u64p), w.ctypes.data_as(u64p),
+                                        ev.ctypes.data_as(u64p)))
+        return w, ev
 
     # ------------------------------------------------------------------ GSZ20 shares (share/gsz20/mod.rs)
     def gsz_open(self, sh: DeviceVec, degree: int, n=None):

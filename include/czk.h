@@ -145,6 +145,26 @@ CZK_API int czk_batch_open(czk_ctx* ctx, int scheme, const czk_vec* sh, const cz
 CZK_API int czk_beaver_batch_mul(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac, const czk_vec* y_sh,
                          const czk_vec* y_mac, size_t n);
 
+/* ---- Plonk / KZG10 leaves: replaces the MpcField hooks mpc-algebra/src/wire/field.rs:395-455 ---------
+ * -> FieldShare::{batch_inv, batch_div, partial_products} (share/field.rs:135-182, stub inv pairs of wire/field.rs:62-77),
+ * DensePolynomial::divide_with_q_and_r by (X - z) (poly/src/polynomial/univariate/mod.rs:133-174; on shares applied to every
+ * share vector, share/add.rs:148-156) and KZG10::open without hiding (poly-commit/src/kzg10/mod.rs:196-262).
+ * KZG10::commit without hiding (kzg10/mod.rs:141-193) is czk_msm_bases over the resident powers_of_g.               */
+CZK_API int czk_vec_prefix_products(czk_ctx* ctx, czk_vec* v, size_t n);   /* v[i] *= v[i-1], plain values (scan) */
+CZK_API int czk_vec_batch_inverse(czk_ctx* ctx, czk_vec* v, size_t n);     /* v[i] = 1 / v[i]; a zero -> CZK_ERR_PROTOCOL */
+/* q_out (n - 1 coefficients, may be NULL) = p / (X - z), rem_out (host, may be NULL) = p(z). */
+CZK_API int czk_poly_div_linear(czk_ctx* ctx, const czk_vec* p, size_t n, const uint64_t z[4], czk_vec* q_out, uint64_t rem_out[4]);
+/* x <- shares of 1 / x.  schemes PLAIN, ADDITIVE, SPDZ (x_mac for SPDZ). */
+CZK_API int czk_share_batch_inv(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac, size_t n);
+/* x <- shares of x / y; y returns holding the shares of 1 / y (batch_mul(xs, batch_inv(ys))). */
+CZK_API int czk_share_batch_div(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac, czk_vec* y_sh, czk_vec* y_mac, size_t n);
+/* x[i] <- shares of x[0] * ... * x[i] (the masked prefix-product protocol). */
+CZK_API int czk_share_partial_products(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac, size_t n);
+/* KZG10 open on one coefficient vector (a plain polynomial, or one share component): eval_out = p(z),
+ * w_xyz = MSM(powers_of_g, coefficients of p / (X - z)) as an affine-normalised Jacobian triple like czk_msm_g1. */
+CZK_API int czk_kzg_open(czk_ctx* ctx, const czk_bases* powers, const czk_vec* p, size_t n, const uint64_t z[4],
+                         uint64_t w_xyz[18], uint64_t eval_out[4]);
+
 /* ---- GSZ20 honest-majority shares: replaces mpc-algebra/src/share/gsz20/mod.rs on the Groth16 path -------
  * n parties, t = (n-1)/2, party j holds p(w^j) over the mixed-radix share domain of size n (n = 2^a or 3*2^a;
  * :94-105).  A share vector is one czk_vec.  The reference's preprocessing stubs are kept (rand() = 1,

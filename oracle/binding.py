@@ -432,3 +432,49 @@ def gsz_open(shares_mont, degree):
     out = np.zeros(4, np.uint64)
     ok = lib().orc_gsz_open(C.c_int(shares_mont.shape[0]), _p(shares_mont), C.c_int(degree), _p(out))
     return out, ok
+
+
+# ------------------------------------------------------------------ Plonk / KZG10 share-level leaves
+SHARE_BATCH_INV, SHARE_BATCH_DIV, SHARE_PARTIAL_PRODUCTS, SHARE_BATCH_MUL = 0, 1, 2, 3
+
+
+def share_op(op, scheme, x_sh, x_mac=None, y_sh=None, y_mac=None, threads=1):
+    """x_sh: (n_parties, k, 4) Montgomery shares (x_mac likewise for SPDZ).  Returns (status, x_sh', x_mac')."""
+    x_sh = np.ascontiguousarray(x_sh, np.uint64).copy()
+    n, k = x_sh.shape[0], x_sh.shape[1]
+
+    def ptrs(a):
+        if a is None:
+            return None, None
+        a = np.ascontiguousarray(a, np.uint64).copy()
+        arr = (C.c_void_p * n)(*[a[p].ctypes.data for p in range(n)])
+        return a, arr
+
+    x_sh, xp = ptrs(x_sh)
+    x_mac, xmp = ptrs(x_mac)
+    y_sh, yp = ptrs(y_sh)
+    y_mac, ymp = ptrs(y_mac)
+    f = lib().orc_share_op
+    f.restype = C.c_int
+    st = f(C.c_int(op), C.c_int(scheme), C.c_int(n), C.c_size_t(k), xp, xmp, yp, ymp, C.c_int(threads))
+    return st, x_sh, x_mac
+
+
+def poly_div_linear(p_mont, z_mont):
+    p_mont = np.ascontiguousarray(p_mont, np.uint64).reshape(-1, 4)
+    n = p_mont.shape[0]
+    q = np.zeros((max(n - 1, 0), 4), np.uint64)
+    rem = np.zeros(4, np.uint64)
+    qbuf = q if n > 1 else np.zeros((1, 4), np.uint64)
+    lib().orc_poly_div_linear(_p(qbuf), _p(rem), _p(p_mont), C.c_size_t(n), _p(np.ascontiguousarray(z_mont, np.uint64)))
+    return q, rem
+
+
+def kzg_open(powers_xy, powers_inf, p_mont, z_mont, threads=1):
+    p_mont = np.ascontiguousarray(p_mont, np.uint64).reshape(-1, 4)
+    w = np.zeros(12, np.uint64)
+    winf = np.zeros(1, np.uint8)
+    ev = np.zeros(4, np.uint64)
+    lib().orc_kzg_open(_p(powers_xy), _p8(powers_inf), _p(p_mont), C.c_size_t(p_mont.shape[0]),
+                       _p(np.ascontiguousarray(z_mont, np.uint64)), _p(w), _p8(winf), _p(ev), C.c_int(threads))
+    return w, int(winf[0]), ev

@@ -673,3 +673,4 @@ EXPORT int orc_divide_by_vanishing_on_coset(uint64_t *data, unsigned log_d, int 
 }
 
 #include "czk_oracle_groth16.inc"
+#include "czk_oracle_plonk.inc"

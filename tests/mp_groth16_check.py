@@ -56,6 +56,25 @@ def main():
     xs = czk_b200.king_share_batch(x, world, seed=3)
     opened = ctx.batch_open(scheme, ctx.vec_from(xs[rank]), ctx.vec_from(xs[rank]) if scheme == czk_b200.SCHEME_SPDZ else None)
     assert (opened.numpy() == x).all()
+    # Plonk leaves on real shares across the ranks: batch_inv, batch_div, partial_products
+    spdz = scheme == czk_b200.SCHEME_SPDZ
+    k = 777
+    xv, yv = o.random_fr_mont(31, k), o.random_fr_mont(32, k)
+    xsh, ysh = czk_b200.king_share_batch(xv, world, seed=41), czk_b200.king_share_batch(yv, world, seed=42)
+    oscheme = o.SCHEME_SPDZ if spdz else o.SCHEME_ADDITIVE
+    for op, name in ((o.SHARE_BATCH_INV, "batch_inv"), (o.SHARE_PARTIAL_PRODUCTS, "partial_products"), (o.SHARE_BATCH_DIV, "batch_div")):
+        xs, xm = ctx.vec_from(xsh[rank]), (ctx.vec_from(xsh[rank]) if spdz else None)
+        ys, ym = ctx.vec_from(ysh[rank]), (ctx.vec_from(ysh[rank]) if spdz else None)
+        if op == o.SHARE_BATCH_INV:
+            ctx.share_batch_inv(scheme, xs, xm)
+        elif op == o.SHARE_PARTIAL_PRODUCTS:
+            ctx.share_partial_products(scheme, xs, xm)
+        else:
+            ctx.share_batch_div(scheme, xs, xm, ys, ym)
+        stt, exp_sh, exp_mac = o.share_op(op, oscheme, xsh, xsh if spdz else None, ysh, ysh if spdz else None)
+        assert stt == 1 and (xs.numpy() == exp_sh[rank]).all(), f"rank {rank}: {name} share differs"
+        if spdz:
+            assert (xm.numpy() == exp_mac[rank]).all(), f"rank {rank}: {name} MAC share differs"
     launch.barrier()
     print(f"[rank {rank}/{world}] groth16 {args.scheme} n={n_sq}: parity ok; net {st}", flush=True)
     party.close()
