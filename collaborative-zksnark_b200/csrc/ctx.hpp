@@ -92,6 +92,7 @@ struct GszTriple {
 struct GszState {
     int n = 0, t = 0;              // parties the tables below were built for, t = (n - 1) / 2
     uint32_t* winv_dev = nullptr;  // n Montgomery Fr: w^-k, w = get_root_of_unity(n)
+    std::vector<HFr> winv_host;    // the same table for the host-side group opens
     HFr n_inv;
     std::vector<GszTriple> queue;  // field triples awaiting hadamard_check
     uint64_t king_computes = 0, opens = 0;

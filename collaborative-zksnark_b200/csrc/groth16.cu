@@ -392,6 +392,7 @@ int czk_king_share_batch(const uint64_t* values, size_t k, int n_parties, uint64
 int gsz_coin(czk_ctx* ctx, HFr* out);
 int gsz_mult1(czk_ctx* ctx, const HFr& x, const HFr& y, HFr* out);
 int czk_gsz_open_scalar_internal(czk_ctx* ctx, const HFr& v, HFr* out);
+int czk_gsz_prepare_internal(czk_ctx* ctx);
 
 struct GszCheckOut {
     uint64_t group_x[4];
@@ -425,15 +426,8 @@ static int gsz_group_open(czk_ctx* ctx, const HPoint<HF>& share, int degree, HPo
     std::vector<uint64_t> send(2 * LIMBS + 1), recv((size_t)n * (2 * LIMBS + 1));
     send[2 * LIMBS] = (uint64_t)GS::to_affine_limbs(share, send.data());
     CZK_TRY(czk_net_allgather_host(ctx, send.data(), recv.data(), rec));
-    HFr w = HFr::one(), n_inv = ctx->gsz.n_inv;
-    // w^-1 of the share domain: recomputed from the table constants kept by the field side
-    std::vector<HFr> winv((size_t)n);
-    {
-        std::vector<uint64_t> tab((size_t)n * 4);
-        CUDA_TRY(ctx, cudaMemcpy(tab.data(), ctx->gsz.winv_dev, (size_t)n * 32, cudaMemcpyDeviceToHost));
-        for (int k = 0; k < n; k++) winv[k] = HFr::from_limbs(tab.data() + 4 * k);
-    }
-    (void)w;
+    const HFr n_inv = ctx->gsz.n_inv;
+    const std::vector<HFr>& winv = ctx->gsz.winv_host;  // w^-k of the share domain (built with the device table)
     for (int i = 0; i < n; i++) {
         HFr sc = HFr::zero();
         for (int j = 0; j < n; j++) sc = HFr::add(sc, winv[(size_t)((i * j) % n)]);
@@ -546,6 +540,7 @@ static int prove_tail_gsz(czk_ctx* ctx, const czk_pk* pk, const uint64_t r_sh[4]
     typedef GShare<HFq, 6> S1;
     typedef GShare<HFq2, 12> S2;
     double t0 = now_ms();
+    CZK_TRY(czk_gsz_prepare_internal(ctx));
     HG1 alpha_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1), HFq::from_limbs(pk->vk_g1 + 6));
     HG1 beta_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1 + 12), HFq::from_limbs(pk->vk_g1 + 18));
     HG1 delta_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1 + 24), HFq::from_limbs(pk->vk_g1 + 30));

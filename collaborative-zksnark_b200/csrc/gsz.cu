@@ -158,8 +158,10 @@ static int gsz_prepare(czk_ctx* ctx) {
     HFr wi = HFr::inv(w);
     std::vector<uint64_t> tab((size_t)n * 4);
     HFr p = HFr::one();
+    g.winv_host.assign((size_t)n, HFr::one());
     for (int k = 0; k < n; k++) {
         p.to_limbs(tab.data() + 4 * k);
+        g.winv_host[(size_t)k] = p;
         p = HFr::mul(p, wi);
     }
     if (g.winv_dev) cudaFree(g.winv_dev);
@@ -264,6 +266,7 @@ static int gsz_open_host(czk_ctx* ctx, const HFr& v, int degree, HFr* out) {
     CUDA_TRY(ctx, cudaMemcpyAsync(out->l, d + 8, 32, cudaMemcpyDeviceToHost, ctx->stream));
     return gsz_check_flag(ctx, "GSZ open");
 }
+int czk_gsz_prepare_internal(czk_ctx* ctx) { return gsz_prepare(ctx); }
 int czk_gsz_open_scalar_internal(czk_ctx* ctx, const HFr& v, HFr* out) {
     CZK_TRY(gsz_prepare(ctx));
     return gsz_open_host(ctx, v, ctx->gsz.t, out);

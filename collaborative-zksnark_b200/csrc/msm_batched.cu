@@ -398,7 +398,7 @@ template <class F>
 struct BatTuning;
 template <>
 struct BatTuning<Fq> {
-    static constexpr int MINB = 3;
+    static constexpr int MINB = 4;  // 128 registers: 4 blocks of 128 threads per SM (measured 5-8 % faster than 3 at 144)
 };
 template <>
 struct BatTuning<Fq2> {

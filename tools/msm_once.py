@@ -14,6 +14,8 @@ rng = np.random.Generator(np.random.PCG64(1))
 sc = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
 sc[:, 3] &= np.uint64((1 << 60) - 1)
 dsc = ctx.vec_from(sc)
+ctx.msm_bases(b, dsc, montgomery=False)  # warm-up: module loading, workspace allocation
+ctx.msm_stats(curve, reset=True)
 for _ in range(3):
     ctx.msm_bases(b, dsc, montgomery=False)
 st = ctx.msm_stats(curve)
