@@ -340,7 +340,8 @@ static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.hist, cap * 4));
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.offsets, cap * 4));
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.buckets, cap * pww * 4));
-        CUDA_TRY(ctx, cudaMalloc((void**)&ws.partial, cap * pww * 4));  // >= nwin * nchunks points
+        // >= nwin * nchunks points, and room for the bit-slice partial sums of the merged form (<= 24 * (2048 + 32) points)
+        CUDA_TRY(ctx, cudaMalloc((void**)&ws.partial, (cap > 65536 ? cap : 65536) * pww * 4));
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.winsum, 256 * (size_t)pww * 4));
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.segcnt, cap * 4));
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.segoff, cap * 4));
@@ -415,9 +416,17 @@ static void msm_host_tail(const uint32_t* winsums, const MsmConfig& cfg, uint64_
         return p;
     };
     P total = P::infinity();
-    for (int w = (int)cfg.bwin - 1; w >= 0; w--) {
-        for (unsigned k = 0; k < cfg.c; k++) total = P::dbl(total);
-        total.add(load((unsigned)w));
+    if (msm_uses_bit_sums(cfg)) {
+        // winsum = the bit-slice sums S_j of the single (merged) bucket set: sum_j 2^j S_j by Horner
+        for (int j = (int)cfg.c - 1; j >= 0; j--) {
+            total = P::dbl(total);
+            total.add(load((unsigned)j));
+        }
+    } else {
+        for (int w = (int)cfg.bwin - 1; w >= 0; w--) {
+            for (unsigned k = 0; k < cfg.c; k++) total = P::dbl(total);
+            total.add(load((unsigned)w));
+        }
     }
     HF ax, ay;
     if (total.to_affine(ax, ay)) {
@@ -440,7 +449,7 @@ static int msm_core(czk_ctx* ctx, int curve, const uint32_t* bases, const uint8_
     CZK_TRY(ws_reserve(ctx, curve, n, cfg));
     CUDA_TRY(ctx, msm_run(curve, bases, inf, scalars, mont != 0, n, cfg, ctx->ws, ctx->stream));
     size_t pw = msm_point_words(curve);
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, ctx->ws.winsum, cfg.bwin * pw * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, ctx->ws.winsum, msm_winsum_points(cfg) * pw * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     {
         float a = 0, m = 0;

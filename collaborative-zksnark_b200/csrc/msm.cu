@@ -285,6 +285,28 @@ __global__ void __launch_bounds__(128) k_msm_reduce_chunks(const uint32_t* __res
     store_point<F>(partial + t * (4 * W), T);
 }
 
+// ------------------------------------------------------------------ 5a'. bit-sliced subset sums (merged windows)
+// sum_b (b+1) B_b = sum_j 2^j S_j with S_j = the sum of the buckets whose weight b+1 has bit j set: c plain sums of
+// nb/2 points each (plus the single bucket of weight nb) - no per-thread scalar multiple, no running sum, every
+// thread adds exactly members/T points.  Thread t of slice j sums the members k = t, t+T, ... of slice j; the k-th
+// member is the weight v = (hi << (j+1)) | (1 << j) | lo with lo = k mod 2^j, hi = k div 2^j.
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_bit_sums(const uint32_t* __restrict__ buckets, uint32_t* __restrict__ partial,
+                                                       unsigned nb, unsigned T) {
+    constexpr int W = FieldIO<F>::W;
+    const unsigned j = blockIdx.y, t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T) return;
+    // members of slice j among the weights 1..nb: nb/2 for j < log2(nb), one (v = nb) for j = log2(nb)
+    const unsigned top = 31 - __clz(nb);
+    const unsigned members = j < top ? nb / 2 : 1;
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    for (unsigned k = t; k < members; k += T) {
+        unsigned v = j < top ? ((((k >> j) << 1) | 1u) << j) | (k & ((1u << j) - 1)) : nb;
+        acc.add(load_point<F>(buckets + (size_t)(v - 1) * (4 * W)));
+    }
+    store_point<F>(partial + ((size_t)j * T + t) * (4 * W), acc);
+}
+
 // ------------------------------------------------------------------ 5b. tree sums of the chunk results
 // block b sums in[b*count .. (b+1)*count) -> out[b]; run twice (chunks -> groups -> window) so that the first
 // level has windows*groups blocks instead of one block per window
@@ -385,15 +407,24 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     unsigned nchunks = cfg.nb / cfg.chunk;
     size_t rthreads = (size_t)cfg.bwin * nchunks;
-    k_msm_reduce_chunks<F><<<(unsigned)((rthreads + 127) / 128), 128, 0, st>>>(ws.buckets, ws.partial, cfg.nb, cfg.chunk, cfg.bwin); CZK_LAUNCHED();
+    unsigned nsums = cfg.bwin;  // points left in winsum for the host tail
+    if (msm_uses_bit_sums(cfg)) {
+        // merged windows: c bit-slice sums (the host tail recombines them with c - 1 doublings)
+        nsums = cfg.c;
+        nchunks = MSM_BITSUM_THREADS;
+        rthreads = (size_t)nsums * nchunks;
+        k_msm_bit_sums<F><<<dim3(nchunks / 128, nsums), 128, 0, st>>>(ws.buckets, ws.partial, cfg.nb, nchunks); CZK_LAUNCHED();
+    } else {
+        k_msm_reduce_chunks<F><<<(unsigned)((rthreads + 127) / 128), 128, 0, st>>>(ws.buckets, ws.partial, cfg.nb, cfg.chunk, cfg.bwin); CZK_LAUNCHED();
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (nchunks >= 2 * WINSUM_GROUPS) {
         // partial[nwin*nchunks] -> segsum scratch [nwin*GROUPS] -> winsum[nwin]   (segsum is free again after the fold)
         uint32_t* mid = ws.partial + rthreads * msm_point_words(FieldIO<F>::W == 12 ? 1 : 2);
-        k_msm_block_sum<F><<<cfg.bwin * WINSUM_GROUPS, WINSUM_THREADS, 0, st>>>(ws.partial, mid, nchunks / WINSUM_GROUPS); CZK_LAUNCHED();
-        k_msm_block_sum<F><<<cfg.bwin, WINSUM_THREADS, 0, st>>>(mid, ws.winsum, WINSUM_GROUPS); CZK_LAUNCHED();
+        k_msm_block_sum<F><<<nsums * WINSUM_GROUPS, WINSUM_THREADS, 0, st>>>(ws.partial, mid, nchunks / WINSUM_GROUPS); CZK_LAUNCHED();
+        k_msm_block_sum<F><<<nsums, WINSUM_THREADS, 0, st>>>(mid, ws.winsum, WINSUM_GROUPS); CZK_LAUNCHED();
     } else {
-        k_msm_block_sum<F><<<cfg.bwin, WINSUM_THREADS, 0, st>>>(ws.partial, ws.winsum, nchunks); CZK_LAUNCHED();
+        k_msm_block_sum<F><<<nsums, WINSUM_THREADS, 0, st>>>(ws.partial, ws.winsum, nchunks); CZK_LAUNCHED();
     }
     if (ws.ev[3]) cudaEventRecord(ws.ev[3], st);
     return cudaGetLastError();
