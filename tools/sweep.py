@@ -35,7 +35,8 @@ def main():
         n = (1 << log_n) - (1 if log_n == 21 else 0)
         b = ctx.bases_synthetic(1, 0x377 + log_n, n, 1024)
         sc = ctx.vec_from(rand_fr(rng, n))
-        ctx.msm_bases(b, sc)
+        for _ in range(3):  # warm-up: module loading, workspace growth, clocks
+            ctx.msm_bases(b, sc)
         reps = 5 if log_n <= 21 else 2
         ctx.msm_stats(1, reset=True)
         t = time.perf_counter()
