@@ -296,7 +296,7 @@ def main():
         "phases_ms": {k: avg(k) for k in phases[0]},
         "times_ms": {"resident": times_res, "e2e": times_e2e},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # the CPU leg runs on rank 0 of the 1-GPU run only
         line["cpu_baseline"] = cpu_reference_leg(1, 0, args.cpu_sample_log_n)
     print(json.dumps(line))
     party.close()

@@ -411,7 +411,7 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
     if (msm_uses_bit_sums(cfg)) {
         // merged windows: c bit-slice sums (the host tail recombines them with c - 1 doublings)
         nsums = cfg.c;
-        nchunks = MSM_BITSUM_THREADS;
+        nchunks = msm_bitsum_threads(cfg);
         rthreads = (size_t)nsums * nchunks;
         k_msm_bit_sums<F><<<dim3(nchunks / 128, nsums), 128, 0, st>>>(ws.buckets, ws.partial, cfg.nb, nchunks); CZK_LAUNCHED();
     } else {

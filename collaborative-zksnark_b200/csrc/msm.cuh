@@ -91,8 +91,9 @@ inline MsmConfig msm_choose_config(size_t n) {
 
 // Merged form with enough buckets: the bucket reduction is c bit-slice sums (k_msm_bit_sums) and winsum holds c points
 // S_0 .. S_{c-1} with sum_b (b+1) B_b = sum_j 2^j S_j; otherwise winsum holds one point per bucket window.
-constexpr unsigned MSM_BITSUM_THREADS = 2048;
+constexpr unsigned MSM_BITSUM_THREADS = 2048;  // threads per slice, at least; nb / 32 for larger bucket sets (16 adds each)
 inline bool msm_uses_bit_sums(const MsmConfig& cfg) { return cfg.merged && cfg.nb >= 2 * MSM_BITSUM_THREADS; }
+inline unsigned msm_bitsum_threads(const MsmConfig& cfg) { return cfg.nb / 32 > MSM_BITSUM_THREADS ? cfg.nb / 32 : MSM_BITSUM_THREADS; }
 inline unsigned msm_winsum_points(const MsmConfig& cfg) { return msm_uses_bit_sums(cfg) ? cfg.c : cfg.bwin; }
 
 struct MsmWorkspace {
