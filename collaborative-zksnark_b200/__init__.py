@@ -21,5 +21,8 @@ from .binding import (  # noqa: F401
     groth16_prove,
     squaring_chain,
     king_share_batch,
+    R1cs,
+    groth16_pk_upload_r1cs,
+    groth16_prove_r1cs,
 )
 from .build import build as build_library  # noqa: F401

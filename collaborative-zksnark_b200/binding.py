@@ -115,6 +115,10 @@ _OPTIONAL_SIGS = {
     "czk_squaring_chain": (C.c_int, [u64p, C.c_size_t, C.c_void_p]),
     "czk_king_share_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_void_p]),
     "czk_groth16_last_phases": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "czk_r1cs_upload": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "czk_r1cs_free": (None, [C.c_void_p, C.c_void_p]),
+    "czk_groth16_pk_upload_r1cs": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t] + [C.c_void_p] * 12 + [C.POINTER(C.c_void_p)]),
+    "czk_groth16_prove_r1cs": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, u64p, u64p, u64p, u8p, u64p, u8p]),
     "czk_groth16_gsz_last_checks": (C.c_int, [C.c_void_p, u64p, u64p, u64p, u8p, u64p]),
 }
 
@@ -619,3 +623,48 @@ def groth16_prove(ctx: Context, scheme: int, pk: ProvingKey, chain_sh, r_sh, s_s
         res.update(field_check=f3.reshape(3, 4), group_check_x=gx, group_check_yz=gyz.reshape(2, 12), group_check_inf=ginf,
                    king_computes=int(cnt[0]), opens=int(cnt[1]))
     return res
+
+
+class R1cs:
+    """Device-resident constraint matrices (czk_r1cs): cs = dict(ncons, ninst, nwit, a=(row_ptr u64, col u32, coeff (nnz,4)), b=..., c=...)."""
+
+    def __init__(self, ctx: Context, cs: dict):
+        self.ctx, self.dims = ctx, (cs["ncons"], cs["ninst"], cs["nwit"])
+        mats = [tuple(np.ascontiguousarray(x) for x in cs[m]) for m in ("a", "b", "c")]
+        rp = (C.c_void_p * 3)(*[m[0].astype(np.uint64, copy=False).ctypes.data for m in mats])
+        col = (C.c_void_p * 3)(*[m[1].astype(np.uint32, copy=False).ctypes.data for m in mats])
+        cf = (C.c_void_p * 3)(*[m[2].astype(np.uint64, copy=False).ctypes.data for m in mats])
+        self._keep = mats
+        h = C.c_void_p()
+        ctx._chk(ctx.lib.czk_r1cs_upload(ctx.h, cs["ncons"], cs["ninst"], cs["nwit"], rp, col, cf, C.byref(h)))
+        self.h = h
+
+    def free(self):
+        if self.h:
+            self.ctx.lib.czk_r1cs_free(self.ctx.h, self.h)
+            self.h = None
+
+
+def groth16_pk_upload_r1cs(ctx: Context, pk: dict) -> "ProvingKey":
+    def p(a):
+        return None if a is None else np.ascontiguousarray(a).ctypes.data
+
+    h = C.c_void_p()
+    ctx._chk(ctx.lib.czk_groth16_pk_upload_r1cs(ctx.h, pk["ncons"], pk["ninst"], pk["nwit"], p(pk["a_query"]), p(pk["a_inf"]),
+                                                p(pk["b_g1_query"]), p(pk["b1_inf"]), p(pk["b_g2_query"]), p(pk["b2_inf"]),
+                                                p(pk["h_query"]), p(pk["h_inf"]), p(pk["l_query"]), p(pk["l_inf"]), p(pk["vk_g1"]),
+                                                p(pk["vk_g2"]), C.byref(h)))
+    return ProvingKey(ctx, h, 0)
+
+
+def groth16_prove_r1cs(ctx: Context, scheme: int, pk: "ProvingKey", cs: R1cs, full_sh, r_sh, s_sh) -> dict:
+    """create_proof + reveal for any circuit: full_sh = this party's shares of [instance, witness]."""
+    full_sh = _np_u64(full_sh, 4)
+    assert full_sh.shape[0] == cs.dims[1] + cs.dims[2]
+    r_sh, s_sh = _np_u64(r_sh), _np_u64(s_sh)
+    proof_sh, proof = np.zeros(48, np.uint64), np.zeros(48, np.uint64)
+    sh_inf, inf = np.zeros(3, np.uint8), np.zeros(3, np.uint8)
+    ctx._chk(ctx.lib.czk_groth16_prove_r1cs(ctx.h, scheme, pk.h, cs.h, full_sh.ctypes.data, r_sh.ctypes.data_as(u64p),
+                                            s_sh.ctypes.data_as(u64p), proof_sh.ctypes.data_as(u64p), sh_inf.ctypes.data_as(u8p),
+                                            proof.ctypes.data_as(u64p), inf.ctypes.data_as(u8p)))
+    return dict(proof_sh=proof_sh, proof_sh_inf=sh_inf, proof=proof, proof_inf=inf)

@@ -9,9 +9,11 @@
 #include "../../include/czk_groth16.h"
 #include "ctx.hpp"
 #include "fr_ops.cuh"
+#include "launch_count.hpp"
 
 struct czk_pk {
-    size_t n_sq = 0, D = 0;
+    size_t n_sq = 0, D = 0;                       // squaring circuit: n_sq squarings; any circuit: n_sq = 0
+    size_t ncons = 0, ninst = 0, nwit = 0;       // constraints, instance variables (incl. the constant one), witness variables
     unsigned log_d = 0;
     czk_bases* q[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // a, b_g1, b_g2, h, l
     uint64_t vk_g1[36];
@@ -25,6 +27,80 @@ static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 static thread_local double g_phases[8];
+
+// A constraint system in CSR form on the device (the reference's ConstraintMatrices, relations/src/r1cs): for matrix
+// m in {A, B, C}, row i holds entries row_ptr[m][i] .. row_ptr[m][i+1] of (col[m], coeff[m]).
+struct czk_r1cs {
+    size_t ncons = 0, ninst = 0, nwit = 0;
+    uint64_t* row_ptr[3] = {nullptr, nullptr, nullptr};
+    uint32_t* col[3] = {nullptr, nullptr, nullptr};
+    uint32_t* coeff[3] = {nullptr, nullptr, nullptr};
+    size_t nnz[3] = {0, 0, 0};
+};
+
+namespace czk {
+// evaluate_constraint (mpc-snarks/src/groth/r1cs_to_qap.rs:12-41) for every row: out[i] = sum_k coeff[k] * assign[col[k]].
+// One thread per row (rows of real circuits hold a handful of terms); the assignment is a share vector, the
+// coefficients are public, so the map is linear in the shares.
+__global__ void k_r1cs_eval(uint32_t* __restrict__ out, const uint64_t* __restrict__ row_ptr, const uint32_t* __restrict__ col,
+                            const uint32_t* __restrict__ coeff, const uint32_t* __restrict__ assign, size_t ncons) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncons; i += (size_t)gridDim.x * blockDim.x) {
+        Fr acc = Fr::zero();
+        for (uint64_t k = row_ptr[i]; k < row_ptr[i + 1]; k++) {
+            const uint4* cq = reinterpret_cast<const uint4*>(coeff) + 2 * k;
+            const uint4* vq = reinterpret_cast<const uint4*>(assign) + 2 * (size_t)col[k];
+            uint4 c0 = cq[0], c1 = cq[1], v0 = vq[0], v1 = vq[1];
+            Fr c, v;
+            c.l[0] = c0.x; c.l[1] = c0.y; c.l[2] = c0.z; c.l[3] = c0.w; c.l[4] = c1.x; c.l[5] = c1.y; c.l[6] = c1.z; c.l[7] = c1.w;
+            v.l[0] = v0.x; v.l[1] = v0.y; v.l[2] = v0.z; v.l[3] = v0.w; v.l[4] = v1.x; v.l[5] = v1.y; v.l[6] = v1.z; v.l[7] = v1.w;
+            acc = Fr::add(acc, Fr::mul(v, c));
+        }
+        uint4* o = reinterpret_cast<uint4*>(out) + 2 * i;
+        o[0] = make_uint4(acc.l[0], acc.l[1], acc.l[2], acc.l[3]);
+        o[1] = make_uint4(acc.l[4], acc.l[5], acc.l[6], acc.l[7]);
+    }
+}
+}  // namespace czk
+
+int czk_r1cs_upload(czk_ctx* ctx, size_t ncons, size_t ninst, size_t nwit, const uint64_t* const row_ptr[3],
+                    const uint32_t* const col[3], const uint64_t* const coeff[3], czk_r1cs** out) {
+    if (!ctx || !out || !row_ptr || !col || !coeff || !ncons || !ninst) return fail(ctx, CZK_ERR_ARG, "czk_r1cs_upload: argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    czk_r1cs* r = new czk_r1cs();
+    r->ncons = ncons;
+    r->ninst = ninst;
+    r->nwit = nwit;
+    for (int m = 0; m < 3; m++) {
+        if (!row_ptr[m] || row_ptr[m][0] != 0) return fail(ctx, CZK_ERR_ARG, "czk_r1cs_upload: row_ptr");
+        size_t nnz = (size_t)row_ptr[m][ncons];
+        for (size_t i = 0; i < ncons; i++)
+            if (row_ptr[m][i] > row_ptr[m][i + 1]) return fail(ctx, CZK_ERR_ARG, "czk_r1cs_upload: row_ptr not monotone");
+        for (size_t k = 0; k < nnz; k++)
+            if (col[m][k] >= ninst + nwit) return fail(ctx, CZK_ERR_ARG, "czk_r1cs_upload: variable index out of range");
+        r->nnz[m] = nnz;
+        CUDA_TRY(ctx, cudaMalloc((void**)&r->row_ptr[m], (ncons + 1) * 8));
+        CUDA_TRY(ctx, cudaMalloc((void**)&r->col[m], (nnz ? nnz : 1) * 4));
+        CUDA_TRY(ctx, cudaMalloc((void**)&r->coeff[m], (nnz ? nnz : 1) * 32));
+        CUDA_TRY(ctx, cudaMemcpyAsync(r->row_ptr[m], row_ptr[m], (ncons + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (nnz) {
+            CUDA_TRY(ctx, cudaMemcpyAsync(r->col[m], col[m], nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(r->coeff[m], coeff[m], nnz * 32, cudaMemcpyHostToDevice, ctx->stream));
+        }
+    }
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    *out = r;
+    return CZK_OK;
+}
+void czk_r1cs_free(czk_ctx* ctx, czk_r1cs* r) {
+    if (!r) return;
+    if (ctx) cudaSetDevice(ctx->device);
+    for (int m = 0; m < 3; m++) {
+        cudaFree(r->row_ptr[m]);
+        cudaFree(r->col[m]);
+        cudaFree(r->coeff[m]);
+    }
+    delete r;
+}
 
 static size_t domain_size_for(size_t n_sq, unsigned* log_d) {
     size_t need = n_sq + 2, d = 1;  // num_constraints + num_instance_variables (r1cs_to_qap.rs:63-64)
@@ -60,6 +136,9 @@ int czk_groth16_pk_upload(czk_ctx* ctx, size_t n_sq, const uint64_t* a_query, co
         return fail(ctx, CZK_ERR_ARG, "czk_groth16_pk_upload: null argument");
     czk_pk* pk = new czk_pk();
     pk->n_sq = n_sq;
+    pk->ncons = n_sq;
+    pk->ninst = 2;
+    pk->nwit = n_sq;
     pk->D = domain_size_for(n_sq, &pk->log_d);
     CZK_TRY(czk_bases_upload(ctx, 1, a_query, a_inf, n_sq + 2, &pk->q[0]));
     CZK_TRY(czk_bases_upload(ctx, 1, b_g1_query, b1_inf, n_sq + 2, &pk->q[1]));
@@ -73,10 +152,41 @@ int czk_groth16_pk_upload(czk_ctx* ctx, size_t n_sq, const uint64_t* a_query, co
     return CZK_OK;
 }
 
+int czk_groth16_pk_upload_r1cs(czk_ctx* ctx, size_t ncons, size_t ninst, size_t nwit, const uint64_t* a_query, const uint8_t* a_inf,
+                               const uint64_t* b_g1_query, const uint8_t* b1_inf, const uint64_t* b_g2_query, const uint8_t* b2_inf,
+                               const uint64_t* h_query, const uint8_t* h_inf, const uint64_t* l_query, const uint8_t* l_inf,
+                               const uint64_t vk_g1[36], const uint64_t vk_g2[72], czk_pk** out) {
+    if (!ctx || !out || !ncons || !ninst || !a_query || !b_g1_query || !b_g2_query || !h_query || (nwit && !l_query) || !vk_g1 || !vk_g2)
+        return fail(ctx, CZK_ERR_ARG, "czk_groth16_pk_upload_r1cs: null argument");
+    czk_pk* pk = new czk_pk();
+    pk->n_sq = 0;
+    pk->ncons = ncons;
+    pk->ninst = ninst;
+    pk->nwit = nwit;
+    size_t need = ncons + ninst;  // r1cs_to_qap.rs:63-64
+    pk->D = 1;
+    pk->log_d = 0;
+    while (pk->D < need) pk->D <<= 1, pk->log_d++;
+    const size_t nvar = ninst + nwit;
+    CZK_TRY(czk_bases_upload(ctx, 1, a_query, a_inf, nvar, &pk->q[0]));
+    CZK_TRY(czk_bases_upload(ctx, 1, b_g1_query, b1_inf, nvar, &pk->q[1]));
+    CZK_TRY(czk_bases_upload(ctx, 2, b_g2_query, b2_inf, nvar, &pk->q[2]));
+    CZK_TRY(czk_bases_upload(ctx, 1, h_query, h_inf, pk->D - 1, &pk->q[3]));
+    CZK_TRY(czk_bases_upload(ctx, 1, l_query, l_inf, nwit, &pk->q[4]));
+    std::memcpy(pk->vk_g1, vk_g1, sizeof pk->vk_g1);
+    std::memcpy(pk->vk_g2, vk_g2, sizeof pk->vk_g2);
+    CZK_TRY(pk_finish(ctx, pk));
+    *out = pk;
+    return CZK_OK;
+}
+
 int czk_groth16_pk_synthetic(czk_ctx* ctx, size_t n_sq, uint64_t seed, czk_pk** out) {
     if (!ctx || !out || !n_sq) return fail(ctx, CZK_ERR_ARG, "czk_groth16_pk_synthetic: argument");
     czk_pk* pk = new czk_pk();
     pk->n_sq = n_sq;
+    pk->ncons = n_sq;
+    pk->ninst = 2;
+    pk->nwit = n_sq;
     pk->D = domain_size_for(n_sq, &pk->log_d);
     // Groth16 queries hold the point at infinity for variables absent from a matrix: flag every 1024th entry
     CZK_TRY(czk_bases_synthetic(ctx, 1, seed * 8 + 1, n_sq + 2, 1024, &pk->q[0]));
@@ -121,23 +231,52 @@ struct ShareVecs {
     czk_vec *am = nullptr, *bm = nullptr, *cm = nullptr;    // SPDZ MAC component
     czk_vec* chain = nullptr;                               // n_sq + 1 uploaded shares
     czk_vec* assign = nullptr;                              // [out, w_0 .. w_{n-1}]
+    czk_vec* full = nullptr;                                // any circuit: [instance, witness] shares
 };
 static void free_share_vecs(czk_ctx* ctx, ShareVecs& v) {
-    for (czk_vec* p : {v.a, v.b, v.c, v.am, v.bm, v.cm, v.chain, v.assign}) czk_vec_free(ctx, p);
+    for (czk_vec* p : {v.a, v.b, v.c, v.am, v.bm, v.cm, v.chain, v.assign, v.full}) czk_vec_free(ctx, p);
     v = ShareVecs();
 }
 
 // r1cs_to_qap.rs:66-110 on this party's shares.  On return v.a (and v.am) hold h; v.chain / v.assign are filled.
+static int witness_map_transforms(czk_ctx* ctx, int scheme, unsigned log_d, ShareVecs& v);
+// cs != nullptr: any circuit, full_sh = this party's shares of [instance, witness] (host); else the squaring chain.
 static int witness_map_dev(czk_ctx* ctx, int scheme, size_t n_sq, unsigned log_d, const uint64_t* chain_sh,
-                           const czk_vec* chain_dev, ShareVecs& v) {
+                           const czk_vec* chain_dev, ShareVecs& v, const czk_r1cs* cs = nullptr, const uint64_t* full_sh = nullptr) {
     const size_t D = (size_t)1 << log_d;
     const bool spdz = scheme == CZK_SCHEME_SPDZ;
     double t0 = now_ms();
-    CZK_TRY(czk_vec_alloc(ctx, n_sq + 1, &v.chain));
-    CZK_TRY(czk_vec_alloc(ctx, n_sq + 1, &v.assign));
     CZK_TRY(czk_vec_alloc(ctx, D, &v.a));
     CZK_TRY(czk_vec_alloc(ctx, D, &v.b));
     CZK_TRY(czk_vec_alloc(ctx, D, &v.c));
+    if (cs) {
+        const size_t nvar = cs->ninst + cs->nwit;
+        CZK_TRY(czk_vec_alloc(ctx, nvar, &v.full));
+        CUDA_TRY(ctx, cudaMemcpyAsync(czk_vec_device_ptr(v.full), full_sh, nvar * 32, cudaMemcpyHostToDevice, ctx->stream));
+        // a[i] = <A_i, z>, b[i] = <B_i, z>, c[i] = <C_i, z>;  a[ncons + i] = z[i] for the instance variables
+        czk_vec* dst[3] = {v.a, v.b, v.c};
+        size_t blocks = (cs->ncons + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        for (int m = 0; m < 3; m++) {
+            czk::k_r1cs_eval<<<(unsigned)blocks, 256, 0, ctx->stream>>>((uint32_t*)dst[m]->d, cs->row_ptr[m], cs->col[m], cs->coeff[m],
+                                                                       (const uint32_t*)v.full->d, cs->ncons);
+            CZK_LAUNCHED();
+        }
+        CUDA_TRY(ctx, cudaGetLastError());
+        CZK_TRY(czk_vec_copy(ctx, v.a, cs->ncons, v.full, 0, cs->ninst));
+        if (spdz) {
+            CZK_TRY(czk_vec_alloc(ctx, D, &v.am));
+            CZK_TRY(czk_vec_alloc(ctx, D, &v.bm));
+            CZK_TRY(czk_vec_alloc(ctx, D, &v.cm));
+            CZK_TRY(czk_vec_copy(ctx, v.am, 0, v.a, 0, D));
+            CZK_TRY(czk_vec_copy(ctx, v.bm, 0, v.b, 0, D));
+            CZK_TRY(czk_vec_copy(ctx, v.cm, 0, v.c, 0, D));
+        }
+        g_phases[0] = now_ms() - t0;
+        return witness_map_transforms(ctx, scheme, log_d, v);
+    }
+    CZK_TRY(czk_vec_alloc(ctx, n_sq + 1, &v.chain));
+    CZK_TRY(czk_vec_alloc(ctx, n_sq + 1, &v.assign));
     if (chain_dev) CZK_TRY(czk_vec_copy(ctx, v.chain, 0, chain_dev, 0, n_sq + 1));
     else CUDA_TRY(ctx, cudaMemcpyAsync(czk_vec_device_ptr(v.chain), chain_sh, (n_sq + 1) * 32, cudaMemcpyHostToDevice, ctx->stream));
     // full_assignment = [one, out] ++ witness;  assignment (prover.rs:118) = [out] ++ witness
@@ -163,7 +302,13 @@ static int witness_map_dev(czk_ctx* ctx, int scheme, size_t n_sq, unsigned log_d
         CZK_TRY(czk_vec_copy(ctx, v.cm, 0, v.c, 0, D));
     }
     g_phases[0] = now_ms() - t0;
-    t0 = now_ms();
+    return witness_map_transforms(ctx, scheme, log_d, v);
+}
+
+static int witness_map_transforms(czk_ctx* ctx, int scheme, unsigned log_d, ShareVecs& v) {
+    const size_t D = (size_t)1 << log_d;
+    const bool spdz = scheme == CZK_SCHEME_SPDZ;
+    double t0 = now_ms();
     czk_vec* comps[2][3] = {{v.a, v.b, v.c}, {v.am, v.bm, v.cm}};
     for (int k = 0; k < (spdz ? 2 : 1); k++) {
         for (int j = 0; j < 2; j++) {  // a, b
@@ -333,7 +478,7 @@ static void shift_pub(const czk_ctx* ctx, int scheme, GShare<HF, LIMBS>& s, cons
 
 static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t* chain_sh, const czk_vec* chain_dev,
                       const uint64_t r_sh[4], const uint64_t s_sh[4], uint64_t proof_sh[48], uint8_t proof_sh_inf[3],
-                      uint64_t proof[48], uint8_t proof_inf[3]);
+                      uint64_t proof[48], uint8_t proof_inf[3], const czk_r1cs* cs = nullptr, const uint64_t* full_sh = nullptr);
 
 int czk_groth16_prove(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t* chain_sh, const uint64_t r_sh[4],
                       const uint64_t s_sh[4], uint64_t proof_sh[48], uint8_t proof_sh_inf[3], uint64_t proof[48],
@@ -346,6 +491,13 @@ int czk_groth16_prove_vec(czk_ctx* ctx, int scheme, const czk_pk* pk, const czk_
                           uint8_t proof_inf[3]) {
     if (!chain_dev || !pk || chain_dev->n < pk->n_sq + 1) return fail(ctx, CZK_ERR_ARG, "czk_groth16_prove_vec: chain vector");
     return prove_impl(ctx, scheme, pk, nullptr, chain_dev, r_sh, s_sh, proof_sh, proof_sh_inf, proof, proof_inf);
+}
+
+int czk_groth16_prove_r1cs(czk_ctx* ctx, int scheme, const czk_pk* pk, const czk_r1cs* cs, const uint64_t* full_sh,
+                           const uint64_t r_sh[4], const uint64_t s_sh[4], uint64_t proof_sh[48], uint8_t proof_sh_inf[3],
+                           uint64_t proof[48], uint8_t proof_inf[3]) {
+    if (!cs || !full_sh) return fail(ctx, CZK_ERR_ARG, "czk_groth16_prove_r1cs: null argument");
+    return prove_impl(ctx, scheme, pk, nullptr, nullptr, r_sh, s_sh, proof_sh, proof_sh_inf, proof, proof_inf, cs, full_sh);
 }
 
 int czk_squaring_chain(const uint64_t start[4], size_t n_sq, uint64_t* out) {
@@ -619,7 +771,7 @@ int czk_groth16_gsz_last_checks(const czk_ctx* ctx, uint64_t field_xyz[12], uint
 
 static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t* chain_sh, const czk_vec* chain_dev,
                       const uint64_t r_sh[4], const uint64_t s_sh[4], uint64_t proof_sh[48], uint8_t proof_sh_inf[3],
-                      uint64_t proof[48], uint8_t proof_inf[3]) {
+                      uint64_t proof[48], uint8_t proof_inf[3], const czk_r1cs* cs, const uint64_t* full_sh) {
     if (!ctx || !pk || !r_sh || !s_sh || !proof_sh || !proof_sh_inf || !proof || !proof_inf)
         return fail(ctx, CZK_ERR_ARG, "czk_groth16_prove: null argument");
     if (scheme == CZK_SCHEME_PLAIN && ctx->nranks != 1) return fail(ctx, CZK_ERR_ARG, "plain scheme needs a 1-party context");
@@ -627,13 +779,21 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     typedef GShare<HFq, 6> S1;
     typedef GShare<HFq2, 12> S2;
     const size_t n_sq = pk->n_sq, D = pk->D;
+    if (!cs && !n_sq) return fail(ctx, CZK_ERR_ARG, "czk_groth16_prove: this key was uploaded for a general circuit - use czk_groth16_prove_r1cs");
     for (int i = 0; i < 8; i++) g_phases[i] = 0;
     ShareVecs v;
-    int rc = witness_map_dev(ctx, scheme, n_sq, pk->log_d, chain_sh, chain_dev, v);
+    if (cs && (cs->ncons != pk->ncons || cs->ninst != pk->ninst || cs->nwit != pk->nwit))
+        return fail(ctx, CZK_ERR_ARG, "czk_groth16_prove_r1cs: the proving key was made for a circuit of another shape");
+    int rc = witness_map_dev(ctx, scheme, n_sq, pk->log_d, chain_sh, chain_dev, v, cs, full_sh);
     if (rc != CZK_OK) {
         free_share_vecs(ctx, v);
         return rc;
     }
+    // scalar vectors of the l-query MSM (the witness) and of the a / b-query MSMs (instance[1..] ++ witness)
+    const czk_vec* wit_vec = cs ? v.full : v.chain;
+    const size_t wit_off = cs ? pk->ninst : 0, n_wit = pk->nwit;
+    const czk_vec* asg_vec = cs ? v.full : v.assign;
+    const size_t asg_off = cs ? 1 : 0, n_asg = pk->ninst + pk->nwit - 1;
     // ---- the five MSMs (prover.rs:104,108,132,143,155); share-local, no communication.
     // SPDZ computes sh and mac as the same MSM of the value shares (spdz.rs:440-446): done once, used twice.
     uint64_t o1[18], o2[36];
@@ -648,19 +808,19 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     h_acc.sh = h_acc.mac = S1::from_jac_out(o1);
     g_phases[2] = now_ms() - t0;
     t0 = now_ms();
-    if ((rc = czk_msm_bases(ctx, pk->q[4], 0, v.chain, 0, 1, n_sq, o1)) != CZK_OK) return fin(rc);
+    if ((rc = czk_msm_bases(ctx, pk->q[4], 0, wit_vec, wit_off, 1, n_wit, o1)) != CZK_OK) return fin(rc);
     l_acc.sh = l_acc.mac = S1::from_jac_out(o1);
     g_phases[3] = now_ms() - t0;
     t0 = now_ms();
-    if ((rc = czk_msm_bases(ctx, pk->q[0], 1, v.assign, 0, 1, n_sq + 1, o1)) != CZK_OK) return fin(rc);
+    if ((rc = czk_msm_bases(ctx, pk->q[0], 1, asg_vec, asg_off, 1, n_asg, o1)) != CZK_OK) return fin(rc);
     a_acc.sh = a_acc.mac = S1::from_jac_out(o1);
     g_phases[4] = now_ms() - t0;
     t0 = now_ms();
-    if ((rc = czk_msm_bases(ctx, pk->q[1], 1, v.assign, 0, 1, n_sq + 1, o1)) != CZK_OK) return fin(rc);
+    if ((rc = czk_msm_bases(ctx, pk->q[1], 1, asg_vec, asg_off, 1, n_asg, o1)) != CZK_OK) return fin(rc);
     b1_acc.sh = b1_acc.mac = S1::from_jac_out(o1);
     g_phases[5] = now_ms() - t0;
     t0 = now_ms();
-    if ((rc = czk_msm_bases(ctx, pk->q[2], 1, v.assign, 0, 1, n_sq + 1, o2)) != CZK_OK) return fin(rc);
+    if ((rc = czk_msm_bases(ctx, pk->q[2], 1, asg_vec, asg_off, 1, n_asg, o2)) != CZK_OK) return fin(rc);
     b2_acc.sh = b2_acc.mac = S2::from_jac_out(o2);
     g_phases[6] = now_ms() - t0;
     free_share_vecs(ctx, v);

@@ -54,6 +54,31 @@ CZK_API int czk_groth16_gsz_last_checks(const czk_ctx* ctx, uint64_t field_xyz[1
 CZK_API int czk_groth16_prove_vec(czk_ctx* ctx, int scheme, const czk_pk* pk, const czk_vec* chain_dev, const uint64_t r_sh[4],
                                   const uint64_t s_sh[4], uint64_t proof_sh[48], uint8_t proof_sh_inf[3], uint64_t proof[48],
                                   uint8_t proof_inf[3]);
+/* ---- any circuit -----------------------------------------------------------------------------------------------------
+ * The entry points above are specialised to the benchmark's squaring circuit (like the reference's `proof` binary); these
+ * take the constraint matrices the reference's prover reads from its ConstraintSystem (`prover.to_matrices()`,
+ * mpc-snarks/src/groth/r1cs_to_qap.rs:47-83): for m in {A, B, C}, row i of matrix m is entries row_ptr[m][i] ..
+ * row_ptr[m][i+1] of (col[m], coeff[m]) with coeff in Montgomery form.  Variables: ninst instance variables (the first is the
+ * constant one) followed by nwit witness variables.  The sparse evaluate_constraint pass (r1cs_to_qap.rs:12-41) runs on
+ * the device, linear in the shares. */
+typedef struct czk_r1cs czk_r1cs;
+CZK_API int czk_r1cs_upload(czk_ctx* ctx, size_t ncons, size_t ninst, size_t nwit, const uint64_t* const row_ptr[3],
+                            const uint32_t* const col[3], const uint64_t* const coeff[3], czk_r1cs** out);
+CZK_API void czk_r1cs_free(czk_ctx* ctx, czk_r1cs* r);
+/* Proving key of a general circuit (groth16/src/generator.rs:109-221): a_query, b_g1_query, b_g2_query: ninst + nwit points;
+ * h_query: D - 1 points with D = next_pow2(ncons + ninst); l_query: nwit points. */
+CZK_API int czk_groth16_pk_upload_r1cs(czk_ctx* ctx, size_t ncons, size_t ninst, size_t nwit, const uint64_t* a_query,
+                                       const uint8_t* a_inf, const uint64_t* b_g1_query, const uint8_t* b1_inf,
+                                       const uint64_t* b_g2_query, const uint8_t* b2_inf, const uint64_t* h_query, const uint8_t* h_inf,
+                                       const uint64_t* l_query, const uint8_t* l_inf, const uint64_t vk_g1[36],
+                                       const uint64_t vk_g2[72], czk_pk** out);
+/* create_proof + reveal on this party's shares of the full assignment [instance, witness] (ninst + nwit Montgomery Fr, host
+ * memory).  Public values are passed in their lowered share form, as the reference's MpcField does when a Public meets a
+ * Shared: additive / SPDZ - the king holds the value, the others 0 (add.rs:88-92); GSZ - every party holds it. */
+CZK_API int czk_groth16_prove_r1cs(czk_ctx* ctx, int scheme, const czk_pk* pk, const czk_r1cs* cs, const uint64_t* full_sh,
+                                   const uint64_t r_sh[4], const uint64_t s_sh[4], uint64_t proof_sh[48], uint8_t proof_sh_inf[3],
+                                   uint64_t proof[48], uint8_t proof_inf[3]);
+
 /* Witness generation of the benchmark circuit (mpc-snarks/src/proof.rs:308-310): out[i] = start^(2^i), i <= n_sq.
  * Host-side, serial by nature, outside the reference's timed section. */
 CZK_API int czk_squaring_chain(const uint64_t start[4], size_t n_sq, uint64_t* out);

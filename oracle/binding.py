@@ -478,3 +478,105 @@ def kzg_open(powers_xy, powers_inf, p_mont, z_mont, threads=1):
     lib().orc_kzg_open(_p(powers_xy), _p8(powers_inf), _p(p_mont), C.c_size_t(p_mont.shape[0]),
                        _p(np.ascontiguousarray(z_mont, np.uint64)), _p(w), _p8(winf), _p(ev), C.c_int(threads))
     return w, int(winf[0]), ev
+
+
+# ------------------------------------------------------------------ Groth16 on an arbitrary R1CS (CSR matrices)
+def random_r1cs(seed: int, n_inst: int, n_free: int, n_cons: int, modulus: int):
+    """A random satisfiable circuit in the shape of ConstraintMatrices: variables [1, inst.., free witnesses.., one product
+    witness per constraint]; constraint i: <A_i, z> * <B_i, z> = z[product_i].  Returns (r1cs dict, assignment ints)."""
+    import random
+
+    rnd = random.Random(seed)
+    z = [1] + [rnd.randrange(modulus) for _ in range(n_inst - 1 + n_free)]
+    rows = {"a": [], "b": [], "c": []}
+    for i in range(n_cons):
+        avail = len(z)
+        vals = {}
+        for m in ("a", "b"):
+            k = rnd.randrange(1, 4)
+            idx = rnd.sample(range(avail), min(k, avail))
+            row = [(1 if rnd.random() < 0.5 else rnd.randrange(1, modulus), j) for j in idx]
+            rows[m].append(row)
+            vals[m] = sum(c * z[j] for c, j in row) % modulus
+        z.append(vals["a"] * vals["b"] % modulus)
+        rows["c"].append([(1, len(z) - 1)])
+    n_wit = len(z) - n_inst
+    cs = dict(ncons=n_cons, ninst=n_inst, nwit=n_wit)
+    for m in ("a", "b", "c"):
+        rp = np.zeros(n_cons + 1, np.uint64)
+        col, cf = [], []
+        for i, row in enumerate(rows[m]):
+            for c, j in row:
+                col.append(j)
+                cf.append(c)
+            rp[i + 1] = len(col)
+        cs[m] = (rp, np.array(col, np.uint32), fr_from_ints(cf))
+    return cs, z
+
+
+def _r1cs_ptrs(cs):
+    keep = []
+    rp = (C.c_void_p * 3)(*[cs[m][0].ctypes.data for m in ("a", "b", "c")])
+    col = (C.c_void_p * 3)(*[cs[m][1].ctypes.data for m in ("a", "b", "c")])
+    cf = (C.c_void_p * 3)(*[cs[m][2].ctypes.data for m in ("a", "b", "c")])
+    return rp, col, cf, keep
+
+
+def groth16_setup_r1cs(cs: dict, toxic_mont: np.ndarray, threads=1) -> dict:
+    nv = cs["ninst"] + cs["nwit"]
+    D = 1
+    while D < cs["ncons"] + cs["ninst"]:
+        D <<= 1
+    pk = dict(D=D, ncons=cs["ncons"], ninst=cs["ninst"], nwit=cs["nwit"],
+              a_query=np.zeros((nv, 12), np.uint64), a_inf=np.zeros(nv, np.uint8),
+              b_g1_query=np.zeros((nv, 12), np.uint64), b1_inf=np.zeros(nv, np.uint8),
+              b_g2_query=np.zeros((nv, 24), np.uint64), b2_inf=np.zeros(nv, np.uint8),
+              h_query=np.zeros((D - 1, 12), np.uint64), h_inf=np.zeros(D - 1, np.uint8),
+              l_query=np.zeros((cs["nwit"], 12), np.uint64), l_inf=np.zeros(cs["nwit"], np.uint8),
+              vk_g1=np.zeros((3, 12), np.uint64), vk_g2=np.zeros((3, 24), np.uint64),
+              gamma_abc_g1=np.zeros((cs["ninst"], 12), np.uint64))
+    rp, col, cf, _ = _r1cs_ptrs(cs)
+    toxic_mont = np.ascontiguousarray(toxic_mont, np.uint64).reshape(7, 4)
+    ok = lib().orc_groth16_setup_r1cs(C.c_size_t(cs["ncons"]), C.c_size_t(cs["ninst"]), C.c_size_t(cs["nwit"]), rp, col, cf,
+                                      _p(toxic_mont), _p(pk["a_query"]), _p8(pk["a_inf"]), _p(pk["b_g1_query"]), _p8(pk["b1_inf"]),
+                                      _p(pk["b_g2_query"]), _p8(pk["b2_inf"]), _p(pk["h_query"]), _p8(pk["h_inf"]),
+                                      _p(pk["l_query"]), _p8(pk["l_inf"]), _p(pk["vk_g1"]), _p(pk["vk_g2"]), _p(pk["gamma_abc_g1"]),
+                                      C.c_int(threads))
+    assert ok
+    return pk
+
+
+def groth16_prove_r1cs(scheme, cs: dict, full_shares, r_sh, s_sh, pk, threads=1, want_h=True):
+    """full_shares: per party, (ninst + nwit, 4) shares of [instance, witness]; entry 0 is the lowered constant one."""
+    n = len(full_shares)
+    D = pk["D"]
+    arrs, ptrs = _chain_ptrs(full_shares)
+    r_sh = np.ascontiguousarray(r_sh, np.uint64).reshape(n, 4)
+    s_sh = np.ascontiguousarray(s_sh, np.uint64).reshape(n, 4)
+    h = np.zeros((n, D, 4), np.uint64) if want_h else None
+    proof_sh = np.zeros((n, 48), np.uint64)
+    proof_sh_inf = np.zeros((n, 3), np.uint8)
+    proof = np.zeros(48, np.uint64)
+    proof_inf = np.zeros(3, np.uint8)
+    rp, col, cf, _ = _r1cs_ptrs(cs)
+    ok = lib().orc_groth16_prove_r1cs(C.c_int(scheme), C.c_int(n), C.c_size_t(cs["ncons"]), C.c_size_t(cs["ninst"]),
+                                      C.c_size_t(cs["nwit"]), rp, col, cf, ptrs, _p(r_sh), _p(s_sh),
+                                      _p(pk["a_query"]), _p8(pk["a_inf"]), _p(pk["b_g1_query"]), _p8(pk["b1_inf"]),
+                                      _p(pk["b_g2_query"]), _p8(pk["b2_inf"]), _p(pk["h_query"]), _p8(pk["h_inf"]),
+                                      _p(pk["l_query"]), _p8(pk["l_inf"]), _p(pk["vk_g1"]), _p(pk["vk_g2"]),
+                                      _p(h) if want_h else None, _p(proof_sh), _p8(proof_sh_inf), _p(proof), _p8(proof_inf),
+                                      C.c_int(threads))
+    return dict(ok=bool(ok), h=h, proof_sh=proof_sh, proof_sh_inf=proof_sh_inf, proof=proof, proof_inf=proof_inf)
+
+
+def r1cs_full_shares(z_ints, n_parties: int, seed: int, scheme):
+    """Shares of the full assignment in the reference's lowering: additive shares of every variable except the constant one,
+    which is Public(1) lowered to 'the king holds 1' (plain: the values themselves)."""
+    z = fr_from_ints(z_ints)
+    if scheme == SCHEME_PLAIN:
+        return [z]
+    sh = [a.copy() for a in king_share_batch(z, n_parties, seed)]
+    one = fr_from_ints([1])[0]
+    for p in range(n_parties):
+        sh[p][0] = one if p == 0 else 0
+    return sh

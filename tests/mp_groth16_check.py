@@ -56,6 +56,17 @@ def main():
     xs = czk_b200.king_share_batch(x, world, seed=3)
     opened = ctx.batch_open(scheme, ctx.vec_from(xs[rank]), ctx.vec_from(xs[rank]) if scheme == czk_b200.SCHEME_SPDZ else None)
     assert (opened.numpy() == x).all()
+    # any circuit: a random R1CS through czk_groth16_prove_r1cs, every rank holding its own shares of the assignment
+    cs, z = o.random_r1cs(seed=77, n_inst=3, n_free=9, n_cons=200, modulus=m.R_MOD)
+    pk2 = o.groth16_setup_r1cs(cs, o.fr_from_ints(toxic), threads=max(1, o.cpu_threads() // world))
+    oscheme2 = o.SCHEME_SPDZ if scheme == czk_b200.SCHEME_SPDZ else o.SCHEME_ADDITIVE
+    full = o.r1cs_full_shares(z, world, seed=8, scheme=oscheme2)
+    exp2 = o.groth16_prove_r1cs(oscheme2, cs, full, r_sh, s_sh, pk2)
+    assert exp2["ok"]
+    dcs, dpk2 = czk_b200.R1cs(ctx, cs), czk_b200.groth16_pk_upload_r1cs(ctx, pk2)
+    got2 = czk_b200.groth16_prove_r1cs(ctx, scheme, dpk2, dcs, full[rank], r_sh[rank], s_sh[rank])
+    assert (got2["proof"] == exp2["proof"]).all(), f"rank {rank}: generic-circuit proof differs"
+    assert (got2["proof_sh"] == exp2["proof_sh"][rank]).all(), f"rank {rank}: generic-circuit proof share differs"
     # Plonk leaves on real shares across the ranks: batch_inv, batch_div, partial_products
     spdz = scheme == czk_b200.SCHEME_SPDZ
     k = 777

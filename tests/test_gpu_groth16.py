@@ -61,3 +61,41 @@ def test_prove_synthetic_key_2_14_matches_oracle(ctx, czk, oracle):
     got = czk.groth16_prove(ctx, czk.SCHEME_SPDZ, dpk, chain, r[0], s[0])
     assert (got["proof"] == exp["proof"]).all() and (got["proof_inf"] == exp["proof_inf"]).all()
     dpk.free()
+
+
+@pytest.mark.parametrize("scheme_name", ["plain", "additive", "spdz", "gsz"])
+@pytest.mark.parametrize("shape", [(3, 4, 21), (2, 50, 3000)])  # (instance variables, free witnesses, constraints)
+def test_prove_any_r1cs_matches_oracle(ctx, czk, oracle, pymodel, scheme_name, shape):
+    """czk_groth16_prove_r1cs: constraint matrices in CSR form, sparse evaluate_constraint on the device
+    (mpc-snarks/src/groth/r1cs_to_qap.rs:12-41,70-83), then the same prover loop.  Random satisfiable circuits with rows
+    of 1-3 terms and arbitrary coefficients; the oracle's generic core is pinned by the exponent check in
+    tests/test_oracle_groth16.py.  One party here; tests/mp_groth16_check.py covers 2+ parties."""
+    ctx.net_init(0, 1, None)
+    ninst, nfree, ncons = shape
+    rnd = random.Random(ncons)
+    cs, z = oracle.random_r1cs(seed=ncons, n_inst=ninst, n_free=nfree, n_cons=ncons, modulus=pymodel.R_MOD)
+    toxic = [rnd.randrange(1, pymodel.R_MOD) for _ in range(7)]
+    pk = oracle.groth16_setup_r1cs(cs, oracle.fr_from_ints(toxic), threads=oracle.cpu_threads())
+    r = oracle.fr_from_ints([rnd.randrange(pymodel.R_MOD)])
+    s = oracle.fr_from_ints([rnd.randrange(pymodel.R_MOD)])
+    dcs = czk.R1cs(ctx, cs)
+    dpk = czk.groth16_pk_upload_r1cs(ctx, pk)
+    if scheme_name == "gsz":
+        # GSZ: every party holds the plaintext (gsz20/mod.rs:202-212); the revealed proof is the single-prover proof
+        full = oracle.r1cs_full_shares(z, 1, seed=1, scheme=oracle.SCHEME_PLAIN)
+        exp = oracle.groth16_prove_r1cs(oracle.SCHEME_PLAIN, cs, full, r, s, pk, threads=oracle.cpu_threads())
+        got = czk.groth16_prove_r1cs(ctx, czk.SCHEME_GSZ, dpk, dcs, full[0], r[0], s[0])
+    else:
+        oscheme = {"plain": oracle.SCHEME_PLAIN, "additive": oracle.SCHEME_ADDITIVE, "spdz": oracle.SCHEME_SPDZ}[scheme_name]
+        scheme = {"plain": czk.SCHEME_PLAIN, "additive": czk.SCHEME_ADDITIVE, "spdz": czk.SCHEME_SPDZ}[scheme_name]
+        full = oracle.r1cs_full_shares(z, 1, seed=1, scheme=oscheme)
+        exp = oracle.groth16_prove_r1cs(oscheme, cs, full, r, s, pk, threads=oracle.cpu_threads())
+        got = czk.groth16_prove_r1cs(ctx, scheme, dpk, dcs, full[0], r[0], s[0])
+        assert (got["proof_sh"] == exp["proof_sh"][0]).all()
+    assert exp["ok"]
+    assert (got["proof"] == exp["proof"]).all() and (got["proof_inf"] == exp["proof_inf"]).all()
+    # the squaring entry points refuse a key of another circuit
+    with pytest.raises(czk.CzkError):
+        czk.groth16_prove(ctx, czk.SCHEME_PLAIN, dpk, np.zeros((1, 4), np.uint64), r[0], s[0])
+    dcs.free()
+    dpk.free()

@@ -138,3 +138,66 @@ def test_larger_circuit_2_8(oracle, pymodel):
     res = oracle.groth16_prove(oracle.SCHEME_PLAIN, n_sq, [chain_m], oracle.fr_from_ints([r]), oracle.fr_from_ints([s]), pk, threads=4)
     h = oracle.fr_to_ints(res["h"][0])
     assert check_in_exponent(pymodel, oracle, n_sq, toxic, oracle.fr_to_ints(chain_m), r, s, h, res["proof"], res["proof_inf"])
+
+
+# ------------------------------------------------------------------ any R1CS, not only the benchmark's squaring chain
+def qap_at_tau_r1cs(pymodel, cs, oracle, tau):
+    m, R = pymodel, pymodel.R_MOD
+    d = m.Domain(cs["ncons"] + cs["ninst"])
+    D = d.size
+    zt = d.vanishing_at(tau)
+    u = [zt * pow(d.group_gen, i, R) * pow(D * (tau - pow(d.group_gen, i, R)), -1, R) % R for i in range(D)]
+    nv = cs["ninst"] + cs["nwit"]
+    out = {}
+    for name in ("a", "b", "c"):
+        rp, col, cf = cs[name]
+        cfi = oracle.fr_to_ints(cf)
+        v = [0] * nv
+        for i in range(cs["ncons"]):
+            for k in range(int(rp[i]), int(rp[i + 1])):
+                v[int(col[k])] = (v[int(col[k])] + u[i] * cfi[k]) % R
+        out[name] = v
+    for i in range(cs["ninst"]):
+        out["a"][i] = (out["a"][i] + u[cs["ncons"] + i]) % R
+    return out["a"], out["b"], out["c"], zt, D
+
+
+@pytest.mark.parametrize("scheme_name,parties", [("plain", 1), ("additive", 2), ("spdz", 3)])
+def test_generic_r1cs_proof_verifies_in_exponent(oracle, pymodel, scheme_name, parties):
+    """groth16/src/test.rs:78-108 on a random circuit (3 instance variables, rows of 1-3 terms, arbitrary coefficients):
+    the generic prover core is the one the squaring entry points use, so this pins it beyond the benchmark circuit."""
+    m, R = pymodel, pymodel.R_MOD
+    rnd = random.Random(99)
+    cs, z = oracle.random_r1cs(seed=5, n_inst=3, n_free=4, n_cons=21, modulus=R)
+    toxic = [rnd.randrange(1, R) for _ in range(7)]
+    alpha, beta, gamma, delta, tau, s1, s2 = toxic
+    pk = oracle.groth16_setup_r1cs(cs, oracle.fr_from_ints(toxic), threads=2)
+    scheme = {"plain": oracle.SCHEME_PLAIN, "additive": oracle.SCHEME_ADDITIVE, "spdz": oracle.SCHEME_SPDZ}[scheme_name]
+    full = oracle.r1cs_full_shares(z, parties, seed=3, scheme=scheme)
+    rho, sigma = rnd.randrange(R), rnd.randrange(R)
+    res = oracle.groth16_prove_r1cs(scheme, cs, full, oracle.fr_from_ints([rho] * parties), oracle.fr_from_ints([sigma] * parties), pk)
+    assert res["ok"]
+    r, s = rho * parties % R, sigma * parties % R
+    hsum = res["h"][0]
+    for p in range(1, parties):
+        hsum = oracle.fr_add(hsum, res["h"][p])
+    h = oracle.fr_to_ints(hsum)
+    a, b, c, zt, D = qap_at_tau_r1cs(m, cs, oracle, tau)
+    nv, ninst = len(z), cs["ninst"]
+    A = (alpha + sum(x * y for x, y in zip(z, a)) + r * delta) % R
+    B = (beta + sum(x * y for x, y in zip(z, b)) + s * delta) % R
+    dinv, ginv = pow(delta, -1, R), pow(gamma, -1, R)
+    l = [(beta * a[i] + alpha * b[i] + c[i]) * dinv % R for i in range(nv)]
+    h_tau = sum(hc * pow(tau, i, R) for i, hc in enumerate(h[:D - 1])) % R
+    Cc = (sum(z[i] * l[i] for i in range(ninst, nv)) + h_tau * zt * dinv + s * A + r * B - r * s * delta) % R
+    g1, g2 = m.g1_mul(m.G1_GEN, s1), m.g2_mul(m.G2_GEN, s2)
+    assert not res["proof_inf"].any()
+    assert oracle.G1.affine_to_ints(res["proof"][:12])[0] == m.g1_mul(g1, A)
+    assert oracle.G2.affine_to_ints(res["proof"][12:36])[0] == m.g2_mul(g2, B)
+    assert oracle.G1.affine_to_ints(res["proof"][36:48])[0] == m.g1_mul(g1, Cc)
+    abc = [(beta * a[i] + alpha * b[i] + c[i]) * ginv % R for i in range(ninst)]
+    assert A * B % R == (alpha * beta + sum(z[i] * abc[i] for i in range(ninst)) * gamma + Cc * delta) % R
+    # a wrong public input breaks the equation
+    bad = list(z[:ninst])
+    bad[1] = (bad[1] + 1) % R
+    assert A * B % R != (alpha * beta + sum(bad[i] * abc[i] for i in range(ninst)) * gamma + Cc * delta) % R
