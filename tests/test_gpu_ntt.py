@@ -64,6 +64,32 @@ def test_ntt_large_roundtrip_and_spot_parity(ctx, oracle, log_d):
     assert (da.numpy() == ds.numpy()).all()
 
 
+def test_ntt_2_24_properties(ctx, oracle, pymodel):
+    """The top of BASELINE config 5's sweep (2^24): round trips of all flavours, linearity, and FFT(p)[i] == p(w^i)
+    at a few indices by Horner (the reference's own identity, radix2/mod.rs:320-360) - size-independent checks."""
+    log_d = 24
+    n = 1 << log_d
+    v = oracle.random_fr_mont(0x24, n)
+    dv = ctx.vec_from(v)
+    ctx.ntt_in_place(dv, log_d)
+    fwd = dv.numpy()
+    gen = oracle.fr_to_ints(oracle.domain_params(n)["group_gen"][None, :])[0]
+    for i in (0, 1, 0x9a5b3c % n, n - 1):
+        x = oracle.fr_from_ints([pow(gen, i, pymodel.R_MOD)])[0]
+        assert (fwd[i] == oracle.poly_eval(v, x)).all(), i
+    ctx.ntt_in_place(dv, log_d, inverse=True)
+    assert (dv.numpy() == v).all()
+    ctx.ntt_in_place(dv, log_d, inverse=False, coset=True)
+    ctx.ntt_in_place(dv, log_d, inverse=True, coset=True)
+    assert (dv.numpy() == v).all()
+    w = oracle.random_fr_mont(0x25, n)
+    da, ds = ctx.vec_from(w), ctx.vec_from(oracle.fr_add(v, w))
+    ctx.ntt_in_place(da, log_d)
+    ctx.ntt_in_place(ds, log_d)
+    ctx.vec_add(da, ctx.vec_from(fwd))
+    assert (da.numpy() == ds.numpy()).all()
+
+
 def test_domain_params_match_oracle(czk, oracle):
     for log_d in (0, 1, 4, 11, 21, 24, 30):
         a = czk.domain_params(log_d)
