@@ -24,5 +24,11 @@ from .binding import (  # noqa: F401
     R1cs,
     groth16_pk_upload_r1cs,
     groth16_prove_r1cs,
+    fr_serialize,
+    fr_deserialize,
+    point_serialize,
+    point_deserialize,
+    groth16_proof_serialize,
+    groth16_proof_deserialize,
 )
 from .build import build as build_library  # noqa: F401

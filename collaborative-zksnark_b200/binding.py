@@ -90,6 +90,12 @@ _SIGS = {
     "czk_share_batch_div": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "czk_share_partial_products": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]),
     "czk_kzg_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, u64p, u64p, u64p]),
+    "czk_fr_serialize": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "czk_fr_deserialize": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p]),
+    "czk_g1_serialize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "czk_g2_serialize": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "czk_g1_deserialize": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "czk_g2_deserialize": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "czk_gsz_open": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_void_p, C.c_size_t]),
     "czk_gsz_king_compute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_size_t]),
     "czk_gsz_batch_mul": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
@@ -115,6 +121,8 @@ _OPTIONAL_SIGS = {
     "czk_squaring_chain": (C.c_int, [u64p, C.c_size_t, C.c_void_p]),
     "czk_king_share_batch": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_uint64, C.c_void_p]),
     "czk_groth16_last_phases": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "czk_groth16_proof_serialize": (C.c_int, [u64p, u8p, C.c_void_p]),
+    "czk_groth16_proof_deserialize": (C.c_int, [C.c_void_p, u64p, u8p]),
     "czk_r1cs_upload": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "czk_r1cs_free": (None, [C.c_void_p, C.c_void_p]),
     "czk_groth16_pk_upload_r1cs": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t] + [C.c_void_p] * 12 + [C.POINTER(C.c_void_p)]),
@@ -668,3 +676,61 @@ def groth16_prove_r1cs(ctx: Context, scheme: int, pk: "ProvingKey", cs: R1cs, fu
                                             s_sh.ctypes.data_as(u64p), proof_sh.ctypes.data_as(u64p), sh_inf.ctypes.data_as(u8p),
                                             proof.ctypes.data_as(u64p), inf.ctypes.data_as(u8p)))
     return dict(proof_sh=proof_sh, proof_sh_inf=sh_inf, proof=proof, proof_inf=inf)
+
+
+# ------------------------------------------------------------------ wire format (ark-serialize canonical encodings; host-side)
+def _ser_chk(rc):
+    if rc:
+        raise CzkError(rc, load_library().czk_last_error(None).decode())
+
+
+def fr_serialize(a) -> bytes:
+    a = _np_u64(a, 4)
+    out = np.zeros(32 * a.shape[0], np.uint8)
+    _ser_chk(load_library().czk_fr_serialize(a.ctypes.data, a.shape[0], out.ctypes.data))
+    return out.tobytes()
+
+
+def fr_deserialize(data: bytes) -> np.ndarray:
+    buf = np.frombuffer(data, np.uint8).copy()
+    n = buf.size // 32
+    out = np.zeros((n, 4), np.uint64)
+    _ser_chk(load_library().czk_fr_deserialize(buf.ctypes.data, n, out.ctypes.data))
+    return out
+
+
+def point_serialize(curve: int, xy, inf=None, compressed=True) -> bytes:
+    w = 12 if curve == 1 else 24
+    xy = _np_u64(xy, w)
+    n = xy.shape[0]
+    sz = (48 if curve == 1 else 96) * (1 if compressed else 2)
+    out = np.zeros(sz * n, np.uint8)
+    infp = None if inf is None else np.ascontiguousarray(inf, np.uint8)
+    fn = load_library().czk_g1_serialize if curve == 1 else load_library().czk_g2_serialize
+    _ser_chk(fn(xy.ctypes.data, None if infp is None else infp.ctypes.data, n, int(compressed), out.ctypes.data))
+    return out.tobytes()
+
+
+def point_deserialize(curve: int, data: bytes, compressed=True, check_subgroup=True):
+    w = 12 if curve == 1 else 24
+    sz = (48 if curve == 1 else 96) * (1 if compressed else 2)
+    buf = np.frombuffer(data, np.uint8).copy()
+    n = buf.size // sz
+    xy, inf = np.zeros((n, w), np.uint64), np.zeros(n, np.uint8)
+    fn = load_library().czk_g1_deserialize if curve == 1 else load_library().czk_g2_deserialize
+    _ser_chk(fn(buf.ctypes.data, n, int(compressed), int(check_subgroup), xy.ctypes.data, inf.ctypes.data))
+    return xy, inf
+
+
+def groth16_proof_serialize(proof, proof_inf) -> bytes:
+    proof, proof_inf = _np_u64(proof), np.ascontiguousarray(proof_inf, np.uint8)
+    out = np.zeros(192, np.uint8)
+    _ser_chk(load_library().czk_groth16_proof_serialize(proof.ctypes.data_as(u64p), proof_inf.ctypes.data_as(u8p), out.ctypes.data))
+    return out.tobytes()
+
+
+def groth16_proof_deserialize(data: bytes):
+    buf = np.frombuffer(data, np.uint8).copy()
+    proof, inf = np.zeros(48, np.uint64), np.zeros(3, np.uint8)
+    _ser_chk(load_library().czk_groth16_proof_deserialize(buf.ctypes.data, proof.ctypes.data_as(u64p), inf.ctypes.data_as(u8p)))
+    return proof, inf

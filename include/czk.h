@@ -165,6 +165,21 @@ CZK_API int czk_share_partial_products(czk_ctx* ctx, int scheme, czk_vec* x_sh, 
 CZK_API int czk_kzg_open(czk_ctx* ctx, const czk_bases* powers, const czk_vec* p, size_t n, const uint64_t z[4],
                          uint64_t w_xyz[18], uint64_t eval_out[4]);
 
+/* ---- wire format: ark-serialize canonical encodings, host-side -------------------------------------
+ * algebra/ff/src/fields/macros.rs:1-87 (Fp: canonical little-endian bytes, flags in the top bits of the last byte),
+ * fields/models/quadratic_extension.rs:600-647 (Fq2: c0 | c1), algebra/serialize/src/flags.rs (SWFlags: bit 7 = y is the
+ * greater of (y, -y), bit 6 = infinity), algebra/ec/src/models/short_weierstrass_jacobian.rs:792-895 (GroupAffine).
+ * Sizes: Fr 32 bytes; G1 48 compressed / 96 uncompressed; G2 96 / 192.  These are what mpc-net messages and
+ * `Proof::serialize` carry, so a GPU party can exchange bytes with a stock party.  No device needed, ctx-free.
+ * Deserialisation returns CZK_ERR_ARG on what the reference rejects (bad flags, non-canonical element, no such point,
+ * and - when check_subgroup != 0, as CanonicalDeserialize does - a point outside the prime-order subgroup).            */
+CZK_API int czk_fr_serialize(const uint64_t* fr_mont, size_t n, uint8_t* out);
+CZK_API int czk_fr_deserialize(const uint8_t* in, size_t n, uint64_t* fr_mont);
+CZK_API int czk_g1_serialize(const uint64_t* xy, const uint8_t* inf, size_t n, int compressed, uint8_t* out);
+CZK_API int czk_g2_serialize(const uint64_t* xy, const uint8_t* inf, size_t n, int compressed, uint8_t* out);
+CZK_API int czk_g1_deserialize(const uint8_t* in, size_t n, int compressed, int check_subgroup, uint64_t* xy, uint8_t* inf);
+CZK_API int czk_g2_deserialize(const uint8_t* in, size_t n, int compressed, int check_subgroup, uint64_t* xy, uint8_t* inf);
+
 /* ---- GSZ20 honest-majority shares: replaces mpc-algebra/src/share/gsz20/mod.rs on the Groth16 path -------
  * n parties, t = (n-1)/2, party j holds p(w^j) over the mixed-radix share domain of size n (n = 2^a or 3*2^a;
  * :94-105).  A share vector is one czk_vec.  The reference's preprocessing stubs are kept (rand() = 1,

@@ -79,6 +79,11 @@ CZK_API int czk_groth16_prove_r1cs(czk_ctx* ctx, int scheme, const czk_pk* pk, c
                                    const uint64_t r_sh[4], const uint64_t s_sh[4], uint64_t proof_sh[48], uint8_t proof_sh_inf[3],
                                    uint64_t proof[48], uint8_t proof_inf[3]);
 
+/* Proof::serialize / deserialize (groth16/src/data_structures.rs: a: G1Affine | b: G2Affine | c: G1Affine, compressed:
+ * 48 + 96 + 48 bytes) on the `proof` / `proof_inf` arrays the prover returns. */
+CZK_API int czk_groth16_proof_serialize(const uint64_t proof[48], const uint8_t proof_inf[3], uint8_t out[192]);
+CZK_API int czk_groth16_proof_deserialize(const uint8_t in[192], uint64_t proof[48], uint8_t proof_inf[3]);
+
 /* Witness generation of the benchmark circuit (mpc-snarks/src/proof.rs:308-310): out[i] = start^(2^i), i <= n_sq.
  * Host-side, serial by nature, outside the reference's timed section. */
 CZK_API int czk_squaring_chain(const uint64_t start[4], size_t n_sq, uint64_t* out);

@@ -330,3 +330,153 @@ def ref_msm_adds(n: int) -> int:
     c = ref_window(n)
     w = (253 + c - 1) // c
     return n * w + 2 * ((1 << c) - 1) * w + 253
+
+
+# ----------------------------------------------------------------------------
+# ark-serialize canonical encodings, restated on Python integers (test infrastructure): the independent model the
+# product's czk_*_serialize / czk_*_deserialize are checked against.
+#   algebra/ff/src/fields/macros.rs:1-87 (Fp), fields/models/quadratic_extension.rs:600-647 (Fq2: c0 | c1),
+#   algebra/serialize/src/flags.rs (SWFlags: bit 7 = y > -y, bit 6 = infinity),
+#   algebra/ec/src/models/short_weierstrass_jacobian.rs:108-118, 792-895 (GroupAffine),
+#   orderings: macros.rs:507-512 (Fp by canonical integer), quadratic_extension.rs:410-419 (Fq2 by (c1, c0)).
+SER_POSITIVE_Y, SER_INFINITY = 1 << 7, 1 << 6
+
+
+def ser_fr(x: int) -> bytes:
+    return (x % R_MOD).to_bytes(32, "little")
+
+
+def deser_fr(b: bytes):
+    v = int.from_bytes(b, "little")
+    return v if v < R_MOD else None  # also rejects a set top bit (EmptyFlags::from_u8)
+
+
+def _fq_bytes(x: int) -> bytearray:
+    return bytearray((x % Q_MOD).to_bytes(48, "little"))
+
+
+def _coord_bytes(g: int, x) -> bytearray:
+    return _fq_bytes(x) if g == 1 else _fq_bytes(x[0]) + _fq_bytes(x[1])
+
+
+def _coord_key(g: int, y):
+    return y if g == 1 else (y[1], y[0])
+
+
+def _F(g: int):
+    return _F1 if g == 1 else _F2
+
+
+def ser_point(g: int, P, compressed=True) -> bytes:
+    """g: 1 = G1, 2 = G2; P: None (infinity) or affine (x, y)."""
+    F = _F(g)
+    if compressed:
+        if P is None:
+            out = _coord_bytes(g, F.zero)
+            out[-1] |= SER_INFINITY
+            return bytes(out)
+        out = _coord_bytes(g, P[0])
+        if _coord_key(g, P[1]) > _coord_key(g, F.neg(P[1])):
+            out[-1] |= SER_POSITIVE_Y
+        return bytes(out)
+    x, y = (F.zero, F.one) if P is None else P
+    out = _coord_bytes(g, x) + _coord_bytes(g, y)
+    if P is None:
+        out[-1] |= SER_INFINITY
+    return bytes(out)
+
+
+def fq_sqrt(a: int):
+    """Tonelli-Shanks; None for a non-residue."""
+    a %= Q_MOD
+    if a == 0:
+        return 0
+    if pow(a, (Q_MOD - 1) // 2, Q_MOD) != 1:
+        return None
+    s, t = 0, Q_MOD - 1
+    while t % 2 == 0:
+        s, t = s + 1, t // 2
+    g = next(k for k in range(2, 100) if pow(k, (Q_MOD - 1) // 2, Q_MOD) != 1)
+    z, x, b, m = pow(g, t, Q_MOD), pow(a, (t + 1) // 2, Q_MOD), pow(a, t, Q_MOD), s
+    while b != 1:
+        k, b2 = 0, b
+        while b2 != 1:
+            b2, k = b2 * b2 % Q_MOD, k + 1
+        w = pow(z, 1 << (m - k - 1), Q_MOD)
+        z, b, x, m = w * w % Q_MOD, b * w * w % Q_MOD, x * w % Q_MOD, k
+    return x
+
+
+def fq2_sqrt(a):
+    """quadratic_extension.rs:360-399 (the complex method), including its None for c1 = 0 with c0 a non-residue."""
+    c0, c1 = a[0] % Q_MOD, a[1] % Q_MOD
+    if c1 == 0:
+        r = fq_sqrt(c0)
+        return None if r is None else (r, 0)
+    alpha = fq_sqrt((c0 * c0 - FQ2_NONRESIDUE * c1 * c1) % Q_MOD)
+    if alpha is None:
+        return None
+    two_inv = pow(2, -1, Q_MOD)
+    delta = (alpha + c0) * two_inv % Q_MOD
+    if fq_sqrt(delta) is None:
+        delta = (delta - alpha) % Q_MOD
+    r0 = fq_sqrt(delta)
+    if not r0:
+        return None
+    cand = (r0, c1 * two_inv % Q_MOD * pow(r0, -1, Q_MOD) % Q_MOD)
+    return cand if fq2_mul(cand, cand) == (c0, c1) else None
+
+
+def deser_point(g: int, b: bytes, compressed=True, check_subgroup=True):
+    """Returns ('ok', P) or ('err', reason) the way GroupAffine::deserialize accepts / rejects."""
+    F = _F(g)
+    n = 48 * g
+    buf = bytearray(b)
+    pos, inf = bool(buf[-1] & SER_POSITIVE_Y), bool(buf[-1] & SER_INFINITY)
+    if pos and inf:
+        return "err", "flags"
+    buf[-1] &= 0xFF ^ (SER_POSITIVE_Y | SER_INFINITY)
+
+    def coord(chunk):
+        vals = [int.from_bytes(chunk[i:i + 48], "little") for i in range(0, len(chunk), 48)]
+        if any(v >= Q_MOD for v in vals):
+            return None
+        return vals[0] if g == 1 else (vals[0], vals[1])
+
+    x = coord(buf[:n])
+    if x is None:
+        return "err", "field"
+    if compressed:
+        if inf:
+            return "ok", None
+        rhs = F.add(F.mul(F.mul(x, x), x), F.b)
+        y = fq_sqrt(rhs) if g == 1 else fq2_sqrt(rhs)
+        if y is None:
+            return "err", "curve"
+        negy = F.neg(y)
+        if not ((_coord_key(g, y) < _coord_key(g, negy)) ^ pos):
+            y = negy
+    else:
+        if pos:
+            return "err", "flags"
+        y = coord(buf[n:])
+        if y is None:
+            return "err", "field"
+        if inf:
+            return "ok", None
+        if not _on_curve(F, (x, y)):
+            return "err", "curve"
+    if check_subgroup and _mul_raw(F, (x, y), R_MOD) is not None:
+        return "err", "subgroup"
+    return "ok", (x, y)
+
+
+def _mul_raw(F, P, k: int):
+    """k * P without reducing k modulo the group order (the subgroup test multiplies by r itself)."""
+    acc = None
+    while k:
+        if k & 1:
+            acc = _add(F, acc, P)
+        P = _add(F, P, P)
+        k >>= 1
+    return acc
