@@ -30,5 +30,7 @@ from .binding import (  # noqa: F401
     point_deserialize,
     groth16_proof_serialize,
     groth16_proof_deserialize,
+    pairing_product_is_one,
+    groth16_verify,
 )
 from .build import build as build_library  # noqa: F401

@@ -123,6 +123,8 @@ _OPTIONAL_SIGS = {
     "czk_groth16_last_phases": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "czk_groth16_proof_serialize": (C.c_int, [u64p, u8p, C.c_void_p]),
     "czk_groth16_proof_deserialize": (C.c_int, [C.c_void_p, u64p, u8p]),
+    "czk_pairing_product_is_one": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
+    "czk_groth16_verify": (C.c_int, [u64p, u64p, C.c_void_p, C.c_size_t, C.c_void_p, u64p, u8p, C.POINTER(C.c_int)]),
     "czk_r1cs_upload": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "czk_r1cs_free": (None, [C.c_void_p, C.c_void_p]),
     "czk_groth16_pk_upload_r1cs": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t] + [C.c_void_p] * 12 + [C.POINTER(C.c_void_p)]),
@@ -734,3 +736,30 @@ def groth16_proof_deserialize(data: bytes):
     proof, inf = np.zeros(48, np.uint64), np.zeros(3, np.uint8)
     _ser_chk(load_library().czk_groth16_proof_deserialize(buf.ctypes.data, proof.ctypes.data_as(u64p), inf.ctypes.data_as(u8p)))
     return proof, inf
+
+
+def pairing_product_is_one(g1_xy, g2_xy, g1_inf=None, g2_inf=None) -> bool:
+    """prod e(P_i, Q_i) == 1 (host-side BLS12-377 pairing of libczk_b200)."""
+    g1_xy, g2_xy = _np_u64(g1_xy, 12), _np_u64(g2_xy, 24)
+    n = g1_xy.shape[0]
+    assert g2_xy.shape[0] == n
+    i1 = None if g1_inf is None else np.ascontiguousarray(g1_inf, np.uint8)
+    i2 = None if g2_inf is None else np.ascontiguousarray(g2_inf, np.uint8)
+    res = C.c_int()
+    _ser_chk(load_library().czk_pairing_product_is_one(g1_xy.ctypes.data, None if i1 is None else i1.ctypes.data, g2_xy.ctypes.data,
+                                                       None if i2 is None else i2.ctypes.data, n, C.byref(res)))
+    return bool(res.value)
+
+
+def groth16_verify(pk: dict, public_inputs, proof, proof_inf) -> bool:
+    """verify_proof on a key dict (vk_g1 = alpha | beta | delta, vk_g2 = beta | gamma | delta, gamma_abc_g1)."""
+    alpha = _np_u64(pk["vk_g1"]).reshape(-1)[:12].copy()
+    vk_g2 = _np_u64(pk["vk_g2"]).reshape(-1).copy()
+    abc = _np_u64(pk["gamma_abc_g1"], 12)
+    pub = _np_u64(public_inputs, 4) if len(public_inputs) else np.zeros((0, 4), np.uint64)
+    assert pub.shape[0] == abc.shape[0] - 1
+    proof, proof_inf = _np_u64(proof), np.ascontiguousarray(proof_inf, np.uint8)
+    ok = C.c_int()
+    _ser_chk(load_library().czk_groth16_verify(alpha.ctypes.data_as(u64p), vk_g2.ctypes.data_as(u64p), abc.ctypes.data, abc.shape[0],
+                                               pub.ctypes.data, proof.ctypes.data_as(u64p), proof_inf.ctypes.data_as(u8p), C.byref(ok)))
+    return bool(ok.value)

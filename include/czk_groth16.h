@@ -84,6 +84,19 @@ CZK_API int czk_groth16_prove_r1cs(czk_ctx* ctx, int scheme, const czk_pk* pk, c
 CZK_API int czk_groth16_proof_serialize(const uint64_t proof[48], const uint8_t proof_inf[3], uint8_t out[192]);
 CZK_API int czk_groth16_proof_deserialize(const uint8_t in[192], uint64_t proof[48], uint8_t proof_inf[3]);
 
+/* ---- verifier, host-side, ctx-free ------------------------------------------------------------------
+ * The acceptance test the reference runs after every benchmark proof (`verify_proof`, mpc-snarks/src/proof.rs:141,
+ * groth16/src/verifier.rs; pairing: algebra/ec/src/models/bls12/mod.rs:59-200).
+ * czk_pairing_product_is_one: result = 1 iff prod_i e(P_i, Q_i) == 1 (P_i in G1: n x 12 limbs, Q_i in G2: n x 24 limbs,
+ * Montgomery affine; infinity flags may be NULL).
+ * czk_groth16_verify: ok = 1 iff e(A, B) == e(alpha, beta) e(gamma_abc[0] + sum_i x_i gamma_abc[i], gamma) e(C, delta).
+ * vk_g2 = beta_g2 | gamma_g2 | delta_g2 (as czk_groth16_pk_vk returns); gamma_abc_g1: ninst points; public_inputs:
+ * ninst - 1 Montgomery Fr (the constant one is implicit). */
+CZK_API int czk_pairing_product_is_one(const uint64_t* g1_xy, const uint8_t* g1_inf, const uint64_t* g2_xy, const uint8_t* g2_inf,
+                                       size_t n, int* result);
+CZK_API int czk_groth16_verify(const uint64_t alpha_g1[12], const uint64_t vk_g2[72], const uint64_t* gamma_abc_g1, size_t ninst,
+                               const uint64_t* public_inputs, const uint64_t proof[48], const uint8_t proof_inf[3], int* ok);
+
 /* Witness generation of the benchmark circuit (mpc-snarks/src/proof.rs:308-310): out[i] = start^(2^i), i <= n_sq.
  * Host-side, serial by nature, outside the reference's timed section. */
 CZK_API int czk_squaring_chain(const uint64_t start[4], size_t n_sq, uint64_t* out);

@@ -480,3 +480,153 @@ def _mul_raw(F, P, k: int):
         P = _add(F, P, P)
         k >>= 1
     return acc
+
+
+# ----------------------------------------------------------------------------
+# BLS12-377 ate pairing on Python integers (test infrastructure): the model the product's host-side verifier
+# (czk_pairing_product_is_one / czk_groth16_verify) is checked against.  The reference computes the same bilinear map with a
+# projective Miller loop and a cyclotomic final exponentiation (algebra/ec/src/models/bls12/mod.rs:59-200,
+# curves/bls12_377/src/curves/mod.rs: x = 0x8508c00000000001, D-type twist over Fq2 with xi = u); here it is the textbook form:
+# untwist Q into E(Fq12), affine Miller loop over t - 1 = x, and f^((q^12 - 1) / r) by plain square-and-multiply.  Same
+# function up to a fixed non-zero power (gcd-free exponents differ), so pairing-PRODUCT checks - all a verifier needs - agree.
+# Tower: Fq2 = Fq[u]/(u^2 + 5), Fq6 = Fq2[v]/(v^3 - u), Fq12 = Fq6[w]/(w^2 - v)   (fields/fq6.rs, fq12.rs).
+BLS_X = 0x8508C00000000001
+FQ2_ZERO, FQ2_ONE = (0, 0), (1, 0)
+
+
+def fq2_mul_xi(a):  # times xi = u
+    return (FQ2_NONRESIDUE * a[1] % Q_MOD, a[0])
+
+
+def fq6_add(a, b):
+    return tuple(fq2_add(x, y) for x, y in zip(a, b))
+
+
+def fq6_sub(a, b):
+    return tuple(fq2_sub(x, y) for x, y in zip(a, b))
+
+
+def fq6_mul(a, b):
+    a0, a1, a2 = a
+    b0, b1, b2 = b
+    c0 = fq2_add(fq2_mul(a0, b0), fq2_mul_xi(fq2_add(fq2_mul(a1, b2), fq2_mul(a2, b1))))
+    c1 = fq2_add(fq2_add(fq2_mul(a0, b1), fq2_mul(a1, b0)), fq2_mul_xi(fq2_mul(a2, b2)))
+    c2 = fq2_add(fq2_add(fq2_mul(a0, b2), fq2_mul(a1, b1)), fq2_mul(a2, b0))
+    return (c0, c1, c2)
+
+
+def fq6_mul_v(a):
+    return (fq2_mul_xi(a[2]), a[0], a[1])
+
+
+def fq6_inv(a):
+    a0, a1, a2 = a
+    t0 = fq2_sub(fq2_mul(a0, a0), fq2_mul_xi(fq2_mul(a1, a2)))
+    t1 = fq2_sub(fq2_mul_xi(fq2_mul(a2, a2)), fq2_mul(a0, a1))
+    t2 = fq2_sub(fq2_mul(a1, a1), fq2_mul(a0, a2))
+    d = fq2_add(fq2_mul(a0, t0), fq2_mul_xi(fq2_add(fq2_mul(a2, t1), fq2_mul(a1, t2))))
+    di = fq2_inv(d)
+    return (fq2_mul(t0, di), fq2_mul(t1, di), fq2_mul(t2, di))
+
+
+FQ6_ZERO = (FQ2_ZERO, FQ2_ZERO, FQ2_ZERO)
+FQ6_ONE = (FQ2_ONE, FQ2_ZERO, FQ2_ZERO)
+FQ12_ONE = (FQ6_ONE, FQ6_ZERO)
+
+
+def fq12_add(a, b):
+    return (fq6_add(a[0], b[0]), fq6_add(a[1], b[1]))
+
+
+def fq12_sub(a, b):
+    return (fq6_sub(a[0], b[0]), fq6_sub(a[1], b[1]))
+
+
+def fq12_mul(a, b):
+    t0, t1 = fq6_mul(a[0], b[0]), fq6_mul(a[1], b[1])
+    c1 = fq6_sub(fq6_sub(fq6_mul(fq6_add(a[0], a[1]), fq6_add(b[0], b[1])), t0), t1)
+    return (fq6_add(t0, fq6_mul_v(t1)), c1)
+
+
+def fq12_inv(a):
+    d = fq6_sub(fq6_mul(a[0], a[0]), fq6_mul_v(fq6_mul(a[1], a[1])))
+    di = fq6_inv(d)
+    return (fq6_mul(a[0], di), fq6_sub(FQ6_ZERO, fq6_mul(a[1], di)))
+
+
+def fq12_pow(a, e: int):
+    res, started = FQ12_ONE, False
+    for i in range(e.bit_length() - 1, -1, -1):
+        if started:
+            res = fq12_mul(res, res)
+        if (e >> i) & 1:
+            res = fq12_mul(res, a)
+            started = True
+    return res
+
+
+def fq12_from_fq(x: int):
+    return (((x % Q_MOD, 0), FQ2_ZERO, FQ2_ZERO), FQ6_ZERO)
+
+
+def g2_untwist(Q):
+    """(x', y') on the twist -> (x' w^2, y' w^3) on E(Fq12): w^2 = v, w^3 = v w."""
+    x, y = Q
+    return ((FQ2_ZERO, x, FQ2_ZERO), FQ6_ZERO), (FQ6_ZERO, (FQ2_ZERO, y, FQ2_ZERO))
+
+
+def miller_loop(P, Q):
+    """f_{x, psi(Q)}(P) for affine P in G1, Q in G2 (neither infinity), without the vertical lines (they lie in Fq6 and
+    die in the final exponentiation)."""
+    xp, yp = fq12_from_fq(P[0]), fq12_from_fq(P[1])
+    xq, yq = g2_untwist(Q)
+    xt, yt = xq, yq
+    f = FQ12_ONE
+    three, two = fq12_from_fq(3), fq12_from_fq(2)
+
+    def line(lam, x0, y0):  # (y_P - y0) - lam (x_P - x0)
+        return fq12_sub(fq12_sub(yp, y0), fq12_mul(lam, fq12_sub(xp, x0)))
+
+    for i in range(BLS_X.bit_length() - 2, -1, -1):
+        lam = fq12_mul(fq12_mul(three, fq12_mul(xt, xt)), fq12_inv(fq12_mul(two, yt)))
+        f = fq12_mul(fq12_mul(f, f), line(lam, xt, yt))
+        x3 = fq12_sub(fq12_sub(fq12_mul(lam, lam), xt), xt)
+        yt = fq12_sub(fq12_mul(lam, fq12_sub(xt, x3)), yt)
+        xt = x3
+        if (BLS_X >> i) & 1:
+            lam = fq12_mul(fq12_sub(yq, yt), fq12_inv(fq12_sub(xq, xt)))
+            f = fq12_mul(f, line(lam, xt, yt))
+            x3 = fq12_sub(fq12_sub(fq12_mul(lam, lam), xt), xq)
+            yt = fq12_sub(fq12_mul(lam, fq12_sub(xt, x3)), yt)
+            xt = x3
+    return f
+
+
+FINAL_EXP = (Q_MOD ** 12 - 1) // R_MOD
+
+
+def pairing(P, Q):
+    """e(P, Q) in Fq12 (1 if either argument is infinity)."""
+    if P is None or Q is None:
+        return FQ12_ONE
+    return fq12_pow(miller_loop(P, Q), FINAL_EXP)
+
+
+def pairing_product_is_one(pairs) -> bool:
+    """prod e(P_i, Q_i) == 1 with ONE final exponentiation (what a Groth16 verifier evaluates)."""
+    f = FQ12_ONE
+    for P, Q in pairs:
+        if P is not None and Q is not None:
+            f = fq12_mul(f, miller_loop(P, Q))
+    return fq12_pow(f, FINAL_EXP) == FQ12_ONE
+
+
+def groth16_verify(vk, proof, public_inputs) -> bool:
+    """groth16/src/verifier.rs: e(A, B) == e(alpha, beta) e(sum x_i gamma_abc_i, gamma) e(C, delta), as one product.
+    vk: dict(alpha_g1, beta_g2, gamma_g2, delta_g2, gamma_abc_g1 list) of affine int points; public_inputs without the one."""
+    A, B, C = proof
+    acc = vk["gamma_abc_g1"][0]
+    for x, pt in zip(public_inputs, vk["gamma_abc_g1"][1:]):
+        acc = g1_add(acc, g1_mul(pt, x))
+    return pairing_product_is_one([(A, B), (g1_neg(vk["alpha_g1"]), vk["beta_g2"]), (g1_neg(acc), vk["gamma_g2"]),
+                                   (g1_neg(C), vk["delta_g2"])])

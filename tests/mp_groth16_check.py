@@ -49,6 +49,7 @@ def main():
     got = czk_b200.groth16_prove(ctx, scheme, dpk, mine, r_sh[rank], s_sh[rank])
     assert (got["proof"] == exp["proof"]).all() and (got["proof_inf"] == exp["proof_inf"]).all(), f"rank {rank}: revealed proof differs"
     assert (got["proof_sh"] == exp["proof_sh"][rank]).all(), f"rank {rank}: proof share differs"
+    assert czk_b200.groth16_verify(pk, chain[n_sq:n_sq + 1], got["proof"], got["proof_inf"]), f"rank {rank}: revealed proof does not verify"
     st = ctx.net_stats()
     assert st["broadcasts"] > 0 and st["bytes_sent"] > 0
     # batch_open parity on a random shared vector

@@ -35,6 +35,14 @@ def test_prove_matches_oracle_single_party(ctx, czk, oracle, pymodel, n_sq, sche
     got = czk.groth16_prove(ctx, scheme, dpk, chain, r[0], s[0])
     assert (got["proof_inf"] == exp["proof_inf"]).all() and (got["proof"] == exp["proof"]).all()
     assert (got["proof_sh"] == exp["proof_sh"][0]).all() and (got["proof_sh_inf"] == exp["proof_sh_inf"][0]).all()
+    # the reference's acceptance test (proof.rs:141 verify_proof): the device proof verifies under the pairing check,
+    # survives Proof::serialize, and is rejected for another public input (groth16/src/test.rs:158-171)
+    public = chain[n_sq:n_sq + 1]
+    wire = czk.groth16_proof_serialize(got["proof"], got["proof_inf"])
+    assert len(wire) == 192
+    back, binf = czk.groth16_proof_deserialize(wire)
+    assert czk.groth16_verify(pk, public, back, binf)
+    assert not czk.groth16_verify(pk, oracle.fr_add(public, oracle.fr_from_ints([1])), got["proof"], got["proof_inf"])
     dpk.free()
 
 
@@ -94,6 +102,7 @@ def test_prove_any_r1cs_matches_oracle(ctx, czk, oracle, pymodel, scheme_name, s
         assert (got["proof_sh"] == exp["proof_sh"][0]).all()
     assert exp["ok"]
     assert (got["proof"] == exp["proof"]).all() and (got["proof_inf"] == exp["proof_inf"]).all()
+    assert czk.groth16_verify(pk, oracle.fr_from_ints(z[1:ninst]), got["proof"], got["proof_inf"])
     # the squaring entry points refuse a key of another circuit
     with pytest.raises(czk.CzkError):
         czk.groth16_prove(ctx, czk.SCHEME_PLAIN, dpk, np.zeros((1, 4), np.uint64), r[0], s[0])
