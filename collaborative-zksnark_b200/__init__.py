@@ -32,5 +32,9 @@ from .binding import (  # noqa: F401
     groth16_proof_deserialize,
     pairing_product_is_one,
     groth16_verify,
+    fixed_base_msm,
+    groth16_setup,
+    groth16_setup_r1cs,
+    pk_verifying_key,
 )
 from .build import build as build_library  # noqa: F401

@@ -125,6 +125,10 @@ _OPTIONAL_SIGS = {
     "czk_groth16_proof_deserialize": (C.c_int, [C.c_void_p, u64p, u8p]),
     "czk_pairing_product_is_one": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int)]),
     "czk_groth16_verify": (C.c_int, [u64p, u64p, C.c_void_p, C.c_size_t, C.c_void_p, u64p, u8p, C.POINTER(C.c_int)]),
+    "czk_groth16_setup": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "czk_groth16_setup_r1cs": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "czk_groth16_pk_gamma_abc": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "czk_fixed_base_msm": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p)]),
     "czk_r1cs_upload": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
     "czk_r1cs_free": (None, [C.c_void_p, C.c_void_p]),
     "czk_groth16_pk_upload_r1cs": (C.c_int, [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t] + [C.c_void_p] * 12 + [C.POINTER(C.c_void_p)]),
@@ -763,3 +767,46 @@ def groth16_verify(pk: dict, public_inputs, proof, proof_inf) -> bool:
     _ser_chk(load_library().czk_groth16_verify(alpha.ctypes.data_as(u64p), vk_g2.ctypes.data_as(u64p), abc.ctypes.data, abc.shape[0],
                                                pub.ctypes.data, proof.ctypes.data_as(u64p), proof_inf.ctypes.data_as(u8p), C.byref(ok)))
     return bool(ok.value)
+
+
+def fixed_base_msm(ctx: Context, curve: int, base_xy, scalars: DeviceVec, n=None, sc_off=0) -> "Bases":
+    """scalars[i] * base as a resident base set (FixedBaseMSM::multi_scalar_mul on the device)."""
+    base_xy = _np_u64(base_xy)
+    n = scalars.n - sc_off if n is None else n
+    h = C.c_void_p()
+    ctx._chk(ctx.lib.czk_fixed_base_msm(ctx.h, curve, base_xy.ctypes.data, scalars.h, sc_off, n, C.byref(h)))
+    return Bases(ctx, h, curve)
+
+
+def groth16_setup(ctx: Context, n_sq: int, toxic_mont) -> "ProvingKey":
+    """generate_parameters for the squaring circuit on the device (toxic: 7 Montgomery Fr)."""
+    toxic = _np_u64(toxic_mont, 4)
+    assert toxic.shape[0] == 7
+    h = C.c_void_p()
+    ctx._chk(ctx.lib.czk_groth16_setup(ctx.h, n_sq, toxic.ctypes.data, C.byref(h)))
+    pk = ProvingKey(ctx, h, n_sq)
+    pk.ninst = 2
+    return pk
+
+
+def groth16_setup_r1cs(ctx: Context, cs: dict, toxic_mont) -> "ProvingKey":
+    toxic = _np_u64(toxic_mont, 4)
+    mats = [tuple(np.ascontiguousarray(x) for x in cs[m]) for m in ("a", "b", "c")]
+    rp = (C.c_void_p * 3)(*[m[0].ctypes.data for m in mats])
+    col = (C.c_void_p * 3)(*[m[1].ctypes.data for m in mats])
+    cf = (C.c_void_p * 3)(*[m[2].ctypes.data for m in mats])
+    h = C.c_void_p()
+    ctx._chk(ctx.lib.czk_groth16_setup_r1cs(ctx.h, cs["ncons"], cs["ninst"], cs["nwit"], rp, col, cf, toxic.ctypes.data, C.byref(h)))
+    pk = ProvingKey(ctx, h, 0)
+    pk.ninst = cs["ninst"]
+    return pk
+
+
+def pk_verifying_key(pk: "ProvingKey") -> dict:
+    """The verifier's view of a key generated on the device: vk_g1 (alpha | beta | delta), vk_g2 (beta | gamma | delta),
+    gamma_abc_g1 - the dict czk_b200.groth16_verify takes."""
+    vk1, vk2 = np.zeros(36, np.uint64), np.zeros(72, np.uint64)
+    pk.ctx._chk(pk.ctx.lib.czk_groth16_pk_vk(pk.h, vk1.ctypes.data_as(u64p), vk2.ctypes.data_as(u64p)))
+    abc = np.zeros((pk.ninst, 12), np.uint64)
+    pk.ctx._chk(pk.ctx.lib.czk_groth16_pk_gamma_abc(pk.h, abc.ctypes.data, pk.ninst))
+    return dict(vk_g1=vk1.reshape(3, 12), vk_g2=vk2.reshape(3, 24), gamma_abc_g1=abc)

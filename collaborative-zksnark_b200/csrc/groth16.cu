@@ -21,6 +21,7 @@ struct czk_pk {
     // first entries of the a / b queries (calculate_coeff adds query[0] on the host)
     uint64_t a0[12], b10[12], b20[24];
     uint8_t a0_inf = 0, b10_inf = 0, b20_inf = 0;
+    std::vector<uint64_t> gamma_abc;  // ninst x 12 limbs when the key was generated here (czk_groth16_setup*), else empty
 };
 
 static double now_ms() {
@@ -177,6 +178,190 @@ int czk_groth16_pk_upload_r1cs(czk_ctx* ctx, size_t ncons, size_t ninst, size_t 
     std::memcpy(pk->vk_g2, vk_g2, sizeof pk->vk_g2);
     CZK_TRY(pk_finish(ctx, pk));
     *out = pk;
+    return CZK_OK;
+}
+
+// ------------------------------------------------------------------------------------------ CRS generation
+// groth16/src/generator.rs:34-221 (generate_parameters) with the toxic waste supplied by the caller:
+// toxic = alpha | beta | gamma | delta | tau | g1_scalar | g2_scalar (7 Montgomery Fr; the reference draws the two generators
+// as random group elements, here they are g1_scalar * G1 and g2_scalar * G2 of the curve's standard generators).
+// The O(D) scalar work (Lagrange coefficients at tau, the QAP polynomials at tau) runs on the host; the five fixed-base
+// multi-scalar multiplications - where the reference spends its time - run on the device and leave the queries resident.
+template <class HF, int LIMBS>
+static void point_to_affine_limbs(const HPoint<HF>& p, uint64_t* xy) {  // infinity is written as (0, 1)
+    HF ax, ay;
+    if (!p.to_affine(ax, ay)) {
+        ax = HF::zero();
+        ay = HF::one();
+    }
+    ax.to_limbs(xy);
+    ay.to_limbs(xy + LIMBS);
+}
+
+static int setup_core(czk_ctx* ctx, size_t ncons, size_t ninst, size_t nwit, const uint64_t* const row_ptr[3],
+                      const uint32_t* const col[3], const uint64_t* const coeff[3], const uint64_t toxic[28], czk_pk* pk) {
+    const HFr alpha = HFr::from_limbs(toxic), beta = HFr::from_limbs(toxic + 4), gamma = HFr::from_limbs(toxic + 8),
+              delta = HFr::from_limbs(toxic + 12), tau = HFr::from_limbs(toxic + 16), s1 = HFr::from_limbs(toxic + 20),
+              s2 = HFr::from_limbs(toxic + 24);
+    if (gamma.is_zero() || delta.is_zero() || s1.is_zero() || s2.is_zero()) return fail(ctx, CZK_ERR_ARG, "groth16 setup: zero toxic value");
+    const size_t nvar = ninst + nwit, D = pk->D;
+    // Lagrange coefficients at tau (radix2/mod.rs:119-181): u_i = Z(tau) w^i / (D (tau - w^i)), one batched inversion
+    HFr w = HFr::from_limbs(FrParams::ROOT_2_47_64);
+    for (unsigned i = pk->log_d; i < FrParams::TWO_ADICITY; i++) w = HFr::sqr(w);
+    const HFr zt = HFr::sub(HFr::pow_u64(tau, (uint64_t)D), HFr::one()), dfe = HFr::from_u64((uint64_t)D);
+    std::vector<HFr> u(D), pre(D);
+    {
+        HFr wi = HFr::one(), acc = HFr::one();
+        for (size_t i = 0; i < D; i++) {
+            HFr den = HFr::mul(HFr::sub(tau, wi), dfe);
+            if (den.is_zero()) return fail(ctx, CZK_ERR_ARG, "groth16 setup: tau lies in the evaluation domain");
+            u[i] = den;
+            pre[i] = acc;
+            acc = HFr::mul(acc, den);
+            wi = HFr::mul(wi, w);
+        }
+        HFr inv = HFr::inv(acc);
+        // walk back: 1/den_i = inv * pre_i ; w^i recomputed from the top
+        std::vector<HFr> wp(D);
+        wi = HFr::one();
+        for (size_t i = 0; i < D; i++) {
+            wp[i] = wi;
+            wi = HFr::mul(wi, w);
+        }
+        for (size_t i = D; i-- > 0;) {
+            HFr di = HFr::mul(inv, pre[i]);
+            inv = HFr::mul(inv, u[i]);
+            u[i] = HFr::mul(HFr::mul(zt, wp[i]), di);
+        }
+    }
+    pre.clear();
+    pre.shrink_to_fit();
+    // a_i(tau), b_i(tau), c_i(tau) per variable (generator.rs:109-121, r1cs_to_qap.rs:51-92)
+    std::vector<HFr> qa(nvar, HFr::zero()), qb(nvar, HFr::zero()), qc(nvar, HFr::zero());
+    for (size_t i = 0; i < ninst; i++) qa[i] = u[ncons + i];
+    std::vector<HFr>* dst[3] = {&qa, &qb, &qc};
+    for (int m = 0; m < 3; m++)
+        for (size_t i = 0; i < ncons; i++)
+            for (uint64_t k = row_ptr[m][i]; k < row_ptr[m][i + 1]; k++) {
+                HFr& x = (*dst[m])[col[m][k]];
+                x = HFr::add(x, HFr::mul(u[i], HFr::from_limbs(coeff[m] + 4 * k)));
+            }
+    const HFr gamma_inv = HFr::inv(gamma), delta_inv = HFr::inv(delta);
+    std::vector<uint64_t> sa(nvar * 4), sb(nvar * 4), sl((nwit ? nwit : 1) * 4), sh((D - 1) * 4);
+    std::vector<HFr> gabc(ninst);
+    for (size_t i = 0; i < nvar; i++) {
+        qa[i].to_limbs(sa.data() + 4 * i);
+        qb[i].to_limbs(sb.data() + 4 * i);
+        HFr x = HFr::add(HFr::add(HFr::mul(beta, qa[i]), HFr::mul(alpha, qb[i])), qc[i]);
+        if (i < ninst) gabc[i] = HFr::mul(x, gamma_inv);
+        else HFr::mul(x, delta_inv).to_limbs(sl.data() + 4 * (i - ninst));
+    }
+    {
+        HFr f = HFr::mul(zt, delta_inv), pw = HFr::one();
+        for (size_t i = 0; i + 1 < D; i++) {
+            HFr::mul(f, pw).to_limbs(sh.data() + 4 * i);
+            pw = HFr::mul(pw, tau);
+        }
+    }
+    u.clear();
+    u.shrink_to_fit();
+    // generators and the verifying-key elements (host: O(ninst) scalar multiplications)
+    auto canon = [](const HFr& x, uint64_t k[4]) { x.from_mont().to_limbs(k); };
+    uint64_t k[4];
+    HG1 g1 = HG1::from_affine(HFq::from_limbs(CurveConsts::G1_GEN), HFq::from_limbs(CurveConsts::G1_GEN + 6));
+    HG2 g2 = HG2::from_affine(HFq2::from_limbs(CurveConsts::G2_GEN), HFq2::from_limbs(CurveConsts::G2_GEN + 12));
+    canon(s1, k);
+    g1 = HG1::mul(g1, k, 4);
+    canon(s2, k);
+    g2 = HG2::mul(g2, k, 4);
+    uint64_t g1_xy[12], g2_xy[24];
+    point_to_affine_limbs<HFq, 6>(g1, g1_xy);
+    point_to_affine_limbs<HFq2, 12>(g2, g2_xy);
+    const HFr v1[3] = {alpha, beta, delta}, v2[3] = {beta, gamma, delta};
+    for (int i = 0; i < 3; i++) {
+        canon(v1[i], k);
+        point_to_affine_limbs<HFq, 6>(HG1::mul(g1, k, 4), pk->vk_g1 + 12 * i);
+        canon(v2[i], k);
+        point_to_affine_limbs<HFq2, 12>(HG2::mul(g2, k, 4), pk->vk_g2 + 24 * i);
+    }
+    pk->gamma_abc.assign(ninst * 12, 0);
+    for (size_t i = 0; i < ninst; i++) {
+        canon(gabc[i], k);
+        point_to_affine_limbs<HFq, 6>(HG1::mul(g1, k, 4), pk->gamma_abc.data() + 12 * i);
+    }
+    // the five queries: fixed-base MSMs on the device, left resident
+    czk_vec *va = nullptr, *vb = nullptr, *vl = nullptr, *vh = nullptr;
+    auto cleanup = [&](int rc) {
+        for (czk_vec* v : {va, vb, vl, vh}) czk_vec_free(ctx, v);
+        return rc;
+    };
+    int rc;
+    if ((rc = czk_vec_alloc(ctx, nvar, &va)) || (rc = czk_vec_alloc(ctx, nvar, &vb)) || (rc = czk_vec_alloc(ctx, nwit ? nwit : 1, &vl)) ||
+        (rc = czk_vec_alloc(ctx, D - 1, &vh)))
+        return cleanup(rc);
+    if ((rc = czk_vec_upload(ctx, va, 0, sa.data(), nvar)) || (rc = czk_vec_upload(ctx, vb, 0, sb.data(), nvar)) ||
+        (nwit && (rc = czk_vec_upload(ctx, vl, 0, sl.data(), nwit))) || (rc = czk_vec_upload(ctx, vh, 0, sh.data(), D - 1)))
+        return cleanup(rc);
+    if ((rc = czk_fixed_base_msm(ctx, 1, g1_xy, va, 0, nvar, &pk->q[0])) || (rc = czk_fixed_base_msm(ctx, 1, g1_xy, vb, 0, nvar, &pk->q[1])) ||
+        (rc = czk_fixed_base_msm(ctx, 2, g2_xy, vb, 0, nvar, &pk->q[2])) || (rc = czk_fixed_base_msm(ctx, 1, g1_xy, vh, 0, D - 1, &pk->q[3])) ||
+        (rc = czk_fixed_base_msm(ctx, 1, g1_xy, vl, 0, nwit, &pk->q[4])))
+        return cleanup(rc);
+    return cleanup(CZK_OK);
+}
+
+int czk_groth16_setup_r1cs(czk_ctx* ctx, size_t ncons, size_t ninst, size_t nwit, const uint64_t* const row_ptr[3],
+                           const uint32_t* const col[3], const uint64_t* const coeff[3], const uint64_t toxic[28], czk_pk** out) {
+    if (!ctx || !out || !row_ptr || !col || !coeff || !toxic || !ncons || !ninst)
+        return fail(ctx, CZK_ERR_ARG, "czk_groth16_setup_r1cs: argument");
+    for (int m = 0; m < 3; m++) {
+        if (!row_ptr[m] || row_ptr[m][0] != 0) return fail(ctx, CZK_ERR_ARG, "czk_groth16_setup_r1cs: row_ptr");
+        for (uint64_t k = 0; k < row_ptr[m][ncons]; k++)
+            if (col[m][k] >= ninst + nwit) return fail(ctx, CZK_ERR_ARG, "czk_groth16_setup_r1cs: variable index out of range");
+    }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    czk_pk* pk = new czk_pk();
+    pk->n_sq = 0;
+    pk->ncons = ncons;
+    pk->ninst = ninst;
+    pk->nwit = nwit;
+    pk->D = 1;
+    pk->log_d = 0;
+    while (pk->D < ncons + ninst) pk->D <<= 1, pk->log_d++;
+    int rc = setup_core(ctx, ncons, ninst, nwit, row_ptr, col, coeff, toxic, pk);
+    if (rc == CZK_OK) rc = pk_finish(ctx, pk);
+    if (rc != CZK_OK) {
+        czk_groth16_pk_free(ctx, pk);
+        return rc;
+    }
+    *out = pk;
+    return CZK_OK;
+}
+
+// the benchmark circuit: variables [one, out, w_0 .. w_{n-1}], constraint i: w_i * w_i = w_{i+1} (the last: = out)
+int czk_groth16_setup(czk_ctx* ctx, size_t n_sq, const uint64_t toxic[28], czk_pk** out) {
+    if (!ctx || !out || !toxic || !n_sq) return fail(ctx, CZK_ERR_ARG, "czk_groth16_setup: argument");
+    std::vector<uint64_t> rp(n_sq + 1), ones(n_sq * 4);
+    std::vector<uint32_t> ab(n_sq), cc(n_sq);
+    const HFr one = HFr::one();
+    for (size_t i = 0; i <= n_sq; i++) rp[i] = i;
+    for (size_t i = 0; i < n_sq; i++) {
+        ab[i] = (uint32_t)(2 + i);
+        cc[i] = (uint32_t)(i + 1 < n_sq ? 2 + i + 1 : 1);
+        one.to_limbs(ones.data() + 4 * i);
+    }
+    const uint64_t* rps[3] = {rp.data(), rp.data(), rp.data()};
+    const uint32_t* cols[3] = {ab.data(), ab.data(), cc.data()};
+    const uint64_t* cfs[3] = {ones.data(), ones.data(), ones.data()};
+    czk_pk* pk = nullptr;
+    CZK_TRY(czk_groth16_setup_r1cs(ctx, n_sq, 2, n_sq, rps, cols, cfs, toxic, &pk));
+    pk->n_sq = n_sq;  // the squaring entry points (czk_groth16_prove) accept this key
+    *out = pk;
+    return CZK_OK;
+}
+
+int czk_groth16_pk_gamma_abc(const czk_pk* pk, uint64_t* out, size_t ninst) {
+    if (!pk || !out || pk->gamma_abc.size() != ninst * 12) return fail(nullptr, CZK_ERR_ARG, "czk_groth16_pk_gamma_abc: this key carries no gamma_abc of that size");
+    std::memcpy(out, pk->gamma_abc.data(), ninst * 12 * 8);
     return CZK_OK;
 }
 

@@ -84,6 +84,22 @@ CZK_API int czk_groth16_prove_r1cs(czk_ctx* ctx, int scheme, const czk_pk* pk, c
 CZK_API int czk_groth16_proof_serialize(const uint64_t proof[48], const uint8_t proof_inf[3], uint8_t out[192]);
 CZK_API int czk_groth16_proof_deserialize(const uint8_t in[192], uint64_t proof[48], uint8_t proof_inf[3]);
 
+/* ---- CRS generation: groth16/src/generator.rs:34-221 with caller-supplied toxic waste ----------------
+ * toxic = alpha | beta | gamma | delta | tau | g1_scalar | g2_scalar (7 Montgomery Fr; the generators are g1_scalar * G1 and
+ * g2_scalar * G2 of the curve's standard generators).  The five queries are computed by fixed-base multi-scalar
+ * multiplications on the device (replacing FixedBaseMSM, algebra/ec/src/msm/fixed_base.rs:12-96) and stay resident in the
+ * returned key, which also carries gamma_abc_g1 for the verifier.  czk_groth16_setup = the benchmark's squaring circuit. */
+CZK_API int czk_groth16_setup(czk_ctx* ctx, size_t n_sq, const uint64_t toxic[28], czk_pk** out);
+CZK_API int czk_groth16_setup_r1cs(czk_ctx* ctx, size_t ncons, size_t ninst, size_t nwit, const uint64_t* const row_ptr[3],
+                                   const uint32_t* const col[3], const uint64_t* const coeff[3], const uint64_t toxic[28],
+                                   czk_pk** out);
+/* gamma_abc_g1 (ninst points) of a key generated by the two calls above. */
+CZK_API int czk_groth16_pk_gamma_abc(const czk_pk* pk, uint64_t* out, size_t ninst);
+/* out[i] = scalars[sc_off + i] * base for i < n as a resident base set, infinity where the scalar is zero
+ * (FixedBaseMSM::multi_scalar_mul + batch normalisation).  curve: 1 = G1 (base 12 limbs), 2 = G2 (24 limbs). */
+CZK_API int czk_fixed_base_msm(czk_ctx* ctx, int curve, const uint64_t* base_xy, const czk_vec* scalars, size_t sc_off, size_t n,
+                               czk_bases** out);
+
 /* ---- verifier, host-side, ctx-free ------------------------------------------------------------------
  * The acceptance test the reference runs after every benchmark proof (`verify_proof`, mpc-snarks/src/proof.rs:141,
  * groth16/src/verifier.rs; pairing: algebra/ec/src/models/bls12/mod.rs:59-200).
