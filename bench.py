@@ -7,9 +7,11 @@
 
 A "step" is one proof: create_random_proof + reveal (mpc-snarks/src/proof.rs:130-139) of the repeated-squaring
 circuit with 2^20 squarings (D = 2^21) under SPDZ shares: 14 NTTs of 2^21, the Beaver product with its opens,
-MSMs of 2^21-1, 2^20, 2^20+1 (x2) G1 terms and 2^20+1 G2 terms, and the O(1) share/group tail.  Synthetic data:
-device-generated CRS bases of the reference's shapes (the proof does not verify; the work is identical), seeded
-witness chain shared additively by the king.  Prints ONE JSON line on rank 0.
+MSMs of 2^21-1, 2^20, 2^20+1 (x2) G1 terms and 2^20+1 G2 terms, and the O(1) share/group tail.  Synthetic data: a
+seeded witness chain shared additively by the king, and a REAL CRS generated on the device from seeded toxic waste
+(czk_groth16_setup) - one more proof is produced after the timed region and verified with the pairing check, so the
+measured path is known to produce valid proofs (--key synthetic: shape-only bases, no verification).
+Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
@@ -159,6 +161,9 @@ def main():
     ap.add_argument("--log-n", type=int, default=LOG_N, help="log2 constraints (default 20 = the BASELINE config)")
     ap.add_argument("--scheme", default="spdz", choices=["spdz", "additive", "plain", "gsz"])
     ap.add_argument("--cpu-sample-log-n", type=int, default=16)
+    ap.add_argument("--key", default="real", choices=["real", "synthetic"],
+                    help="real: CRS generated on the device from seeded toxic waste, the timed proof is verified with the pairing "
+                         "check after the timed region; synthetic: device-generated bases of the same shapes (no verification)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -194,7 +199,19 @@ def main():
 
     # ---- setup (untimed, like the reference: CRS + king_share_batch happen before start_timer!, proof.rs:113-129)
     imad_peak, _ = ctx.microbench(0, 8, 256, 2000)  # measured IMAD.WIDE.U32 issue rate: the integer roofline denominator
-    pk = czk_b200.ProvingKey.synthetic(ctx, n_sq, seed=0x377)
+    key_kind = args.key
+    pk = None
+    if key_kind == "real":
+        try:
+            rng = np.random.Generator(np.random.PCG64(0x377))
+            toxic = rng.integers(0, 1 << 64, size=(7, 4), dtype=np.uint64)
+            toxic[:, 3] &= np.uint64((1 << 60) - 1)  # < 2^252 < r: valid Montgomery limbs, same on every rank
+            pk = czk_b200.groth16_setup(ctx, n_sq, toxic)
+        except Exception as exc:  # fall back to the shape-only key rather than lose the measurement
+            print(f"bench.py: real key generation failed ({exc}); using a synthetic key", file=sys.stderr)
+            key_kind = "synthetic"
+    if pk is None:
+        pk = czk_b200.ProvingKey.synthetic(ctx, n_sq, seed=0x377)
     D = pk.domain_size
     start = np.array([0x1234567, 0x89abcdef, 0x55aa55aa, 0x0123], np.uint64)
     if args.scheme == "gsz":
@@ -245,6 +262,13 @@ def main():
     ms_e2e, times_e2e, phases_e2e, _, _, _ = timed(False, args.steps)
     clocks = sampler.stop()
 
+    # acceptance check outside the timed region (mpc-snarks/src/proof.rs:141 verify_proof): one more proof, verified
+    verified = None
+    if key_kind == "real":
+        _, res = step(True)
+        if rank == 0:
+            start_el = czk_b200.squaring_chain(start, n_sq)[n_sq:n_sq + 1]
+            verified = bool(czk_b200.groth16_verify(czk_b200.pk_verifying_key(pk), start_el, res["proof"], res["proof_inf"]))
     if rank != 0:
         party.close()
         return 0
@@ -273,7 +297,10 @@ def main():
         "vs_baseline": (ms_res / PUBLISHED_MS[world]) if (args.log_n == LOG_N and world in PUBLISHED_MS) else None,
         "dtype": "u32 limbs (Montgomery Fr/Fq), integer", "data": "synthetic",
         "config": {"workload": f"groth16 {args.scheme} 2^{args.log_n} constraints (D=2^{D.bit_length() - 1}) BLS12-377, one party per GPU",
-                   "parties": world, "l2": "256 MiB flush write between iterations", "bases": "device-generated synthetic CRS of the reference's shapes",
+                   "parties": world, "l2": "256 MiB flush write between iterations",
+                   "bases": ("real CRS generated on the device from seeded toxic waste (czk_groth16_setup); the proof is verified after the timed region"
+                             if key_kind == "real" else "device-generated synthetic CRS of the reference's shapes"),
+                   "proof_verified": verified,
                    "published_reference_ms": PUBLISHED_MS.get(world)},
         "clocks": clocks,
         "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": int((n_sq + 1) * 32), "d2h_bytes_per_step": int(2 * 48 * 8 + 6 + 5 * 16 * 192)},

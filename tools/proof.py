@@ -42,7 +42,11 @@ def main():
     else:
         assert world == 1, "local proving is a single process"
         scheme = czk_b200.SCHEME_PLAIN
-    pk = czk_b200.ProvingKey.synthetic(ctx, n_sq, seed=1)  # generate_random_parameters stand-in (untimed)
+    # generate_random_parameters (proof.rs:113-117, untimed): a real CRS on the device from seeded toxic waste
+    rng = np.random.Generator(np.random.PCG64(1))
+    toxic = rng.integers(0, 1 << 64, size=(7, 4), dtype=np.uint64)
+    toxic[:, 3] &= np.uint64((1 << 60) - 1)
+    pk = czk_b200.groth16_setup(ctx, n_sq, toxic)
     if args.mode == "mpc" and args.alg == "gsz":
         # king_share_batch under GSZ hands every party the value itself (gsz20/mod.rs:202-212)
         mine = czk_b200.squaring_chain(np.array([3, 1, 4, 1], np.uint64), n_sq)
@@ -54,8 +58,11 @@ def main():
     ctx.net_reset_stats()
     launch.barrier()
     t = time.perf_counter()
-    czk_b200.groth16_prove(ctx, scheme, pk, mine, r, s)
+    res = czk_b200.groth16_prove(ctx, scheme, pk, mine, r, s)
     dt = launch.max_over_ranks(time.perf_counter() - t)
+    if rank == 0:  # verify_proof(&pvk, &pf, &[public input]) (proof.rs:141)
+        out = czk_b200.squaring_chain(np.array([3, 1, 4, 1], np.uint64), n_sq)[n_sq:n_sq + 1]
+        assert czk_b200.groth16_verify(czk_b200.pk_verifying_key(pk), out, res["proof"], res["proof_inf"]), "proof does not verify"
     if rank == 0:
         unit = f"{dt:.3f}s" if dt >= 1 else (f"{dt * 1e3:.3f}ms" if dt >= 1e-3 else f"{dt * 1e6:.3f}µs")
         print(f"End:     timed section ............................................................{unit}")
