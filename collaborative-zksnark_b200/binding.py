@@ -11,6 +11,7 @@ All arrays are numpy uint64 limb arrays in the reference's Montgomery in-memory 
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
@@ -31,7 +32,9 @@ class CzkError(RuntimeError):
 
 
 def library_path() -> Path:
-    return _HERE / "libczk_b200.so"
+    # CZK_B200_LIB: another build of the same library (A/B runs of kernel variants on one GPU box)
+    override = os.environ.get("CZK_B200_LIB")
+    return Path(override) if override else _HERE / "libczk_b200.so"
 
 
 _SIGS = {

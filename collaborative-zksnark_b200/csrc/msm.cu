@@ -390,11 +390,15 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
     }();
     if (ws.batched && n * cfg.nwin >= bat_min_entries && n * cfg.nwin >= total * bat_min_load) {
         // tree of batched affine additions (msm_batched.cu); needs the longest bucket to know the number of rounds
+        // and the last bucket's run, which fixes the exact slot count of every round (grid sizing)
         if ((e = cudaMemcpyAsync(ws.host_word, ws.queue + 4, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(ws.host_word + 1, ws.offsets + (total - 1), 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(ws.host_word + 2, ws.hist + (total - 1), 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
         if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-        const uint32_t maxlen = *ws.host_word;
+        const uint32_t maxlen = ws.host_word[0], last_len = ws.host_word[2], last_start = ws.host_word[1] - last_len;
         if ((e = msm_batched_accumulate(FieldIO<F>::W == 12 ? 1 : 2, bases, ws.sorted, ws.offsets, ws.hist, total, n * cfg.nwin, maxlen,
-                                        ws.bat_a, ws.bat_b, ws.bat_prefix, ws.buckets, ws.queue + 3, ws.sm_count, st)) != cudaSuccess)
+                                        last_start, last_len, ws.bat_a, ws.bat_b, ws.bat_prefix, ws.buckets, ws.queue + 3, ws.sm_count,
+                                        st)) != cudaSuccess)
             return e;
         gate = ws.queue + 3;
     }

@@ -134,13 +134,15 @@ cudaError_t msm_run(int curve, const uint32_t* bases, const uint8_t* inf, const 
 size_t msm_point_words(int curve);  // 4 coordinates
 
 // Batched-affine bucket accumulation (msm_batched.cu).  ends / hist: the counting sort's bucket ends and lengths;
-// entries: an upper bound on the sorted entries (n * windows); maxlen: the longest bucket.  Writes `buckets` (XYZZ)
+// entries: an upper bound on the sorted entries (n * windows); maxlen: the longest bucket; last_start / last_len: the last
+// bucket's run in the sorted list (they fix every round's exact slot count).  Writes `buckets` (XYZZ)
 // unless an addition without an affine formula was met, in which case *flag becomes non-zero and the caller's XYZZ
 // kernel must run.  pa / pb / prefix: scratch of the sizes msm_batched_bytes reports.
 size_t msm_batched_bytes(int curve, size_t entries, size_t nb, size_t* pa, size_t* pb, size_t* pre);
 cudaError_t msm_batched_accumulate(int curve, const uint32_t* bases, const uint32_t* sorted, const uint32_t* ends,
-                                   const uint32_t* hist, size_t nb, size_t entries, uint32_t maxlen, uint32_t* pa, uint32_t* pb,
-                                   uint32_t* prefix, uint32_t* buckets, uint32_t* flag, int sm_count, cudaStream_t st);
+                                   const uint32_t* hist, size_t nb, size_t entries, uint32_t maxlen, uint32_t last_start,
+                                   uint32_t last_len, uint32_t* pa, uint32_t* pb, uint32_t* prefix, uint32_t* buckets, uint32_t* flag,
+                                   int sm_count, cudaStream_t st);
 // out[i] = 1 / in[i] in Fq (Montgomery), 0 -> 0: the block inversion of the batched path, exposed for its parity test
 cudaError_t fq_inverse_batch(const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st);
 

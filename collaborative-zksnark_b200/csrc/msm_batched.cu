@@ -161,10 +161,13 @@ struct TreeIO<Fq2> {
 };
 // products inside the two hot loops: inlined (for Fq2 the out-of-line bodies cost a round trip through local memory per
 // operand; measured below)
+#ifndef BAT_FQ_CALL
+#define BAT_FQ_CALL 0
+#endif
 template <int INL>
-__device__ __forceinline__ Fq hot_mul(const Fq& a, const Fq& b) { return Fq::mul(a, b); }
+__device__ __forceinline__ Fq hot_mul(const Fq& a, const Fq& b) { return BAT_FQ_CALL ? Fq::mul_ni(a, b) : Fq::mul(a, b); }
 template <int INL>
-__device__ __forceinline__ Fq hot_sqr(const Fq& a) { return Fq::sqr(a); }
+__device__ __forceinline__ Fq hot_sqr(const Fq& a) { return BAT_FQ_CALL ? Fq::mul_ni(a, a) : Fq::sqr(a); }
 template <int INL>
 __device__ __forceinline__ Fq2 hot_mul(const Fq2& a, const Fq2& b) { return INL ? Fq2::mul_inl(a, b) : Fq2::mul(a, b); }
 template <int INL>
@@ -175,68 +178,96 @@ __device__ __forceinline__ Fq2 cold_mul(const Fq2& a, const Fq2& b) { return Fq2
 
 // ------------------------------------------------------------------ one round
 struct BatCursor {
-    uint32_t b, s_in, len_in, s_out, len_out, next_s_out;
+    uint32_t b, s_in, len_in, s_out, next_s_out;
+    __device__ __forceinline__ uint32_t len_out() const { return (len_in + 1) >> 1; }
 };
 __device__ __forceinline__ void bat_seek(const BatGeom& g, BatCursor& c, uint32_t b) {
     c.b = b;
     c.s_in = bat_start(g, b, g.r);
     c.len_in = bat_len(g, b, g.r);
     c.s_out = (c.s_in >> 1) + b;
-    c.len_out = (c.len_in + 1) >> 1;
     c.next_s_out = b + 1 < g.nb ? (bat_start(g, b + 1, g.r) >> 1) + b + 1 : 0xffffffffu;
-}
-
-template <class F, bool FIRST>
-__device__ __forceinline__ void bat_load_x(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                           const uint32_t* __restrict__ in, uint32_t pos, F& x) {
-    constexpr int W = FieldIO<F>::W;
-    if (FIRST) {
-        uint32_t e = sorted[pos];
-        x = FieldIO<F>::load(bases + (size_t)(e & 0x7fffffffu) * (2 * W));
-    } else {
-        x = FieldIO<F>::load_rw(in + (size_t)pos * (2 * W));
-    }
-}
-// round 0: the point named by a sorted entry (index | sign << 31); later rounds: slot `pos` of the point array
-template <class F, bool FIRST>
-__device__ __forceinline__ void bat_load_xy(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ in, uint32_t pos,
-                                            uint32_t entry, F& x, F& y) {
-    constexpr int W = FieldIO<F>::W;
-    if (FIRST) {
-        const uint32_t* p = bases + (size_t)(entry & 0x7fffffffu) * (2 * W);
-        x = FieldIO<F>::load(p);
-        y = FieldIO<F>::load(p + W);
-        if (entry >> 31) y = F::neg(y);
-    } else {
-        const uint32_t* p = in + (size_t)pos * (2 * W);
-        x = FieldIO<F>::load_rw(p);
-        y = FieldIO<F>::load_rw(p + W);
-    }
 }
 
 constexpr int BAT_THREADS = 128;
 #ifndef BAT_INLINE_FQ2
 #define BAT_INLINE_FQ2 1
 #endif
+// ------------------------------------------------------------------ one round
+// How the operands reach a thread was tuned against the ncu source view (profiles/r1_summary.md).  With 128 registers
+// per thread (4 blocks of 128 per SM) nothing can be prefetched into registers: a first version that fetched the sorted
+// entries one slot ahead had them spilled at once, which waits for the load just the same, and a third of all stall
+// samples sat on (i) those entries, (ii) the prefix product pre[j-1], loaded at its point of use, (iii) the y negation
+// placed right behind the gathers.  So the SMALL operands of the next slot - its two sorted entries and its prefix
+// product - travel by cp.async into per-thread shared-memory cells (double buffered by slot parity: a copy never
+// targets a cell that is being read) while the current slot is computed; no register is held while they fly.  The
+// 96-byte point gathers go straight to registers, issued at the top of a slot and first consumed after the 1/d
+// product.  (Staging the gathers through shared memory as well was 18 % slower: 30 more LDGSTS/LDS per slot and the
+// copy queue throttles.)
+__device__ __forceinline__ void cp_async16(uint4* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t* smem, const void* gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+__device__ __forceinline__ void words_to(Fq& r, const uint32_t* w) {
+#pragma unroll
+    for (int i = 0; i < 12; i++) r.l[i] = w[i];
+}
+__device__ __forceinline__ void words_to(Fq2& r, const uint32_t* w) {
+    words_to(r.c0, w);
+    words_to(r.c1, w + 12);
+}
+// one field element per thread and parity: chunk c of thread tid at cell[(par * CH + c) * BAT_THREADS + tid]
+template <class F>
+struct StageIO {
+    static constexpr int W = FieldIO<F>::W, CH = W / 4;
+    __device__ __forceinline__ static void fetch(uint4* cell, int par, unsigned tid, const uint32_t* g) {
+#pragma unroll
+        for (int c = 0; c < CH; c++) cp_async16(cell + (par * CH + c) * BAT_THREADS + tid, g + 4 * c);
+    }
+    __device__ __forceinline__ static F ld(const uint4* cell, int par, unsigned tid) {
+        uint32_t w[W];
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            const uint4 v = cell[(par * CH + c) * BAT_THREADS + tid];
+            w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
+        }
+        F r;
+        words_to(r, w);
+        return r;
+    }
+};
+template <class F>
+constexpr size_t bat_smem_bytes() {  // product tree + 2 prefix cells + 2 x 2 entry cells per thread
+    return (size_t)FieldIO<F>::W * 256 * 4 + (size_t)2 * (FieldIO<F>::W / 4) * BAT_THREADS * 16 + (size_t)4 * BAT_THREADS * 4;
+}
+
 template <class F, bool FIRST, int MINB>
 __global__ void __launch_bounds__(BAT_THREADS, MINB)
-    k_bat_round(BatGeom g, const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ in,
-                uint32_t* __restrict__ out, uint32_t* __restrict__ prefix, uint32_t* __restrict__ flag, const int B) {
-    constexpr int W = FieldIO<F>::W;
-    __shared__ uint32_t tree[W * 256];
+    k_bat_round(BatGeom g, const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                       const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* __restrict__ prefix,
+                       uint32_t* __restrict__ flag, const int B) {
+    constexpr int W = FieldIO<F>::W, CH = W / 4;
+    extern __shared__ uint4 bat_smem[];
+    uint32_t* const tree = reinterpret_cast<uint32_t*>(bat_smem);
+    uint4* const pcell = bat_smem + (W * 256) / 4;
+    uint32_t* const ecell = reinterpret_cast<uint32_t*>(pcell + 2 * CH * BAT_THREADS);  // [par][which][tid]
     const unsigned tid = threadIdx.x;
-    // slots actually in use this round: block-uniform early exit before any barrier
     const uint32_t used = (bat_start(g, g.nb - 1, g.r) >> 1) + (g.nb - 1) + ((bat_len(g, g.nb - 1, g.r) + 1) >> 1);
     const size_t block_first = (size_t)blockIdx.x * BAT_THREADS * B;
     if (block_first >= used) return;
     const size_t o0 = block_first + (size_t)tid * B;
-    // prefix scratch: element j of thread tid of this block, coalesced across the block
     uint32_t* const pre = prefix + ((size_t)blockIdx.x * B * BAT_THREADS + tid) * W;
     constexpr size_t PRE_STRIDE = (size_t)BAT_THREADS * W;
 
     BatCursor c;
     {
-        // largest b with S_{r+1}(b) <= o0   (S_{r+1} is strictly increasing and S_{r+1}(0) = 0)
         uint32_t lo = 0, hi = g.nb - 1;
         const uint32_t target = o0 > 0xfffffffeull ? 0xfffffffeu : (uint32_t)o0;
         while (lo < hi) {
@@ -248,38 +279,64 @@ __global__ void __launch_bounds__(BAT_THREADS, MINB)
         bat_seek(g, c, lo);
     }
     const F one = F::one();
-    // ---- phase 1: running product of the differences (the next pair's x coordinates are fetched while the current
-    // product is formed: the gathers of round 0 are random 48-byte reads of a multi-GB table)
+    // descriptor of the slot whose small operands are in flight: bit 0 live, bit 1 pair; m_pos = its first input position
+    uint32_t m_fl = 0, m_pos = 0;
+    auto point_ptr = [&](uint32_t pos, uint32_t e) -> const uint32_t* {
+        return FIRST ? bases + (size_t)(e & 0x7fffffffu) * (2 * W) : in + (size_t)pos * (2 * W);
+    };
+    auto ldp = [&](const uint32_t* q) -> F { return FIRST ? FieldIO<F>::load(q) : FieldIO<F>::load_rw(q); };
+    auto fetch_entries = [&](int par) {
+        if (FIRST && (m_fl & 1u)) cp_async4(ecell + (par * 2 + 0) * BAT_THREADS + tid, sorted + m_pos);
+        if (FIRST && (m_fl & 2u)) cp_async4(ecell + (par * 2 + 1) * BAT_THREADS + tid, sorted + m_pos + 1);
+    };
+    auto entry = [&](int par, int which) -> uint32_t { return FIRST ? ecell[(par * 2 + which) * BAT_THREADS + tid] : 0u; };
+    // ---- phase 1: running product of the differences x2 - x1
+    auto meta1 = [&](size_t o) {
+        while (o >= c.next_s_out) bat_seek(g, c, c.b + 1);
+        const uint32_t k = (uint32_t)(o - c.s_out);
+        const bool pair = k < c.len_out() && 2 * k + 1 < c.len_in;
+        m_pos = c.s_in + 2 * k;
+        m_fl = pair ? 3u : 0u;
+    };
     F acc = one;
     F nx1, nx2;
     bool npair;
     {
-        while (o0 >= c.next_s_out) bat_seek(g, c, c.b + 1);
-        const uint32_t k = (uint32_t)(o0 - c.s_out);
-        npair = k < c.len_out && 2 * k + 1 < c.len_in;
+        meta1(o0);
+        npair = m_fl & 2u;
         if (npair) {
-            bat_load_x<F, FIRST>(bases, sorted, in, c.s_in + 2 * k, nx1);
-            bat_load_x<F, FIRST>(bases, sorted, in, c.s_in + 2 * k + 1, nx2);
+            const uint32_t e1 = FIRST ? sorted[m_pos] : 0u, e2 = FIRST ? sorted[m_pos + 1] : 0u;
+            nx1 = ldp(point_ptr(m_pos, e1));
+            nx2 = ldp(point_ptr(m_pos + 1, e2));
         }
+        if (B > 1) {
+            meta1(o0 + 1);
+            fetch_entries(1);
+        }
+        cp_async_commit();
     }
 #pragma unroll 1
     for (int j = 0; j < B; j++) {
         const bool pair = npair;
         F x1 = nx1, x2 = nx2;
         if (j + 1 < B) {
-            const size_t o = o0 + j + 1;
-            while (o >= c.next_s_out) bat_seek(g, c, c.b + 1);
-            const uint32_t k = (uint32_t)(o - c.s_out);
-            npair = k < c.len_out && 2 * k + 1 < c.len_in;
+            const int par = (j + 1) & 1;
+            cp_async_wait_all();
+            npair = m_fl & 2u;
             if (npair) {
-                bat_load_x<F, FIRST>(bases, sorted, in, c.s_in + 2 * k, nx1);
-                bat_load_x<F, FIRST>(bases, sorted, in, c.s_in + 2 * k + 1, nx2);
+                nx1 = ldp(point_ptr(m_pos, entry(par, 0)));
+                nx2 = ldp(point_ptr(m_pos + 1, entry(par, 1)));
             }
+            if (j + 2 < B) {
+                meta1(o0 + j + 2);
+                fetch_entries(par ^ 1);
+            }
+            cp_async_commit();
         }
         F d = one;
         if (pair) {
             d = F::sub(x2, x1);
-            if (d.is_zero()) {  // P + P or P + (-P): no affine formula; the XYZZ kernel will redo the buckets
+            if (d.is_zero()) {
                 atomicOr(flag, 1u);
                 d = one;
             }
@@ -287,9 +344,23 @@ __global__ void __launch_bounds__(BAT_THREADS, MINB)
         acc = j == 0 ? d : hot_mul<BAT_INLINE_FQ2>(acc, d);
         FieldIO<F>::store(pre + (size_t)j * PRE_STRIDE, acc);
     }
-    // ---- phase 2: one inversion for the block
+    // ---- phase 2: one inversion for the block (the last slot's small operands fly meanwhile)
     TreeIO<F>::st(tree, 128 + tid, acc);
     __syncthreads();
+    auto meta3 = [&](size_t o) {
+        while (o < c.s_out) bat_seek(g, c, c.b - 1);
+        const uint32_t k = (uint32_t)(o - c.s_out);
+        const bool live = k < c.len_out(), pair = live && 2 * k + 1 < c.len_in;
+        m_pos = c.s_in + 2 * k;
+        m_fl = (live ? 1u : 0u) | (pair ? 2u : 0u);
+    };
+    auto fetch_small = [&](int j) {  // slot j's entries and the prefix product below it, into the cells of j's parity
+        fetch_entries(j & 1);
+        if (j > 0) StageIO<F>::fetch(pcell, j & 1, tid, pre + (size_t)(j - 1) * PRE_STRIDE);
+        cp_async_commit();
+    };
+    meta3(o0 + B - 1);
+    fetch_small(B - 1);
 #pragma unroll 1
     for (unsigned width = 64; width >= 1; width >>= 1) {
         if (tid < width) {
@@ -310,56 +381,50 @@ __global__ void __launch_bounds__(BAT_THREADS, MINB)
         }
         __syncthreads();
     }
-    F inv = TreeIO<F>::ld(tree, 128 + tid);  // 1 / (this thread's product)
+    F inv = TreeIO<F>::ld(tree, 128 + tid);
     // ---- phase 3: peel the inverses off backwards and form the sums
-    // the cursor (and in round 0 the sorted entries) run one slot ahead of the arithmetic: when a slot's turn comes its
-    // gather addresses are already known, so only ONE memory latency is exposed per slot instead of two dependent ones
-    uint32_t n_pos = 0, n_e1 = 0, n_e2 = 0;
-    bool n_live = false, n_pair = false;
-    {
-        const size_t o = o0 + B - 1;
-        while (o < c.s_out) bat_seek(g, c, c.b - 1);
-        const uint32_t k = (uint32_t)(o - c.s_out);
-        n_live = k < c.len_out;
-        n_pair = n_live && 2 * k + 1 < c.len_in;
-        n_pos = c.s_in + 2 * k;
-        if (FIRST && n_live) n_e1 = sorted[n_pos];
-        if (FIRST && n_pair) n_e2 = sorted[n_pos + 1];
-    }
 #pragma unroll 1
     for (int j = B - 1; j >= 0; j--) {
         const size_t o = o0 + j;
-        const bool live = n_live, pair = n_pair;
-        const uint32_t pos = n_pos, e1 = n_e1, e2 = n_e2;
+        const bool live = m_fl & 1u, pair = m_fl & 2u;
+        const int par = j & 1;
+        cp_async_wait_all();
+        const uint32_t e1 = entry(par, 0), e2 = entry(par, 1);
         F x1, y1, x2, y2, d = one;
-        if (live) bat_load_xy<F, FIRST>(bases, in, pos, e1, x1, y1);
-        if (pair) bat_load_xy<F, FIRST>(bases, in, pos + 1, e2, x2, y2);
-        if (j > 0) {
-            const size_t on = o - 1;
-            while (on < c.s_out) bat_seek(g, c, c.b - 1);
-            const uint32_t k = (uint32_t)(on - c.s_out);
-            n_live = k < c.len_out;
-            n_pair = n_live && 2 * k + 1 < c.len_in;
-            n_pos = c.s_in + 2 * k;
-            if (FIRST && n_live) n_e1 = sorted[n_pos];
-            if (FIRST && n_pair) n_e2 = sorted[n_pos + 1];
+        if (live) {
+            const uint32_t* p = point_ptr(m_pos, e1);
+            x1 = ldp(p);
+            y1 = ldp(p + W);
         }
-        // 1 / d_j = inv * prefix_{j-1}: independent of the points just requested, so it runs under their latency
-        F dinv = inv;
-        if (j > 0) dinv = hot_mul<BAT_INLINE_FQ2>(inv, FieldIO<F>::load_rw(pre + (size_t)(j - 1) * PRE_STRIDE));
         if (pair) {
+            const uint32_t* p = point_ptr(m_pos + 1, e2);
+            x2 = ldp(p);
+            y2 = ldp(p + W);
+        }
+        F dinv = inv;
+        if (j > 0) {
+            const F pj = StageIO<F>::ld(pcell, par, tid);
+            meta3(o - 1);
+            fetch_small(j - 1);
+            dinv = hot_mul<BAT_INLINE_FQ2>(inv, pj);  // runs under the gathers' latency
+        }
+        // order chosen for register pressure: lambda first (y2 and 1/d die), then d and the running inverse
+        if (FIRST && live && (e1 >> 31)) y1 = F::neg(y1);
+        F lam;
+        if (pair) {
+            if (FIRST && (e2 >> 31)) y2 = F::neg(y2);
+            lam = hot_mul<BAT_INLINE_FQ2>(F::sub(y2, y1), dinv);
             d = F::sub(x2, x1);
             if (d.is_zero()) d = one;
         }
         if (j > 0) inv = hot_mul<BAT_INLINE_FQ2>(inv, d);
         uint32_t* dst = out + o * (2 * W);
         if (pair) {
-            F lam = hot_mul<BAT_INLINE_FQ2>(F::sub(y2, y1), dinv);
             F x3 = F::sub(F::sub(hot_sqr<BAT_INLINE_FQ2>(lam), x1), x2);
             F y3 = F::sub(hot_mul<BAT_INLINE_FQ2>(lam, F::sub(x1, x3)), y1);
             FieldIO<F>::store(dst, x3);
             FieldIO<F>::store(dst + W, y3);
-        } else if (live) {  // odd leftover: carried to the next round unchanged
+        } else if (live) {
             FieldIO<F>::store(dst, x1);
             FieldIO<F>::store(dst + W, y1);
         }
@@ -400,16 +465,53 @@ template <>
 struct BatTuning<Fq> {
     static constexpr int MINB = 4;  // 128 registers: 4 blocks of 128 threads per SM (measured 5-8 % faster than 3 at 144)
 };
+#ifndef BAT_FQ2_MINB
+#define BAT_FQ2_MINB 2
+#endif
 template <>
 struct BatTuning<Fq2> {
-    static constexpr int MINB = 2;
+    static constexpr int MINB = BAT_FQ2_MINB;
 };
-static int bat_pick_b(size_t slots, int sm_count, int minb) {
-    size_t want_blocks = (size_t)sm_count * minb * 2;
-    static const int bmax = bat_env("CZK_BAT_BMAX", 64);
-    int b = bmax < BAT_B_MIN ? BAT_B_MIN : (bmax > BAT_B_MAX ? BAT_B_MAX : bmax);
-    while (b > BAT_B_MIN && slots / ((size_t)BAT_THREADS * b) < want_blocks) b >>= 1;
-    return b;
+// Slots per thread for a round with `used` slots.  A block's life is B slot-times plus the block-wide inversion (phase 2,
+// ~BETA slot-times: 13 % of a block at B = 64 in the ncu source view), and the grid runs in waves of `resident` blocks, so
+// the round costs about ceil(blocks / resident) * (B + BETA): pick the B that makes k waves exactly full for the cheapest
+// k.  (Measured on 2^21 G1 terms, round 0 = 15.8 M slots on 592 resident blocks: B = 64 -> 3.3 waves 11.2 ms,
+// 96 -> 2.2 waves 11.0 ms, 80 -> 2.6 waves 10.2 ms, 128 -> 1.6 waves 10.3 ms.)
+template <class F>
+struct BatBeta;
+template <>
+struct BatBeta<Fq> {
+    static constexpr int VALUE = 10;
+};
+template <>
+struct BatBeta<Fq2> {
+    static constexpr int VALUE = 4;
+};
+static int bat_pick_b(size_t used, size_t resident, int beta_dflt) {
+    static const int bmax_env = bat_env("CZK_BAT_BMAX", BAT_B_MAX);
+    static const int beta_env = bat_env("CZK_BAT_BETA", 0);
+    const size_t bmax = bmax_env < BAT_B_MIN ? BAT_B_MIN : (bmax_env > BAT_B_MAX ? BAT_B_MAX : bmax_env);
+    const size_t beta = beta_env > 0 ? beta_env : beta_dflt;
+    const size_t per_wave = (size_t)BAT_THREADS * resident;
+    size_t k0 = (used + per_wave * bmax - 1) / (per_wave * bmax);  // fewest waves that B <= bmax allows
+    if (k0 == 0) k0 = 1;
+    size_t best_b = bmax, best_cost = ~(size_t)0;
+    for (size_t k = k0; k < k0 + 6; k++) {
+        size_t b = (used + per_wave * k - 1) / (per_wave * k);
+        if (b < BAT_B_MIN) b = BAT_B_MIN;
+        if (b > bmax) b = bmax;
+        const size_t cost = k * (b + beta);
+        if (cost < best_cost) best_cost = cost, best_b = b;
+        if (b == BAT_B_MIN) break;
+    }
+    return (int)best_b;
+}
+// slots of the array that round r writes, from the last bucket's run (S_0, L_0): the closed form of the layout comment
+static size_t bat_used(uint32_t last_start, uint32_t last_len, size_t nb, int r) {
+    uint64_t s = last_start;
+    for (int i = 0; i < r; i++) s = (s >> 1) + (nb - 1);
+    const uint64_t len = ((uint64_t)last_len + ((1ull << r) - 1)) >> r;
+    return (size_t)((s >> 1) + (nb - 1) + ((len + 1) >> 1));
 }
 
 size_t msm_batched_bytes(int curve, size_t entries, size_t nb, size_t* pa, size_t* pb, size_t* pre) {
@@ -417,29 +519,37 @@ size_t msm_batched_bytes(int curve, size_t entries, size_t nb, size_t* pa, size_
     *pa = bat_bound(entries, nb, 1) * pt;
     *pb = bat_bound(entries, nb, 2) * pt;
     size_t slots = bat_bound(entries, nb, 1), per_block = (size_t)BAT_THREADS * BAT_B_MAX;
-    *pre = ((slots + per_block - 1) / per_block) * per_block * el;
+    *pre = ((slots + per_block - 1) / per_block + 1) * per_block * el;  // a round's last block may overhang by < one block
     return *pa + *pb + *pre;
 }
 
 template <class F>
 static cudaError_t msm_batched_t(const uint32_t* bases, const uint32_t* sorted, const uint32_t* ends, const uint32_t* hist,
-                                 size_t nb, size_t entries, uint32_t maxlen, uint32_t* pa, uint32_t* pb, uint32_t* prefix,
-                                 uint32_t* buckets, uint32_t* flag, int sm_count, cudaStream_t st) {
+                                 size_t nb, size_t entries, uint32_t maxlen, uint32_t last_start, uint32_t last_len, uint32_t* pa,
+                                 uint32_t* pb, uint32_t* prefix, uint32_t* buckets, uint32_t* flag, int sm_count, cudaStream_t st) {
     constexpr int MINB = BatTuning<F>::MINB;
     int rounds = 1;  // at least one: round 0 turns (index | sign) entries into points
     while (rounds < 32 && (((uint64_t)maxlen + ((1ull << rounds) - 1)) >> rounds) > BAT_WALK) rounds++;
     BatGeom g{ends, hist, (uint32_t)nb, 0};
     uint32_t* bufs[2] = {pa, pb};
+    constexpr size_t smem = bat_smem_bytes<F>();
+    static const cudaError_t attr = [] {
+        cudaError_t e1 = cudaFuncSetAttribute(k_bat_round<F, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e2 = cudaFuncSetAttribute(k_bat_round<F, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        return e1 != cudaSuccess ? e1 : e2;
+    }();
+    if (attr != cudaSuccess) return attr;
     for (int r = 0; r < rounds; r++) {
         g.r = r;
-        size_t slots = bat_bound(entries, nb, r + 1);
-        const int B = bat_pick_b(slots, sm_count, MINB);
+        size_t slots = bat_used(last_start, last_len, nb, r);
+        if (slots > bat_bound(entries, nb, r + 1)) return cudaErrorInvalidValue;  // the buffers are sized by the bound
+        const int B = bat_pick_b(slots, (size_t)sm_count * MINB, BatBeta<F>::VALUE);
         const size_t per_block = (size_t)BAT_THREADS * B;
         unsigned blocks = (unsigned)((slots + per_block - 1) / per_block);
         uint32_t* dst = bufs[r & 1];
         const uint32_t* src = r ? bufs[(r - 1) & 1] : nullptr;
-        if (r == 0) k_bat_round<F, true, MINB><<<blocks, BAT_THREADS, 0, st>>>(g, bases, sorted, nullptr, dst, prefix, flag, B);
-        else k_bat_round<F, false, MINB><<<blocks, BAT_THREADS, 0, st>>>(g, nullptr, nullptr, src, dst, prefix, flag, B);
+        if (r == 0) k_bat_round<F, true, MINB><<<blocks, BAT_THREADS, smem, st>>>(g, bases, sorted, nullptr, dst, prefix, flag, B);
+        else k_bat_round<F, false, MINB><<<blocks, BAT_THREADS, smem, st>>>(g, nullptr, nullptr, src, dst, prefix, flag, B);
         CZK_LAUNCHED();
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
@@ -450,10 +560,14 @@ static cudaError_t msm_batched_t(const uint32_t* bases, const uint32_t* sorted, 
 }
 
 cudaError_t msm_batched_accumulate(int curve, const uint32_t* bases, const uint32_t* sorted, const uint32_t* ends,
-                                   const uint32_t* hist, size_t nb, size_t entries, uint32_t maxlen, uint32_t* pa, uint32_t* pb,
-                                   uint32_t* prefix, uint32_t* buckets, uint32_t* flag, int sm_count, cudaStream_t st) {
-    if (curve == 1) return msm_batched_t<Fq>(bases, sorted, ends, hist, nb, entries, maxlen, pa, pb, prefix, buckets, flag, sm_count, st);
-    return msm_batched_t<Fq2>(bases, sorted, ends, hist, nb, entries, maxlen, pa, pb, prefix, buckets, flag, sm_count, st);
+                                   const uint32_t* hist, size_t nb, size_t entries, uint32_t maxlen, uint32_t last_start,
+                                   uint32_t last_len, uint32_t* pa, uint32_t* pb, uint32_t* prefix, uint32_t* buckets, uint32_t* flag,
+                                   int sm_count, cudaStream_t st) {
+    if (curve == 1)
+        return msm_batched_t<Fq>(bases, sorted, ends, hist, nb, entries, maxlen, last_start, last_len, pa, pb, prefix, buckets, flag,
+                                 sm_count, st);
+    return msm_batched_t<Fq2>(bases, sorted, ends, hist, nb, entries, maxlen, last_start, last_len, pa, pb, prefix, buckets, flag,
+                              sm_count, st);
 }
 
 }  // namespace czk
