@@ -35,9 +35,10 @@ PUBLISHED_MS = {1: 127400.0, 2: 320400.0, 3: 323300.0}
 # The dominant "kernel" is the bucket accumulation of one G1 MSM: 5 launches of k_bat_round<Fq> (halving rounds of the
 # batched-affine tree) + k_bat_finish<Fq>; it is timed as one unit by CUDA events on the launching stream.
 ACC_KERNEL = "k_bat_round<Fq> x5 + k_bat_finish<Fq> (bucket accumulation of one G1 MSM)"
-# ncu --set full capture of those launches (profiles/r1_summary.md): dram__bytes_read + write summed over the rounds of
-# the 2^21-1 term MSM; the 2^20 term MSMs move half of it -> mean over the step's 4 G1 MSMs
-NCU_TRAFFIC_BYTES_2_21 = 22.8e9
+# ncu --set full capture of those launches (profiles/r1_summary.md): dram__bytes_read + write of the 2^21-1 term MSM's
+# round 0 (14.44 GB) and round 1 (4.57 GB) as captured, later rounds halving (sum 23.5 GB); the 2^20 term MSMs move half
+# of it -> mean over the step's 4 G1 MSMs
+NCU_TRAFFIC_BYTES_2_21 = 23.5e9
 NCU_TRAFFIC_BYTES_PER_LAUNCH = NCU_TRAFFIC_BYTES_2_21 * (1 + 3 * 0.5) / 4
 
 

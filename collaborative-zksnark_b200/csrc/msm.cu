@@ -377,12 +377,12 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
                                                                             ws.queue, ws.heavy, total, max_items, seg, heavy_len); CZK_LAUNCHED();
     if (ws.ev[0]) cudaEventRecord(ws.ev[0], st);
     const uint32_t* gate = nullptr;
-    // worth it only when buckets are long (merged windows over a large base set): below ~2^20 terms the rounds' fixed
-    // latencies (one block-wide inversion each) cost more than the multiplications they save (measured: 2^19 terms
-    // 3.87 ms walk vs 4.22 ms tree, 2^20 terms 7.55 vs 6.72); CZK_BAT_MIN_ENTRIES / CZK_BAT_MIN_LOAD override for A/B runs
+    // worth it only when buckets are long (merged windows over a large base set): the rounds' fixed latencies (one
+    // block-wide inversion each) must be paid back by the multiplications saved (measured: 2^19 terms 3.88 ms walk vs
+    // 2.88 ms tree, 2^20 terms 7.55 vs 5.15); CZK_BAT_MIN_ENTRIES / CZK_BAT_MIN_LOAD override for A/B runs
     static const size_t bat_min_entries = [] {
         const char* e = getenv("CZK_BAT_MIN_ENTRIES");
-        return e ? (size_t)atoll(e) : (size_t)12 << 20;  // measured crossover: 2^19 terms x 15 windows lose, 2^20 x 15 win
+        return e ? (size_t)atoll(e) : (size_t)6 << 20;  // 2^19 terms x 15 windows and up
     }();
     static const size_t bat_min_load = [] {
         const char* e = getenv("CZK_BAT_MIN_LOAD");
