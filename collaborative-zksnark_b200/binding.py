@@ -507,8 +507,9 @@ class Context:
         return dict(king_computes=int(out[0]), opens=int(out[1]))
 
     # ------------------------------------------------------------------ diagnostics
-    def msm_set_batched(self, enabled: bool):
-        self._chk(self.lib.czk_msm_set_batched(self.h, int(enabled)))
+    def msm_set_batched(self, enabled, always: bool = False):
+        """enabled: use the batched-affine tree (from ~2^19 terms); always=True: at every size."""
+        self._chk(self.lib.czk_msm_set_batched(self.h, 2 if (enabled and always) else int(bool(enabled))))
 
     def fq_inverse(self, a):
         a = _np_u64(a, 6)

@@ -803,6 +803,7 @@ int czk_msm_set_batched(czk_ctx* ctx, int enabled) {
     if (!ctx) return CZK_ERR_ARG;
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     ctx->ws.batched = enabled != 0;
+    ctx->ws.batched_always = enabled == 2;
     ctx->ws.batched_forced = true;
     return CZK_OK;
 }

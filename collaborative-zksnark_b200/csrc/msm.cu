@@ -388,7 +388,7 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
         const char* e = getenv("CZK_BAT_MIN_LOAD");
         return e ? (size_t)atoll(e) : (size_t)64;
     }();
-    if (ws.batched && n * cfg.nwin >= bat_min_entries && n * cfg.nwin >= total * bat_min_load) {
+    if (ws.batched && n && (ws.batched_always || (n * cfg.nwin >= bat_min_entries && n * cfg.nwin >= total * bat_min_load))) {
         // tree of batched affine additions (msm_batched.cu); needs the longest bucket to know the number of rounds
         // and the last bucket's run, which fixes the exact slot count of every round (grid sizing)
         if ((e = cudaMemcpyAsync(ws.host_word, ws.queue + 4, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;

@@ -117,6 +117,7 @@ struct MsmWorkspace {
     uint32_t* host_word = nullptr;                             // pinned: the longest-bucket readback
     bool batched = true;                                       // CZK_BATCHED=0 keeps the XYZZ walk
     bool batched_forced = false;                               // set by czk_msm_set_batched
+    bool batched_always = false;                               // czk_msm_set_batched(ctx, 2): ignore the size thresholds (tests)
     int sm_count = 148;
     int seg_point_words = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // accumulate start/stop, whole MSM start/stop

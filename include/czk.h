@@ -205,7 +205,8 @@ CZK_API int czk_gsz_stats(const czk_ctx* ctx, uint64_t out[2]);
  *         (point, window) pairs = upper bound on mixed additions (sum of n * windows) }. */
 CZK_API int czk_msm_stats(czk_ctx* ctx, int curve, double out[5], int reset);
 /* Bucket accumulation algorithm: 1 (default) = tree of batched affine additions with the XYZZ walk as the fallback for
- * inputs that need P + P / P + (-P); 0 = the XYZZ walk only.  Same results; for A/B measurements and tests. */
+ * inputs that need P + P / P + (-P), taken from ~2^19 terms up; 0 = the XYZZ walk only; 2 = the tree at every size (so
+ * that small test inputs exercise it).  Same results; for A/B measurements and tests. */
 CZK_API int czk_msm_set_batched(czk_ctx* ctx, int enabled);
 /* out[i] = in[i]^-1 in Fq (n x 6 limbs, Montgomery; 0 -> 0) with the device's binary-Euclid inversion (the one inversion
  * per block of the batched-affine path; algebra/ff/src/fields/macros.rs:368-422).  Host buffers. */

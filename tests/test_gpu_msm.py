@@ -205,10 +205,13 @@ def test_msm_batched_affine_equals_xyzz_walk(ctx, oracle, g):
     exp = _oracle_msm(G, xy, None, sc)
     try:
         ctx.msm_set_batched(False)
+        l0 = ctx.launches
         walk = _msm(ctx, G, xy, None, sc)
-        ctx.msm_set_batched(True)
+        l1 = ctx.launches
+        ctx.msm_set_batched(True, always=True)  # small inputs: the tree would not be chosen by size
         tree = _msm(ctx, G, xy, None, sc)
         assert walk == exp and tree == exp
+        assert ctx.launches - l1 > l1 - l0, "the round kernels of the affine tree did not run"
         rep = np.repeat(xy[:1], 700, axis=0)
         sc7 = oracle.random_fr_mont(73, 700)
         assert _msm(ctx, G, rep, None, sc7) == _oracle_msm(G, rep, None, sc7)
