@@ -5,6 +5,7 @@
 // Beaver-on-groups step of share/group.rs:70-109.  The O(1) group operations run on the host (host_field.hpp).
 #include <chrono>
 #include <cstdlib>
+#include <future>
 
 #include "../../include/czk_groth16.h"
 #include "ctx.hpp"
@@ -869,9 +870,28 @@ static int gsz_g1_product_check(czk_ctx* ctx, std::vector<HFr> x, std::vector<HG
     return CZK_OK;
 }
 
+// r * delta_g1, s * delta_g1 and s * delta_g2 (prover.rs:118-160) depend on the key and on the blinding shares only: a host
+// thread computes them while the device runs the witness map and the MSMs (serial, they were half of the 3 ms tail).
+struct TailPre {
+    HG1 r_delta, s_delta;
+    HG2 s_delta_g2;
+};
+static TailPre tail_precompute(const czk_pk* pk, const uint64_t r_sh[4], const uint64_t s_sh[4]) {
+    const HG1 delta_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1 + 24), HFq::from_limbs(pk->vk_g1 + 30));
+    const HG2 delta_g2 = HG2::from_affine(HFq2::from_limbs(pk->vk_g2 + 48), HFq2::from_limbs(pk->vk_g2 + 60));
+    uint64_t rk[4], sk[4];
+    fr_canonical(r_sh, rk);
+    fr_canonical(s_sh, sk);
+    TailPre t;
+    t.r_delta = HG1::mul(delta_g1, rk, 4);
+    t.s_delta = HG1::mul(delta_g1, sk, 4);
+    t.s_delta_g2 = HG2::mul(delta_g2, sk, 4);
+    return t;
+}
+
 // create_proof's group arithmetic on GSZ shares + pf.reveal(); the first group reveal runs every queued product check
 // (:900-905, :1700-1711).  r, s: the value every party holds (the reference's rand() stub gives 1).
-static int prove_tail_gsz(czk_ctx* ctx, const czk_pk* pk, const uint64_t r_sh[4], const uint64_t s_sh[4], const HG1& h_acc,
+static int prove_tail_gsz(czk_ctx* ctx, const czk_pk* pk, const TailPre& pre, const uint64_t r_sh[4], const uint64_t s_sh[4], const HG1& h_acc,
                           const HG1& l_acc, const HG1& a_acc, const HG1& b1_acc, const HG2& b2_acc, uint64_t proof_sh[48],
                           uint8_t proof_sh_inf[3], uint64_t proof[48], uint8_t proof_inf[3]) {
     typedef GShare<HFq, 6> S1;
@@ -880,21 +900,19 @@ static int prove_tail_gsz(czk_ctx* ctx, const czk_pk* pk, const uint64_t r_sh[4]
     CZK_TRY(czk_gsz_prepare_internal(ctx));
     HG1 alpha_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1), HFq::from_limbs(pk->vk_g1 + 6));
     HG1 beta_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1 + 12), HFq::from_limbs(pk->vk_g1 + 18));
-    HG1 delta_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1 + 24), HFq::from_limbs(pk->vk_g1 + 30));
     HG2 beta_g2 = HG2::from_affine(HFq2::from_limbs(pk->vk_g2), HFq2::from_limbs(pk->vk_g2 + 12));
-    HG2 delta_g2 = HG2::from_affine(HFq2::from_limbs(pk->vk_g2 + 48), HFq2::from_limbs(pk->vk_g2 + 60));
     const HFr r = HFr::from_limbs(r_sh), s = HFr::from_limbs(s_sh);
     std::vector<HFr> gx;
     std::vector<HG1> gy, gz;
     // r_s_delta_g1 = (delta * r) * s
-    HG1 rsd = pt_scale(delta_g1, r), t;
+    HG1 rsd = pre.r_delta, t;
     gx.push_back(s);
     gy.push_back(rsd);
     CZK_TRY(gsz_g1_mult(ctx, s, rsd, &t));
     rsd = t;
     gz.push_back(rsd);
     // g_a = r*delta + a_query[0] + MSM + alpha   (shift adds public points at every party, :971-974)
-    HG1 g_a = pt_scale(delta_g1, r);
+    HG1 g_a = pre.r_delta;
     g_a.add(S1::from_affine_limbs(pk->a0, pk->a0_inf));
     g_a.add(a_acc);
     g_a.add(alpha_g1);
@@ -903,11 +921,11 @@ static int prove_tail_gsz(czk_ctx* ctx, const czk_pk* pk, const uint64_t r_sh[4]
     gy.push_back(g_a);
     CZK_TRY(gsz_g1_mult(ctx, s, g_a, &s_g_a));
     gz.push_back(s_g_a);
-    HG1 g1_b = pt_scale(delta_g1, s);
+    HG1 g1_b = pre.s_delta;
     g1_b.add(S1::from_affine_limbs(pk->b10, pk->b10_inf));
     g1_b.add(b1_acc);
     g1_b.add(beta_g1);
-    HG2 g2_b = pt_scale(delta_g2, s);
+    HG2 g2_b = pre.s_delta_g2;
     g2_b.add(S2::from_affine_limbs(pk->b20, pk->b20_inf));
     g2_b.add(b2_acc);
     g2_b.add(beta_g2);
@@ -966,6 +984,7 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     const size_t n_sq = pk->n_sq, D = pk->D;
     if (!cs && !n_sq) return fail(ctx, CZK_ERR_ARG, "czk_groth16_prove: this key was uploaded for a general circuit - use czk_groth16_prove_r1cs");
     for (int i = 0; i < 8; i++) g_phases[i] = 0;
+    std::future<TailPre> tail_pre = std::async(std::launch::async, tail_precompute, pk, r_sh, s_sh);
     ShareVecs v;
     if (cs && (cs->ncons != pk->ncons || cs->ninst != pk->ninst || cs->nwit != pk->nwit))
         return fail(ctx, CZK_ERR_ARG, "czk_groth16_prove_r1cs: the proving key was made for a circuit of another shape");
@@ -1011,25 +1030,21 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     free_share_vecs(ctx, v);
 
     if (scheme == CZK_SCHEME_GSZ)
-        return prove_tail_gsz(ctx, pk, r_sh, s_sh, h_acc.sh, l_acc.sh, a_acc.sh, b1_acc.sh, b2_acc.sh, proof_sh, proof_sh_inf, proof, proof_inf);
+        return prove_tail_gsz(ctx, pk, tail_pre.get(), r_sh, s_sh, h_acc.sh, l_acc.sh, a_acc.sh, b1_acc.sh, b2_acc.sh, proof_sh, proof_sh_inf, proof, proof_inf);
     // ---- O(1) group arithmetic on shares (prover.rs:110-177)
     t0 = now_ms();
     HG1 alpha_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1), HFq::from_limbs(pk->vk_g1 + 6));
     HG1 beta_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1 + 12), HFq::from_limbs(pk->vk_g1 + 18));
-    HG1 delta_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1 + 24), HFq::from_limbs(pk->vk_g1 + 30));
     HG2 beta_g2 = HG2::from_affine(HFq2::from_limbs(pk->vk_g2), HFq2::from_limbs(pk->vk_g2 + 12));
-    HG2 delta_g2 = HG2::from_affine(HFq2::from_limbs(pk->vk_g2 + 48), HFq2::from_limbs(pk->vk_g2 + 60));
     HFr r = HFr::from_limbs(r_sh), s = HFr::from_limbs(s_sh);
-    uint64_t rk[4], sk[4];
-    fr_canonical(r_sh, rk);
-    fr_canonical(s_sh, sk);
+    const TailPre pre = tail_pre.get();
     // from_add_shared scalars: mac = share (key 1), so scale_pub_group gives sh == mac (spdz.rs:419-423)
     S1 rsd;
-    rsd.sh = rsd.mac = HG1::mul(delta_g1, rk, 4);  // delta_g1 * r
+    rsd.sh = rsd.mac = pre.r_delta;  // delta_g1 * r
     CZK_TRY((group_scale_shared<HFq, 6>(ctx, scheme, rsd, s, s)));  // ... * s
     // A = r*delta + a_query[0] + MSM + alpha   (calculate_coeff, prover.rs:216-232)
     S1 g_a;
-    g_a.sh = g_a.mac = HG1::mul(delta_g1, rk, 4);
+    g_a.sh = g_a.mac = pre.r_delta;
     shift_pub(ctx, scheme, g_a, S1::from_affine_limbs(pk->a0, pk->a0_inf));
     g_a.sh.add(a_acc.sh);
     g_a.mac.add(a_acc.mac);
@@ -1037,13 +1052,13 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     S1 s_g_a = g_a;
     CZK_TRY((group_scale_shared<HFq, 6>(ctx, scheme, s_g_a, s, s)));
     S1 g1_b;
-    g1_b.sh = g1_b.mac = HG1::mul(delta_g1, sk, 4);
+    g1_b.sh = g1_b.mac = pre.s_delta;
     shift_pub(ctx, scheme, g1_b, S1::from_affine_limbs(pk->b10, pk->b10_inf));
     g1_b.sh.add(b1_acc.sh);
     g1_b.mac.add(b1_acc.mac);
     shift_pub(ctx, scheme, g1_b, beta_g1);
     S2 g2_b;
-    g2_b.sh = g2_b.mac = HG2::mul(delta_g2, sk, 4);
+    g2_b.sh = g2_b.mac = pre.s_delta_g2;
     shift_pub(ctx, scheme, g2_b, S2::from_affine_limbs(pk->b20, pk->b20_inf));
     g2_b.sh.add(b2_acc.sh);
     g2_b.mac.add(b2_acc.mac);

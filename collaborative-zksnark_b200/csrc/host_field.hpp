@@ -240,11 +240,24 @@ struct HPoint {
     }
     void negate() { y = F::neg(y); }
     // scalar given as canonical little-endian u64 limbs
+    // k * p, k = nk little-endian 64-bit limbs: fixed 4-bit windows over a table of 1p .. 15p
     static HPoint mul(const HPoint& p, const uint64_t* k, int nk) {
+        int top = nk * 64 - 1;
+        while (top >= 0 && !((k[top / 64] >> (top % 64)) & 1)) top--;
+        if (top < 0) return infinity();
+        HPoint tab[16];
+        tab[0] = infinity();
+        tab[1] = p;
+        for (int i = 2; i < 16; i++) {
+            tab[i] = (i & 1) ? tab[i - 1] : dbl(tab[i / 2]);
+            if (i & 1) tab[i].add(p);
+        }
         HPoint acc = infinity();
-        for (int i = nk * 64 - 1; i >= 0; i--) {
-            acc = dbl(acc);
-            if ((k[i / 64] >> (i % 64)) & 1) acc.add(p);
+        for (int w = top / 4; w >= 0; w--) {
+            if (!acc.is_inf())
+                for (int j = 0; j < 4; j++) acc = dbl(acc);
+            const unsigned d = (unsigned)(k[w / 16] >> (4 * (w % 16))) & 15u;
+            if (d) acc.add(tab[d]);
         }
         return acc;
     }
