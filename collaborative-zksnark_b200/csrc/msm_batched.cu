@@ -161,13 +161,10 @@ struct TreeIO<Fq2> {
 };
 // products inside the two hot loops: inlined (for Fq2 the out-of-line bodies cost a round trip through local memory per
 // operand; measured below)
-#ifndef BAT_FQ_CALL
-#define BAT_FQ_CALL 0
-#endif
 template <int INL>
-__device__ __forceinline__ Fq hot_mul(const Fq& a, const Fq& b) { return BAT_FQ_CALL ? Fq::mul_ni(a, b) : Fq::mul(a, b); }
+__device__ __forceinline__ Fq hot_mul(const Fq& a, const Fq& b) { return Fq::mul(a, b); }
 template <int INL>
-__device__ __forceinline__ Fq hot_sqr(const Fq& a) { return BAT_FQ_CALL ? Fq::mul_ni(a, a) : Fq::sqr(a); }
+__device__ __forceinline__ Fq hot_sqr(const Fq& a) { return Fq::sqr(a); }
 template <int INL>
 __device__ __forceinline__ Fq2 hot_mul(const Fq2& a, const Fq2& b) { return INL ? Fq2::mul_inl(a, b) : Fq2::mul(a, b); }
 template <int INL>
@@ -176,7 +173,7 @@ __device__ __forceinline__ Fq2 hot_sqr(const Fq2& a) { return INL ? Fq2::sqr_inl
 __device__ __forceinline__ Fq cold_mul(const Fq& a, const Fq& b) { return Fq::mul_ni(a, b); }
 __device__ __forceinline__ Fq2 cold_mul(const Fq2& a, const Fq2& b) { return Fq2::mul(a, b); }
 
-// ------------------------------------------------------------------ one round
+// ------------------------------------------------------------------ walking the slot geometry
 struct BatCursor {
     uint32_t b, s_in, len_in, s_out, next_s_out;
     __device__ __forceinline__ uint32_t len_out() const { return (len_in + 1) >> 1; }
@@ -250,9 +247,8 @@ constexpr size_t bat_smem_bytes() {  // product tree + 2 prefix cells + 2 x 2 en
 
 template <class F, bool FIRST, int MINB>
 __global__ void __launch_bounds__(BAT_THREADS, MINB)
-    k_bat_round(BatGeom g, const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                       const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* __restrict__ prefix,
-                       uint32_t* __restrict__ flag, const int B) {
+    k_bat_round(BatGeom g, const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ in,
+                uint32_t* __restrict__ out, uint32_t* __restrict__ prefix, uint32_t* __restrict__ flag, const int B) {
     constexpr int W = FieldIO<F>::W, CH = W / 4;
     extern __shared__ uint4 bat_smem[];
     uint32_t* const tree = reinterpret_cast<uint32_t*>(bat_smem);
@@ -465,12 +461,9 @@ template <>
 struct BatTuning<Fq> {
     static constexpr int MINB = 4;  // 128 registers: 4 blocks of 128 threads per SM (measured 5-8 % faster than 3 at 144)
 };
-#ifndef BAT_FQ2_MINB
-#define BAT_FQ2_MINB 2
-#endif
 template <>
 struct BatTuning<Fq2> {
-    static constexpr int MINB = BAT_FQ2_MINB;
+    static constexpr int MINB = 2;  // 255 registers; 3 blocks at 168 registers spill 450 bytes and measured 12 % slower
 };
 // Slots per thread for a round with `used` slots.  A block's life is B slot-times plus the block-wide inversion (phase 2,
 // ~BETA slot-times: 13 % of a block at B = 64 in the ncu source view), and the grid runs in waves of `resident` blocks, so
