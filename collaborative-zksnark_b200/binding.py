@@ -70,6 +70,8 @@ _SIGS = {
     "czk_bases_len": (C.c_size_t, [C.c_void_p]),
     "czk_bases_precompute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint]),
     "czk_msm_bases": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_size_t, u64p]),
+    "czk_msm_bases_multi": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_size_t,
+                                      C.POINTER(u64p), C.POINTER(C.c_double)]),
     "czk_bases_synthetic": (C.c_int, [C.c_void_p, C.c_int, C.c_uint64, C.c_size_t, C.c_size_t, C.POINTER(C.c_void_p)]),
     "czk_bases_download": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_void_p]),
     "czk_net_unique_id": (C.c_int, [C.c_void_p]),
@@ -394,6 +396,15 @@ class Context:
         out = np.zeros(3 * (w // 2), np.uint64)
         self._chk(self.lib.czk_msm_bases(self.h, bases.h, base_off, scalars.h, sc_off, int(montgomery), n, out.ctypes.data_as(u64p)))
         return out
+
+    def msm_bases_multi(self, bases_list, scalars: DeviceVec, n=None, base_off=0, sc_off=0, montgomery=True):
+        """One scalar vector against several resident base sets (shared digit sort where the sets allow it)."""
+        n = min(min(len(b) for b in bases_list) - base_off, scalars.n - sc_off) if n is None else n
+        outs = [np.zeros(18 if b.curve == 1 else 36, np.uint64) for b in bases_list]
+        hs = (C.c_void_p * len(bases_list))(*[b.h for b in bases_list])
+        ps = (u64p * len(bases_list))(*[o.ctypes.data_as(u64p) for o in outs])
+        self._chk(self.lib.czk_msm_bases_multi(self.h, hs, len(bases_list), base_off, scalars.h, sc_off, int(montgomery), n, ps, None))
+        return outs
 
     # ------------------------------------------------------------------ MpcNet
     def net_init(self, rank, nranks, unique_id: bytes | None):

@@ -5,6 +5,7 @@
 #include <nccl.h>
 
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -310,6 +311,7 @@ static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
         cudaFree(ws.scalars);
         cudaFree(ws.sorted);
         ws.scalars = ws.sorted = nullptr;
+        ws.alloc_epoch++;
         size_t cap = n + n / 16 + 64;
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.scalars, cap * 32));
         // worst case windows for this n: ceil(254/2) covers every config
@@ -322,6 +324,7 @@ static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
         if (need > ws.cap_n * 4 * 32) {
             CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
             cudaFree(ws.sorted);
+            ws.alloc_epoch++;
             CUDA_TRY(ctx, cudaMalloc((void**)&ws.sorted, need));
         }
     }
@@ -335,6 +338,7 @@ static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
         cudaFree(ws.segcnt);
         cudaFree(ws.segoff);
         ws.hist = ws.offsets = ws.buckets = ws.partial = ws.winsum = ws.segcnt = ws.segoff = nullptr;
+        ws.alloc_epoch++;
         size_t cap = total > ws.cap_buckets ? total : ws.cap_buckets;
         int pww = pw > ws.point_words ? pw : ws.point_words;
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.hist, cap * 4));
@@ -357,6 +361,7 @@ static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
             cudaFree(ws.items);
             cudaFree(ws.heavy);
             ws.segsum = ws.items = ws.heavy = nullptr;
+            ws.alloc_epoch++;
             size_t cap = items + items / 8;
             int pww = pw > ws.seg_point_words ? pw : ws.seg_point_words;
             CUDA_TRY(ctx, cudaMalloc((void**)&ws.segsum, cap * (size_t)pww * 4));
@@ -442,12 +447,14 @@ static void msm_host_tail(const uint32_t* winsums, const MsmConfig& cfg, uint64_
 }
 
 static int msm_core(czk_ctx* ctx, int curve, const uint32_t* bases, const uint8_t* inf, const uint32_t* scalars, int mont,
-                    size_t n, uint64_t* out_xyz, const MsmConfig* merged_cfg = nullptr) {
+                    size_t n, uint64_t* out_xyz, const MsmConfig* merged_cfg = nullptr, bool reuse_plan = false) {
     if (n >= ((size_t)1 << 31)) return fail(ctx, CZK_ERR_ARG, "msm: more than 2^31 - 1 terms");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     MsmConfig cfg = merged_cfg ? *merged_cfg : msm_choose_config(n ? n : 1);
+    const uint64_t epoch = ctx->ws.alloc_epoch;
     CZK_TRY(ws_reserve(ctx, curve, n, cfg));
-    CUDA_TRY(ctx, msm_run(curve, bases, inf, scalars, mont != 0, n, cfg, ctx->ws, ctx->stream));
+    if (ctx->ws.alloc_epoch != epoch) reuse_plan = false;  // a plan buffer moved: the previous plan is gone
+    CUDA_TRY(ctx, msm_run(curve, bases, inf, scalars, mont != 0, n, cfg, ctx->ws, ctx->stream, reuse_plan));
     size_t pw = msm_point_words(curve);
     CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, ctx->ws.winsum, msm_winsum_points(cfg) * pw * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
@@ -560,6 +567,64 @@ int czk_msm_bases(czk_ctx* ctx, const czk_bases* b, size_t base_off, const czk_v
     }
     return msm_core(ctx, b->curve, b->xy + base_off * pw, b->inf ? b->inf + base_off : nullptr,
                     (const uint32_t*)(sc->d + 4 * sc_off), scalars_montgomery, n, out_xyz);
+}
+
+// Several MSMs over one scalar vector: out[k] = sum_i scalars[sc_off + i] * b[k][base_off + i].  The first base set runs
+// in full; a later one reuses its plan (digit decomposition + bucket sort, ~0.5 ms at 2^20 terms) when it addresses a
+// precomputed table of the same shape and carries the same infinity flags, and runs as an MSM of its own otherwise.
+int czk_msm_bases_multi(czk_ctx* ctx, const czk_bases* const* b, int count, size_t base_off, const czk_vec* sc, size_t sc_off,
+                        int scalars_montgomery, size_t n, uint64_t* const* out_xyz, double* ms_out) {
+    if (!ctx || !b || !out_xyz || count < 1) return fail(ctx, CZK_ERR_ARG, "czk_msm_bases_multi: argument");
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now();
+    auto lap = [&](int k) {
+        double t1 = now();
+        if (ms_out) ms_out[k] = t1 - t0;
+        t0 = t1;
+    };
+    for (int k = 0; k < count; k++)
+        if (!b[k] || !out_xyz[k]) return fail(ctx, CZK_ERR_ARG, "czk_msm_bases_multi: null entry");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    const czk_bases* lead = b[0];
+    const bool tabled = lead->table && n >= 1024;
+    if (tabled) {  // size the workspace for every set first, so that no later reservation moves the plan
+        for (int k = 0; k < count; k++) {
+            if (!b[k]->table || b[k]->pre_c != lead->pre_c || b[k]->n != lead->n) continue;
+            MsmConfig cfg = msm_merged_config(lead->pre_c, lead->n, base_off);
+            CZK_TRY(ws_reserve(ctx, b[k]->curve, n, cfg));
+        }
+    }
+    CZK_TRY(czk_msm_bases(ctx, lead, base_off, sc, sc_off, scalars_montgomery, n, out_xyz[0]));
+    lap(0);
+    for (int k = 1; k < count; k++) {
+        const czk_bases* o = b[k];
+        bool share = tabled && o->table && o->pre_c == lead->pre_c && o->n == lead->n && base_off + n <= o->n && sc_off + n <= sc->n &&
+                     (o->inf != nullptr) == (lead->inf != nullptr);
+        if (share && o->inf) {
+            CUDA_TRY(ctx, cudaMemsetAsync(ctx->flag, 0, 4, ctx->stream));
+            CUDA_TRY(ctx, msm_flags_differ(o->inf + base_off, lead->inf + base_off, n, ctx->flag, ctx->stream));
+            uint32_t differ = 1;
+            CUDA_TRY(ctx, cudaMemcpyAsync(&differ, ctx->flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            if (differ) {  // its other users expect it clear
+                CUDA_TRY(ctx, cudaMemsetAsync(ctx->flag, 0, 4, ctx->stream));
+            }
+            share = differ == 0;
+        }
+        if (!share) {
+            // the workspace then holds THAT set's plan, while later sets are compared with the lead's flags: stop sharing
+            for (; k < count; k++) {
+                CZK_TRY(czk_msm_bases(ctx, b[k], base_off, sc, sc_off, scalars_montgomery, n, out_xyz[k]));
+                lap(k);
+            }
+            return CZK_OK;
+        }
+        MsmConfig cfg = msm_merged_config(o->pre_c, o->n, base_off);
+        CZK_TRY(msm_core(ctx, o->curve, o->table, o->inf ? o->inf + base_off : nullptr, (const uint32_t*)(sc->d + 4 * sc_off),
+                         scalars_montgomery, n, out_xyz[k], &cfg, true));
+        lap(k);
+    }
+    return CZK_OK;
 }
 
 static uint64_t splitmix(uint64_t& x) {

@@ -1015,18 +1015,15 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     if ((rc = czk_msm_bases(ctx, pk->q[4], 0, wit_vec, wit_off, 1, n_wit, o1)) != CZK_OK) return fin(rc);
     l_acc.sh = l_acc.mac = S1::from_jac_out(o1);
     g_phases[3] = now_ms() - t0;
-    t0 = now_ms();
-    if ((rc = czk_msm_bases(ctx, pk->q[0], 1, asg_vec, asg_off, 1, n_asg, o1)) != CZK_OK) return fin(rc);
-    a_acc.sh = a_acc.mac = S1::from_jac_out(o1);
-    g_phases[4] = now_ms() - t0;
-    t0 = now_ms();
-    if ((rc = czk_msm_bases(ctx, pk->q[1], 1, asg_vec, asg_off, 1, n_asg, o1)) != CZK_OK) return fin(rc);
-    b1_acc.sh = b1_acc.mac = S1::from_jac_out(o1);
-    g_phases[5] = now_ms() - t0;
-    t0 = now_ms();
-    if ((rc = czk_msm_bases(ctx, pk->q[2], 1, asg_vec, asg_off, 1, n_asg, o2)) != CZK_OK) return fin(rc);
-    b2_acc.sh = b2_acc.mac = S2::from_jac_out(o2);
-    g_phases[6] = now_ms() - t0;
+    {  // a, b_g1, b_g2: one scalar vector, three base sets - the digit sort is shared where the key allows it
+        uint64_t o1b[18];
+        const czk_bases* sets[3] = {pk->q[0], pk->q[1], pk->q[2]};
+        uint64_t* outs[3] = {o1, o1b, o2};
+        if ((rc = czk_msm_bases_multi(ctx, sets, 3, 1, asg_vec, asg_off, 1, n_asg, outs, &g_phases[4])) != CZK_OK) return fin(rc);
+        a_acc.sh = a_acc.mac = S1::from_jac_out(o1);
+        b1_acc.sh = b1_acc.mac = S1::from_jac_out(o1b);
+        b2_acc.sh = b2_acc.mac = S2::from_jac_out(o2);
+    }
     free_share_vecs(ctx, v);
 
     if (scheme == CZK_SCHEME_GSZ)

@@ -335,23 +335,25 @@ __global__ void __launch_bounds__(WINSUM_THREADS) k_msm_block_sum(const uint32_t
 
 template <class F>
 static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const uint32_t* scalars, bool mont, size_t n,
-                             const MsmConfig& cfg, MsmWorkspace& ws, cudaStream_t st) {
+                             const MsmConfig& cfg, MsmWorkspace& ws, cudaStream_t st, bool reuse_plan) {
     size_t total = (size_t)cfg.bwin * cfg.nb;
     cudaError_t e;
     if (ws.ev[2]) cudaEventRecord(ws.ev[2], st);
-    if ((e = cudaMemsetAsync(ws.hist, 0, total * sizeof(uint32_t), st)) != cudaSuccess) return e;
-    if (n) {
-        unsigned blocks = (unsigned)((n + 255) / 256);
-        k_msm_prepare<<<blocks, 256, 0, st>>>(scalars, inf, ws.scalars, ws.hist, n, cfg.c, cfg.nwin, cfg.nb, mont ? 1 : 0, (int)cfg.merged); CZK_LAUNCHED();
+    if (!reuse_plan) {  // steps 1-3: digits, histogram, scan, scatter
+        if ((e = cudaMemsetAsync(ws.hist, 0, total * sizeof(uint32_t), st)) != cudaSuccess) return e;
+        if (n) {
+            unsigned blocks = (unsigned)((n + 255) / 256);
+            k_msm_prepare<<<blocks, 256, 0, st>>>(scalars, inf, ws.scalars, ws.hist, n, cfg.c, cfg.nwin, cfg.nb, mont ? 1 : 0, (int)cfg.merged); CZK_LAUNCHED();
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
+        k_exclusive_scan<<<1, 1024, 0, st>>>(ws.hist, ws.offsets, total); CZK_LAUNCHED();
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    }
-    k_exclusive_scan<<<1, 1024, 0, st>>>(ws.hist, ws.offsets, total); CZK_LAUNCHED();
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (n) {
-        unsigned blocks = (unsigned)((n + 255) / 256);
-        k_msm_scatter<<<blocks, 256, 0, st>>>(ws.scalars, ws.offsets, ws.sorted, n, cfg.c, cfg.nwin, cfg.nb, (int)cfg.merged, cfg.table_stride,
-                                                cfg.table_off); CZK_LAUNCHED();
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (n) {
+            unsigned blocks = (unsigned)((n + 255) / 256);
+            k_msm_scatter<<<blocks, 256, 0, st>>>(ws.scalars, ws.offsets, ws.sorted, n, cfg.c, cfg.nwin, cfg.nb, (int)cfg.merged, cfg.table_stride,
+                                                    cfg.table_off); CZK_LAUNCHED();
+            if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
     }
     // segment length: at least the mean load of a busy bucket, and ~sqrt(n) so that neither the per-segment
     // walk nor the fold over segments can exceed O(sqrt(n)) serial additions whatever the digits are
@@ -369,12 +371,17 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
     size_t max_items = total + (n * cfg.nwin) / seg + 1;
     if (max_items > ws.cap_items) return cudaErrorInvalidValue;
     // queue words: 0 item count, 1 queue head, 2 heavy count, 3 "affine path gave up" flag, 4 longest bucket
-    if ((e = cudaMemsetAsync(ws.queue, 0, 32, st)) != cudaSuccess) return e;
-    k_msm_seg_counts<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.hist, ws.segcnt, total, seg, ws.queue + 4); CZK_LAUNCHED();
-    k_exclusive_scan<<<1, 1024, 0, st>>>(ws.segcnt, ws.segoff, total); CZK_LAUNCHED();
-    uint32_t heavy_len = (uint32_t)(2 * ((n * cfg.nwin) / total + 1) + 16);
-    k_msm_build_items<<<(unsigned)((max_items + 255) / 256), 256, 0, st>>>(ws.offsets, ws.hist, ws.segoff, ws.segcnt, (uint4*)ws.items,
-                                                                            ws.queue, ws.heavy, total, max_items, seg, heavy_len); CZK_LAUNCHED();
+    if (reuse_plan) {  // the items and their counts stand; rewind the queue head and clear the flag
+        if ((e = cudaMemsetAsync(ws.queue + 1, 0, 4, st)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(ws.queue + 3, 0, 4, st)) != cudaSuccess) return e;
+    } else {
+        if ((e = cudaMemsetAsync(ws.queue, 0, 32, st)) != cudaSuccess) return e;
+        k_msm_seg_counts<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(ws.hist, ws.segcnt, total, seg, ws.queue + 4); CZK_LAUNCHED();
+        k_exclusive_scan<<<1, 1024, 0, st>>>(ws.segcnt, ws.segoff, total); CZK_LAUNCHED();
+        uint32_t heavy_len = (uint32_t)(2 * ((n * cfg.nwin) / total + 1) + 16);
+        k_msm_build_items<<<(unsigned)((max_items + 255) / 256), 256, 0, st>>>(ws.offsets, ws.hist, ws.segoff, ws.segcnt, (uint4*)ws.items,
+                                                                                ws.queue, ws.heavy, total, max_items, seg, heavy_len); CZK_LAUNCHED();
+    }
     if (ws.ev[0]) cudaEventRecord(ws.ev[0], st);
     const uint32_t* gate = nullptr;
     // worth it only when buckets are long (merged windows over a large base set): the rounds' fixed latencies (one
@@ -391,11 +398,16 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
     if (ws.batched && n && (ws.batched_always || (n * cfg.nwin >= bat_min_entries && n * cfg.nwin >= total * bat_min_load))) {
         // tree of batched affine additions (msm_batched.cu); needs the longest bucket to know the number of rounds
         // and the last bucket's run, which fixes the exact slot count of every round (grid sizing)
-        if ((e = cudaMemcpyAsync(ws.host_word, ws.queue + 4, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-        if ((e = cudaMemcpyAsync(ws.host_word + 1, ws.offsets + (total - 1), 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-        if ((e = cudaMemcpyAsync(ws.host_word + 2, ws.hist + (total - 1), 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-        const uint32_t maxlen = ws.host_word[0], last_len = ws.host_word[2], last_start = ws.host_word[1] - last_len;
+        if (!reuse_plan) {
+            if ((e = cudaMemcpyAsync(ws.host_word, ws.queue + 4, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+            if ((e = cudaMemcpyAsync(ws.host_word + 1, ws.offsets + (total - 1), 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+            if ((e = cudaMemcpyAsync(ws.host_word + 2, ws.hist + (total - 1), 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+            if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+            ws.plan_maxlen = ws.host_word[0];
+            ws.plan_last_len = ws.host_word[2];
+            ws.plan_last_start = ws.host_word[1] - ws.plan_last_len;
+        }
+        const uint32_t maxlen = ws.plan_maxlen, last_len = ws.plan_last_len, last_start = ws.plan_last_start;
         if ((e = msm_batched_accumulate(FieldIO<F>::W == 12 ? 1 : 2, bases, ws.sorted, ws.offsets, ws.hist, total, n * cfg.nwin, maxlen,
                                         last_start, last_len, ws.bat_a, ws.bat_b, ws.bat_prefix, ws.buckets, ws.queue + 3, ws.sm_count,
                                         st)) != cudaSuccess)
@@ -444,9 +456,21 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
 }
 
 cudaError_t msm_run(int curve, const uint32_t* bases, const uint8_t* inf, const uint32_t* scalars, bool scalars_mont,
-                    size_t n, const MsmConfig& cfg, MsmWorkspace& ws, cudaStream_t st) {
-    if (curve == 1) return msm_run_t<Fq>(bases, inf, scalars, scalars_mont, n, cfg, ws, st);
-    return msm_run_t<Fq2>(bases, inf, scalars, scalars_mont, n, cfg, ws, st);
+                    size_t n, const MsmConfig& cfg, MsmWorkspace& ws, cudaStream_t st, bool reuse_plan) {
+    if (curve == 1) return msm_run_t<Fq>(bases, inf, scalars, scalars_mont, n, cfg, ws, st, reuse_plan);
+    return msm_run_t<Fq2>(bases, inf, scalars, scalars_mont, n, cfg, ws, st, reuse_plan);
+}
+
+__global__ void k_flags_differ(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, size_t n, uint32_t* __restrict__ differ) {
+    bool d = false;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) d |= a[i] != b[i];
+    if (__any_sync(0xffffffffu, d) && (threadIdx.x & 31) == 0) atomicOr(differ, 1u);
+}
+cudaError_t msm_flags_differ(const uint8_t* a, const uint8_t* b, size_t n, uint32_t* differ, cudaStream_t st) {
+    if (!n) return cudaSuccess;
+    size_t blocks = (n + 255) / 256;
+    k_flags_differ<<<(unsigned)(blocks < 1024 ? blocks : 1024), 256, 0, st>>>(a, b, n, differ); CZK_LAUNCHED();
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------ merged-window table

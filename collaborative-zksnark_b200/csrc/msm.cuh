@@ -124,13 +124,20 @@ struct MsmWorkspace {
     size_t cap_n = 0;
     size_t cap_buckets = 0;
     int point_words = 0;
+    // the last run's plan (sorted entries, bucket runs, item queue) can serve another base set: see msm_run's reuse_plan
+    uint64_t alloc_epoch = 0;                        // bumped whenever a plan buffer is reallocated
+    uint32_t plan_maxlen = 0, plan_last_start = 0, plan_last_len = 0;  // what the batched path read back for that plan
 };
 
 // curve: 1 = G1 (Fq, 12 words per coordinate), 2 = G2 (Fq2, 24 words per coordinate)
 // bases: n affine points, x | y, Montgomery, 16-byte aligned; inf: n bytes or nullptr.
 // scalars: n x 8 words.  winsum_out: device buffer of cfg.nwin XYZZ points.
+// reuse_plan: the workspace still holds the plan of the previous run, which had the same scalars, n, cfg and infinity flags
+// (the caller's claim): skip the digit decomposition and the bucket sort, run accumulation and reduction over `bases`.
 cudaError_t msm_run(int curve, const uint32_t* bases, const uint8_t* inf, const uint32_t* scalars, bool scalars_mont,
-                    size_t n, const MsmConfig& cfg, MsmWorkspace& ws, cudaStream_t st);
+                    size_t n, const MsmConfig& cfg, MsmWorkspace& ws, cudaStream_t st, bool reuse_plan = false);
+// *differ (device word, must be zero on entry) becomes non-zero iff a[i] != b[i] for some i < n
+cudaError_t msm_flags_differ(const uint8_t* a, const uint8_t* b, size_t n, uint32_t* differ, cudaStream_t st);
 
 size_t msm_point_words(int curve);  // 4 coordinates
 

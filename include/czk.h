@@ -107,6 +107,13 @@ CZK_API int czk_bases_precompute(czk_ctx* ctx, czk_bases* b, unsigned c);
 /* MSM of bases[base_off .. base_off+n) by the device scalars sc[sc_off .. sc_off+n). */
 CZK_API int czk_msm_bases(czk_ctx* ctx, const czk_bases* b, size_t base_off, const czk_vec* sc, size_t sc_off,
                   int scalars_montgomery, size_t n, uint64_t* out_xyz);
+/* Several MSMs over ONE scalar vector: out_xyz[k] = sum_i sc[sc_off + i] * b[k][base_off + i], k < count.  Groth16's a-,
+ * b_g1- and b_g2-query MSMs all take the full assignment (groth16/src/prover.rs:80-89, mpc-snarks/src/groth/prover.rs:
+ * 104-160): the digit decomposition and the bucket sort are done once for every base set that addresses a precomputed
+ * table of the first set's shape and carries its infinity flags (checked on the device); any other set runs as an MSM
+ * of its own.  Same results as `count` calls of czk_msm_bases.  ms_out (optional): wall ms per set. */
+CZK_API int czk_msm_bases_multi(czk_ctx* ctx, const czk_bases* const* b, int count, size_t base_off, const czk_vec* sc, size_t sc_off,
+                        int scalars_montgomery, size_t n, uint64_t* const* out_xyz, double* ms_out);
 /* Synthetic bases for benchmarks: P_i = (k0 + i*k1 + i^2*k2) * G with seeded 248-bit k0, k1, k2 (distinct points of
  * the prime-order subgroup, generated on the device), every `inf_every`-th entry flagged infinity (0 = none). */
 CZK_API int czk_bases_synthetic(czk_ctx* ctx, int curve, uint64_t seed, size_t n, size_t inf_every, czk_bases** out);

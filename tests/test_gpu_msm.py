@@ -171,6 +171,45 @@ def test_msm_merged_window_table_matches_oracle(ctx, oracle, g):
         b.free()
 
 
+@pytest.mark.parametrize("tree", [False, True])
+def test_msm_bases_multi_shares_the_digit_sort(ctx, oracle, tree):
+    """czk_msm_bases_multi == the oracle for every base set: two G1 sets and a G2 set with the lead's infinity flags
+    (one digit sort serves all three, prover.rs:104-160), a set with other flags in the middle (it and everything
+    after it run as MSMs of their own), sets without a table, and the query[1..] sub-range the prover uses.  Both
+    accumulation algorithms (the small input takes the affine tree only when told to)."""
+    n = 1 << 12
+    sets = [(oracle.G1, 1, 81), (oracle.G1, 1, 82), (oracle.G2, 2, 83), (oracle.G1, 1, 84)]
+    inf = np.zeros(n, np.uint8)
+    inf[3::61] = 1
+    other = np.zeros(n, np.uint8)
+    other[4::61] = 1
+    sc = oracle.random_fr_mont(85, n)
+    dsc = ctx.vec_from(sc)
+    xys = [make_points(G, n, seed=seed) for G, _, seed in sets]
+
+    def check(flags, tables, base_off=0):
+        bs = [ctx.bases_upload(curve, xy, f) for (_, curve, _), xy, f in zip(sets, xys, flags)]
+        for b, t in zip(bs, tables):
+            if t:
+                b.precompute(11)
+        m = n - base_off
+        outs = ctx.msm_bases_multi(bs, dsc, n=m, base_off=base_off)
+        for (G, _, _), xy, f, out in zip(sets, xys, flags, outs):
+            assert jac_to_affine_ints(G, out) == _oracle_msm(G, xy[base_off:], f[base_off:], sc[:m])
+        for b in bs:
+            b.free()
+
+    try:
+        ctx.msm_set_batched(True, always=tree)
+        check([inf, inf, inf, inf], [True] * 4)
+        check([inf, inf, inf, inf], [True] * 4, base_off=1)
+        check([inf, other, inf, inf], [True] * 4)
+        check([inf, inf, inf, other], [True, True, True, False])
+        check([inf, inf, inf, inf], [False] * 4)
+    finally:
+        ctx.msm_set_batched(True)
+
+
 def test_msm_merged_large_and_linear(ctx, oracle, pymodel):
     n = 1 << 18
     b = ctx.bases_synthetic(1, seed=71, n=n, inf_every=1024)
