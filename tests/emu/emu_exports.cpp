@@ -5,6 +5,7 @@
 #include "../../collaborative-zksnark_b200/csrc/ec.cuh"
 #include "../../collaborative-zksnark_b200/csrc/msm_digits.cuh"
 #include "../../collaborative-zksnark_b200/csrc/fq13.cuh"
+#include "../../collaborative-zksnark_b200/csrc/fq_inverse.cuh"
 
 using namespace czk;
 #define EXPORT extern "C" __attribute__((visibility("default")))
@@ -54,6 +55,13 @@ EXPORT void emu_fq_sub(uint64_t* r, const uint64_t* a, const uint64_t* b, size_t
 }
 EXPORT void emu_fq_inv(uint64_t* r, const uint64_t* a, size_t n) {
     for (size_t i = 0; i < n; i++) st(r + 6 * i, Fq::inv_fermat(ld<Fq>(a + 6 * i)));
+}
+// the batched-step binary GCD inversion (csrc/fq_inverse.cuh)
+EXPORT void emu_fq_inv_bingcd(uint64_t* r, const uint64_t* a, size_t n) {
+    for (size_t i = 0; i < n; i++) st(r + 6 * i, BinGcd<FqParams>::inverse(ld<Fq>(a + 6 * i)));
+}
+EXPORT void emu_fr_inv_bingcd(uint64_t* r, const uint64_t* a, size_t n) {
+    for (size_t i = 0; i < n; i++) st(r + 4 * i, BinGcd<FrParams>::inverse(ld<Fr>(a + 4 * i)));
 }
 EXPORT void emu_fq2_mul(uint64_t* r, const uint64_t* a, const uint64_t* b, size_t n) {
     for (size_t i = 0; i < n; i++) st2(r + 12 * i, Fq2::mul(ld2(a + 12 * i), ld2(b + 12 * i)));

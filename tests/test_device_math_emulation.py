@@ -70,6 +70,28 @@ def test_fq2_and_inversions(emu, oracle, pymodel):
     assert (o4 == oracle.fr_into_repr(y)).all()
 
 
+def test_batched_step_binary_gcd_inversion(emu, oracle, pymodel):
+    """csrc/fq_inverse.cuh (Pornin's batched binary GCD, 31 steps per round on 64-bit approximations) against the oracle's
+    restatement of the reference's inverse (macros.rs:368-422): random values, the values that need every round (powers of
+    two, p - 1, small numbers whose partner is the full-length modulus) and values that fit one or two limbs."""
+    rnd = random.Random(11)
+    for mod, from_ints, inv, fn, nl in ((pymodel.Q_MOD, oracle.fq_from_ints, oracle.fq_inv, emu.emu_fq_inv_bingcd, 6),
+                                        (pymodel.R_MOD, oracle.fr_from_ints, oracle.fr_inv, emu.emu_fr_inv_bingcd, 4)):
+        bits = mod.bit_length()
+        vals = [1, 2, 3, mod - 1, mod - 2, (mod + 1) // 2, 1 << (bits - 1), (1 << (bits - 1)) + 1, 1 << 31, (1 << 31) - 1, 1 << 32,
+                (1 << 62) + 1, (1 << 64) - 1, 1 << 64, (1 << 95) + 12345]
+        vals += [rnd.randrange(1, mod) for _ in range(1500)]
+        vals += [rnd.randrange(1, 1 << k) for k in (1, 5, 31, 33, 63, 64, 65, 100, 200) for _ in range(30)]
+        # the device sees Montgomery-form inputs: take these integers AS the Montgomery limbs too (any value < p is one)
+        x = from_ints(vals)
+        out = np.zeros_like(x)
+        fn(P(out), P(x), C.c_size_t(len(vals)))
+        assert (out == inv(x)).all()
+        raw = np.array([[(v >> (64 * i)) & (2**64 - 1) for i in range(nl)] for v in vals], dtype=np.uint64)
+        fn(P(out), P(raw), C.c_size_t(len(vals)))
+        assert (out == inv(raw)).all()
+
+
 @pytest.mark.parametrize("g", ["g1", "g2"])
 def test_xyzz_bucket_accumulation(emu, oracle, pymodel, g):
     """Signed accumulation exactly like a device bucket, incl. P+P (doubling branch), P + -P, and the
