@@ -984,7 +984,12 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     const size_t n_sq = pk->n_sq, D = pk->D;
     if (!cs && !n_sq) return fail(ctx, CZK_ERR_ARG, "czk_groth16_prove: this key was uploaded for a general circuit - use czk_groth16_prove_r1cs");
     for (int i = 0; i < 8; i++) g_phases[i] = 0;
-    std::future<TailPre> tail_pre = std::async(std::launch::async, tail_precompute, pk, r_sh, s_sh);
+    std::future<TailPre> tail_pre;
+    try {
+        tail_pre = std::async(std::launch::async, tail_precompute, pk, r_sh, s_sh);
+    } catch (const std::exception&) {  // no thread to be had: the tail computes them itself
+    }
+    auto tail_pre_get = [&] { return tail_pre.valid() ? tail_pre.get() : tail_precompute(pk, r_sh, s_sh); };
     ShareVecs v;
     if (cs && (cs->ncons != pk->ncons || cs->ninst != pk->ninst || cs->nwit != pk->nwit))
         return fail(ctx, CZK_ERR_ARG, "czk_groth16_prove_r1cs: the proving key was made for a circuit of another shape");
@@ -1027,14 +1032,14 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     free_share_vecs(ctx, v);
 
     if (scheme == CZK_SCHEME_GSZ)
-        return prove_tail_gsz(ctx, pk, tail_pre.get(), r_sh, s_sh, h_acc.sh, l_acc.sh, a_acc.sh, b1_acc.sh, b2_acc.sh, proof_sh, proof_sh_inf, proof, proof_inf);
+        return prove_tail_gsz(ctx, pk, tail_pre_get(), r_sh, s_sh, h_acc.sh, l_acc.sh, a_acc.sh, b1_acc.sh, b2_acc.sh, proof_sh, proof_sh_inf, proof, proof_inf);
     // ---- O(1) group arithmetic on shares (prover.rs:110-177)
     t0 = now_ms();
     HG1 alpha_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1), HFq::from_limbs(pk->vk_g1 + 6));
     HG1 beta_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1 + 12), HFq::from_limbs(pk->vk_g1 + 18));
     HG2 beta_g2 = HG2::from_affine(HFq2::from_limbs(pk->vk_g2), HFq2::from_limbs(pk->vk_g2 + 12));
     HFr r = HFr::from_limbs(r_sh), s = HFr::from_limbs(s_sh);
-    const TailPre pre = tail_pre.get();
+    const TailPre pre = tail_pre_get();
     // from_add_shared scalars: mac = share (key 1), so scale_pub_group gives sh == mac (spdz.rs:419-423)
     S1 rsd;
     rsd.sh = rsd.mac = pre.r_delta;  // delta_g1 * r
