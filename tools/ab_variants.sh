@@ -3,8 +3,8 @@
 #   here (build container):   tools/ab_variants.sh build bingcd=-DBAT_BINGCD=1 [name=flags ...]
 #   on the box (via gpurun):  gpurun -- 'bash tools/ab_variants.sh run bingcd [name ...] | tee gpurun_out/ab.log'
 # `run` times G1 2^21 / 2^20 and G2 2^20 accumulations for the shipped library and every named variant, then runs the MSM
-# parity tests against each variant (CZK_B200_LIB).  variants/ is git-ignored; remember it travels with the snapshot
-# (~25 MB per variant) unless listed in .gpurunignore - remove the variants/ line there before `run`.
+# parity tests against each variant (CZK_B200_LIB).  variants/ is git-ignored but travels with the snapshot
+# (~25 MB per variant): delete it when done.
 set -e
 cd "$(dirname "$0")/.."
 mode=$1; shift
