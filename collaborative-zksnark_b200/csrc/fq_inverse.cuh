@@ -3,13 +3,13 @@
 // The reference inverts with the binary extended Euclidean algorithm (algebra/ff/src/fields/macros.rs:368-422): up to
 // 2 * 377 one-bit steps, every one of them a shift and a conditional add / subtract over all twelve limbs of four
 // numbers - about 75 000 dependent instructions on a single GPU lane, which is what the other 127 lanes of the block wait
-// for.  This is the same binary GCD with the one-bit steps batched 31 at a time (T. Pornin, "Optimized Binary GCD for
-// Modular Inversion", ePrint 2020/972, algorithm 2): the 31 steps are run on 64-bit approximations of a and b (their
-// low 31 bits and their top 33 bits, aligned to the longer of the two) while the update factors f0, g0, f1, g1
-// (|f| + |g| <= 2^31) are collected, and only then applied to the full numbers
-//     (a, b) <- ((a f0 + b g0) / 2^31, (a f1 + b g1) / 2^31)          exact divisions, signs fixed up afterwards
-//     (u, v) <- ((u f0 + v g0) / 2^31, (u f1 + v g1) / 2^31)  mod p   one Montgomery-style reduction by 2^31 each
-// 2 * 377 - 1 = 753 steps are enough for every input, i.e. 25 rounds of 31; one more round is run for margin (a round on
+// for.  This is the same binary GCD with the one-bit steps batched 30 at a time (T. Pornin, "Optimized Binary GCD for
+// Modular Inversion", ePrint 2020/972, algorithm 2): the 30 steps are run on 64-bit approximations of a and b (their
+// low 30 bits and their top 32 bits, aligned to the longer of the two) while the update factors f0, g0, f1, g1
+// (|f| + |g| <= 2^30: 32-bit registers) are collected, and only then applied to the full numbers
+//     (a, b) <- ((a f0 + b g0) / 2^30, (a f1 + b g1) / 2^30)          exact divisions, signs fixed up afterwards
+//     (u, v) <- ((u f0 + v g0) / 2^30, (u f1 + v g1) / 2^30)  mod p   one Montgomery-style reduction by 2^30 each
+// 2 * 377 - 1 = 753 steps are enough for every input, i.e. 26 rounds of 30; one more round is run for margin (a round on
 // a = 0, b = 1 changes nothing).  The invariants a = u * y / K and b = v * y / K (mod p) hold throughout, so starting
 // from u = K = R^2 the result v = K / y is the inverse of a Montgomery-form input in Montgomery form - bit-identical to
 // the reference's result, because a field element has one representation.  Plain 64-bit C++ (no carry intrinsics): it
@@ -31,7 +31,9 @@ CZK_HD int clz32(uint32_t x) {  // x != 0
 template <class P>
 struct BinGcd {
     static constexpr int N = P::N;
-    static constexpr int ROUNDS = (2 * 32 * N - 1) / 31 + 2;  // >= ceil((2 * bits - 1) / 31) + 1 for any modulus of N limbs
+    static constexpr int STEPS = 30;                                    // binary-GCD steps per round
+    static constexpr int ROUNDS = (2 * 32 * N - 1 + STEPS - 1) / STEPS + 1;  // ceil((2 bits - 1) / STEPS) + 1, bits <= 32 N
+    static constexpr uint32_t LOW_MASK = (1u << STEPS) - 1;
 
     // r (N + 1 limbs) = x * k
     CZK_HD static void mul_word(uint32_t* r, const uint32_t* x, uint32_t k) {
@@ -55,12 +57,12 @@ struct BinGcd {
         }
         r[N] += (uint32_t)c;
     }
-    // out (N limbs) = r (N + 1 limbs) >> 31
-    CZK_HD static void shr31(uint32_t* out, const uint32_t* r) {
+    // out (N limbs) = r (N + 1 limbs) >> STEPS
+    CZK_HD static void shr_steps(uint32_t* out, const uint32_t* r) {
 #pragma unroll
-        for (int i = 0; i < N; i++) out[i] = (r[i] >> 31) | (r[i + 1] << 1);
+        for (int i = 0; i < N; i++) out[i] = (r[i] >> STEPS) | (r[i + 1] << (32 - STEPS));
     }
-    // |x fa +- y ga| / 2^31 into out; returns true when the signed value x (+-fa) + y (+-ga) is negative (or zero with
+    // |x fa +- y ga| / 2^STEPS into out; returns true when the signed value x (+-fa) + y (+-ga) is negative (or zero with
     // mixed signs, where the sign does not matter).  fneg / gneg: the signs of the two factors.
     CZK_HD static bool lincomb_exact(uint32_t* out, const uint32_t* x, uint32_t fa, bool fneg, const uint32_t* y, uint32_t ga,
                                      bool gneg) {
@@ -90,10 +92,10 @@ struct BinGcd {
             }
             neg = fneg ? !br : (br != 0);
         }
-        shr31(out, t);
+        shr_steps(out, t);
         return neg;
     }
-    // out = (x (+-fa) + y (+-ga)) / 2^31 mod p, for x, y in [0, p)
+    // out = (x (+-fa) + y (+-ga)) / 2^STEPS mod p, for x, y in [0, p)
     CZK_HD static void lincomb_mod(uint32_t* out, const uint32_t* x, uint32_t fa, bool fneg, const uint32_t* y, uint32_t ga, bool gneg) {
         uint32_t xe[N], ye[N], m[N];
         {
@@ -110,10 +112,10 @@ struct BinGcd {
         }
         uint32_t t[N + 1];
         mul_word(t, xe, fa);
-        mad_word(t, ye, ga);                             // <= p * 2^31
-        const uint32_t q = (0u - t[0]) & 0x7fffffffu;    // p = 1 mod 2^32: -p^-1 = -1 mod 2^31
-        mad_word(t, m, q);                               // = 0 mod 2^31, < p * 2^32
-        shr31(out, t);                                   // < 2 p
+        mad_word(t, ye, ga);                       // <= p * 2^STEPS
+        const uint32_t q = (0u - t[0]) & LOW_MASK;  // p = 1 mod 2^32: -p^-1 = -1 mod 2^STEPS
+        mad_word(t, m, q);                         // = 0 mod 2^STEPS, < p * 2^(STEPS + 1)
+        shr_steps(out, t);                         // < 2 p
         uint32_t d[N];
         uint64_t br = 0;
 #pragma unroll
@@ -128,7 +130,7 @@ struct BinGcd {
 
     // y^-1 for y != 0, Montgomery form in and out
     CZK_HD static Fp<P> inverse(const Fp<P>& y) {
-        static_assert(P::INV32 == 0xffffffffu, "the reduction by 2^31 above uses p = 1 mod 2^32");
+        static_assert(P::INV32 == 0xffffffffu, "the reduction by 2^STEPS above uses p = 1 mod 2^32");
         uint32_t a[N], b[N], u[N], v[N];
 #pragma unroll
         for (int i = 0; i < N; i++) {
@@ -139,7 +141,7 @@ struct BinGcd {
         }
 #pragma unroll 1
         for (int round = 0; round < ROUNDS; round++) {
-            // 64-bit approximations: low 31 bits | top 33 bits of the longer of a, b (exact when both fit 64 bits)
+            // 64-bit approximations: low STEPS bits | top 32 bits of the longer of a, b (exact when both fit 64 bits)
             uint32_t ah = a[1], al = a[0], bh = b[1], bl = b[0];
             bool found = false;
 #pragma unroll
@@ -154,25 +156,26 @@ struct BinGcd {
             uint64_t xa = ((uint64_t)ah << 32) | al, xb = ((uint64_t)bh << 32) | bl;
             if (found) {
                 const int lz = clz32(ah | bh);
-                xa = ((xa >> (31 - lz)) << 31) | (a[0] & 0x7fffffffu);
-                xb = ((xb >> (31 - lz)) << 31) | (b[0] & 0x7fffffffu);
+                // the pair (top word, next word) holds 64 - lz significant bits of the longer number: keep its top 32
+                xa = ((xa >> (32 - lz)) << STEPS) | (a[0] & LOW_MASK);
+                xb = ((xb >> (32 - lz)) << STEPS) | (b[0] & LOW_MASK);
             }
-            // 31 binary-GCD steps on the approximations, collecting the factors
-            int64_t f0 = 1, g0 = 0, f1 = 0, g1 = 1;
+            // STEPS binary-GCD steps on the approximations, collecting the factors
+            int32_t f0 = 1, g0 = 0, f1 = 0, g1 = 1;
 #pragma unroll 1
-            for (int j = 0; j < 31; j++) {
+            for (int j = 0; j < STEPS; j++) {
                 const bool odd = xa & 1u;
                 const bool swap = odd && xa < xb;
                 const uint64_t ta = swap ? xb : xa, tb = swap ? xa : xb;
-                const int64_t tf0 = swap ? f1 : f0, tf1 = swap ? f0 : f1, tg0 = swap ? g1 : g0, tg1 = swap ? g0 : g1;
+                const int32_t tf0 = swap ? f1 : f0, tf1 = swap ? f0 : f1, tg0 = swap ? g1 : g0, tg1 = swap ? g0 : g1;
                 xa = (odd ? ta - tb : ta) >> 1;
                 xb = tb;
                 f0 = odd ? tf0 - tf1 : tf0;
                 g0 = odd ? tg0 - tg1 : tg0;
-                f1 = tf1 << 1;
-                g1 = tg1 << 1;
+                f1 = tf1 * 2;
+                g1 = tg1 * 2;
             }
-            // apply them: magnitudes fit 32 bits (|f| + |g| <= 2^31)
+            // apply them: |f| + |g| <= 2^STEPS
             bool fn0 = f0 < 0, gn0 = g0 < 0, fn1 = f1 < 0, gn1 = g1 < 0;
             const uint32_t fa0 = (uint32_t)(fn0 ? -f0 : f0), ga0 = (uint32_t)(gn0 ? -g0 : g0);
             const uint32_t fa1 = (uint32_t)(fn1 ? -f1 : f1), ga1 = (uint32_t)(gn1 ? -g1 : g1);
