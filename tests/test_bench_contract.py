@@ -33,3 +33,14 @@ def test_reference_arm_prints_one_json_line():
 def test_reference_arm_other_ranks_exit_quietly():
     r = _run({"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"})
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_czk_arm_refuses_to_run_without_a_gpu():
+    import pytest
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present: the czk arm would run the whole benchmark")
+    r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1"], capture_output=True, text=True, cwd=str(ROOT), timeout=300)
+    assert r.returncode != 0 and r.stdout.strip() == ""
+    assert "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
