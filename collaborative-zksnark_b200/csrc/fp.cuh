@@ -208,6 +208,32 @@ struct Fp {
         reduce_once(r.l);
         return r;
     }
+    // Two independent products with their rows interleaved in program order (the carry primitives are `asm volatile`,
+    // so two plain mul() calls stay one after the other and ptxas never overlaps them): four carry chains in flight
+    // instead of two.  An experiment for kernels that run few warps per scheduler (microbench kind 15); 2 x 26
+    // accumulator registers.
+    CZK_HD static void mul2(const Fp& a, const Fp& b, const Fp& c, const Fp& d, Fp& ab, Fp& cd) {
+        uint32_t m[N], e1[N], o1[N], e2[N], o2[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) m[i] = P::modc(i);
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            mont_row<P>(e1, o1, a.l, b.l[i], m, i == 0);
+            mont_row<P>(e2, o2, c.l, d.l[i], m, i == 0);
+            mont_row<P>(o1, e1, a.l, b.l[i + 1], m, false);
+            mont_row<P>(o2, e2, c.l, d.l[i + 1], m, false);
+        }
+        ab.l[0] = add_cc(e1[0], o1[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) ab.l[i] = addc_cc(e1[i], o1[i + 1]);
+        ab.l[N - 1] = addc(e1[N - 1], 0);
+        cd.l[0] = add_cc(e2[0], o2[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) cd.l[i] = addc_cc(e2[i], o2[i + 1]);
+        cd.l[N - 1] = addc(e2[N - 1], 0);
+        reduce_once(ab.l);
+        reduce_once(cd.l);
+    }
     CZK_HD static Fp sqr(const Fp& a) { return mul(a, a); }
     // Same product with the a_i*b_j halves kept unfused (see chain_mad); `opaque_zero` must be a run-time zero the
     // compiler cannot see through (loaded from memory).

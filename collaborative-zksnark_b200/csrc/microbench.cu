@@ -204,6 +204,23 @@ __global__ void k_mb_mul(uint64_t* out, int iters, uint32_t seed) {
     for (int i = 0; i < F::N; i++) acc ^= (uint64_t)(x.l[i] ^ y.l[i]) << (i & 31);
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
+// kind 15: TWO independent Fq product chains per thread - does a second product in flight (4 carry chains instead of 2)
+// raise the multiply-pipe utilisation of a lone warp?  (kind 3 reaches 67 % of the 4-warp rate with one warp per scheduler.)
+__global__ void __launch_bounds__(256) k_mb_mul_x2(uint64_t* out, int iters, uint32_t seed) {
+    Fq x = Fq::one(), y = Fq::r2(), u = Fq::r2(), v = Fq::one();
+    x.l[0] ^= seed + threadIdx.x;
+    y.l[1] ^= blockIdx.x;
+    u.l[2] ^= seed ^ threadIdx.x;
+    v.l[3] ^= blockIdx.x + 7u;
+    for (int i = 0; i < iters; i++) {
+        Fq::mul2(x, y, u, v, x, u);
+        Fq::mul2(y, x, v, u, y, v);
+    }
+    uint64_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < Fq::N; i++) acc ^= (uint64_t)(x.l[i] ^ y.l[i] ^ u.l[i] ^ v.l[i]) << (i & 31);
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
+}
 __global__ void k_mb_madd(uint64_t* out, int iters, uint32_t seed) {
     XYZZ<Fq> acc = XYZZ<Fq>::from_affine(Fq::r2(), Fq::one());
     Fq px = Fq::one(), py = Fq::r2();
@@ -298,6 +315,7 @@ cudaError_t microbench_run(int kind, int blocks, int threads, int iters, uint64_
         case 12: k_mb_mul_regmod<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 2.0 * iters; break;
         case 13: k_mb_wide_carry_clean<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 24.0 * iters; break;
         case 14: k_mb_wide_plus_add<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 16.0 * iters; break;
+        case 15: k_mb_mul_x2<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 4.0 * iters; break;
         case 9: k_mb_mul13<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 2.0 * iters; break;
         case 10: k_mb_madd13<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 1.0 * iters; break;
         default: return cudaErrorInvalidValue;

@@ -56,6 +56,14 @@ EXPORT void emu_fq_sub(uint64_t* r, const uint64_t* a, const uint64_t* b, size_t
 EXPORT void emu_fq_inv(uint64_t* r, const uint64_t* a, size_t n) {
     for (size_t i = 0; i < n; i++) st(r + 6 * i, Fq::inv_fermat(ld<Fq>(a + 6 * i)));
 }
+EXPORT void emu_fq_mul2(uint64_t* r1, uint64_t* r2, const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* d, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        Fq x, y;
+        Fq::mul2(ld<Fq>(a + 6 * i), ld<Fq>(b + 6 * i), ld<Fq>(c + 6 * i), ld<Fq>(d + 6 * i), x, y);
+        st(r1 + 6 * i, x);
+        st(r2 + 6 * i, y);
+    }
+}
 // the batched-step binary GCD inversion (csrc/fq_inverse.cuh)
 EXPORT void emu_fq_inv_bingcd(uint64_t* r, const uint64_t* a, size_t n) {
     for (size_t i = 0; i < n; i++) st(r + 6 * i, BinGcd<FqParams>::inverse(ld<Fq>(a + 6 * i)));

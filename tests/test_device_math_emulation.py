@@ -70,6 +70,15 @@ def test_fq2_and_inversions(emu, oracle, pymodel):
     assert (o4 == oracle.fr_into_repr(y)).all()
 
 
+def test_interleaved_double_product(emu, oracle, pymodel):
+    """Fp::mul2 (two products with interleaved rows) == two products; aliasing an output with an input as the microbenchmark does."""
+    rnd = random.Random(13)
+    a, b, c, d = (oracle.fq_from_ints([rnd.randrange(pymodel.Q_MOD) for _ in range(300)]) for _ in range(4))
+    r1, r2 = np.zeros_like(a), np.zeros_like(a)
+    emu.emu_fq_mul2(P(r1), P(r2), P(a), P(b), P(c), P(d), C.c_size_t(300))
+    assert (r1 == oracle.fq_mul(a, b)).all() and (r2 == oracle.fq_mul(c, d)).all()
+
+
 def test_batched_step_binary_gcd_inversion(emu, oracle, pymodel):
     """csrc/fq_inverse.cuh (Pornin's batched binary GCD, 31 steps per round on 64-bit approximations) against the oracle's
     restatement of the reference's inverse (macros.rs:368-422): random values, the values that need every round (powers of
