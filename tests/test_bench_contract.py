@@ -23,11 +23,23 @@ def test_reference_arm_prints_one_json_line():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "ms" and d["higher_is_better"] is False
-    assert d["metric"] == "groth16_proof_ms_2^20_r1cs_bls12_377"
+    # a reduced sample (this test runs 2^8 to stay fast) must be labelled as such and never scaled into `value`:
+    # the default (--cpu-sample-log-n 20) measures the BASELINE config itself
+    assert d["metric"] == "groth16_proof_ms_2^8_r1cs_bls12_377"
     cb = d["cpu_baseline"]
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] > 0 and "2^8" in cb["sample"]
+    assert cb["same_config"] is False and cb["extrapolated"] is True and cb["log_n"] == 8
+    assert abs(cb["extrapolated_2^20_ms"] - cb["value"] * 4096) < 1e-6 * cb["value"] * 4096
     assert d["e2e"] == {"value": d["value"], "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["config"]["workload"].startswith("groth16 spdz 2^20")
+    assert d["config"]["workload"].startswith("groth16 spdz 2^8") and d["config"]["same_config"] is False
+
+
+def test_reference_arm_defaults_to_the_baseline_config():
+    sys.path.insert(0, str(ROOT))
+    import bench
+
+    ap_default = [a for a in open(ROOT / "bench.py").read().splitlines() if "add_argument(\"--cpu-sample-log-n\"" in a]
+    assert ap_default and "default=LOG_N" in ap_default[0] and bench.LOG_N == 20
 
 
 def test_reference_arm_other_ranks_exit_quietly():
