@@ -106,6 +106,12 @@ _SIGS = {
     "czk_gsz_batch_mul": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]),
     "czk_gsz_check_products": (C.c_int, [C.c_void_p, u64p]),
     "czk_gsz_stats": (C.c_int, [C.c_void_p, u64p]),
+    "czk_net_link_bytes": (C.c_int, [C.c_void_p, u64p]),
+    "czk_diag_sim_batch_open": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                          C.c_size_t, C.POINTER(C.c_uint32)]),
+    "czk_diag_sim_beaver_mul": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                          C.POINTER(C.c_void_p), C.c_size_t, C.POINTER(C.c_uint32)]),
+    "czk_diag_gsz_open_gathered": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_uint, C.c_size_t, C.c_void_p, C.POINTER(C.c_uint32)]),
     "czk_msm_set_batched": (C.c_int, [C.c_void_p, C.c_int]),
     "czk_fq_inverse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "czk_msm_stats": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_double), C.c_int]),
@@ -457,6 +463,43 @@ class Context:
         n = x_sh.n if n is None else n
         self._chk(self.lib.czk_beaver_batch_mul(self.h, scheme, x_sh.h, x_mac.h if x_mac is not None else None, y_sh.h,
                                                 y_mac.h if y_mac is not None else None, n))
+
+    def net_link_bytes(self):
+        out = np.zeros(2, np.uint64)
+        self.lib.czk_net_link_bytes(self.h, out.ctypes.data_as(u64p))
+        return {"sent": int(out[0]), "received": int(out[1])}
+
+    @staticmethod
+    def _handles(vecs):
+        if vecs is None:
+            return None
+        return (C.c_void_p * len(vecs))(*[v.h for v in vecs])
+
+    def sim_batch_open(self, scheme, sh, mac=None, n=None):
+        """N-party batch_open simulated on this GPU (diagnostics): sh / mac are lists of DeviceVec, one per party.
+        Returns (opened vector of every party, per-party MAC-check flags)."""
+        parties = len(sh)
+        n = sh[0].n if n is None else n
+        out = [DeviceVec(self, n) for _ in range(parties)]
+        flags = (C.c_uint32 * parties)()
+        self._chk(self.lib.czk_diag_sim_batch_open(self.h, scheme, parties, self._handles(sh), self._handles(mac), self._handles(out), n, flags))
+        return out, list(flags)
+
+    def sim_batch_mul(self, scheme, x_sh, x_mac, y_sh, y_mac, n=None):
+        """N-party Beaver product simulated on this GPU (diagnostics): x_sh[q] (x_mac[q]) *= y for every party q."""
+        parties = len(x_sh)
+        n = x_sh[0].n if n is None else n
+        flags = (C.c_uint32 * parties)()
+        self._chk(self.lib.czk_diag_sim_beaver_mul(self.h, scheme, parties, self._handles(x_sh), self._handles(x_mac), self._handles(y_sh),
+                                                   self._handles(y_mac), n, flags))
+        return list(flags)
+
+    def gsz_open_gathered(self, gathered: DeviceVec, parties: int, degree: int, k: int):
+        """open_degree_vec on a party-major (parties x k) matrix of gathered shares; returns (values, degree-check flag)."""
+        out = DeviceVec(self, k)
+        flag = C.c_uint32(0)
+        self._chk(self.lib.czk_diag_gsz_open_gathered(self.h, gathered.h, parties, degree, k, out.h, C.byref(flag)))
+        return out, int(flag.value)
 
     # ------------------------------------------------------------------ Plonk / KZG10 leaves
     def prefix_products(self, v: DeviceVec, n=None):

@@ -788,80 +788,7 @@ void czk_net_reset_stats(czk_ctx* ctx) {
     for (int i = 0; i < 5; i++) ctx->stats[i] = 0;
 }
 
-// ------------------------------------------------------------------------------------------ shares
-// out[i] = sum over parties of sh[i]; SPDZ additionally exchanges sigma = mac_share*x - mac and checks sum == 0
-static int open_raw(czk_ctx* ctx, int scheme, const uint32_t* sh, const uint32_t* mac, uint32_t* out, size_t n) {
-    if (scheme == CZK_SCHEME_PLAIN) {
-        if (out != sh) CUDA_TRY(ctx, cudaMemcpyAsync(out, sh, n * 32, cudaMemcpyDeviceToDevice, ctx->stream));
-        return CZK_OK;
-    }
-    size_t bytes = n * 32;
-    CZK_TRY(scratch_reserve(ctx, ctx->open_gather, bytes * (size_t)ctx->nranks));
-    uint32_t* gath = (uint32_t*)ctx->open_gather.p;
-    CZK_TRY(czk_net_allgather_dev(ctx, sh, gath, bytes));
-    CUDA_TRY(ctx, fr_sum_parties(out, gath, n, ctx->nranks, ctx->stream));
-    if (scheme == CZK_SCHEME_SPDZ) {
-        if (!mac) return fail(ctx, CZK_ERR_ARG, "SPDZ open needs the MAC share vector");
-        CZK_TRY(scratch_reserve(ctx, ctx->open_sigma, bytes));
-        HFr ms = ctx->rank == 0 ? HFr::one() : HFr::zero();  // spdz.rs:31-37 (global MAC key stubbed to 1)
-        CUDA_TRY(ctx, fr_spdz_sigma((uint32_t*)ctx->open_sigma.p, out, mac, ms.l, n, ctx->stream));
-        // atomic_broadcast (channel.rs:50-75): the data round; the SHA-256 commitment round of the reference
-        // is host-side bookkeeping between mutually distrusting machines and is not reproduced inside one box
-        CZK_TRY(czk_net_allgather_dev(ctx, ctx->open_sigma.p, gath, bytes));
-        CUDA_TRY(ctx, fr_check_zero_sum(gath, n, ctx->nranks, ctx->flag, ctx->stream));
-        uint32_t flag = 0;
-        CUDA_TRY(ctx, cudaMemcpyAsync(&flag, ctx->flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        if (flag) {
-            cudaMemsetAsync(ctx->flag, 0, 4, ctx->stream);
-            return fail(ctx, CZK_ERR_PROTOCOL, "SPDZ MAC check failed (spdz.rs:182 assert!(sum.is_zero()))");
-        }
-    }
-    return CZK_OK;
-}
-
-int czk_batch_open(czk_ctx* ctx, int scheme, const czk_vec* sh, const czk_vec* mac, czk_vec* out_pub, size_t n) {
-    if (!ctx || !sh || !out_pub || n > sh->n || n > out_pub->n || (mac && n > mac->n))
-        return fail(ctx, CZK_ERR_ARG, "czk_batch_open: range");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    return open_raw(ctx, scheme, (const uint32_t*)sh->d, mac ? (const uint32_t*)mac->d : nullptr, (uint32_t*)out_pub->d, n);
-}
-
-int czk_beaver_batch_mul(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac, const czk_vec* y_sh, const czk_vec* y_mac,
-                         size_t n) {
-    if (!ctx || !x_sh || !y_sh || n > x_sh->n || n > y_sh->n) return fail(ctx, CZK_ERR_ARG, "czk_beaver_batch_mul: range");
-    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    if (scheme == CZK_SCHEME_PLAIN) return czk_vec_mul(ctx, x_sh, y_sh, n);
-    // GszFieldShare::batch_mul (gsz20/mod.rs:309-315): king degree reduction, triple queued for the product check
-    if (scheme == CZK_SCHEME_GSZ) return czk_gsz_batch_mul(ctx, x_sh, y_sh, n, 1);
-    bool spdz = scheme == CZK_SCHEME_SPDZ;
-    if (spdz && (!x_mac || !y_mac || n > x_mac->n || n > y_mac->n)) return fail(ctx, CZK_ERR_ARG, "SPDZ product needs MAC vectors");
-    size_t bytes = n * 32;
-    CZK_TRY(scratch_reserve(ctx, ctx->open_sx, bytes));
-    CZK_TRY(scratch_reserve(ctx, ctx->open_oy, bytes));
-    CZK_TRY(scratch_reserve(ctx, ctx->open_d, bytes));
-    if (spdz) CZK_TRY(scratch_reserve(ctx, ctx->open_dm, bytes));
-    // stub triple (wire/field.rs:41-77): x = y = z = from_add_shared(1 at the king, 0 elsewhere);
-    // SPDZ from_add_shared(f) sets mac = f * mac() = f (spdz.rs:138-143)
-    HFr t = ctx->rank == 0 ? HFr::one() : HFr::zero();
-    HFr king = t;  // additive shift lands at the king; SPDZ MAC shift uses mac_share, same stub value
-    uint32_t* d = (uint32_t*)ctx->open_d.p;
-    uint32_t* dm = spdz ? (uint32_t*)ctx->open_dm.p : nullptr;
-    uint32_t* sx = (uint32_t*)ctx->open_sx.p;
-    uint32_t* oy = (uint32_t*)ctx->open_oy.p;
-    // sx = open(s + x)
-    CUDA_TRY(ctx, fr_add_const(d, (const uint32_t*)x_sh->d, t.l, n, ctx->stream));
-    if (spdz) CUDA_TRY(ctx, fr_add_const(dm, (const uint32_t*)x_mac->d, t.l, n, ctx->stream));
-    CZK_TRY(open_raw(ctx, scheme, d, dm, sx, n));
-    // oy = open(o + y)
-    CUDA_TRY(ctx, fr_add_const(d, (const uint32_t*)y_sh->d, t.l, n, ctx->stream));
-    if (spdz) CUDA_TRY(ctx, fr_add_const(dm, (const uint32_t*)y_mac->d, t.l, n, ctx->stream));
-    CZK_TRY(open_raw(ctx, scheme, d, dm, oy, n));
-    // z - sx*y - oy*x + shift(sx*oy)
-    CUDA_TRY(ctx, fr_beaver_finish((uint32_t*)x_sh->d, sx, oy, t.l, t.l, t.l, king.l, n, ctx->stream));
-    if (spdz) CUDA_TRY(ctx, fr_beaver_finish((uint32_t*)x_mac->d, sx, oy, t.l, t.l, t.l, king.l, n, ctx->stream));
-    return CZK_OK;
-}
+// shares: czk_batch_open / czk_beaver_batch_mul live in shares.cu
 
 // ------------------------------------------------------------------------------------------ diagnostics
 int czk_msm_set_batched(czk_ctx* ctx, int enabled) {

@@ -114,7 +114,8 @@ struct czk_ctx {
     // network
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
-    uint64_t stats[5] = {0, 0, 0, 0, 0};
+    uint64_t stats[5] = {0, 0, 0, 0, 0};  // mpc-net's own accounting (what the reference would count)
+    uint64_t link_bytes[2] = {0, 0};      // bytes this rank actually sent / received over NVLink
     GszState gsz;
     // kernel timing of the MSM (CUDA events on the launching stream), per curve: [0] G1, [1] G2
     double acc_ms[2] = {0, 0}, msm_ms[2] = {0, 0}, acc_terms[2] = {0, 0}, acc_entries[2] = {0, 0};

@@ -74,45 +74,6 @@ cudaError_t fr_scale_by_tables(uint32_t* a, const uint32_t* lo, const uint32_t* 
     return cudaGetLastError();
 }
 
-__global__ void k_fr_sum_parties(uint32_t* out, const uint32_t* g, size_t n, int parties) {
-    GRID_STRIDE(i, n) {
-        Fr acc = ldv(g, i);
-        for (int p = 1; p < parties; p++) acc = Fr::add(acc, ldv(g, (size_t)p * n + i));
-        stv(out, i, acc);
-    }
-}
-cudaError_t fr_sum_parties(uint32_t* out, const uint32_t* gathered, size_t n, int parties, cudaStream_t st) {
-    if (!n) return cudaSuccess;
-    k_fr_sum_parties<<<grid_for(n, 256), 256, 0, st>>>(out, gathered, n, parties); CZK_LAUNCHED();
-    return cudaGetLastError();
-}
-
-__global__ void k_fr_spdz_sigma(uint32_t* sigma, const uint32_t* x, const uint32_t* mac, FrConst ms, size_t n) {
-    Fr m = cst(ms);
-    GRID_STRIDE(i, n) stv(sigma, i, Fr::sub(Fr::mul(m, ldv(x, i)), ldv(mac, i)));
-}
-cudaError_t fr_spdz_sigma(uint32_t* sigma, const uint32_t* x, const uint32_t* mac, const uint64_t mac_share[4], size_t n,
-                          cudaStream_t st) {
-    if (!n) return cudaSuccess;
-    k_fr_spdz_sigma<<<grid_for(n, 256), 256, 0, st>>>(sigma, x, mac, mk(mac_share), n); CZK_LAUNCHED();
-    return cudaGetLastError();
-}
-
-__global__ void k_fr_check_zero_sum(const uint32_t* g, size_t n, int parties, uint32_t* flag) {
-    uint32_t bad = 0;
-    GRID_STRIDE(i, n) {
-        Fr acc = ldv(g, i);
-        for (int p = 1; p < parties; p++) acc = Fr::add(acc, ldv(g, (size_t)p * n + i));
-        if (!acc.is_zero()) bad = 1;
-    }
-    if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flag, 1u);
-}
-cudaError_t fr_check_zero_sum(const uint32_t* gathered, size_t n, int parties, uint32_t* flag, cudaStream_t st) {
-    if (!n) return cudaSuccess;
-    k_fr_check_zero_sum<<<grid_for(n, 256), 256, 0, st>>>(gathered, n, parties, flag); CZK_LAUNCHED();
-    return cudaGetLastError();
-}
-
 __global__ void k_fr_add_const(uint32_t* d, const uint32_t* x, FrConst t, size_t n) {
     Fr tt = cst(t);
     GRID_STRIDE(i, n) stv(d, i, Fr::add(ldv(x, i), tt));
@@ -120,25 +81,6 @@ __global__ void k_fr_add_const(uint32_t* d, const uint32_t* x, FrConst t, size_t
 cudaError_t fr_add_const(uint32_t* d, const uint32_t* x, const uint64_t tx[4], size_t n, cudaStream_t st) {
     if (!n) return cudaSuccess;
     k_fr_add_const<<<grid_for(n, 256), 256, 0, st>>>(d, x, mk(tx), n); CZK_LAUNCHED();
-    return cudaGetLastError();
-}
-
-__global__ void k_fr_beaver_finish_n(uint32_t* out, const uint32_t* sx, const uint32_t* oy, FrConst tx, FrConst ty, FrConst tz,
-                                     FrConst shift, size_t n) {
-    Fr x = cst(tx), y = cst(ty), z = cst(tz), sh = cst(shift);
-    GRID_STRIDE(i, n) {
-        Fr d = ldv(sx, i), e = ldv(oy, i);
-        // z.sub(y.scale(&sx)).sub(x.scale(&oy)).shift(&(sx * oy))
-        Fr r = Fr::sub(z, Fr::mul(y, d));
-        r = Fr::sub(r, Fr::mul(x, e));
-        r = Fr::add(r, Fr::mul(sh, Fr::mul(d, e)));
-        stv(out, i, r);
-    }
-}
-cudaError_t fr_beaver_finish(uint32_t* out, const uint32_t* sx, const uint32_t* oy, const uint64_t tx[4],
-                             const uint64_t ty[4], const uint64_t tz[4], const uint64_t shift[4], size_t n, cudaStream_t st) {
-    if (!n) return cudaSuccess;
-    k_fr_beaver_finish_n<<<grid_for(n, 256), 256, 0, st>>>(out, sx, oy, mk(tx), mk(ty), mk(tz), mk(shift), n); CZK_LAUNCHED();
     return cudaGetLastError();
 }
 

@@ -286,6 +286,41 @@ int gsz_mult1(czk_ctx* ctx, const HFr& x, const HFr& y, HFr* out) {
     return CZK_OK;
 }
 
+// diagnostics: open_degree_vec on a caller-supplied party-major matrix of gathered shares (parties x k), any party count
+// with a share domain - the interpolation and the degree check of k_gsz_open on genuine N-party inputs, on one GPU
+int czk_diag_gsz_open_gathered(czk_ctx* ctx, const czk_vec* gathered, int parties, unsigned degree, size_t k, czk_vec* out_pub,
+                               uint32_t* flag_out) {
+    if (!ctx || !gathered || !out_pub || !flag_out || parties < 1 || parties > 64 || !k || gathered->n < (size_t)parties * k || out_pub->n < k)
+        return fail(ctx, CZK_ERR_ARG, "czk_diag_gsz_open_gathered: argument");
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    HFr w;
+    if (!gsz_root_of_unity((size_t)parties, &w)) return fail(ctx, CZK_ERR_ARG, "GSZ: no share domain of this size (n must be 2^a or 3 * 2^a)");
+    HFr wi = HFr::inv(w), p = HFr::one();
+    std::vector<uint64_t> tab((size_t)parties * 4);
+    for (int j = 0; j < parties; j++) {
+        p.to_limbs(tab.data() + 4 * j);
+        p = HFr::mul(p, wi);
+    }
+    uint32_t* winv = nullptr;
+    uint32_t* flag = nullptr;
+    CUDA_TRY(ctx, cudaMalloc((void**)&winv, (size_t)parties * 32 + 4));
+    flag = winv + (size_t)parties * 8;
+    int rc = CZK_OK;
+    cudaError_t e = cudaMemcpyAsync(winv, tab.data(), (size_t)parties * 32, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(flag, 0, 4, ctx->stream);
+    if (e == cudaSuccess) {
+        HFr n_inv = HFr::inv(HFr::from_u64((uint64_t)parties));
+        k_gsz_open<<<g_grid(k, 256), 256, 0, ctx->stream>>>((uint32_t*)out_pub->d, (const uint32_t*)gathered->d, k, parties, (int)degree, winv,
+                                                            g_mk(n_inv.l), flag); CZK_LAUNCHED();
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(flag_out, flag, 4, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = fail(ctx, CZK_ERR_CUDA, std::string("czk_diag_gsz_open_gathered: ") + cudaGetErrorString(e));
+    cudaFree(winv);
+    return rc;
+}
+
 // ------------------------------------------------------------------------------------------ C ABI
 int czk_gsz_open(czk_ctx* ctx, const czk_vec* sh, unsigned degree, czk_vec* out_pub, size_t n) {
     if (!ctx || !sh || !out_pub || n > sh->n || n > out_pub->n) return fail(ctx, CZK_ERR_ARG, "czk_gsz_open: range");

@@ -229,18 +229,18 @@ __device__ __forceinline__ void words_to(Fq2& r, const uint32_t* w) {
     words_to(r.c1, w + 12);
 }
 // one field element per thread and parity: chunk c of thread tid at cell[(par * CH + c) * BAT_THREADS + tid]
-template <class F>
+template <class F, int THREADS = BAT_THREADS>
 struct StageIO {
     static constexpr int W = FieldIO<F>::W, CH = W / 4;
     __device__ __forceinline__ static void fetch(uint4* cell, int par, unsigned tid, const uint32_t* g) {
 #pragma unroll
-        for (int c = 0; c < CH; c++) cp_async16(cell + (par * CH + c) * BAT_THREADS + tid, g + 4 * c);
+        for (int c = 0; c < CH; c++) cp_async16(cell + (par * CH + c) * THREADS + tid, g + 4 * c);
     }
     __device__ __forceinline__ static F ld(const uint4* cell, int par, unsigned tid) {
         uint32_t w[W];
 #pragma unroll
         for (int c = 0; c < CH; c++) {
-            const uint4 v = cell[(par * CH + c) * BAT_THREADS + tid];
+            const uint4 v = cell[(par * CH + c) * THREADS + tid];
             w[4 * c] = v.x; w[4 * c + 1] = v.y; w[4 * c + 2] = v.z; w[4 * c + 3] = v.w;
         }
         F r;
@@ -435,6 +435,214 @@ __global__ void __launch_bounds__(BAT_THREADS, MINB)
     }
 }
 
+// ------------------------------------------------------------------ one round on G2: two lanes per slot
+// The same round for Fq2 points with every slot owned by a PAIR of adjacent lanes: the even lane holds the c0 component
+// of every Fq2 value, the odd lane c1.  Sums, differences, negations and zero tests of Fq2 are component-wise, so they
+// split for free; a product needs both components of both operands, which the partner supplies by 24 warp shuffles,
+// and each lane then forms ONE lazily reduced sum of two base-field products (Fp::mul_sum2, one Montgomery reduction):
+//     c0 = a0 b0 + (-5 a1) b1          c1 = a1 b0 + a0 b1          (quadratic_extension.rs:569-583 without Karatsuba)
+// 2 x (2 * 144 + 132) = 840 wide multiply-adds per Fq2 product against 3 x 276 = 828 for Karatsuba on one lane - the
+// same arithmetic - but a lane carries HALF the state: 128 registers instead of 255, so 4 warps per scheduler are
+// resident instead of 2 (the one-lane kernel sat at 41 % of the base-field product rate, profiles/r1_summary.md).
+// Shuffles need the whole warp, so the products of a slot are executed unconditionally (a slot that only copies a
+// leftover point computes on zeros and stores the copy); every condition that guards a store is identical in both
+// lanes of a pair.
+constexpr int G2L_THREADS = 2 * BAT_THREADS;
+__device__ __forceinline__ Fq g2l_mul(const Fq& a, const Fq& b, const unsigned h) {
+    uint32_t sa[12], pa[12];
+    Fq::neg_times5_unreduced(a, sa);  // the odd lane hands out -5 a1 (as 5 (p - a1) < 2^380), the even lane a0
+    Fq pb, y1, y2;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        pa[i] = __shfl_xor_sync(0xffffffffu, h ? sa[i] : a.l[i], 1);
+        pb.l[i] = __shfl_xor_sync(0xffffffffu, b.l[i], 1);
+        y1.l[i] = h ? pb.l[i] : b.l[i];  // b0 in both lanes
+        y2.l[i] = h ? b.l[i] : pb.l[i];  // b1 in both lanes
+    }
+    return Fq::mul_sum2(a, y1, pa, y2);
+}
+__device__ __forceinline__ bool g2l_both(bool mine) {  // true iff the condition holds in both lanes of the pair
+    return mine && __shfl_xor_sync(0xffffffffu, mine ? 1u : 0u, 1) != 0u;
+}
+constexpr size_t g2l_smem_bytes() {  // Fq2 product tree + 2 prefix cells (one component) + 2 x 2 entry cells, per thread
+    return (size_t)24 * 256 * 4 + (size_t)2 * 3 * G2L_THREADS * 16 + (size_t)4 * G2L_THREADS * 4;
+}
+
+template <bool FIRST, int MINB>
+__global__ void __launch_bounds__(G2L_THREADS, MINB)
+    k_bat_round_g2l(BatGeom g, const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ in,
+                    uint32_t* __restrict__ out, uint32_t* __restrict__ prefix, uint32_t* __restrict__ flag, const int B) {
+    constexpr int W = 24, HW = 12, CH = 3;  // words of an Fq2 element, of one component, 16-byte chunks of a component
+    typedef StageIO<Fq, G2L_THREADS> Stage;
+    extern __shared__ uint4 bat_smem[];
+    uint32_t* const tree = reinterpret_cast<uint32_t*>(bat_smem);
+    uint4* const pcell = bat_smem + (W * 256) / 4;
+    uint32_t* const ecell = reinterpret_cast<uint32_t*>(pcell + 2 * CH * G2L_THREADS);  // [par][which][tid]
+    const unsigned tid = threadIdx.x, ow = tid >> 1, h = tid & 1;
+    const uint32_t used = (bat_start(g, g.nb - 1, g.r) >> 1) + (g.nb - 1) + ((bat_len(g, g.nb - 1, g.r) + 1) >> 1);
+    const size_t block_first = (size_t)blockIdx.x * BAT_THREADS * B;
+    if (block_first >= used) return;
+    const size_t o0 = block_first + (size_t)ow * B;
+    uint32_t* const pre = prefix + ((size_t)blockIdx.x * B * BAT_THREADS + ow) * W + HW * h;
+    constexpr size_t PRE_STRIDE = (size_t)BAT_THREADS * W;
+    uint32_t* const mytree = tree + HW * 256 * h;  // this lane's component of the limb-major Fq2 tree
+
+    BatCursor c;
+    {
+        uint32_t lo = 0, hi = g.nb - 1;
+        const uint32_t target = o0 > 0xfffffffeull ? 0xfffffffeu : (uint32_t)o0;
+        while (lo < hi) {
+            uint32_t mid = lo + (hi - lo + 1) / 2;
+            uint32_t s = (bat_start(g, mid, g.r) >> 1) + mid;
+            if (s <= target) lo = mid;
+            else hi = mid - 1;
+        }
+        bat_seek(g, c, lo);
+    }
+    const Fq one = h ? Fq::zero() : Fq::one();  // this lane's component of 1
+    uint32_t m_fl = 0, m_pos = 0;
+    auto point_ptr = [&](uint32_t pos, uint32_t e) -> const uint32_t* {
+        return (FIRST ? bases + (size_t)(e & 0x7fffffffu) * (2 * W) : in + (size_t)pos * (2 * W)) + HW * h;
+    };
+    auto ldp = [&](const uint32_t* q) -> Fq { return FIRST ? FieldIO<Fq>::load(q) : FieldIO<Fq>::load_rw(q); };
+    auto fetch_entries = [&](int par) {
+        if (FIRST && (m_fl & 1u)) cp_async4(ecell + (par * 2 + 0) * G2L_THREADS + tid, sorted + m_pos);
+        if (FIRST && (m_fl & 2u)) cp_async4(ecell + (par * 2 + 1) * G2L_THREADS + tid, sorted + m_pos + 1);
+    };
+    auto entry = [&](int par, int which) -> uint32_t { return FIRST ? ecell[(par * 2 + which) * G2L_THREADS + tid] : 0u; };
+    // ---- phase 1: running product of the differences x2 - x1
+    auto meta1 = [&](size_t o) {
+        while (o >= c.next_s_out) bat_seek(g, c, c.b + 1);
+        const uint32_t k = (uint32_t)(o - c.s_out);
+        const bool pair = k < c.len_out() && 2 * k + 1 < c.len_in;
+        m_pos = c.s_in + 2 * k;
+        m_fl = pair ? 3u : 0u;
+    };
+    Fq acc = one;
+    Fq nx1 = Fq::zero(), nx2 = Fq::zero();
+    bool npair;
+    {
+        meta1(o0);
+        npair = m_fl & 2u;
+        if (npair) {
+            const uint32_t e1 = FIRST ? sorted[m_pos] : 0u, e2 = FIRST ? sorted[m_pos + 1] : 0u;
+            nx1 = ldp(point_ptr(m_pos, e1));
+            nx2 = ldp(point_ptr(m_pos + 1, e2));
+        }
+        if (B > 1) {
+            meta1(o0 + 1);
+            fetch_entries(1);
+        }
+        cp_async_commit();
+    }
+#pragma unroll 1
+    for (int j = 0; j < B; j++) {
+        const bool pair = npair;
+        const Fq x1 = nx1, x2 = nx2;
+        if (j + 1 < B) {
+            const int par = (j + 1) & 1;
+            cp_async_wait_all();
+            npair = m_fl & 2u;
+            if (npair) {
+                nx1 = ldp(point_ptr(m_pos, entry(par, 0)));
+                nx2 = ldp(point_ptr(m_pos + 1, entry(par, 1)));
+            }
+            if (j + 2 < B) {
+                meta1(o0 + j + 2);
+                fetch_entries(par ^ 1);
+            }
+            cp_async_commit();
+        }
+        Fq d = Fq::sub(x2, x1);
+        const bool dz = g2l_both(d.is_zero());
+        if (pair && dz) atomicOr(flag, 1u);
+        if (!pair || dz) d = one;
+        acc = j == 0 ? d : g2l_mul(acc, d, h);
+        FieldIO<Fq>::store(pre + (size_t)j * PRE_STRIDE, acc);
+    }
+    // ---- phase 2: one inversion for the block (the Fq2 tree is walked by single lanes on whole elements: cold code)
+    TreeIO<Fq>::st(mytree, 128 + ow, acc);
+    __syncthreads();
+    auto meta3 = [&](size_t o) {
+        while (o < c.s_out) bat_seek(g, c, c.b - 1);
+        const uint32_t k = (uint32_t)(o - c.s_out);
+        const bool live = k < c.len_out(), pair = live && 2 * k + 1 < c.len_in;
+        m_pos = c.s_in + 2 * k;
+        m_fl = (live ? 1u : 0u) | (pair ? 2u : 0u);
+    };
+    auto fetch_small = [&](int j) {
+        fetch_entries(j & 1);
+        if (j > 0) Stage::fetch(pcell, j & 1, tid, pre + (size_t)(j - 1) * PRE_STRIDE);
+        cp_async_commit();
+    };
+    meta3(o0 + B - 1);
+    fetch_small(B - 1);
+#pragma unroll 1
+    for (unsigned width = 64; width >= 1; width >>= 1) {
+        if (tid < width) {
+            unsigned i = width + tid;
+            TreeIO<Fq2>::st(tree, i, cold_mul(TreeIO<Fq2>::ld(tree, 2 * i), TreeIO<Fq2>::ld(tree, 2 * i + 1)));
+        }
+        __syncthreads();
+    }
+    if (tid == 0) TreeIO<Fq2>::st(tree, 1, field_inverse(TreeIO<Fq2>::ld(tree, 1)));
+    __syncthreads();
+#pragma unroll 1
+    for (unsigned width = 1; width <= 64; width <<= 1) {
+        if (tid < width) {
+            unsigned i = width + tid;
+            Fq2 inv_i = TreeIO<Fq2>::ld(tree, i), l = TreeIO<Fq2>::ld(tree, 2 * i), r = TreeIO<Fq2>::ld(tree, 2 * i + 1);
+            TreeIO<Fq2>::st(tree, 2 * i, cold_mul(inv_i, r));
+            TreeIO<Fq2>::st(tree, 2 * i + 1, cold_mul(inv_i, l));
+        }
+        __syncthreads();
+    }
+    Fq inv = TreeIO<Fq>::ld(mytree, 128 + ow);
+    // ---- phase 3: peel the inverses off backwards and form the sums
+#pragma unroll 1
+    for (int j = B - 1; j >= 0; j--) {
+        const size_t o = o0 + j;
+        const bool live = m_fl & 1u, pair = m_fl & 2u;
+        const int par = j & 1;
+        cp_async_wait_all();
+        const uint32_t e1 = entry(par, 0), e2 = entry(par, 1);
+        Fq x1 = Fq::zero(), y1 = Fq::zero(), x2 = Fq::zero(), y2 = Fq::zero();
+        if (live) {
+            const uint32_t* p = point_ptr(m_pos, e1);
+            x1 = ldp(p);
+            y1 = ldp(p + W);
+        }
+        if (pair) {
+            const uint32_t* p = point_ptr(m_pos + 1, e2);
+            x2 = ldp(p);
+            y2 = ldp(p + W);
+        }
+        Fq dinv = inv;
+        if (j > 0) {
+            const Fq pj = Stage::ld(pcell, par, tid);
+            meta3(o - 1);
+            fetch_small(j - 1);
+            dinv = g2l_mul(inv, pj, h);  // runs under the gathers' latency
+        }
+        if (FIRST && live && (e1 >> 31)) y1 = Fq::neg(y1);
+        if (FIRST && pair && (e2 >> 31)) y2 = Fq::neg(y2);
+        const Fq lam = g2l_mul(Fq::sub(y2, y1), dinv, h);
+        Fq d = Fq::sub(x2, x1);
+        if (!pair || g2l_both(d.is_zero())) d = one;
+        if (j > 0) inv = g2l_mul(inv, d, h);
+        uint32_t* dst = out + o * (2 * W) + HW * h;
+        const Fq x3 = Fq::sub(Fq::sub(g2l_mul(lam, lam, h), x1), x2);
+        const Fq y3 = Fq::sub(g2l_mul(lam, Fq::sub(x1, x3), h), y1);
+        if (pair) {
+            FieldIO<Fq>::store(dst, x3);
+            FieldIO<Fq>::store(dst + W, y3);
+        } else if (live) {
+            FieldIO<Fq>::store(dst, x1);
+            FieldIO<Fq>::store(dst + W, y1);
+        }
+    }
+}
+
 // buckets[b] = sum of the (few) points left in bucket b after the halving rounds, as XYZZ for the reduction kernels.
 // The late rounds of the tree hold little work but each still costs a block-wide inversion; once every bucket is
 // down to BAT_WALK points or fewer, a plain mixed-addition walk (one thread per bucket, every special case of the
@@ -524,19 +732,30 @@ size_t msm_batched_bytes(int curve, size_t entries, size_t nb, size_t* pa, size_
     return *pa + *pb + *pre;
 }
 
+#ifndef BAT_G2_LANES
+#define BAT_G2_LANES 1
+#endif
+constexpr int G2L_MINB = 2;  // 2 blocks of 256 threads at 128 registers
 template <class F>
 static cudaError_t msm_batched_t(const uint32_t* bases, const uint32_t* sorted, const uint32_t* ends, const uint32_t* hist,
                                  size_t nb, size_t entries, uint32_t maxlen, uint32_t last_start, uint32_t last_len, uint32_t* pa,
                                  uint32_t* pb, uint32_t* prefix, uint32_t* buckets, uint32_t* flag, int sm_count, cudaStream_t st) {
     constexpr int MINB = BatTuning<F>::MINB;
+    constexpr bool LANES = BAT_G2_LANES && FieldIO<F>::W == 24;
     int rounds = 1;  // at least one: round 0 turns (index | sign) entries into points
     while (rounds < 32 && (((uint64_t)maxlen + ((1ull << rounds) - 1)) >> rounds) > BAT_WALK) rounds++;
     BatGeom g{ends, hist, (uint32_t)nb, 0};
     uint32_t* bufs[2] = {pa, pb};
-    constexpr size_t smem = bat_smem_bytes<F>();
+    constexpr size_t smem = LANES ? g2l_smem_bytes() : bat_smem_bytes<F>();
     static const cudaError_t attr = [] {
-        cudaError_t e1 = cudaFuncSetAttribute(k_bat_round<F, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        cudaError_t e2 = cudaFuncSetAttribute(k_bat_round<F, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e1, e2;
+        if (LANES) {
+            e1 = cudaFuncSetAttribute(k_bat_round_g2l<true, G2L_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e2 = cudaFuncSetAttribute(k_bat_round_g2l<false, G2L_MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        } else {
+            e1 = cudaFuncSetAttribute(k_bat_round<F, true, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e2 = cudaFuncSetAttribute(k_bat_round<F, false, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        }
         return e1 != cudaSuccess ? e1 : e2;
     }();
     if (attr != cudaSuccess) return attr;
@@ -544,12 +763,15 @@ static cudaError_t msm_batched_t(const uint32_t* bases, const uint32_t* sorted, 
         g.r = r;
         size_t slots = bat_used(last_start, last_len, nb, r);
         if (slots > bat_bound(entries, nb, r + 1)) return cudaErrorInvalidValue;  // the buffers are sized by the bound
-        const int B = bat_pick_b(slots, (size_t)sm_count * MINB, BatBeta<F>::VALUE);
+        const int B = bat_pick_b(slots, (size_t)sm_count * (LANES ? G2L_MINB : MINB), BatBeta<F>::VALUE);
         const size_t per_block = (size_t)BAT_THREADS * B;
         unsigned blocks = (unsigned)((slots + per_block - 1) / per_block);
         uint32_t* dst = bufs[r & 1];
         const uint32_t* src = r ? bufs[(r - 1) & 1] : nullptr;
-        if (r == 0) k_bat_round<F, true, MINB><<<blocks, BAT_THREADS, smem, st>>>(g, bases, sorted, nullptr, dst, prefix, flag, B);
+        if (LANES) {
+            if (r == 0) k_bat_round_g2l<true, G2L_MINB><<<blocks, G2L_THREADS, smem, st>>>(g, bases, sorted, nullptr, dst, prefix, flag, B);
+            else k_bat_round_g2l<false, G2L_MINB><<<blocks, G2L_THREADS, smem, st>>>(g, nullptr, nullptr, src, dst, prefix, flag, B);
+        } else if (r == 0) k_bat_round<F, true, MINB><<<blocks, BAT_THREADS, smem, st>>>(g, bases, sorted, nullptr, dst, prefix, flag, B);
         else k_bat_round<F, false, MINB><<<blocks, BAT_THREADS, smem, st>>>(g, nullptr, nullptr, src, dst, prefix, flag, B);
         CZK_LAUNCHED();
         cudaError_t e = cudaGetLastError();

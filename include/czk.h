@@ -207,6 +207,24 @@ CZK_API int czk_gsz_check_products(czk_ctx* ctx, uint64_t final_xyz[12]);
 CZK_API int czk_gsz_stats(const czk_ctx* ctx, uint64_t out[2]);
 
 /* ---- diagnostics --------------------------------------------------------------------------------- */
+/* Bytes this rank actually moved over NVLink { sent, received } since context creation.  czk_net_stats keeps mpc-net's own
+ * accounting (what the reference's Stats line would show for the same protocol steps: an SPDZ open counts 3 broadcasts
+ * of N-1 full messages, multi.rs:145-174 + channel.rs:50-75); the device path exchanges slices (see csrc/shares.cu), so
+ * the two differ by design. */
+CZK_API int czk_net_link_bytes(const czk_ctx* ctx, uint64_t out[2]);
+/* N-party additive / SPDZ protocol arithmetic on ONE GPU: party q's vectors are sh[q] (mac[q]); the same kernels, slice
+ * geometry and per-party constants as czk_batch_open / czk_beaver_batch_mul run for every simulated party, with the
+ * collectives replaced by direct addressing between the parties' buffers.  flags_out[q] != 0: party q's slice of the
+ * SPDZ MAC check failed (the product entry points return CZK_ERR_PROTOCOL in that case).  parties <= 16.
+ * Replaces nothing in the reference: test infrastructure for share/add.rs:121-125, spdz.rs:166-185, field.rs:97-127. */
+CZK_API int czk_diag_sim_batch_open(czk_ctx* ctx, int scheme, int parties, const czk_vec* const* sh, const czk_vec* const* mac,
+                                    czk_vec* const* out_pub, size_t n, uint32_t* flags_out);
+CZK_API int czk_diag_sim_beaver_mul(czk_ctx* ctx, int scheme, int parties, czk_vec* const* x_sh, czk_vec* const* x_mac,
+                                    const czk_vec* const* y_sh, const czk_vec* const* y_mac, size_t n, uint32_t* flags_out);
+/* GSZ open_degree_vec (gsz20/mod.rs:440-459) on a caller-supplied party-major matrix of gathered shares (parties x k):
+ * out_pub = the values at 0, *flag_out != 0 iff some polynomial has degree > `degree`. */
+CZK_API int czk_diag_gsz_open_gathered(czk_ctx* ctx, const czk_vec* gathered, int parties, unsigned degree, size_t k, czk_vec* out_pub,
+                                       uint32_t* flag_out);
 /* Device timing (CUDA events on the context's stream) of the MSMs run so far on this context, per curve:
  * out = { bucket-accumulation kernel ms (sum), its launch count, terms processed (sum of n), whole-MSM device ms (sum),
  *         (point, window) pairs = upper bound on mixed additions (sum of n * windows) }. */

@@ -155,3 +155,20 @@ EXPORT int emu_g1_sum13(uint64_t* out_xy, const uint64_t* xy, const uint8_t* sig
     st(out_xy + 6, Fq::mul(s.y, zzzi));
     return 0;
 }
+// The two-lane Fq2 product of the G2 bucket kernel (csrc/msm_batched.cu): lane 0 owns c0, lane 1 owns c1; each lane
+// computes ONE lazily reduced sum of two products (Fp::mul_sum2).  Here both lanes are evaluated one after the other.
+//   c0 = a0 b0 + (-5 a1) b1      c1 = a1 b0 + a0 b1
+EXPORT void emu_fq2_mul_two_lanes(uint64_t* r, const uint64_t* a, const uint64_t* b, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        Fq2 x = ld2(a + 12 * i), y = ld2(b + 12 * i);
+        uint32_t m5[12];
+        Fq::neg_times5_unreduced(x.c1, m5);
+        Fq2 out;
+        out.c0 = Fq::mul_sum2(x.c0, y.c0, m5, y.c1);
+        out.c1 = Fq::mul_sum2(x.c1, y.c0, x.c0.l, y.c1);
+        st2(r + 12 * i, out);
+    }
+}
+EXPORT void emu_fr_mul_sum2(uint64_t* r, const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* d, size_t n) {
+    for (size_t i = 0; i < n; i++) st(r + 4 * i, Fr::mul_sum2(ld<Fr>(a + 4 * i), ld<Fr>(b + 4 * i), ld<Fr>(c + 4 * i).l, ld<Fr>(d + 4 * i)));
+}

@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--scheme", default="spdz", choices=["additive", "spdz", "gsz"])
     ap.add_argument("--log-n", type=int, default=10)
     ap.add_argument("--squarings", type=int, default=0, help="exact number of squarings (overrides --log-n)")
+    ap.add_argument("--corrupt-mac", action="store_true", help="negative case: rank 1 corrupts one MAC share, every rank must see the check fail")
     args = ap.parse_args()
     party = launch.Party()
     ctx, rank, world = party.ctx, party.rank, party.world
@@ -30,6 +31,8 @@ def main():
     n_sq = args.squarings or (1 << args.log_n)
     if args.scheme == "gsz":
         return main_gsz(party, n_sq)
+    if args.corrupt_mac:
+        return main_corrupt(party)
     rnd = random.Random(1234 + n_sq)
     toxic = [rnd.randrange(1, m.R_MOD) for _ in range(7)]
     pk = o.groth16_setup(n_sq, o.fr_from_ints(toxic), threads=max(1, o.cpu_threads() // world))
@@ -89,6 +92,32 @@ def main():
             assert (xm.numpy() == exp_mac[rank]).all(), f"rank {rank}: {name} MAC share differs"
     launch.barrier()
     print(f"[rank {rank}/{world}] groth16 {args.scheme} n={n_sq}: parity ok; net {st}", flush=True)
+    party.close()
+
+
+def main_corrupt(party):
+    """SPDZ open and product with one corrupted MAC share at rank 1: the slice owner's flag is all-gathered, so the
+    call must fail with CZK_ERR_PROTOCOL on EVERY rank (spdz.rs:182 assert!s at every party), and the next call must work."""
+    ctx, rank, world = party.ctx, party.rank, party.world
+    k = 1000
+    x, y = o.random_fr_mont(5, k), o.random_fr_mont(6, k)
+    xs, ys = czk_b200.king_share_batch(x, world, seed=3), czk_b200.king_share_batch(y, world, seed=4)
+    mac = xs[rank].copy()
+    if rank == 1:
+        mac[k - 1] = o.random_fr_mont(7, 1)[0]
+    for what in ("open", "mul"):
+        try:
+            if what == "open":
+                ctx.batch_open(czk_b200.SCHEME_SPDZ, ctx.vec_from(xs[rank]), ctx.vec_from(mac))
+            else:
+                ctx.batch_mul(czk_b200.SCHEME_SPDZ, ctx.vec_from(xs[rank]), ctx.vec_from(mac), ctx.vec_from(ys[rank]), ctx.vec_from(ys[rank]))
+            raise AssertionError(f"rank {rank}: {what} accepted a corrupted MAC share")
+        except czk_b200.CzkError as e:
+            assert e.code == 5, e
+    opened = ctx.batch_open(czk_b200.SCHEME_SPDZ, ctx.vec_from(xs[rank]), ctx.vec_from(xs[rank]))
+    assert (opened.numpy() == x).all()
+    launch.barrier()
+    print(f"[rank {rank}/{world}] corrupted MAC detected by open and mul; clean open ok", flush=True)
     party.close()
 
 

@@ -136,3 +136,34 @@ def test_signed_digit_decomposition(emu, oracle, pymodel, c):
         emu.emu_signed_digits(out.ctypes.data_as(C.POINTER(C.c_int32)), P(oracle.ints_to_limbs([s], 4)), C.c_uint(c), C.c_uint(nwin))
         assert sum(int(d) << (c * w) for w, d in enumerate(out)) == s
         assert all(abs(int(d)) <= 1 << (c - 1) for d in out)
+
+
+def test_lazy_reduction_sum_of_two_products(emu, oracle, pymodel):
+    """Fp::mul_sum2 = (a b + c d) / R with one Montgomery reduction, and the two-lane Fq2 product built from it (the G2
+    bucket kernel: lane 0 computes c0 = a0 b0 - 5 a1 b1 with -5 a1 passed as the UNREDUCED integer 5 (p - a1), lane 1
+    computes c1 = a1 b0 + a0 b1), against the oracle's Karatsuba Fq2 product (quadratic_extension.rs:569-583)."""
+    rnd = random.Random(17)
+    q = pymodel.Q_MOD
+    n = 600
+    ints = [[rnd.randrange(q) for _ in range(2 * n)] for _ in range(2)]
+    # extremes: zero / p - 1 components in every combination (5 (p - 0) = 5 p is the largest unreduced operand)
+    edge = [0, q - 1, 1, q - 2]
+    k = 0
+    for u in edge:
+        for v in edge:
+            for w in edge:
+                ints[0][2 * k], ints[0][2 * k + 1], ints[1][2 * k], ints[1][2 * k + 1] = u, v, w, edge[(k * 7) % 4]
+                k += 1
+    a = oracle.fq_from_ints(ints[0]).reshape(-1, 12)
+    b = oracle.fq_from_ints(ints[1]).reshape(-1, 12)
+    # the same integers taken AS Montgomery limbs as well (any value < p is a valid element): covers limbs like 0 and p - 1
+    for x, y in ((a, b), (np.array([[(v >> (64 * i)) & (2**64 - 1) for v in pair for i in range(6)] for pair in zip(ints[0][::2], ints[0][1::2])], np.uint64),
+                          np.array([[(v >> (64 * i)) & (2**64 - 1) for v in pair for i in range(6)] for pair in zip(ints[1][::2], ints[1][1::2])], np.uint64))):
+        out = np.zeros_like(x)
+        emu.emu_fq2_mul_two_lanes(P(out), P(x), P(y), C.c_size_t(x.shape[0]))
+        assert (out == oracle.fq2_mul(x, y)).all()
+    r = pymodel.R_MOD
+    fa, fb, fc, fd = (oracle.fr_from_ints([rnd.randrange(r) for _ in range(500)]) for _ in range(4))
+    fo = np.zeros_like(fa)
+    emu.emu_fr_mul_sum2(P(fo), P(fa), P(fb), P(fc), P(fd), C.c_size_t(500))
+    assert (fo == oracle.fr_add(oracle.fr_mul(fa, fb), oracle.fr_mul(fc, fd))).all()

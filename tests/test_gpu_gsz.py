@@ -66,3 +66,53 @@ def test_gsz_at_baseline_domain_2_21(ctx, czk, oracle):
     assert (xs.numpy() == oracle.fr_mul(x, y)).all()
     fx, fy, fz = ctx.gsz_check_products()
     assert (oracle.fr_mul(fx[None, :], fy[None, :])[0] == fz).all()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# open_degree_vec (gsz20/mod.rs:440-459) on genuine N-party Shamir shares, on ONE GPU: czk_diag_gsz_open_gathered feeds
+# k_gsz_open - the kernel behind czk_gsz_open / czk_gsz_king_compute - a party-major matrix of gathered shares.
+def _shamir_shares(oracle, parties, coeffs):
+    """coeffs: (t + 1, k, 4) Montgomery coefficients of k polynomials -> (parties, k, 4): party j holds p_i(w^j).
+    The powers w^(j c) come from the oracle's own sharing of the monomial X^c (orc_gsz_share)."""
+    tp1, k = coeffs.shape[0], coeffs.shape[1]
+    one = oracle.fr_from_ints([1])[0]
+    out = np.zeros((parties, k, 4), np.uint64)
+    for c in range(tp1):
+        mono = np.zeros((c + 1, 4), np.uint64)
+        mono[c] = one
+        w_pows = oracle.gsz_share(parties, mono)  # (parties, 4): w^(j c)
+        for j in range(parties):
+            out[j] = oracle.fr_add(out[j], oracle.fr_mul(coeffs[c], np.broadcast_to(w_pows[j], (k, 4)).copy()))
+    return out
+
+
+@pytest.mark.parametrize("parties,k", [(2, 1 << 10), (3, 1000), (4, 1 << 10), (8, 1 << 10), (6, 333), (8, 1 << 21)])
+def test_gsz_open_degree_vec_on_n_party_shares(ctx, czk, oracle, parties, k):
+    t = (parties - 1) // 2
+    coeffs = np.stack([oracle.random_fr_mont(500 + 10 * parties + c, k) for c in range(t + 1)])
+    shares = _shamir_shares(oracle, parties, coeffs)
+    # spot-check the construction against the oracle's per-polynomial sharing and opening
+    for i in (0, k - 1):
+        assert (oracle.gsz_share(parties, coeffs[:, i]) == shares[:, i]).all()
+        val, ok = oracle.gsz_open(shares[:, i], t)
+        assert ok and (val == coeffs[0, i]).all()
+    gathered = ctx.vec_from(shares.reshape(parties * k, 4))
+    out, flag = ctx.gsz_open_gathered(gathered, parties, t, k)
+    assert flag == 0 and (out.numpy() == coeffs[0]).all()
+    if t >= 1:
+        # the product of two degree-t sharings has degree 2t: it opens at 2t and must FAIL the degree-t check
+        prod = oracle.fr_mul(shares.reshape(-1, 4), shares.reshape(-1, 4))
+        secrets2 = oracle.fr_mul(coeffs[0], coeffs[0])
+        out, flag = ctx.gsz_open_gathered(ctx.vec_from(prod), parties, 2 * t, k)
+        assert flag == 0 and (out.numpy() == secrets2).all()
+        out, flag = ctx.gsz_open_gathered(ctx.vec_from(prod), parties, t, k)
+        assert flag == 1, "degree check did not fire"
+        assert (out.numpy() == secrets2).all()  # the value at 0 is still the interpolated one (the reference asserts after computing it)
+        _, ok = oracle.gsz_open(prod.reshape(parties, k, 4)[:, 0], t)
+        assert not ok
+    # one corrupted share among many: the flag must fire (n > t + 1 parties) wherever it sits
+    if parties >= 3:
+        bad = shares.copy()
+        bad[parties - 1, k // 3] = oracle.random_fr_mont(999, 1)[0]
+        _, flag = ctx.gsz_open_gathered(ctx.vec_from(bad.reshape(parties * k, 4)), parties, t, k)
+        assert flag == 1

@@ -1,0 +1,49 @@
+"""The real N-party path - one rank per GPU, NCCL slice exchange / all-gather / king gather - under pytest: spawns
+`torchrun tests/mp_groth16_check.py` for additive, SPDZ and GSZ and keeps the raw per-rank output under gpurun_out/.
+Skipped on a box with one GPU (there the N-party ARITHMETIC is covered by the single-GPU simulation in
+test_gpu_shares.py / test_gpu_gsz.py; this file covers the transport)."""
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _gpus():
+    import torch
+
+    return torch.cuda.device_count() if torch.cuda.is_available() else 0
+
+
+def _run(nproc, scheme, extra=(), port=29641):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(ROOT / "tests" / "mp_groth16_check.py"), "--scheme", scheme, *extra]
+    r = subprocess.run(cmd, capture_output=True, text=True, cwd=str(ROOT), timeout=900)
+    out = ROOT / "gpurun_out"
+    out.mkdir(exist_ok=True)
+    (out / f"mp_pytest_{scheme}_{nproc}.log").write_text(" ".join(cmd) + "\n" + r.stdout + "\n--- stderr ---\n" + r.stderr[-20000:])
+    return r
+
+
+@pytest.mark.parametrize("scheme", ["additive", "spdz", "gsz"])
+@pytest.mark.parametrize("nproc", [2, 3, 4, 8])
+def test_torchrun_multi_party_parity(scheme, nproc):
+    if _gpus() < nproc:
+        pytest.skip(f"needs {nproc} GPUs, this box has {_gpus()}")
+    r = _run(nproc, scheme, port=29641 + nproc)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    ok = [l for l in r.stdout.splitlines() if "parity ok" in l]
+    assert len(ok) == nproc, r.stdout[-3000:]
+
+
+def test_torchrun_corrupted_share_trips_the_mac_check():
+    """Negative case over the real transport: one rank corrupts a MAC share, EVERY rank must get CZK_ERR_PROTOCOL."""
+    if _gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = _run(2, "spdz", extra=["--corrupt-mac"], port=29671)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert len([l for l in r.stdout.splitlines() if "corrupted MAC detected" in l]) == 2, r.stdout[-3000:]
