@@ -254,6 +254,33 @@ struct Fp {
         reduce_once(r.l);
         return r;
     }
+    // mul_sum2 with the multiplier limbs produced on demand: fbd(i, b_i, d_i) (the two-lane Fq2 product fetches
+    // them from the partner lane row by row instead of holding two more N-limb operands in registers)
+    template <class FBD>
+    CZK_HD static Fp mul_sum2_f(const Fp& a, const uint32_t* c, FBD fbd) {
+        uint32_t m[N], even[N], odd[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) m[i] = P::modc(i);
+#pragma unroll
+        for (int i = 0; i < N; i += 2) {
+            uint32_t bi, di;
+            fbd(i, bi, di);
+            mont_row_acc<P>(even, odd, a.l, bi, i == 0);
+            mont_row_acc2<P>(even, odd, c, di);
+            mont_row_red<P>(even, odd, m);
+            fbd(i + 1, bi, di);
+            mont_row_acc<P>(odd, even, a.l, bi, false);
+            mont_row_acc2<P>(odd, even, c, di);
+            mont_row_red<P>(odd, even, m);
+        }
+        Fp r;
+        r.l[0] = add_cc(even[0], odd[1]);
+#pragma unroll
+        for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(even[i], odd[i + 1]);
+        r.l[N - 1] = addc(even[N - 1], 0);
+        reduce_once(r.l);
+        return r;
+    }
     // 5 (p - a) as an unreduced N-limb integer (< 5 p + 1 <= 2^(32 N - 4)): -5 a mod p for mul_sum2's `c` operand
     CZK_HD static void neg_times5_unreduced(const Fp& a, uint32_t* out) {
         uint32_t t[N];

@@ -449,20 +449,24 @@ __global__ void __launch_bounds__(BAT_THREADS, MINB)
 // lanes of a pair.
 constexpr int G2L_THREADS = 2 * BAT_THREADS;
 __device__ __forceinline__ Fq g2l_mul(const Fq& a, const Fq& b, const unsigned h) {
-    uint32_t sa[12], pa[12];
-    Fq::neg_times5_unreduced(a, sa);  // the odd lane hands out -5 a1 (as 5 (p - a1) < 2^380), the even lane a0
-    Fq pb, y1, y2;
+    uint32_t pa[12];
+    {
+        uint32_t sa[12];
+        Fq::neg_times5_unreduced(a, sa);  // the odd lane hands out -5 a1 (as 5 (p - a1) < 2^380), the even lane a0
 #pragma unroll
-    for (int i = 0; i < 12; i++) {
-        pa[i] = __shfl_xor_sync(0xffffffffu, h ? sa[i] : a.l[i], 1);
-        pb.l[i] = __shfl_xor_sync(0xffffffffu, b.l[i], 1);
-        y1.l[i] = h ? pb.l[i] : b.l[i];  // b0 in both lanes
-        y2.l[i] = h ? b.l[i] : pb.l[i];  // b1 in both lanes
+        for (int i = 0; i < 12; i++) pa[i] = __shfl_xor_sync(0xffffffffu, h ? sa[i] : a.l[i], 1);
     }
-    return Fq::mul_sum2(a, y1, pa, y2);
+    // multiplier limbs row by row: b0 (first product) and b1 (second product) in BOTH lanes, one shuffle per row
+    auto rows = [&](int i, uint32_t& b0, uint32_t& b1) {
+        const uint32_t pb = __shfl_xor_sync(0xffffffffu, b.l[i], 1);
+        b0 = h ? pb : b.l[i];
+        b1 = h ? b.l[i] : pb;
+    };
+    return Fq::mul_sum2_f(a, pa, rows);
 }
 __device__ __forceinline__ bool g2l_both(bool mine) {  // true iff the condition holds in both lanes of the pair
-    return mine && __shfl_xor_sync(0xffffffffu, mine ? 1u : 0u, 1) != 0u;
+    const unsigned theirs = __shfl_xor_sync(0xffffffffu, mine ? 1u : 0u, 1);  // never behind a short-circuit: every lane shuffles
+    return mine && theirs != 0u;
 }
 constexpr size_t g2l_smem_bytes() {  // Fq2 product tree + 2 prefix cells (one component) + 2 x 2 entry cells, per thread
     return (size_t)24 * 256 * 4 + (size_t)2 * 3 * G2L_THREADS * 16 + (size_t)4 * G2L_THREADS * 4;
@@ -628,7 +632,8 @@ __global__ void __launch_bounds__(G2L_THREADS, MINB)
         if (FIRST && pair && (e2 >> 31)) y2 = Fq::neg(y2);
         const Fq lam = g2l_mul(Fq::sub(y2, y1), dinv, h);
         Fq d = Fq::sub(x2, x1);
-        if (!pair || g2l_both(d.is_zero())) d = one;
+        const bool dz = g2l_both(d.is_zero());  // evaluated by every lane (a shuffle), whatever `pair` says
+        if (!pair || dz) d = one;
         if (j > 0) inv = g2l_mul(inv, d, h);
         uint32_t* dst = out + o * (2 * W) + HW * h;
         const Fq x3 = Fq::sub(Fq::sub(g2l_mul(lam, lam, h), x1), x2);
