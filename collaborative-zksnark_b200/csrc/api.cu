@@ -54,6 +54,16 @@ int czk_ctx_create(int device, czk_ctx** out) {
     }
     CUDA_TRY(ctx, cudaMalloc((void**)&ctx->flag, 4));
     CUDA_TRY(ctx, cudaMemset(ctx->flag, 0, 4));
+    for (cudaEvent_t& e : ctx->ev_phase) CUDA_TRY(ctx, cudaEventCreate(&e));
+    for (MsmLane& l : ctx->lanes) {
+        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaEventCreateWithFlags(&l.ev_in, cudaEventDisableTiming));
+        for (MsmSlot& sl : l.slots) {
+            CUDA_TRY(ctx, cudaMallocHost(&sl.pinned, 256 * 96 * 4));  // up to 256 XYZZ points of G2
+            CUDA_TRY(ctx, cudaEventCreateWithFlags(&sl.ev_done, cudaEventDisableTiming));
+            for (cudaEvent_t& e : sl.ev_t) CUDA_TRY(ctx, cudaEventCreate(&e));
+        }
+    }
     *out = ctx;
     return CZK_OK;
 }
@@ -62,7 +72,6 @@ static void free_ws(MsmWorkspace& ws) {
     cudaFree(ws.bat_a);
     cudaFree(ws.bat_b);
     cudaFree(ws.bat_prefix);
-    if (ws.host_word) cudaFreeHost(ws.host_word);
     cudaFree(ws.scalars);
     cudaFree(ws.hist);
     cudaFree(ws.offsets);
@@ -94,19 +103,33 @@ void czk_ctx_destroy(czk_ctx* ctx) {
         cudaFree(d.gi_lo);
         cudaFree(d.gi_hi);
     }
-    free_ws(ctx->ws);
+    for (MsmLane& l : ctx->lanes) {
+        if (l.stream) cudaStreamSynchronize(l.stream);
+        for (int i = 0; i < 4; i++) l.ws.ev[i] = nullptr;  // owned by the slots
+        free_ws(l.ws);
+        for (MsmSlot& sl : l.slots) {
+            if (sl.pinned) cudaFreeHost(sl.pinned);
+            if (sl.ev_done) cudaEventDestroy(sl.ev_done);
+            for (cudaEvent_t e : sl.ev_t)
+                if (e) cudaEventDestroy(e);
+        }
+        if (l.ev_in) cudaEventDestroy(l.ev_in);
+        if (l.stream) cudaStreamDestroy(l.stream);
+    }
     gsz_release(ctx);
     for (Scratch* s : {&ctx->up_bases, &ctx->up_inf, &ctx->up_scalars, &ctx->up_vec, &ctx->open_gather, &ctx->open_sigma,
                        &ctx->open_sx, &ctx->open_oy, &ctx->open_d, &ctx->open_dm})
         cudaFree(s->p);
-    if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cudaFree(ctx->flag);
+    for (cudaEvent_t e : ctx->ev_phase)
+        if (e) cudaEventDestroy(e);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
 int czk_ctx_sync(czk_ctx* ctx) {
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    for (MsmLane& l : ctx->lanes) CUDA_TRY(ctx, cudaStreamSynchronize(l.stream));
     return CZK_OK;
 }
 void* czk_ctx_stream(czk_ctx* ctx) { return (void*)ctx->stream; }
@@ -300,36 +323,43 @@ int czk_vec_divide_by_vanishing_on_coset(czk_ctx* ctx, czk_vec* a, unsigned log_
 }
 
 // ------------------------------------------------------------------------------------------ MSM
-static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
-    MsmWorkspace& ws = ctx->ws;
+static int ws_reserve(czk_ctx* ctx, MsmLane& lane, int curve, size_t n, const MsmConfig& cfg) {
+    MsmWorkspace& ws = lane.ws;
+    cudaStream_t lane_stream = lane.stream;
     size_t total = (size_t)cfg.bwin * cfg.nb;
     int pw = (int)msm_point_words(curve);
     bool grow_n = n > ws.cap_n;
     bool grow_b = total > ws.cap_buckets || pw > ws.point_words;
     if (grow_n) {
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(lane_stream));
         cudaFree(ws.scalars);
         cudaFree(ws.sorted);
         ws.scalars = ws.sorted = nullptr;
+        ws.cap_n = 0;  // capacities are recorded only after every allocation of the group succeeded
+        ws.cap_sorted_bytes = 0;
         ws.alloc_epoch++;
         size_t cap = n + n / 16 + 64;
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.scalars, cap * 32));
         // worst case windows for this n: ceil(254/2) covers every config
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.sorted, cap * 4 * 32));
         ws.cap_n = cap;
+        ws.cap_sorted_bytes = cap * 4 * 32;
     }
     // `sorted` holds n * nwin entries; the allocation above budgets 32 windows, small-c configs need more
     if ((size_t)cfg.nwin > 32) {
         size_t need = n * cfg.nwin * 4;
-        if (need > ws.cap_n * 4 * 32) {
-            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        if (need > ws.cap_sorted_bytes) {
+            CUDA_TRY(ctx, cudaStreamSynchronize(lane_stream));
             cudaFree(ws.sorted);
+            ws.sorted = nullptr;
+            ws.cap_sorted_bytes = 0;
             ws.alloc_epoch++;
             CUDA_TRY(ctx, cudaMalloc((void**)&ws.sorted, need));
+            ws.cap_sorted_bytes = need;
         }
     }
     if (grow_b) {
-        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CUDA_TRY(ctx, cudaStreamSynchronize(lane_stream));
         cudaFree(ws.hist);
         cudaFree(ws.offsets);
         cudaFree(ws.buckets);
@@ -341,6 +371,8 @@ static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
         ws.alloc_epoch++;
         size_t cap = total > ws.cap_buckets ? total : ws.cap_buckets;
         int pww = pw > ws.point_words ? pw : ws.point_words;
+        ws.cap_buckets = 0;
+        ws.point_words = 0;
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.hist, cap * 4));
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.offsets, cap * 4));
         CUDA_TRY(ctx, cudaMalloc((void**)&ws.buckets, cap * pww * 4));
@@ -356,7 +388,7 @@ static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
         // per-segment sums: one slot per bucket plus one per `seg` sorted entries (see msm_run)
         size_t items = total + (n * cfg.nwin) / 32 + 64;
         if (items > ws.cap_items || pw > ws.seg_point_words) {
-            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(lane_stream));
             cudaFree(ws.segsum);
             cudaFree(ws.items);
             cudaFree(ws.heavy);
@@ -364,12 +396,13 @@ static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
             ws.alloc_epoch++;
             size_t cap = items + items / 8;
             int pww = pw > ws.seg_point_words ? pw : ws.seg_point_words;
+            ws.cap_items = 0;
+            ws.seg_point_words = 0;
             CUDA_TRY(ctx, cudaMalloc((void**)&ws.segsum, cap * (size_t)pww * 4));
             CUDA_TRY(ctx, cudaMalloc((void**)&ws.items, cap * 16));
             CUDA_TRY(ctx, cudaMalloc((void**)&ws.heavy, cap * 4));
             if (!ws.queue) {
                 CUDA_TRY(ctx, cudaMalloc((void**)&ws.queue, 64));
-                CUDA_TRY(ctx, cudaMallocHost((void**)&ws.host_word, 64));
                 const char* env = getenv("CZK_BATCHED");
                 if (!ws.batched_forced) ws.batched = !(env && atoi(env) == 0);
                 cudaDeviceProp prop;
@@ -387,7 +420,7 @@ static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
                                                                       {&ws.bat_prefix, &ws.cap_bat_prefix, pre}};
         for (auto& b : bufs) {
             if (b.need <= *b.cap) continue;
-            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(lane_stream));
             cudaFree(*b.p);
             *b.p = nullptr;
             *b.cap = 0;
@@ -395,14 +428,6 @@ static int ws_reserve(czk_ctx* ctx, int curve, size_t n, const MsmConfig& cfg) {
             CUDA_TRY(ctx, cudaMalloc((void**)b.p, want));
             *b.cap = want;
         }
-    }
-    for (int i = 0; i < 4; i++)
-        if (!ws.ev[i]) CUDA_TRY(ctx, cudaEventCreate(&ws.ev[i]));
-    size_t pin = 256 * 96 * 4;
-    if (ctx->pinned_cap < pin) {
-        if (ctx->pinned) cudaFreeHost(ctx->pinned);
-        CUDA_TRY(ctx, cudaMallocHost(&ctx->pinned, pin));
-        ctx->pinned_cap = pin;
     }
     return CZK_OK;
 }
@@ -446,33 +471,67 @@ static void msm_host_tail(const uint32_t* winsums, const MsmConfig& cfg, uint64_
     }
 }
 
-static int msm_core(czk_ctx* ctx, int curve, const uint32_t* bases, const uint8_t* inf, const uint32_t* scalars, int mont,
-                    size_t n, uint64_t* out_xyz, const MsmConfig* merged_cfg = nullptr, bool reuse_plan = false) {
+// Enqueue one MSM on a lane: everything up to the window sums landing in the lane's pinned buffer.  No host
+// synchronisation (the number of halving rounds is decided on the device), so the caller can put several MSMs - and other
+// work on the context stream - in flight before collecting.  The lane's work is ordered after whatever is already
+// enqueued on the context stream (the scalars may come from there).
+static int msm_enqueue(czk_ctx* ctx, int lane_idx, int curve, const uint32_t* bases, const uint8_t* inf, const uint32_t* scalars,
+                       int mont, size_t n, const MsmConfig* merged_cfg, bool reuse_plan, MsmJob* job) {
     if (n >= ((size_t)1 << 31)) return fail(ctx, CZK_ERR_ARG, "msm: more than 2^31 - 1 terms");
+    if (lane_idx < 0 || lane_idx >= CZK_MSM_LANES) return fail(ctx, CZK_ERR_ARG, "msm: lane");
+    MsmLane& lane = ctx->lanes[lane_idx];
+    if (lane.enqueued - lane.collected >= CZK_MSM_SLOTS) return fail(ctx, CZK_ERR_ARG, "msm: too many uncollected jobs on this lane");
+    MsmSlot& slot = lane.slots[lane.enqueued % CZK_MSM_SLOTS];
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     MsmConfig cfg = merged_cfg ? *merged_cfg : msm_choose_config(n ? n : 1);
-    const uint64_t epoch = ctx->ws.alloc_epoch;
-    CZK_TRY(ws_reserve(ctx, curve, n, cfg));
-    if (ctx->ws.alloc_epoch != epoch) reuse_plan = false;  // a plan buffer moved: the previous plan is gone
-    CUDA_TRY(ctx, msm_run(curve, bases, inf, scalars, mont != 0, n, cfg, ctx->ws, ctx->stream, reuse_plan));
+    const uint64_t epoch = lane.ws.alloc_epoch;
+    CZK_TRY(ws_reserve(ctx, lane, curve, n, cfg));
+    if (lane.ws.alloc_epoch != epoch) reuse_plan = false;  // a plan buffer moved: the previous plan is gone
+    CUDA_TRY(ctx, cudaEventRecord(lane.ev_in, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamWaitEvent(lane.stream, lane.ev_in, 0));
+    for (int i = 0; i < 4; i++) lane.ws.ev[i] = slot.ev_t[i];
+    CUDA_TRY(ctx, msm_run(curve, bases, inf, scalars, mont != 0, n, cfg, lane.ws, lane.stream, reuse_plan));
     size_t pw = msm_point_words(curve);
-    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->pinned, ctx->ws.winsum, msm_winsum_points(cfg) * pw * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CUDA_TRY(ctx, cudaMemcpyAsync(slot.pinned, lane.ws.winsum, msm_winsum_points(cfg) * pw * 4, cudaMemcpyDeviceToHost, lane.stream));
+    CUDA_TRY(ctx, cudaEventRecord(slot.ev_done, lane.stream));
+    job->seq = lane.enqueued++;
+    job->lane = lane_idx;
+    job->curve = curve;
+    job->n = n;
+    job->cfg = cfg;
+    return CZK_OK;
+}
+// Wait for a job's window sums and finish on the host: sum_w 2^(cw) W_w (or the bit-slice Horner) + one affine normalisation.
+int msm_collect(czk_ctx* ctx, MsmJob* job, uint64_t* out_xyz, double* device_ms) {
+    if (!job || job->lane < 0) return fail(ctx, CZK_ERR_ARG, "msm: no job to collect");
+    MsmLane& lane = ctx->lanes[job->lane];
+    if (job->seq != lane.collected) return fail(ctx, CZK_ERR_ARG, "msm: jobs of a lane are collected in the order they were enqueued");
+    MsmSlot& slot = lane.slots[job->seq % CZK_MSM_SLOTS];
+    CUDA_TRY(ctx, cudaEventSynchronize(slot.ev_done));
+    lane.collected++;
     {
         float a = 0, m = 0;
-        if (cudaEventElapsedTime(&a, ctx->ws.ev[0], ctx->ws.ev[1]) == cudaSuccess &&
-            cudaEventElapsedTime(&m, ctx->ws.ev[2], ctx->ws.ev[3]) == cudaSuccess) {
-            int k = curve == 1 ? 0 : 1;
+        if (cudaEventElapsedTime(&a, slot.ev_t[0], slot.ev_t[1]) == cudaSuccess &&
+            cudaEventElapsedTime(&m, slot.ev_t[2], slot.ev_t[3]) == cudaSuccess) {
+            int k = job->curve == 1 ? 0 : 1;
             ctx->acc_ms[k] += a;
             ctx->msm_ms[k] += m;
-            ctx->acc_terms[k] += (double)n;
-            ctx->acc_entries[k] += (double)n * cfg.nwin;
+            ctx->acc_terms[k] += (double)job->n;
+            ctx->acc_entries[k] += (double)job->n * job->cfg.nwin;
             ctx->acc_launches[k] += 1;
+            if (device_ms) *device_ms = m;
         }
     }
-    if (curve == 1) msm_host_tail<HFq, 6>((const uint32_t*)ctx->pinned, cfg, out_xyz);
-    else msm_host_tail<HFq2, 12>((const uint32_t*)ctx->pinned, cfg, out_xyz);
+    if (job->curve == 1) msm_host_tail<HFq, 6>((const uint32_t*)slot.pinned, job->cfg, out_xyz);
+    else msm_host_tail<HFq2, 12>((const uint32_t*)slot.pinned, job->cfg, out_xyz);
+    job->lane = -1;
     return CZK_OK;
+}
+static int msm_core(czk_ctx* ctx, int curve, const uint32_t* bases, const uint8_t* inf, const uint32_t* scalars, int mont,
+                    size_t n, uint64_t* out_xyz, const MsmConfig* merged_cfg = nullptr, bool reuse_plan = false) {
+    MsmJob job;
+    CZK_TRY(msm_enqueue(ctx, 0, curve, bases, inf, scalars, mont, n, merged_cfg, reuse_plan, &job));
+    return msm_collect(ctx, &job, out_xyz, nullptr);
 }
 
 static int msm_host_entry(czk_ctx* ctx, int curve, const uint64_t* bases_xy, const uint8_t* inf, const uint64_t* scalars,
@@ -524,7 +583,7 @@ int czk_bases_upload(czk_ctx* ctx, int curve, const uint64_t* bases_xy, const ui
 }
 void czk_bases_free(czk_ctx* ctx, czk_bases* b) {
     if (!b) return;
-    if (ctx) cudaStreamSynchronize(ctx->stream);
+    if (ctx) czk_ctx_sync(ctx);  // an MSM lane may still be reading the points
     cudaFree(b->xy);
     cudaFree(b->inf);
     cudaFree(b->table);
@@ -555,18 +614,27 @@ int czk_bases_precompute(czk_ctx* ctx, czk_bases* b, unsigned c) {
     return CZK_OK;
 }
 
-int czk_msm_bases(czk_ctx* ctx, const czk_bases* b, size_t base_off, const czk_vec* sc, size_t sc_off, int scalars_montgomery,
-                  size_t n, uint64_t* out_xyz) {
-    if (!ctx || !b || !sc || !out_xyz || base_off + n > b->n || sc_off + n > sc->n)
-        return fail(ctx, CZK_ERR_ARG, "czk_msm_bases: range");
+// czk_msm_bases without the wait: the MSM is enqueued on `lane` (0 or 1) and runs concurrently with the other lane and with
+// the context stream; msm_collect returns its result.  Internal (ctx.hpp): the Groth16 prover keeps its five MSMs and the
+// witness map in flight together.
+int msm_bases_enqueue(czk_ctx* ctx, int lane, const czk_bases* b, size_t base_off, const czk_vec* sc, size_t sc_off,
+                      int scalars_montgomery, size_t n, MsmJob* job) {
+    if (!ctx || !b || !sc || !job || base_off + n > b->n || sc_off + n > sc->n) return fail(ctx, CZK_ERR_ARG, "czk_msm_bases: range");
     size_t pw = b->curve == 1 ? 24 : 48;
     if (b->table && n >= 1024) {
         MsmConfig cfg = msm_merged_config(b->pre_c, b->n, base_off);
-        return msm_core(ctx, b->curve, b->table, b->inf ? b->inf + base_off : nullptr, (const uint32_t*)(sc->d + 4 * sc_off),
-                        scalars_montgomery, n, out_xyz, &cfg);
+        return msm_enqueue(ctx, lane, b->curve, b->table, b->inf ? b->inf + base_off : nullptr, (const uint32_t*)(sc->d + 4 * sc_off),
+                           scalars_montgomery, n, &cfg, false, job);
     }
-    return msm_core(ctx, b->curve, b->xy + base_off * pw, b->inf ? b->inf + base_off : nullptr,
-                    (const uint32_t*)(sc->d + 4 * sc_off), scalars_montgomery, n, out_xyz);
+    return msm_enqueue(ctx, lane, b->curve, b->xy + base_off * pw, b->inf ? b->inf + base_off : nullptr,
+                       (const uint32_t*)(sc->d + 4 * sc_off), scalars_montgomery, n, nullptr, false, job);
+}
+int czk_msm_bases(czk_ctx* ctx, const czk_bases* b, size_t base_off, const czk_vec* sc, size_t sc_off, int scalars_montgomery,
+                  size_t n, uint64_t* out_xyz) {
+    if (!out_xyz) return fail(ctx, CZK_ERR_ARG, "czk_msm_bases: range");
+    MsmJob job;
+    CZK_TRY(msm_bases_enqueue(ctx, 0, b, base_off, sc, sc_off, scalars_montgomery, n, &job));
+    return msm_collect(ctx, &job, out_xyz, nullptr);
 }
 
 // Several MSMs over one scalar vector: out[k] = sum_i scalars[sc_off + i] * b[k][base_off + i].  The first base set runs
@@ -591,7 +659,7 @@ int czk_msm_bases_multi(czk_ctx* ctx, const czk_bases* const* b, int count, size
         for (int k = 0; k < count; k++) {
             if (!b[k]->table || b[k]->pre_c != lead->pre_c || b[k]->n != lead->n) continue;
             MsmConfig cfg = msm_merged_config(lead->pre_c, lead->n, base_off);
-            CZK_TRY(ws_reserve(ctx, b[k]->curve, n, cfg));
+            CZK_TRY(ws_reserve(ctx, ctx->lanes[0], b[k]->curve, n, cfg));
         }
     }
     CZK_TRY(czk_msm_bases(ctx, lead, base_off, sc, sc_off, scalars_montgomery, n, out_xyz[0]));
@@ -793,10 +861,12 @@ void czk_net_reset_stats(czk_ctx* ctx) {
 // ------------------------------------------------------------------------------------------ diagnostics
 int czk_msm_set_batched(czk_ctx* ctx, int enabled) {
     if (!ctx) return CZK_ERR_ARG;
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    ctx->ws.batched = enabled != 0;
-    ctx->ws.batched_always = enabled == 2;
-    ctx->ws.batched_forced = true;
+    CZK_TRY(czk_ctx_sync(ctx));
+    for (MsmLane& l : ctx->lanes) {
+        l.ws.batched = enabled != 0;
+        l.ws.batched_always = enabled == 2;
+        l.ws.batched_forced = true;
+    }
     return CZK_OK;
 }
 int czk_fq_inverse(czk_ctx* ctx, const uint64_t* in, uint64_t* out, size_t n) {

@@ -100,17 +100,41 @@ struct GszState {
     Scratch dot_partial, one_elem, pad_x, pad_y, gather;
 };
 
+// One of the two MSM pipelines of a context: its own stream, workspace and pinned staging for the window sums, so that two
+// MSMs can be in flight at once (the serial / latency-bound stretches of one - digit sort, finish walk, bucket reduction,
+// host tail - run under the other's accumulation rounds).  Lane 0 also serves the synchronous entry points.
+constexpr int CZK_MSM_SLOTS = 4;  // jobs that may wait uncollected on one lane
+struct MsmSlot {
+    void* pinned = nullptr;          // the job's window sums land here
+    cudaEvent_t ev_done = nullptr;   // ... and this fires when they have
+    cudaEvent_t ev_t[4] = {nullptr, nullptr, nullptr, nullptr};  // accumulate start/stop, whole MSM start/stop (device timing)
+};
+struct MsmLane {
+    cudaStream_t stream = nullptr;
+    MsmWorkspace ws;
+    MsmSlot slots[CZK_MSM_SLOTS];
+    cudaEvent_t ev_in = nullptr;  // recorded on the context stream: the lane's work starts after everything enqueued before it
+    uint64_t enqueued = 0, collected = 0;  // jobs are collected in the order they were enqueued
+};
+// An MSM in flight (enqueued on a lane, not yet collected)
+struct MsmJob {
+    int lane = -1, curve = 1;
+    uint64_t seq = 0;
+    size_t n = 0;
+    MsmConfig cfg;
+};
+constexpr int CZK_MSM_LANES = 2;
+
 struct czk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
     std::map<int, Domain> domains;
-    MsmWorkspace ws;
-    void* pinned = nullptr;  // host staging for window sums
-    size_t pinned_cap = 0;
+    MsmLane lanes[CZK_MSM_LANES];
     Scratch up_bases, up_inf, up_scalars, up_vec;  // staging for the host-pointer entry points
     Scratch open_gather, open_sigma, open_sx, open_oy, open_d, open_dm;
     uint32_t* flag = nullptr;
+    cudaEvent_t ev_phase[2] = {nullptr, nullptr};  // witness-map start / stop on the context stream (phase report)
     // network
     int rank = 0, nranks = 1;
     ncclComm_t comm = nullptr;
@@ -121,6 +145,15 @@ struct czk_ctx {
     double acc_ms[2] = {0, 0}, msm_ms[2] = {0, 0}, acc_terms[2] = {0, 0}, acc_entries[2] = {0, 0};
     uint64_t acc_launches[2] = {0, 0};
 };
+
+// asynchronous MSM over resident bases (api.cu): enqueue on lane 0 / 1, collect in enqueue order per lane
+int msm_bases_enqueue(czk_ctx* ctx, int lane, const czk_bases* b, size_t base_off, const czk_vec* sc, size_t sc_off,
+                      int scalars_montgomery, size_t n, MsmJob* job);
+int msm_collect(czk_ctx* ctx, MsmJob* job, uint64_t* out_xyz, double* device_ms);
+
+// shares.cu: the Beaver product without the final verdict read-back, and the read-back itself (one stream synchronisation)
+int sh_beaver_mul_enqueue(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac, const czk_vec* y_sh, const czk_vec* y_mac, size_t n);
+int sh_collect_flags(czk_ctx* ctx, const char* what);
 
 inline int fail(czk_ctx* ctx, int code, const std::string& msg) {
     czk_tls_error() = msg;

@@ -5,6 +5,7 @@
 // Beaver-on-groups step of share/group.rs:70-109.  The O(1) group operations run on the host (host_field.hpp).
 #include <chrono>
 #include <cstdlib>
+#include <functional>
 #include <future>
 
 #include "../../include/czk_groth16.h"
@@ -425,10 +426,15 @@ static void free_share_vecs(czk_ctx* ctx, ShareVecs& v) {
 }
 
 // r1cs_to_qap.rs:66-110 on this party's shares.  On return v.a (and v.am) hold h; v.chain / v.assign are filled.
-static int witness_map_transforms(czk_ctx* ctx, int scheme, unsigned log_d, ShareVecs& v);
+// defer_check: leave the SPDZ MAC verdict of the Beaver product on the device and do not wait for the stream (the prover
+// reads the verdict once, at the end of the proof, so the whole proof is enqueued without a host round trip).
+static int witness_map_transforms(czk_ctx* ctx, int scheme, unsigned log_d, ShareVecs& v, bool defer_check = false);
 // cs != nullptr: any circuit, full_sh = this party's shares of [instance, witness] (host); else the squaring chain.
+// after_inputs (optional) runs once the share vectors the MSMs need (chain / assign / full) are enqueued, before the
+// transforms: the prover uses it to put its witness-only MSMs in flight under the witness map.
 static int witness_map_dev(czk_ctx* ctx, int scheme, size_t n_sq, unsigned log_d, const uint64_t* chain_sh,
-                           const czk_vec* chain_dev, ShareVecs& v, const czk_r1cs* cs = nullptr, const uint64_t* full_sh = nullptr) {
+                           const czk_vec* chain_dev, ShareVecs& v, const czk_r1cs* cs = nullptr, const uint64_t* full_sh = nullptr,
+                           const std::function<int()>& after_inputs = nullptr, bool defer_check = false) {
     const size_t D = (size_t)1 << log_d;
     const bool spdz = scheme == CZK_SCHEME_SPDZ;
     double t0 = now_ms();
@@ -459,7 +465,8 @@ static int witness_map_dev(czk_ctx* ctx, int scheme, size_t n_sq, unsigned log_d
             CZK_TRY(czk_vec_copy(ctx, v.cm, 0, v.c, 0, D));
         }
         g_phases[0] = now_ms() - t0;
-        return witness_map_transforms(ctx, scheme, log_d, v);
+        if (after_inputs) CZK_TRY(after_inputs());
+        return witness_map_transforms(ctx, scheme, log_d, v, defer_check);
     }
     CZK_TRY(czk_vec_alloc(ctx, n_sq + 1, &v.chain));
     CZK_TRY(czk_vec_alloc(ctx, n_sq + 1, &v.assign));
@@ -488,13 +495,15 @@ static int witness_map_dev(czk_ctx* ctx, int scheme, size_t n_sq, unsigned log_d
         CZK_TRY(czk_vec_copy(ctx, v.cm, 0, v.c, 0, D));
     }
     g_phases[0] = now_ms() - t0;
-    return witness_map_transforms(ctx, scheme, log_d, v);
+    if (after_inputs) CZK_TRY(after_inputs());
+    return witness_map_transforms(ctx, scheme, log_d, v, defer_check);
 }
 
-static int witness_map_transforms(czk_ctx* ctx, int scheme, unsigned log_d, ShareVecs& v) {
+static int witness_map_transforms(czk_ctx* ctx, int scheme, unsigned log_d, ShareVecs& v, bool defer_check) {
     const size_t D = (size_t)1 << log_d;
     const bool spdz = scheme == CZK_SCHEME_SPDZ;
     double t0 = now_ms();
+    if (ctx->ev_phase[0]) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_phase[0], ctx->stream));
     czk_vec* comps[2][3] = {{v.a, v.b, v.c}, {v.am, v.bm, v.cm}};
     for (int k = 0; k < (spdz ? 2 : 1); k++) {
         for (int j = 0; j < 2; j++) {  // a, b
@@ -502,7 +511,9 @@ static int witness_map_transforms(czk_ctx* ctx, int scheme, unsigned log_d, Shar
             CZK_TRY(czk_ntt_vec(ctx, comps[k][j], log_d, 0, 1));  // coset_fft_in_place
         }
     }
-    CZK_TRY(czk_beaver_batch_mul(ctx, scheme, v.a, v.am, v.b, v.bm, D));  // F::batch_product_in_place(&mut ab, &b)
+    // F::batch_product_in_place(&mut ab, &b)
+    if (defer_check && (scheme == CZK_SCHEME_SPDZ || scheme == CZK_SCHEME_ADDITIVE)) CZK_TRY(sh_beaver_mul_enqueue(ctx, scheme, v.a, v.am, v.b, v.bm, D));
+    else CZK_TRY(czk_beaver_batch_mul(ctx, scheme, v.a, v.am, v.b, v.bm, D));
     for (int k = 0; k < (spdz ? 2 : 1); k++) {
         CZK_TRY(czk_ntt_vec(ctx, comps[k][2], log_d, 1, 0));
         CZK_TRY(czk_ntt_vec(ctx, comps[k][2], log_d, 0, 1));
@@ -510,8 +521,11 @@ static int witness_map_transforms(czk_ctx* ctx, int scheme, unsigned log_d, Shar
         CZK_TRY(czk_vec_divide_by_vanishing_on_coset(ctx, comps[k][0], log_d));          // /= Z_H(g)
         CZK_TRY(czk_ntt_vec(ctx, comps[k][0], log_d, 1, 1));                             // coset_ifft_in_place
     }
-    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    g_phases[1] = now_ms() - t0;
+    if (ctx->ev_phase[1]) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_phase[1], ctx->stream));
+    if (!defer_check) {
+        CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        g_phases[1] = now_ms() - t0;
+    }
     return CZK_OK;
 }
 
@@ -993,48 +1007,66 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     ShareVecs v;
     if (cs && (cs->ncons != pk->ncons || cs->ninst != pk->ninst || cs->nwit != pk->nwit))
         return fail(ctx, CZK_ERR_ARG, "czk_groth16_prove_r1cs: the proving key was made for a circuit of another shape");
-    int rc = witness_map_dev(ctx, scheme, n_sq, pk->log_d, chain_sh, chain_dev, v, cs, full_sh);
-    if (rc != CZK_OK) {
-        free_share_vecs(ctx, v);
-        return rc;
-    }
-    // scalar vectors of the l-query MSM (the witness) and of the a / b-query MSMs (instance[1..] ++ witness)
-    const czk_vec* wit_vec = cs ? v.full : v.chain;
-    const size_t wit_off = cs ? pk->ninst : 0, n_wit = pk->nwit;
-    const czk_vec* asg_vec = cs ? v.full : v.assign;
-    const size_t asg_off = cs ? 1 : 0, n_asg = pk->ninst + pk->nwit - 1;
     // ---- the five MSMs (prover.rs:104,108,132,143,155); share-local, no communication.
     // SPDZ computes sh and mac as the same MSM of the value shares (spdz.rs:440-446): done once, used twice.
-    uint64_t o1[18], o2[36];
-    S1 h_acc, l_acc, a_acc, b1_acc;
-    S2 b2_acc;
+    // Four of them take only the assignment, so they are enqueued BEFORE the witness map, on the context's two MSM lanes
+    // (lane 0: l, b_g1, then h; lane 1: b_g2, a): the transforms run on the context stream under their accumulation rounds,
+    // and the serial stretches of one MSM (digit sort, finish walk, bucket reduction, host tail) run under another's rounds.
+    // Nothing is read back between the kernels of an MSM, so the host only waits when it collects.
+    MsmJob job_h, job_l, job_a, job_b1, job_b2;
+    auto drain = [&] {  // error path: nothing of this proof may still be in flight when the share vectors are freed
+        czk_ctx_sync(ctx);
+        for (MsmLane& l : ctx->lanes) l.collected = l.enqueued;
+        cudaMemsetAsync(ctx->flag, 0, 4, ctx->stream);  // a verdict nobody read must not leak into the next call
+    };
+    auto enqueue_witness_msms = [&]() -> int {
+        // scalar vectors of the l-query MSM (the witness) and of the a / b-query MSMs (instance[1..] ++ witness)
+        const czk_vec* wit_vec = cs ? v.full : v.chain;
+        const size_t wit_off = cs ? pk->ninst : 0, n_wit = pk->nwit;
+        const czk_vec* asg_vec = cs ? v.full : v.assign;
+        const size_t asg_off = cs ? 1 : 0, n_asg = pk->ninst + pk->nwit - 1;
+        CZK_TRY(msm_bases_enqueue(ctx, 0, pk->q[4], 0, wit_vec, wit_off, 1, n_wit, &job_l));
+        CZK_TRY(msm_bases_enqueue(ctx, 1, pk->q[2], 1, asg_vec, asg_off, 1, n_asg, &job_b2));
+        CZK_TRY(msm_bases_enqueue(ctx, 0, pk->q[1], 1, asg_vec, asg_off, 1, n_asg, &job_b1));
+        CZK_TRY(msm_bases_enqueue(ctx, 1, pk->q[0], 1, asg_vec, asg_off, 1, n_asg, &job_a));
+        return CZK_OK;
+    };
+    int rc = witness_map_dev(ctx, scheme, n_sq, pk->log_d, chain_sh, chain_dev, v, cs, full_sh, enqueue_witness_msms, true);
     auto fin = [&](int c) {
+        drain();
         free_share_vecs(ctx, v);
         return c;
     };
-    double t0 = now_ms();
-    if ((rc = czk_msm_bases(ctx, pk->q[3], 0, v.a, 0, 1, D - 1, o1)) != CZK_OK) return fin(rc);
-    h_acc.sh = h_acc.mac = S1::from_jac_out(o1);
-    g_phases[2] = now_ms() - t0;
-    t0 = now_ms();
-    if ((rc = czk_msm_bases(ctx, pk->q[4], 0, wit_vec, wit_off, 1, n_wit, o1)) != CZK_OK) return fin(rc);
+    if (rc != CZK_OK) return fin(rc);
+    if ((rc = msm_bases_enqueue(ctx, 0, pk->q[3], 0, v.a, 0, 1, D - 1, &job_h)) != CZK_OK) return fin(rc);
+    uint64_t o1[18], o2[36];
+    S1 h_acc, l_acc, a_acc, b1_acc;
+    S2 b2_acc;
+    // collect in each lane's enqueue order; the phase figures are each job's device time on its own stream (the jobs overlap,
+    // so they do not add up to the proof time)
+    if ((rc = msm_collect(ctx, &job_l, o1, &g_phases[3])) != CZK_OK) return fin(rc);
     l_acc.sh = l_acc.mac = S1::from_jac_out(o1);
-    g_phases[3] = now_ms() - t0;
-    {  // a, b_g1, b_g2: one scalar vector, three base sets - the digit sort is shared where the key allows it
-        uint64_t o1b[18];
-        const czk_bases* sets[3] = {pk->q[0], pk->q[1], pk->q[2]};
-        uint64_t* outs[3] = {o1, o1b, o2};
-        if ((rc = czk_msm_bases_multi(ctx, sets, 3, 1, asg_vec, asg_off, 1, n_asg, outs, &g_phases[4])) != CZK_OK) return fin(rc);
-        a_acc.sh = a_acc.mac = S1::from_jac_out(o1);
-        b1_acc.sh = b1_acc.mac = S1::from_jac_out(o1b);
-        b2_acc.sh = b2_acc.mac = S2::from_jac_out(o2);
+    if ((rc = msm_collect(ctx, &job_b2, o2, &g_phases[6])) != CZK_OK) return fin(rc);
+    b2_acc.sh = b2_acc.mac = S2::from_jac_out(o2);
+    if ((rc = msm_collect(ctx, &job_b1, o1, &g_phases[5])) != CZK_OK) return fin(rc);
+    b1_acc.sh = b1_acc.mac = S1::from_jac_out(o1);
+    if ((rc = msm_collect(ctx, &job_a, o1, &g_phases[4])) != CZK_OK) return fin(rc);
+    a_acc.sh = a_acc.mac = S1::from_jac_out(o1);
+    if ((rc = msm_collect(ctx, &job_h, o1, &g_phases[2])) != CZK_OK) return fin(rc);
+    h_acc.sh = h_acc.mac = S1::from_jac_out(o1);
+    // the h MSM waited for the witness map, so the context stream is idle now: the SPDZ MAC verdict of the Beaver product
+    // (spdz.rs:182) is read here, once per proof
+    if (scheme == CZK_SCHEME_SPDZ && (rc = sh_collect_flags(ctx, "czk_groth16_prove (witness-map product)")) != CZK_OK) return fin(rc);
+    {
+        float wm = 0;
+        if (ctx->ev_phase[0] && cudaEventElapsedTime(&wm, ctx->ev_phase[0], ctx->ev_phase[1]) == cudaSuccess) g_phases[1] = wm;
     }
     free_share_vecs(ctx, v);
 
     if (scheme == CZK_SCHEME_GSZ)
         return prove_tail_gsz(ctx, pk, tail_pre_get(), r_sh, s_sh, h_acc.sh, l_acc.sh, a_acc.sh, b1_acc.sh, b2_acc.sh, proof_sh, proof_sh_inf, proof, proof_inf);
     // ---- O(1) group arithmetic on shares (prover.rs:110-177)
-    t0 = now_ms();
+    double t0 = now_ms();
     HG1 alpha_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1), HFq::from_limbs(pk->vk_g1 + 6));
     HG1 beta_g1 = HG1::from_affine(HFq::from_limbs(pk->vk_g1 + 12), HFq::from_limbs(pk->vk_g1 + 18));
     HG2 beta_g2 = HG2::from_affine(HFq2::from_limbs(pk->vk_g2), HFq2::from_limbs(pk->vk_g2 + 12));

@@ -396,21 +396,10 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
         return e ? (size_t)atoll(e) : (size_t)64;
     }();
     if (ws.batched && n && (ws.batched_always || (n * cfg.nwin >= bat_min_entries && n * cfg.nwin >= total * bat_min_load))) {
-        // tree of batched affine additions (msm_batched.cu); needs the longest bucket to know the number of rounds
-        // and the last bucket's run, which fixes the exact slot count of every round (grid sizing)
-        if (!reuse_plan) {
-            if ((e = cudaMemcpyAsync(ws.host_word, ws.queue + 4, 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-            if ((e = cudaMemcpyAsync(ws.host_word + 1, ws.offsets + (total - 1), 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-            if ((e = cudaMemcpyAsync(ws.host_word + 2, ws.hist + (total - 1), 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
-            if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-            ws.plan_maxlen = ws.host_word[0];
-            ws.plan_last_len = ws.host_word[2];
-            ws.plan_last_start = ws.host_word[1] - ws.plan_last_len;
-        }
-        const uint32_t maxlen = ws.plan_maxlen, last_len = ws.plan_last_len, last_start = ws.plan_last_start;
-        if ((e = msm_batched_accumulate(FieldIO<F>::W == 12 ? 1 : 2, bases, ws.sorted, ws.offsets, ws.hist, total, n * cfg.nwin, maxlen,
-                                        last_start, last_len, ws.bat_a, ws.bat_b, ws.bat_prefix, ws.buckets, ws.queue + 3, ws.sm_count,
-                                        st)) != cudaSuccess)
+        // tree of batched affine additions (msm_batched.cu).  The longest bucket (queue word 4, written by k_msm_seg_counts)
+        // decides the number of halving rounds on the device: nothing is read back, the whole MSM is enqueued in one go
+        if ((e = msm_batched_accumulate(FieldIO<F>::W == 12 ? 1 : 2, bases, ws.sorted, ws.offsets, ws.hist, total, n * cfg.nwin, ws.queue + 4,
+                                        ws.bat_a, ws.bat_b, ws.bat_prefix, ws.buckets, ws.queue + 3, ws.sm_count, st)) != cudaSuccess)
             return e;
         gate = ws.queue + 3;
     }

@@ -114,7 +114,6 @@ struct MsmWorkspace {
     // batched-affine accumulation (msm_batched.cu): ping-pong point arrays, prefix-product scratch
     uint32_t *bat_a = nullptr, *bat_b = nullptr, *bat_prefix = nullptr;
     size_t cap_bat_a = 0, cap_bat_b = 0, cap_bat_prefix = 0;  // bytes
-    uint32_t* host_word = nullptr;                             // pinned: the longest-bucket readback
     bool batched = true;                                       // CZK_BATCHED=0 keeps the XYZZ walk
     bool batched_forced = false;                               // set by czk_msm_set_batched
     bool batched_always = false;                               // czk_msm_set_batched(ctx, 2): ignore the size thresholds (tests)
@@ -122,11 +121,11 @@ struct MsmWorkspace {
     int seg_point_words = 0;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};  // accumulate start/stop, whole MSM start/stop
     size_t cap_n = 0;
+    size_t cap_sorted_bytes = 0;
     size_t cap_buckets = 0;
     int point_words = 0;
     // the last run's plan (sorted entries, bucket runs, item queue) can serve another base set: see msm_run's reuse_plan
     uint64_t alloc_epoch = 0;                        // bumped whenever a plan buffer is reallocated
-    uint32_t plan_maxlen = 0, plan_last_start = 0, plan_last_len = 0;  // what the batched path read back for that plan
 };
 
 // curve: 1 = G1 (Fq, 12 words per coordinate), 2 = G2 (Fq2, 24 words per coordinate)
@@ -142,15 +141,14 @@ cudaError_t msm_flags_differ(const uint8_t* a, const uint8_t* b, size_t n, uint3
 size_t msm_point_words(int curve);  // 4 coordinates
 
 // Batched-affine bucket accumulation (msm_batched.cu).  ends / hist: the counting sort's bucket ends and lengths;
-// entries: an upper bound on the sorted entries (n * windows); maxlen: the longest bucket; last_start / last_len: the last
-// bucket's run in the sorted list (they fix every round's exact slot count).  Writes `buckets` (XYZZ)
+// entries: an upper bound on the sorted entries (n * windows), which sizes the grids; maxlen_dev: DEVICE word holding the
+// longest bucket, from which the kernels themselves decide how many halving rounds run.  Writes `buckets` (XYZZ)
 // unless an addition without an affine formula was met, in which case *flag becomes non-zero and the caller's XYZZ
 // kernel must run.  pa / pb / prefix: scratch of the sizes msm_batched_bytes reports.
 size_t msm_batched_bytes(int curve, size_t entries, size_t nb, size_t* pa, size_t* pb, size_t* pre);
 cudaError_t msm_batched_accumulate(int curve, const uint32_t* bases, const uint32_t* sorted, const uint32_t* ends,
-                                   const uint32_t* hist, size_t nb, size_t entries, uint32_t maxlen, uint32_t last_start,
-                                   uint32_t last_len, uint32_t* pa, uint32_t* pb, uint32_t* prefix, uint32_t* buckets, uint32_t* flag,
-                                   int sm_count, cudaStream_t st);
+                                   const uint32_t* hist, size_t nb, size_t entries, const uint32_t* maxlen_dev, uint32_t* pa,
+                                   uint32_t* pb, uint32_t* prefix, uint32_t* buckets, uint32_t* flag, int sm_count, cudaStream_t st);
 // out[i] = 1 / in[i] in Fq (Montgomery), 0 -> 0: the block inversion of the batched path, exposed for its parity test
 cudaError_t fq_inverse_batch(const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st);
 

@@ -45,6 +45,21 @@ __device__ __forceinline__ uint32_t bat_len(const BatGeom& g, uint32_t b, int r)
     return (uint32_t)(((uint64_t)g.hist[b] + ((1ull << r) - 1)) >> r);
 }
 
+// How many halving rounds a bucket set needs is decided ON THE DEVICE from the longest bucket (a word the sort leaves in
+// the workspace), so the host enqueues a whole MSM without reading anything back: it launches as many round kernels as
+// the worst case needs, and a round whose input already has at most `walk` points per bucket returns at once.
+__host__ __device__ __forceinline__ uint32_t bat_len_after(uint32_t maxlen, int r) {
+    return (uint32_t)(((uint64_t)maxlen + ((1ull << r) - 1)) >> r);
+}
+__host__ __device__ __forceinline__ bool bat_round_runs(int r, uint32_t maxlen, uint32_t walk) {
+    return r == 0 || bat_len_after(maxlen, r) > walk;  // round 0 always runs: it turns (index | sign) entries into points
+}
+__host__ __device__ __forceinline__ int bat_rounds_needed(uint32_t maxlen, uint32_t walk, int launched) {
+    int rounds = 1;
+    while (rounds < launched && bat_len_after(maxlen, rounds) > walk) rounds++;
+    return rounds;
+}
+
 // ------------------------------------------------------------------ inversion (one thread per block)
 // a^-1 for a != 0, Montgomery form in and out: the binary extended Euclidean algorithm of the reference
 // (algebra/ff/src/fields/macros.rs:368-422) on 32-bit limbs; b starts at R^2 so the result is already in Montgomery form.
@@ -256,8 +271,10 @@ constexpr size_t bat_smem_bytes() {  // product tree + 2 prefix cells + 2 x 2 en
 template <class F, bool FIRST, int MINB>
 __global__ void __launch_bounds__(BAT_THREADS, MINB)
     k_bat_round(BatGeom g, const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ in,
-                uint32_t* __restrict__ out, uint32_t* __restrict__ prefix, uint32_t* __restrict__ flag, const int B) {
+                uint32_t* __restrict__ out, uint32_t* __restrict__ prefix, uint32_t* __restrict__ flag, const int B,
+                const uint32_t* __restrict__ maxlen_p, const uint32_t walk) {
     constexpr int W = FieldIO<F>::W, CH = W / 4;
+    if (!bat_round_runs(g.r, *maxlen_p, walk)) return;  // the halving already brought every bucket under `walk` points
     extern __shared__ uint4 bat_smem[];
     uint32_t* const tree = reinterpret_cast<uint32_t*>(bat_smem);
     uint4* const pcell = bat_smem + (W * 256) / 4;
@@ -475,8 +492,10 @@ constexpr size_t g2l_smem_bytes() {  // Fq2 product tree + 2 prefix cells (one c
 template <bool FIRST, int MINB>
 __global__ void __launch_bounds__(G2L_THREADS, MINB)
     k_bat_round_g2l(BatGeom g, const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ in,
-                    uint32_t* __restrict__ out, uint32_t* __restrict__ prefix, uint32_t* __restrict__ flag, const int B) {
+                    uint32_t* __restrict__ out, uint32_t* __restrict__ prefix, uint32_t* __restrict__ flag, const int B,
+                    const uint32_t* __restrict__ maxlen_p, const uint32_t walk) {
     constexpr int W = 24, HW = 12, CH = 3;  // words of an Fq2 element, of one component, 16-byte chunks of a component
+    if (!bat_round_runs(g.r, *maxlen_p, walk)) return;
     typedef StageIO<Fq, G2L_THREADS> Stage;
     extern __shared__ uint4 bat_smem[];
     uint32_t* const tree = reinterpret_cast<uint32_t*>(bat_smem);
@@ -654,14 +673,17 @@ __global__ void __launch_bounds__(G2L_THREADS, MINB)
 // reference's add_assign_mixed handled by XYZZ::add_affine) finishes them in one launch.
 constexpr uint32_t BAT_WALK = 24;
 template <class F>
-__global__ void __launch_bounds__(128) k_bat_finish(BatGeom g, const uint32_t* __restrict__ in, uint32_t* __restrict__ buckets,
-                                                     const uint32_t* __restrict__ flag) {
+__global__ void __launch_bounds__(128) k_bat_finish(BatGeom g, const uint32_t* __restrict__ in_a, const uint32_t* __restrict__ in_b,
+                                                     uint32_t* __restrict__ buckets, const uint32_t* __restrict__ flag,
+                                                     const uint32_t* __restrict__ maxlen_p, const uint32_t walk, const int launched) {
     constexpr int W = FieldIO<F>::W;
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= g.nb || *flag) return;
+    const int rounds = bat_rounds_needed(*maxlen_p, walk, launched);  // round r wrote buffer r & 1
+    const uint32_t* in = ((rounds - 1) & 1) ? in_b : in_a;
     XYZZ<F> p = XYZZ<F>::infinity();
-    const uint32_t len = bat_len(g, b, g.r);
-    const uint32_t* src = in + (size_t)bat_start(g, b, g.r) * (2 * W);
+    const uint32_t len = bat_len(g, b, rounds);
+    const uint32_t* src = in + (size_t)bat_start(g, b, rounds) * (2 * W);
     for (uint32_t i = 0; i < len; i++, src += 2 * W) p.add_affine(FieldIO<F>::load_rw(src), FieldIO<F>::load_rw(src + W));
     store_point<F>(buckets + (size_t)b * (4 * W), p);
 }
@@ -720,14 +742,6 @@ static int bat_pick_b(size_t used, size_t resident, int beta_dflt) {
     }
     return (int)best_b;
 }
-// slots of the array that round r writes, from the last bucket's run (S_0, L_0): the closed form of the layout comment
-static size_t bat_used(uint32_t last_start, uint32_t last_len, size_t nb, int r) {
-    uint64_t s = last_start;
-    for (int i = 0; i < r; i++) s = (s >> 1) + (nb - 1);
-    const uint64_t len = ((uint64_t)last_len + ((1ull << r) - 1)) >> r;
-    return (size_t)((s >> 1) + (nb - 1) + ((len + 1) >> 1));
-}
-
 size_t msm_batched_bytes(int curve, size_t entries, size_t nb, size_t* pa, size_t* pb, size_t* pre) {
     const size_t pt = (curve == 1 ? 24 : 48) * 4, el = pt / 2;
     *pa = bat_bound(entries, nb, 1) * pt;
@@ -743,12 +757,17 @@ size_t msm_batched_bytes(int curve, size_t entries, size_t nb, size_t* pa, size_
 constexpr int G2L_MINB = 2;  // 2 blocks of 256 threads at 128 registers
 template <class F>
 static cudaError_t msm_batched_t(const uint32_t* bases, const uint32_t* sorted, const uint32_t* ends, const uint32_t* hist,
-                                 size_t nb, size_t entries, uint32_t maxlen, uint32_t last_start, uint32_t last_len, uint32_t* pa,
-                                 uint32_t* pb, uint32_t* prefix, uint32_t* buckets, uint32_t* flag, int sm_count, cudaStream_t st) {
+                                 size_t nb, size_t entries, const uint32_t* maxlen_p, uint32_t* pa, uint32_t* pb, uint32_t* prefix,
+                                 uint32_t* buckets, uint32_t* flag, int sm_count, cudaStream_t st) {
     constexpr int MINB = BatTuning<F>::MINB;
     constexpr bool LANES = BAT_G2_LANES && FieldIO<F>::W == 24;
-    int rounds = 1;  // at least one: round 0 turns (index | sign) entries into points
-    while (rounds < 32 && (((uint64_t)maxlen + ((1ull << rounds) - 1)) >> rounds) > BAT_WALK) rounds++;
+    // points per bucket at which the tree stops and k_bat_finish walks (measured, 2^20 G2 terms: 24 -> 14.5 ms, 12 -> 14.2, 6 -> 14.2;
+    // 2^21 G1 terms: 24 -> 9.63, 12 -> 9.67, 6 -> 9.76)
+    static const uint32_t walk = (uint32_t)bat_env(FieldIO<F>::W == 24 ? "CZK_BAT_WALK_G2" : "CZK_BAT_WALK_G1", FieldIO<F>::W == 24 ? 12 : (int)BAT_WALK);
+    // rounds to LAUNCH: what the worst case needs (every entry in one bucket), or the usual case plus a margin when the
+    // caller caps it; rounds that are not needed return at once (bat_round_runs), and k_bat_finish walks whatever is left
+    int launched = 1;
+    while (launched < 26 && bat_len_after((uint32_t)(entries > 0xffffffffull ? 0xffffffffu : entries), launched) > walk) launched++;
     BatGeom g{ends, hist, (uint32_t)nb, 0};
     uint32_t* bufs[2] = {pa, pb};
     constexpr size_t smem = LANES ? g2l_smem_bytes() : bat_smem_bytes<F>();
@@ -764,38 +783,35 @@ static cudaError_t msm_batched_t(const uint32_t* bases, const uint32_t* sorted, 
         return e1 != cudaSuccess ? e1 : e2;
     }();
     if (attr != cudaSuccess) return attr;
-    for (int r = 0; r < rounds; r++) {
+    for (int r = 0; r < launched; r++) {
         g.r = r;
-        size_t slots = bat_used(last_start, last_len, nb, r);
-        if (slots > bat_bound(entries, nb, r + 1)) return cudaErrorInvalidValue;  // the buffers are sized by the bound
+        // the grid and the slots per thread come from the host's bound on the round's slots (entries / 2^(r+1) + 2 nb: within
+        // a fraction of a percent of the real count for the rounds that matter); blocks past the real end return at once
+        const size_t slots = bat_bound(entries, nb, r + 1);
         const int B = bat_pick_b(slots, (size_t)sm_count * (LANES ? G2L_MINB : MINB), BatBeta<F>::VALUE);
         const size_t per_block = (size_t)BAT_THREADS * B;
         unsigned blocks = (unsigned)((slots + per_block - 1) / per_block);
         uint32_t* dst = bufs[r & 1];
         const uint32_t* src = r ? bufs[(r - 1) & 1] : nullptr;
         if (LANES) {
-            if (r == 0) k_bat_round_g2l<true, G2L_MINB><<<blocks, G2L_THREADS, smem, st>>>(g, bases, sorted, nullptr, dst, prefix, flag, B);
-            else k_bat_round_g2l<false, G2L_MINB><<<blocks, G2L_THREADS, smem, st>>>(g, nullptr, nullptr, src, dst, prefix, flag, B);
-        } else if (r == 0) k_bat_round<F, true, MINB><<<blocks, BAT_THREADS, smem, st>>>(g, bases, sorted, nullptr, dst, prefix, flag, B);
-        else k_bat_round<F, false, MINB><<<blocks, BAT_THREADS, smem, st>>>(g, nullptr, nullptr, src, dst, prefix, flag, B);
+            if (r == 0) k_bat_round_g2l<true, G2L_MINB><<<blocks, G2L_THREADS, smem, st>>>(g, bases, sorted, nullptr, dst, prefix, flag, B, maxlen_p, walk);
+            else k_bat_round_g2l<false, G2L_MINB><<<blocks, G2L_THREADS, smem, st>>>(g, nullptr, nullptr, src, dst, prefix, flag, B, maxlen_p, walk);
+        } else if (r == 0) k_bat_round<F, true, MINB><<<blocks, BAT_THREADS, smem, st>>>(g, bases, sorted, nullptr, dst, prefix, flag, B, maxlen_p, walk);
+        else k_bat_round<F, false, MINB><<<blocks, BAT_THREADS, smem, st>>>(g, nullptr, nullptr, src, dst, prefix, flag, B, maxlen_p, walk);
         CZK_LAUNCHED();
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    g.r = rounds;
-    k_bat_finish<F><<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(g, bufs[(rounds - 1) & 1], buckets, flag); CZK_LAUNCHED();
+    k_bat_finish<F><<<(unsigned)((nb + 127) / 128), 128, 0, st>>>(g, pa, pb, buckets, flag, maxlen_p, walk, launched); CZK_LAUNCHED();
     return cudaGetLastError();
 }
 
 cudaError_t msm_batched_accumulate(int curve, const uint32_t* bases, const uint32_t* sorted, const uint32_t* ends,
-                                   const uint32_t* hist, size_t nb, size_t entries, uint32_t maxlen, uint32_t last_start,
-                                   uint32_t last_len, uint32_t* pa, uint32_t* pb, uint32_t* prefix, uint32_t* buckets, uint32_t* flag,
-                                   int sm_count, cudaStream_t st) {
+                                   const uint32_t* hist, size_t nb, size_t entries, const uint32_t* maxlen_dev, uint32_t* pa,
+                                   uint32_t* pb, uint32_t* prefix, uint32_t* buckets, uint32_t* flag, int sm_count, cudaStream_t st) {
     if (curve == 1)
-        return msm_batched_t<Fq>(bases, sorted, ends, hist, nb, entries, maxlen, last_start, last_len, pa, pb, prefix, buckets, flag,
-                                 sm_count, st);
-    return msm_batched_t<Fq2>(bases, sorted, ends, hist, nb, entries, maxlen, last_start, last_len, pa, pb, prefix, buckets, flag,
-                              sm_count, st);
+        return msm_batched_t<Fq>(bases, sorted, ends, hist, nb, entries, maxlen_dev, pa, pb, prefix, buckets, flag, sm_count, st);
+    return msm_batched_t<Fq2>(bases, sorted, ends, hist, nb, entries, maxlen_dev, pa, pb, prefix, buckets, flag, sm_count, st);
 }
 
 }  // namespace czk

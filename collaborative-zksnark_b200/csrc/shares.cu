@@ -317,7 +317,7 @@ static int sh_reserve(czk_ctx* ctx, const ShShape& s, ShJob& j) {
 
 // One read-back per protocol call: every rank's verdict word is all-gathered (a failed check anywhere fails everywhere,
 // like the reference's assert! at every party), then read with the stream synchronised once.
-static int sh_collect_flags(czk_ctx* ctx, const char* what) {
+int sh_collect_flags(czk_ctx* ctx, const char* what) {
     uint32_t flags[SH_MAXP] = {0};
     const int N = ctx->nranks;
     if (N > 1) {
@@ -369,6 +369,15 @@ int czk_beaver_batch_mul(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac
     if (scheme == CZK_SCHEME_PLAIN) return czk_vec_mul(ctx, x_sh, y_sh, n);
     // GszFieldShare::batch_mul (gsz20/mod.rs:309-315): king degree reduction, triple queued for the product check
     if (scheme == CZK_SCHEME_GSZ) return czk_gsz_batch_mul(ctx, x_sh, y_sh, n, 1);
+    CZK_TRY(sh_beaver_mul_enqueue(ctx, scheme, x_sh, x_mac, y_sh, y_mac, n));
+    if (scheme == CZK_SCHEME_SPDZ && n) return sh_collect_flags(ctx, "czk_beaver_batch_mul");
+    return CZK_OK;
+}
+
+// The additive / SPDZ product, enqueued only: for SPDZ the verdict of the MAC check stays on the device (ctx->flag) until
+// sh_collect_flags reads it.
+int sh_beaver_mul_enqueue(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac, const czk_vec* y_sh, const czk_vec* y_mac, size_t n) {
+    if (!ctx || !x_sh || !y_sh || n > x_sh->n || n > y_sh->n) return fail(ctx, CZK_ERR_ARG, "czk_beaver_batch_mul: range");
     if (scheme != CZK_SCHEME_ADDITIVE && scheme != CZK_SCHEME_SPDZ) return fail(ctx, CZK_ERR_ARG, "czk_beaver_batch_mul: scheme");
     const bool spdz = scheme == CZK_SCHEME_SPDZ;
     if (spdz && (!x_mac || !y_mac || n > x_mac->n || n > y_mac->n)) return fail(ctx, CZK_ERR_ARG, "SPDZ product needs MAC vectors");
@@ -385,9 +394,7 @@ int czk_beaver_batch_mul(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac
     j.out_mac = spdz ? (uint32_t*)x_mac->d : nullptr;
     sh_count_reference_open(ctx, scheme, n);  // the reference opens s + x and o + y one after the other
     sh_count_reference_open(ctx, scheme, n);
-    CZK_TRY(sh_run_nccl(ctx, s, j));
-    if (spdz) return sh_collect_flags(ctx, "czk_beaver_batch_mul");
-    return CZK_OK;
+    return sh_run_nccl(ctx, s, j);
 }
 
 int czk_net_link_bytes(const czk_ctx* ctx, uint64_t out[2]) {
