@@ -16,6 +16,11 @@ from .binding import (  # noqa: F401
     SCHEME_ADDITIVE,
     SCHEME_SPDZ,
     SCHEME_GSZ,
+    NTT_FFT,
+    NTT_IFFT,
+    NTT_COSET_FFT,
+    NTT_COSET_IFFT,
+    NTT_IFFT_COSET_FFT,
     ProvingKey,
     groth16_witness_map,
     groth16_prove,

@@ -20,6 +20,7 @@ _HERE = Path(__file__).resolve().parent
 _LIB = None
 
 SCHEME_PLAIN, SCHEME_ADDITIVE, SCHEME_SPDZ, SCHEME_GSZ = 0, 1, 2, 3
+NTT_FFT, NTT_IFFT, NTT_COSET_FFT, NTT_COSET_IFFT, NTT_IFFT_COSET_FFT = 0, 1, 2, 3, 4
 
 u64p = C.POINTER(C.c_uint64)
 u8p = C.POINTER(C.c_uint8)
@@ -56,6 +57,8 @@ _SIGS = {
     "czk_ntt_fr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int]),
     "czk_ntt_fr_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int]),
     "czk_ntt_vec": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int]),
+    "czk_ntt_fr_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint, C.c_int]),
+    "czk_ntt_vec_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint, C.c_int]),
     "czk_domain_params": (C.c_int, [C.c_uint, u64p, u64p, u64p, u64p]),
     "czk_vec_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "czk_vec_sub": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -463,6 +466,11 @@ class Context:
         n = x_sh.n if n is None else n
         self._chk(self.lib.czk_beaver_batch_mul(self.h, scheme, x_sh.h, x_mac.h if x_mac is not None else None, y_sh.h,
                                                 y_mac.h if y_mac is not None else None, n))
+
+    def ntt_batch(self, vecs, log_d: int, op: int):
+        """The same transform over several device vectors in one grid per pass (czk_ntt_vec_batch).
+        op: NTT_FFT / NTT_IFFT / NTT_COSET_FFT / NTT_COSET_IFFT / NTT_IFFT_COSET_FFT."""
+        self._chk(self.lib.czk_ntt_vec_batch(self.h, self._handles(vecs), len(vecs), log_d, op))
 
     def net_link_bytes(self):
         out = np.zeros(2, np.uint64)

@@ -100,6 +100,7 @@ void czk_ctx_destroy(czk_ctx* ctx) {
         cudaFree(d.tw);
         cudaFree(d.g_lo);
         cudaFree(d.g_hi);
+        cudaFree(d.g_hi_sinv);
         cudaFree(d.gi_lo);
         cudaFree(d.gi_hi);
     }
@@ -219,16 +220,18 @@ static int get_domain(czk_ctx* ctx, int log_d, Domain** out) {
     d.lo_log = log_d < 10 ? log_d : 10;
     size_t half = log_d ? ((size_t)1 << (log_d - 1)) : 1;
     size_t nlo = (size_t)1 << d.lo_log, nhi = (size_t)1 << (log_d - d.lo_log);
-    CUDA_TRY(ctx, cudaMalloc((void**)&d.tw, half * 32));
+    CUDA_TRY(ctx, cudaMalloc((void**)&d.tw, (half + 1) * 32));  // omega^k, 0 <= k <= D/2 (the last entry is -1: inverse twiddles read -tw[D/2 - e])
+    CUDA_TRY(ctx, cudaMalloc((void**)&d.g_hi_sinv, nhi * 32));
     CUDA_TRY(ctx, cudaMalloc((void**)&d.g_lo, nlo * 32));
     CUDA_TRY(ctx, cudaMalloc((void**)&d.g_hi, nhi * 32));
     CUDA_TRY(ctx, cudaMalloc((void**)&d.gi_lo, nlo * 32));
     CUDA_TRY(ctx, cudaMalloc((void**)&d.gi_hi, nhi * 32));
     HFr one = HFr::one();
-    CUDA_TRY(ctx, ntt_build_powers(d.tw, d.group_gen.l, one.l, half, ctx->stream));
+    CUDA_TRY(ctx, ntt_build_powers(d.tw, d.group_gen.l, one.l, log_d ? half + 1 : 1, ctx->stream));
     CUDA_TRY(ctx, ntt_build_powers(d.g_lo, g.l, one.l, nlo, ctx->stream));
     HFr g_hi = HFr::pow_u64(g, (uint64_t)nlo);
     CUDA_TRY(ctx, ntt_build_powers(d.g_hi, g_hi.l, one.l, nhi, ctx->stream));
+    CUDA_TRY(ctx, ntt_build_powers(d.g_hi_sinv, g_hi.l, d.size_inv.l, nhi, ctx->stream));  // D^-1 g^i: between an iFFT and a coset FFT
     CUDA_TRY(ctx, ntt_build_powers(d.gi_lo, d.generator_inv.l, one.l, nlo, ctx->stream));
     HFr gi_hi = HFr::pow_u64(d.generator_inv, (uint64_t)nlo);
     CUDA_TRY(ctx, ntt_build_powers(d.gi_hi, gi_hi.l, d.size_inv.l, nhi, ctx->stream));
@@ -237,20 +240,91 @@ static int get_domain(czk_ctx* ctx, int log_d, Domain** out) {
     return CZK_OK;
 }
 
-int czk_ntt_fr_dev(czk_ctx* ctx, uint64_t* dev_data, unsigned log_d, int inverse, int coset) {
-    if (!ctx || !dev_data) return fail(ctx, CZK_ERR_ARG, "czk_ntt_fr_dev: null argument");
-    if (log_d > 30) return fail(ctx, CZK_ERR_ARG, "czk_ntt_fr_dev: log_d > 30 unsupported");
-    if (log_d == 0) return CZK_OK;  // size-1 domain: every transform is the identity
+static NttScale scale_tables(const uint32_t* lo, const uint32_t* hi, int lo_log, bool bitrev) {
+    NttScale sc;
+    sc.mode = 2;
+    sc.bitrev = bitrev ? 1 : 0;
+    sc.lo = lo;
+    sc.hi = hi;
+    sc.lo_log = lo_log;
+    return sc;
+}
+// op: CZK_NTT_FFT / IFFT / COSET_FFT / COSET_IFFT, or CZK_NTT_IFFT_COSET_FFT = ifft_in_place followed by coset_fft_in_place
+// (r1cs_to_qap.rs:85-90), which runs as an inverse DIF + a forward DIT with no bit-reversal pass between or after.
+static int ntt_batch_dev(czk_ctx* ctx, uint32_t* const* data, int count, unsigned log_d, int op) {
+    if (!ctx || (count > 0 && !data) || count < 0) return fail(ctx, CZK_ERR_ARG, "czk_ntt: null argument");
+    if (log_d > 30) return fail(ctx, CZK_ERR_ARG, "czk_ntt: log_d > 30 unsupported");
+    if (op < 0 || op > CZK_NTT_IFFT_COSET_FFT) return fail(ctx, CZK_ERR_ARG, "czk_ntt: unknown transform");
+    if (log_d == 0 || count == 0) return CZK_OK;  // size-1 domain: every transform is the identity
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     Domain* d;
     CZK_TRY(get_domain(ctx, (int)log_d, &d));
-    uint32_t* data = reinterpret_cast<uint32_t*>(dev_data);
-    if (!inverse && coset) CUDA_TRY(ctx, ntt_scale_by_powers(data, d->g_lo, d->g_hi, d->lo_log, (int)log_d, ctx->stream));
-    CUDA_TRY(ctx, ntt_run_passes(data, d->tw, (int)log_d, inverse != 0, ctx->stream));
-    if (!inverse) CUDA_TRY(ctx, ntt_bitrev_scale(data, (int)log_d, 0, nullptr, nullptr, nullptr, 0, ctx->stream));
-    else if (!coset) CUDA_TRY(ctx, ntt_bitrev_scale(data, (int)log_d, 1, d->size_inv.l, nullptr, nullptr, 0, ctx->stream));
-    else CUDA_TRY(ctx, ntt_bitrev_scale(data, (int)log_d, 2, nullptr, d->gi_lo, d->gi_hi, d->lo_log, ctx->stream));
+    const bool inverse = op == CZK_NTT_IFFT || op == CZK_NTT_COSET_IFFT || op == CZK_NTT_IFFT_COSET_FFT;
+    const NttScale none;
+    for (int at = 0; at < count; at += NTT_MAX_BATCH) {
+        const int cnt = count - at < NTT_MAX_BATCH ? count - at : NTT_MAX_BATCH;
+        uint32_t* const* v = data + at;
+        if (op == CZK_NTT_IFFT_COSET_FFT && log_d > 2) {
+            CUDA_TRY(ctx, ntt_run_tiles(v, cnt, d->tw, (int)log_d, true, false, none, none, ctx->stream));  // natural -> bit-reversed
+            // D^-1 g^i on the way into the forward transform; position p holds coefficient bitrev(p)
+            CUDA_TRY(ctx, ntt_run_tiles(v, cnt, d->tw, (int)log_d, false, true, scale_tables(d->g_lo, d->g_hi_sinv, d->lo_log, true), none,
+                                        ctx->stream));
+            continue;
+        }
+        if (op == CZK_NTT_IFFT_COSET_FFT) {  // <= 4 points: the tiny kernel works in natural order
+            NttScale sinv;
+            sinv.mode = 1;
+            for (int i = 0; i < 4; i++) sinv.c[2 * i] = (uint32_t)d->size_inv.l[i], sinv.c[2 * i + 1] = (uint32_t)(d->size_inv.l[i] >> 32);
+            CUDA_TRY(ctx, ntt_run_tiles(v, cnt, d->tw, (int)log_d, true, false, none, sinv, ctx->stream));
+            CUDA_TRY(ctx, ntt_run_tiles(v, cnt, d->tw, (int)log_d, false, false, scale_tables(d->g_lo, d->g_hi, d->lo_log, false), none, ctx->stream));
+            continue;
+        }
+        const NttScale pre = op == CZK_NTT_COSET_FFT ? scale_tables(d->g_lo, d->g_hi, d->lo_log, false) : none;
+        if (log_d <= 2) {
+            NttScale post = none;
+            if (op == CZK_NTT_IFFT) {
+                post.mode = 1;
+                for (int i = 0; i < 4; i++) post.c[2 * i] = (uint32_t)d->size_inv.l[i], post.c[2 * i + 1] = (uint32_t)(d->size_inv.l[i] >> 32);
+            } else if (op == CZK_NTT_COSET_IFFT) post = scale_tables(d->gi_lo, d->gi_hi, d->lo_log, false);
+            CUDA_TRY(ctx, ntt_run_tiles(v, cnt, d->tw, (int)log_d, inverse, false, pre, post, ctx->stream));
+            continue;
+        }
+        CUDA_TRY(ctx, ntt_run_tiles(v, cnt, d->tw, (int)log_d, inverse, false, pre, none, ctx->stream));
+        for (int i = 0; i < cnt; i++) {  // back to natural order; the inverse transforms' scaling rides on the swap
+            if (op == CZK_NTT_IFFT) CUDA_TRY(ctx, ntt_bitrev_scale(v[i], (int)log_d, 1, d->size_inv.l, nullptr, nullptr, 0, ctx->stream));
+            else if (op == CZK_NTT_COSET_IFFT) CUDA_TRY(ctx, ntt_bitrev_scale(v[i], (int)log_d, 2, nullptr, d->gi_lo, d->gi_hi, d->lo_log, ctx->stream));
+            else CUDA_TRY(ctx, ntt_bitrev_scale(v[i], (int)log_d, 0, nullptr, nullptr, nullptr, 0, ctx->stream));
+        }
+    }
     return CZK_OK;
+}
+
+int czk_ntt_fr_dev(czk_ctx* ctx, uint64_t* dev_data, unsigned log_d, int inverse, int coset) {
+    if (!ctx || !dev_data) return fail(ctx, CZK_ERR_ARG, "czk_ntt_fr_dev: null argument");
+    uint32_t* v = reinterpret_cast<uint32_t*>(dev_data);
+    return ntt_batch_dev(ctx, &v, 1, log_d, (inverse ? 1 : 0) | (coset ? 2 : 0));
+}
+
+int czk_ntt_fr_batch(czk_ctx* ctx, uint64_t* const* dev_vecs, int count, unsigned log_d, int op) {
+    if (!ctx || (count > 0 && !dev_vecs) || count < 0) return fail(ctx, CZK_ERR_ARG, "czk_ntt_fr_batch: null argument");
+    std::vector<uint32_t*> v((size_t)count);
+    for (int i = 0; i < count; i++) {
+        if (!dev_vecs[i]) return fail(ctx, CZK_ERR_ARG, "czk_ntt_fr_batch: null vector");
+        v[(size_t)i] = reinterpret_cast<uint32_t*>(dev_vecs[i]);
+        for (int j = 0; j < i; j++)
+            if (dev_vecs[j] == dev_vecs[i]) return fail(ctx, CZK_ERR_ARG, "czk_ntt_fr_batch: the same vector twice");
+    }
+    return ntt_batch_dev(ctx, v.data(), count, log_d, op);
+}
+
+int czk_ntt_vec_batch(czk_ctx* ctx, czk_vec* const* vecs, int count, unsigned log_d, int op) {
+    if (!ctx || (count > 0 && !vecs) || count < 0) return fail(ctx, CZK_ERR_ARG, "czk_ntt_vec_batch: null argument");
+    std::vector<uint64_t*> v((size_t)count);
+    for (int i = 0; i < count; i++) {
+        if (!vecs[i] || vecs[i]->n < ((size_t)1 << log_d)) return fail(ctx, CZK_ERR_ARG, "czk_ntt_vec_batch: vector shorter than the domain");
+        v[(size_t)i] = vecs[i]->d;
+    }
+    return czk_ntt_fr_batch(ctx, v.data(), count, log_d, op);
 }
 
 int czk_ntt_vec(czk_ctx* ctx, czk_vec* v, unsigned log_d, int inverse, int coset) {

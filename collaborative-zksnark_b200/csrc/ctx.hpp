@@ -75,7 +75,7 @@ struct czk_bases {
 struct Domain {
     int log_d = 0;
     uint32_t* tw = nullptr;
-    uint32_t *g_lo = nullptr, *g_hi = nullptr, *gi_lo = nullptr, *gi_hi = nullptr;
+    uint32_t *g_lo = nullptr, *g_hi = nullptr, *gi_lo = nullptr, *gi_hi = nullptr, *g_hi_sinv = nullptr;
     int lo_log = 0;
     HFr size_inv, group_gen, group_gen_inv, generator_inv;
 };

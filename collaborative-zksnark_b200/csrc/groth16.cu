@@ -505,21 +505,27 @@ static int witness_map_transforms(czk_ctx* ctx, int scheme, unsigned log_d, Shar
     double t0 = now_ms();
     if (ctx->ev_phase[0]) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_phase[0], ctx->stream));
     czk_vec* comps[2][3] = {{v.a, v.b, v.c}, {v.am, v.bm, v.cm}};
-    for (int k = 0; k < (spdz ? 2 : 1); k++) {
-        for (int j = 0; j < 2; j++) {  // a, b
-            CZK_TRY(czk_ntt_vec(ctx, comps[k][j], log_d, 1, 0));  // ifft_in_place
-            CZK_TRY(czk_ntt_vec(ctx, comps[k][j], log_d, 0, 1));  // coset_fft_in_place
-        }
+    const int ncomp = spdz ? 2 : 1;
+    // ifft_in_place + coset_fft_in_place on a, b and c (r1cs_to_qap.rs:85-90,95-98): none of them depends on the product,
+    // so all (3, or 6 with the SPDZ MAC vectors, which go through every linear map separately: spdz.rs:186-208) run as
+    // ONE batched transform pair - an inverse DIF feeding a forward DIT, no reordering pass
+    {
+        czk_vec* all[6];
+        int cnt = 0;
+        for (int k = 0; k < ncomp; k++)
+            for (int j = 0; j < 3; j++) all[cnt++] = comps[k][j];
+        CZK_TRY(czk_ntt_vec_batch(ctx, all, cnt, log_d, CZK_NTT_IFFT_COSET_FFT));
     }
     // F::batch_product_in_place(&mut ab, &b)
     if (defer_check && (scheme == CZK_SCHEME_SPDZ || scheme == CZK_SCHEME_ADDITIVE)) CZK_TRY(sh_beaver_mul_enqueue(ctx, scheme, v.a, v.am, v.b, v.bm, D));
     else CZK_TRY(czk_beaver_batch_mul(ctx, scheme, v.a, v.am, v.b, v.bm, D));
-    for (int k = 0; k < (spdz ? 2 : 1); k++) {
-        CZK_TRY(czk_ntt_vec(ctx, comps[k][2], log_d, 1, 0));
-        CZK_TRY(czk_ntt_vec(ctx, comps[k][2], log_d, 0, 1));
-        CZK_TRY(czk_vec_sub(ctx, comps[k][0], comps[k][2], D));                         // ab -= c
-        CZK_TRY(czk_vec_divide_by_vanishing_on_coset(ctx, comps[k][0], log_d));          // /= Z_H(g)
-        CZK_TRY(czk_ntt_vec(ctx, comps[k][0], log_d, 1, 1));                             // coset_ifft_in_place
+    for (int k = 0; k < ncomp; k++) {
+        CZK_TRY(czk_vec_sub(ctx, comps[k][0], comps[k][2], D));                 // ab -= c
+        CZK_TRY(czk_vec_divide_by_vanishing_on_coset(ctx, comps[k][0], log_d));  // /= Z_H(g)
+    }
+    {
+        czk_vec* ab[2] = {comps[0][0], comps[1][0]};
+        CZK_TRY(czk_ntt_vec_batch(ctx, ab, ncomp, log_d, CZK_NTT_COSET_IFFT));  // coset_ifft_in_place
     }
     if (ctx->ev_phase[1]) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_phase[1], ctx->stream));
     if (!defer_check) {

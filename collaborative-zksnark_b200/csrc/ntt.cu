@@ -1,5 +1,6 @@
 // Device kernels of the Fr NTT (see ntt.cuh for the design and the reference lines replaced).
 #include "ntt.cuh"
+#include "ntt_tile.cuh"
 
 #include "launch_count.hpp"
 
@@ -69,89 +70,172 @@ cudaError_t ntt_build_powers(uint32_t* table, const uint64_t base[4], const uint
 }
 
 // ---------------------------------------------------------------------------------------------
-// One pass = r consecutive DIF stages on 2^r x 2^cl tiles held in shared memory (limb-major).
-__global__ void __launch_bounds__(NTT_THREADS)
-k_ntt_pass(uint32_t* __restrict__ data, const uint32_t* __restrict__ tw, int log_d, int s, int r, int cl, int inverse) {
-    extern __shared__ uint32_t sm[];
-    const int tile_log = r + cl;
-    const int tile = 1 << tile_log;
-    const int L = log_d - s - r;
-    const size_t half_d = (size_t)1 << (log_d - 1);
-    const size_t blk = blockIdx.x;
-    const size_t lowblk = blk & (((size_t)1 << (L - cl)) - 1);
-    const size_t hi = blk >> (L - cl);
-    const size_t base = (hi << (r + L)) | (lowblk << cl);
-    const int cmask = (1 << cl) - 1;
+// One pass on one tile per block (ntt_tile.cuh has the per-thread arithmetic).  The tile travels by bulk asynchronous
+// copies (TMA, cp.async.bulk): warp 0 issues one copy per tile row into shared memory, every thread waits on the
+// mbarrier the copies complete on, the register phases run with one __syncthreads() between them, and warp 0 sends the
+// rows back with bulk stores.  No thread ever computes a global address for data, and the tile's layout in shared
+// memory is the vector's own (32 bytes per element), so a row is one contiguous copy.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst), "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
 
-    for (int e = threadIdx.x; e < tile; e += NTT_THREADS) {
-        int mid = e >> cl, lowc = e & cmask;
-        size_t g = base | ((size_t)mid << L) | (size_t)lowc;
-        Fr v = ld_fr(data, g);
-#pragma unroll
-        for (int k = 0; k < 8; k++) sm[k * tile + e] = v.l[k];
+struct NttVecs {
+    uint32_t* p[NTT_MAX_BATCH];
+};
+struct SmemTile {
+    uint4* t;  // element e = t[2e], t[2e + 1]
+    __device__ __forceinline__ Fr load(unsigned e) const {
+        const uint4 a = t[2 * e], b = t[2 * e + 1];
+        Fr r;
+        r.l[0] = a.x; r.l[1] = a.y; r.l[2] = a.z; r.l[3] = a.w;
+        r.l[4] = b.x; r.l[5] = b.y; r.l[6] = b.z; r.l[7] = b.w;
+        return r;
+    }
+    __device__ __forceinline__ void store(unsigned e, const Fr& v) const {
+        t[2 * e] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
+        t[2 * e + 1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+    }
+};
+
+template <bool DIT, bool SCALE>
+__global__ void __launch_bounds__(NTT_TILE_THREADS, NTT_BLOCKS_PER_SM)
+k_ntt_tile(NttVecs vecs, const uint32_t* __restrict__ tw, int n, int s, int r, int cl, int inverse, int first_pass, int last_pass,
+           NttScale pre, NttScale post) {
+    extern __shared__ __align__(128) uint4 tile4[];
+    __shared__ __align__(8) uint64_t bar;
+    const int tile_log = r + cl, L = n - s - r;
+    const unsigned te = 1u << tile_log, tid = threadIdx.x;
+    uint32_t* const data = vecs.p[blockIdx.y];
+    const size_t blk = blockIdx.x;
+    const size_t lowblk = blk & (((size_t)1 << (L - cl)) - 1), hi = blk >> (L - cl);
+    NttTileGeom g{n, s, r, cl, L, (hi << (r + L)) | (lowblk << cl)};
+    // rows of the tile in the vector: 2^r rows of 2^cl elements, 2^L apart - one contiguous run when L == cl
+    const unsigned rows = L == cl ? 1u : (1u << r);
+    const unsigned row_bytes = (L == cl ? te : (1u << cl)) * 32u;
+    const size_t row_stride = (size_t)1 << L;  // elements
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-
-    for (int u = 0; u < r; u++) {
-        const int b = r - 1 - u;
-        const int t_stage = s + u;
-        for (int p = threadIdx.x; p < (tile >> 1); p += NTT_THREADS) {
-            int lowc = p & cmask;
-            int q = p >> cl;
-            int mid_lo = ((q >> b) << (b + 1)) | (q & ((1 << b) - 1));
-            int e0 = (mid_lo << cl) | lowc;
-            int e1 = e0 | (1 << (b + cl));
-            size_t j = ((size_t)(mid_lo & ((1 << b) - 1)) << L) | (lowblk << cl) | (size_t)lowc;
-            size_t ex = j << t_stage;
-            Fr w;
-            if (!inverse) {
-                w = ldg_fr(tw, ex);
-            } else {
-                // w^-ex = -w^(D/2 - ex) for ex > 0
-                w = (ex == 0) ? Fr::one() : Fr::neg(ldg_fr(tw, half_d - ex));
-            }
-            Fr a, c;
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                a.l[k] = sm[k * tile + e0];
-                c.l[k] = sm[k * tile + e1];
-            }
-            Fr sum = Fr::add(a, c);
-            Fr diff = Fr::mul(Fr::sub(a, c), w);
-#pragma unroll
-            for (int k = 0; k < 8; k++) {
-                sm[k * tile + e0] = sum.l[k];
-                sm[k * tile + e1] = diff.l[k];
-            }
-        }
-        __syncthreads();
+    if (tid < 32) {
+        if (tid == 0) mbar_expect_tx(&bar, te * 32u);
+        __syncwarp();
+        for (unsigned m = tid; m < rows; m += 32)
+            bulk_g2s(reinterpret_cast<uint8_t*>(tile4) + (size_t)m * row_bytes, data + (g.base + m * row_stride) * 8, row_bytes, &bar);
     }
-
-    for (int e = threadIdx.x; e < tile; e += NTT_THREADS) {
-        int mid = e >> cl, lowc = e & cmask;
-        size_t g = base | ((size_t)mid << L) | (size_t)lowc;
-        Fr v;
-#pragma unroll
-        for (int k = 0; k < 8; k++) v.l[k] = sm[k * tile + e];
-        st_fr(data, g, v);
+    SmemTile tile{tile4};
+    auto ldtw = [](const uint32_t* table, size_t i) -> Fr { return ldg_fr(table, i); };
+    const int nph = ntt_num_phases(r);
+    mbar_wait(&bar, 0);
+    for (int ph = 0; ph < nph; ph++) {
+        int kp, jlo, ns;
+        ntt_phase_geom(r, cl, DIT, ph, kp, jlo, ns);
+        if (tid < te / 8)
+            ntt_phase_thread<DIT, SCALE>(tile, tid, g, inverse != 0, kp, jlo, ns, tw, first_pass && ph == 0, last_pass && ph == nph - 1, pre, post,
+                                         ldtw);
+        if (ph + 1 < nph) __syncthreads();
+    }
+    // the generic-proxy writes of every thread must be visible to the bulk-copy (async proxy) reads
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (tid < 32) {
+        for (unsigned m = tid; m < rows; m += 32)
+            bulk_s2g(data + (g.base + m * row_stride) * 8, reinterpret_cast<uint8_t*>(tile4) + (size_t)m * row_bytes, row_bytes);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // shared memory may be released once it has been read
     }
 }
 
-cudaError_t ntt_run_passes(uint32_t* data, const uint32_t* tw, int log_d, bool inverse, cudaStream_t st) {
-    if (log_d == 0) return cudaSuccess;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << NTT_TILE_LOG);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
+// log_d <= 2: the whole transform in one thread (naive DFT over at most 4 points)
+__global__ void k_ntt_small(NttVecs vecs, const uint32_t* __restrict__ tw, int n, int inverse, NttScale pre, NttScale post) {
+    if (threadIdx.x || blockIdx.x) return;
+    uint32_t* data = vecs.p[blockIdx.y];
+    const unsigned d = 1u << n, half = d >> 1;
+    auto ldtw = [](const uint32_t* table, size_t i) -> Fr { return ldg_fr(table, i); };
+    Fr x[4], y[4];
+    for (unsigned i = 0; i < d; i++) {
+        x[i] = ld_fr(data, i);
+        if (pre.mode) x[i] = Fr::mul(x[i], ntt_scale_factor(pre, i, n, ldtw));
     }
-    NttPlan plan = ntt_make_plan(log_d);
-    for (int i = 0; i < plan.npass; i++) {
-        const NttPlanPass& p = plan.pass[i];
-        int tile_log = p.r + p.cl;
-        size_t blocks = (size_t)1 << (log_d - tile_log);
-        size_t smem = (size_t)32 << tile_log;
-        k_ntt_pass<<<(unsigned)blocks, NTT_THREADS, smem, st>>>(data, tw, log_d, p.s, p.r, p.cl, inverse ? 1 : 0); CZK_LAUNCHED();
+    for (unsigned i = 0; i < d; i++) {
+        Fr acc = Fr::zero();
+        for (unsigned j = 0; j < d; j++) {
+            unsigned e = (i * j) & (d - 1);
+            if (inverse) e = (d - e) & (d - 1);
+            Fr w = e < half || half == 0 ? ldg_fr(tw, e) : Fr::neg(ldg_fr(tw, e - half));  // omega^(e) = -omega^(e - d/2)
+            acc = Fr::add(acc, Fr::mul(x[j], w));
+        }
+        y[i] = acc;
+    }
+    for (unsigned i = 0; i < d; i++) {
+        Fr v = y[i];
+        if (post.mode) v = Fr::mul(v, ntt_scale_factor(post, i, n, ldtw));
+        st_fr(data, i, v);
+    }
+}
+
+// All the passes of one in-place transform over `count` vectors.  dit = false: natural order in, bit-reversed out;
+// dit = true: bit-reversed in, natural order out.  (log_d <= 2: natural in and out whatever `dit` says.)
+cudaError_t ntt_run_tiles(uint32_t* const* data, int count, const uint32_t* tw, int log_d, bool inverse, bool dit, const NttScale& pre,
+                          const NttScale& post, cudaStream_t st) {
+    if (log_d == 0 || count == 0) return cudaSuccess;
+    if (count > NTT_MAX_BATCH) return cudaErrorInvalidValue;
+    NttVecs v{};
+    for (int i = 0; i < count; i++) v.p[i] = data[i];
+    if (log_d <= 2) {
+        k_ntt_small<<<dim3(1, count), 32, 0, st>>>(v, tw, log_d, inverse ? 1 : 0, pre, post); CZK_LAUNCHED();
+        return cudaGetLastError();
+    }
+    static const cudaError_t attr = [] {
+        cudaError_t e = cudaFuncSetAttribute(k_ntt_tile<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << NTT_TILE_LOG);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ntt_tile<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << NTT_TILE_LOG);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ntt_tile<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << NTT_TILE_LOG);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(k_ntt_tile<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 32 << NTT_TILE_LOG);
+        return e;
+    }();
+    if (attr != cudaSuccess) return attr;
+    const NttPlan plan = ntt_make_plan(log_d);
+    for (int k = 0; k < plan.npass; k++) {
+        const NttPass& p = plan.pass[dit ? plan.npass - 1 - k : k];
+        const int tile_log = p.r + p.cl;
+        const unsigned blocks = 1u << (log_d - tile_log);
+        const size_t smem = (size_t)32 << tile_log;
+        const unsigned threads = (1u << tile_log) / 8 < 32 ? 32 : (1u << tile_log) / 8;
+        const int first = k == 0, last = k == plan.npass - 1;
+        const bool scale = (first && pre.mode) || (last && post.mode);  // only those passes run the variant that carries scaling code
+        const dim3 grid(blocks, count);
+        if (dit && scale) k_ntt_tile<true, true><<<grid, threads, smem, st>>>(v, tw, log_d, p.s, p.r, p.cl, inverse ? 1 : 0, first, last, pre, post);
+        else if (dit) k_ntt_tile<true, false><<<grid, threads, smem, st>>>(v, tw, log_d, p.s, p.r, p.cl, inverse ? 1 : 0, first, last, pre, post);
+        else if (scale) k_ntt_tile<false, true><<<grid, threads, smem, st>>>(v, tw, log_d, p.s, p.r, p.cl, inverse ? 1 : 0, first, last, pre, post);
+        else k_ntt_tile<false, false><<<grid, threads, smem, st>>>(v, tw, log_d, p.s, p.r, p.cl, inverse ? 1 : 0, first, last, pre, post);
+        CZK_LAUNCHED();
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

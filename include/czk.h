@@ -72,6 +72,19 @@ CZK_API int czk_vec_zero(czk_ctx* ctx, czk_vec* v, size_t offset, size_t n);
 CZK_API int czk_ntt_fr(czk_ctx* ctx, uint64_t* host_data, unsigned log_d, int inverse, int coset); /* host buffer in/out */
 CZK_API int czk_ntt_fr_dev(czk_ctx* ctx, uint64_t* dev_data, unsigned log_d, int inverse, int coset);
 CZK_API int czk_ntt_vec(czk_ctx* ctx, czk_vec* v, unsigned log_d, int inverse, int coset);
+/* Batched form: the same transform over `count` device vectors (distinct, each 2^log_d elements), all of them in ONE grid
+ * per pass - what the generic `T: DomainCoeff<F>` call amounts to for SPDZ (value and MAC vectors, spdz.rs:186-208) and
+ * for the a / b / c vectors of the witness map (r1cs_to_qap.rs:85-110).
+ * op: one of the four transforms, or CZK_NTT_IFFT_COSET_FFT = ifft_in_place followed by coset_fft_in_place on the same
+ * vector (r1cs_to_qap.rs:85-90): same result as the two calls, computed as an inverse decimation-in-frequency pass
+ * sequence feeding a forward decimation-in-time one, with the D^-1 g^i scaling fused in and no reordering pass. */
+#define CZK_NTT_FFT 0
+#define CZK_NTT_IFFT 1
+#define CZK_NTT_COSET_FFT 2
+#define CZK_NTT_COSET_IFFT 3
+#define CZK_NTT_IFFT_COSET_FFT 4
+CZK_API int czk_ntt_fr_batch(czk_ctx* ctx, uint64_t* const* dev_vecs, int count, unsigned log_d, int op);
+CZK_API int czk_ntt_vec_batch(czk_ctx* ctx, czk_vec* const* vecs, int count, unsigned log_d, int op);
 /* Domain constants as Radix2EvaluationDomain::new computes them (radix2/mod.rs:51-82). */
 CZK_API int czk_domain_params(unsigned log_d, uint64_t group_gen[4], uint64_t group_gen_inv[4], uint64_t size_inv[4],
                       uint64_t generator_inv[4]);

@@ -172,3 +172,94 @@ EXPORT void emu_fq2_mul_two_lanes(uint64_t* r, const uint64_t* a, const uint64_t
 EXPORT void emu_fr_mul_sum2(uint64_t* r, const uint64_t* a, const uint64_t* b, const uint64_t* c, const uint64_t* d, size_t n) {
     for (size_t i = 0; i < n; i++) st(r + 4 * i, Fr::mul_sum2(ld<Fr>(a + 4 * i), ld<Fr>(b + 4 * i), ld<Fr>(c + 4 * i).l, ld<Fr>(d + 4 * i)));
 }
+
+// ---- the NTT tile arithmetic (csrc/ntt_tile.cuh) run thread by thread on the host: every pass, tile, phase and thread of
+// ntt_run_tiles, with the tile accessor addressing the vector directly.  Same composition of passes, scalings and bit
+// reversal as ntt_batch_dev (csrc/api.cu).  op: 0 fft, 1 ifft, 2 coset fft, 3 coset ifft, 4 ifft then coset fft.
+#include <vector>
+#include "../../collaborative-zksnark_b200/csrc/ntt_tile.cuh"
+namespace {
+struct HostTile {
+    uint64_t* data;
+    NttTileGeom g;
+    size_t idx(unsigned e) const { return g.base | ((size_t)(e >> g.cl) << g.L) | (size_t)(e & ((1u << g.cl) - 1u)); }
+    Fr load(unsigned e) const { return ld<Fr>(data + 4 * idx(e)); }
+    void store(unsigned e, const Fr& v) const { st(data + 4 * idx(e), v); }
+};
+Fr host_ldtw(const uint32_t* table, size_t i) { return ntt_ld_words(table + 8 * i); }
+void host_run_tiles(uint64_t* data, const uint32_t* tw, int n, bool inverse, bool dit, const NttScale& pre, const NttScale& post, int tile_log) {
+    const NttPlan plan = ntt_make_plan(n, tile_log);
+    for (int k = 0; k < plan.npass; k++) {
+        const NttPass& p = plan.pass[dit ? plan.npass - 1 - k : k];
+        const int tl = p.r + p.cl, L = n - p.s - p.r;
+        const size_t blocks = (size_t)1 << (n - tl);
+        for (size_t blk = 0; blk < blocks; blk++) {
+            const size_t lowblk = blk & (((size_t)1 << (L - p.cl)) - 1), hi = blk >> (L - p.cl);
+            HostTile tile{data, NttTileGeom{n, p.s, p.r, p.cl, L, (hi << (p.r + L)) | (lowblk << p.cl)}};
+            const int nph = ntt_num_phases(p.r);
+            for (int ph = 0; ph < nph; ph++) {
+                int kp, jlo, ns;
+                ntt_phase_geom(p.r, p.cl, dit, ph, kp, jlo, ns);
+                for (unsigned u = 0; u < (1u << tl) / 8; u++) {
+                    const bool first = k == 0 && ph == 0, last = k == plan.npass - 1 && ph == nph - 1;
+                    if (dit) ntt_phase_thread<true, true>(tile, u, tile.g, inverse, kp, jlo, ns, tw, first, last, pre, post, host_ldtw);
+                    else ntt_phase_thread<false, true>(tile, u, tile.g, inverse, kp, jlo, ns, tw, first, last, pre, post, host_ldtw);
+                }
+            }
+        }
+    }
+}
+std::vector<uint32_t> powers(const Fr& base, const Fr& c, size_t count) {
+    std::vector<uint32_t> t(count * 8);
+    Fr cur = c;
+    for (size_t k = 0; k < count; k++) {
+        for (int i = 0; i < 8; i++) t[8 * k + i] = cur.l[i];
+        cur = Fr::mul(cur, base);
+    }
+    return t;
+}
+}  // namespace
+EXPORT int emu_ntt(uint64_t* data, int n, int op, int tile_log, const uint64_t* omega, const uint64_t* gen, const uint64_t* gen_inv,
+                   const uint64_t* size_inv) {
+    if (n < 3 || tile_log < 4) return 0;  // smaller domains take the device's tiny kernel
+    const size_t d = (size_t)1 << n;
+    const Fr one = Fr::one(), w = ld<Fr>(omega), g = ld<Fr>(gen), gi = ld<Fr>(gen_inv), sinv = ld<Fr>(size_inv);
+    const std::vector<uint32_t> tw = powers(w, one, d / 2 + 1);
+    const int lo_log = n < 10 ? n : 10;
+    const size_t nlo = (size_t)1 << lo_log, nhi = (size_t)1 << (n - lo_log);
+    auto table_pair = [&](const Fr& base, const Fr& c, std::vector<uint32_t>& lo, std::vector<uint32_t>& hi) {
+        lo = powers(base, one, nlo);
+        hi = powers(Fr::pow_u64(base, nlo), c, nhi);
+    };
+    std::vector<uint32_t> g_lo, g_hi, g_hi_sinv, gi_lo, gi_hi;
+    table_pair(g, one, g_lo, g_hi);
+    table_pair(g, sinv, g_lo, g_hi_sinv);
+    table_pair(gi, sinv, gi_lo, gi_hi);
+    auto tables = [&](const std::vector<uint32_t>& lo, const std::vector<uint32_t>& hi, bool bitrev) {
+        NttScale sc;
+        sc.mode = 2;
+        sc.bitrev = bitrev ? 1 : 0;
+        sc.lo = lo.data();
+        sc.hi = hi.data();
+        sc.lo_log = lo_log;
+        return sc;
+    };
+    const NttScale none;
+    const bool inverse = op == 1 || op == 3 || op == 4;
+    if (op == 4) {
+        host_run_tiles(data, tw.data(), n, true, false, none, none, tile_log);
+        host_run_tiles(data, tw.data(), n, false, true, tables(g_lo, g_hi_sinv, true), none, tile_log);
+        return 1;
+    }
+    host_run_tiles(data, tw.data(), n, inverse, false, op == 2 ? tables(g_lo, g_hi, false) : none, none, tile_log);
+    // k_bitrev_scale: swap into natural order, the inverse scalings ride along
+    std::vector<uint64_t> tmp(data, data + 4 * d);
+    for (size_t i = 0; i < d; i++) {
+        const size_t r = ntt_bitrev((uint32_t)i, n);
+        Fr v = ld<Fr>(tmp.data() + 4 * r);  // the element at position r lands at i
+        if (op == 1) v = Fr::mul(v, sinv);
+        if (op == 3) v = Fr::mul(v, Fr::mul(host_ldtw(gi_lo.data(), i & (nlo - 1)), host_ldtw(gi_hi.data(), i >> lo_log)));
+        st(data + 4 * i, v);
+    }
+    return 1;
+}

@@ -167,3 +167,26 @@ def test_lazy_reduction_sum_of_two_products(emu, oracle, pymodel):
     fo = np.zeros_like(fa)
     emu.emu_fr_mul_sum2(P(fo), P(fa), P(fb), P(fc), P(fd), C.c_size_t(500))
     assert (fo == oracle.fr_add(oracle.fr_mul(fa, fb), oracle.fr_mul(fc, fd))).all()
+
+
+@pytest.mark.parametrize("n,tile_log", [(3, 11), (4, 11), (5, 11), (7, 11), (10, 11), (11, 11), (12, 11), (13, 11), (14, 11),
+                                        (9, 5), (10, 6), (11, 6), (12, 6), (13, 7), (15, 6), (16, 7)])
+def test_ntt_tile_phases_match_oracle(emu, oracle, n, tile_log):
+    """csrc/ntt_tile.cuh - the register-phase NTT the device runs (DIF and DIT orders, inverse twiddles as -tw[D/2 - e],
+    unit-twiddle shortcuts, fused scalings, the pass plan) - executed thread by thread on the host for all five
+    transforms and compared with the oracle's restatement of radix2/fft.rs.  Small tiles force multi-pass plans (up to
+    4 passes) at sizes the CPU finishes quickly; tile_log 11 is the device's own plan."""
+    d = 1 << n
+    dp = oracle.domain_params(d)
+    gen22 = oracle.fr_from_ints([22])[0]  # the coset shift: Fr::multiplicative_generator() (fr.rs, GENERATOR)
+    x = oracle.random_fr_mont(0x47 + n, d)
+    f = emu.emu_ntt
+    f.restype = C.c_int
+    for op in range(5):
+        got = x.copy()
+        assert f(P(got), n, op, tile_log, P(dp["group_gen"]), P(gen22), P(dp["generator_inv"]), P(dp["size_inv"])) == 1
+        if op < 4:
+            exp = oracle.ntt(x, inverse=bool(op & 1), coset=bool(op & 2))
+        else:
+            exp = oracle.ntt(oracle.ntt(x, inverse=True, coset=False), inverse=False, coset=True)
+        assert (got == exp).all(), (n, tile_log, op)

@@ -124,3 +124,36 @@ def test_pointwise_helpers(ctx, oracle, pymodel):
     dx = ctx.vec_from(x)
     ctx.divide_by_vanishing_on_coset(dx, log_d)
     assert (dx.numpy() == oracle.divide_by_vanishing_on_coset(x)).all()
+
+
+@pytest.mark.parametrize("log_d", [1, 2, 3, 4, 9, 11, 12, 14, 17, 20, 21])
+def test_ntt_batch_and_fused_pair_match_oracle(ctx, czk, oracle, log_d):
+    """czk_ntt_vec_batch: several vectors per grid, all five ops.  CZK_NTT_IFFT_COSET_FFT (the witness map's transform
+    pair, r1cs_to_qap.rs:85-90, run as inverse DIF -> forward DIT with the scaling fused) must equal ifft followed by
+    coset_fft of the oracle bit for bit."""
+    n = 1 << log_d
+    count = 3 if log_d <= 17 else 2
+    vs = [oracle.random_fr_mont(0x900 + 7 * log_d + i, n) for i in range(count)]
+    th = oracle.cpu_threads()
+    for op in (czk.NTT_FFT, czk.NTT_IFFT, czk.NTT_COSET_FFT, czk.NTT_COSET_IFFT, czk.NTT_IFFT_COSET_FFT):
+        if log_d >= 20 and op in (czk.NTT_FFT, czk.NTT_IFFT):
+            continue  # the large sizes keep to the ops the witness map uses (the others are covered above at every size)
+        dv = [ctx.vec_from(v) for v in vs]
+        ctx.ntt_batch(dv, log_d, op)
+        for v, d in zip(vs, dv):
+            if op == czk.NTT_IFFT_COSET_FFT:
+                exp = oracle.ntt(oracle.ntt(v, True, False, threads=th), False, True, threads=th)
+            else:
+                exp = oracle.ntt(v, bool(op & 1), bool(op & 2), threads=th)
+            assert (d.numpy() == exp).all(), (log_d, op)
+
+
+def test_ntt_batch_rejects_bad_arguments(ctx, czk, oracle):
+    v = ctx.vec_from(oracle.random_fr_mont(1, 16))
+    with pytest.raises(czk.CzkError):
+        ctx.ntt_batch([v, v], 4, czk.NTT_FFT)  # the same vector twice
+    with pytest.raises(czk.CzkError):
+        ctx.ntt_batch([v], 5, czk.NTT_FFT)  # shorter than the domain
+    with pytest.raises(czk.CzkError):
+        ctx.ntt_batch([v], 4, 7)  # no such transform
+    ctx.ntt_batch([], 4, czk.NTT_FFT)  # nothing to do

@@ -11,7 +11,7 @@ mode=$1; shift
 if [ "$mode" = build ]; then
   for spec in "$@"; do
     name=${spec%%=*}; flags=${spec#*=}
-    tools/build_variant.sh "$name" $flags
+    tools/build_variant.sh "$name" msm_batched.cu $flags
   done
   rm -f variants/*.o
   exit 0
