@@ -32,14 +32,14 @@ LOG_N = 20
 METRIC = "groth16_proof_ms_2^20_r1cs_bls12_377"
 # BASELINE.md section 1 (reference's published figures, GCP n2-standard-2, 1 physical core per party)
 PUBLISHED_MS = {1: 127400.0, 2: 320400.0, 3: 323300.0}
-# The dominant "kernel" is the bucket accumulation of one G1 MSM: 5 launches of k_bat_round<Fq> (halving rounds of the
-# batched-affine tree) + k_bat_finish<Fq>; it is timed as one unit by CUDA events on the launching stream.
-ACC_KERNEL = "k_bat_round<Fq> x5 + k_bat_finish<Fq> (bucket accumulation of one G1 MSM)"
-# ncu --set full capture of those launches (profiles/r1_summary.md): dram__bytes_read + write of the 2^21-1 term MSM's
-# round 0 (14.44 GB) and round 1 (4.57 GB) as captured, later rounds halving (sum 23.5 GB); the 2^20 term MSMs move half
-# of it -> mean over the step's 4 G1 MSMs
-NCU_TRAFFIC_BYTES_2_21 = 23.5e9
-NCU_TRAFFIC_BYTES_PER_LAUNCH = NCU_TRAFFIC_BYTES_2_21 * (1 + 3 * 0.5) / 4
+# The dominant kernel is the bucket accumulation of a G1 MSM: the halving rounds k_bat_round<Fq> (batched affine additions)
+# + k_bat_finish<Fq>.  It is timed ALONE (one h-query-shaped MSM of 2^21 - 1 terms per launch, L2 flushed between launches)
+# by CUDA events on the launching stream inside the library (czk_msm_stats): inside a proof the MSMs overlap each other
+# and the witness map, so their in-proof event times are not kernel times.
+ACC_KERNEL = "k_bat_round<Fq> x rounds + k_bat_finish<Fq>: bucket accumulation of the 2^21-1-term h-query MSM, timed alone"
+# ncu --set full capture of exactly those launches (profiles/r2_ncu_accumulate_g1.csv, tools/r2_ncu_acc.sh): sum over ALL the
+# rounds and the finish kernel of dram__bytes_read.sum + dram__bytes_write.sum for one 2^21-1-term accumulation
+NCU_TRAFFIC_BYTES_PER_LAUNCH = None  # filled from profiles/r2_traffic.json when it exists (written by tools/make_profiles.py)
 
 
 def ref_msm_adds(n: int) -> int:
@@ -167,6 +167,138 @@ def run_reference(args):
     return 0
 
 
+PLONK_METRIC = "plonk_wiring_proof_ms_2^{}_bls12_377"
+
+
+def run_plonk_reference(args):
+    """BASELINE config 3's data path on the host CPU: the oracle's restatement of Prover::prove_wiring, one party's work."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return 0
+    from oracle import binding as o
+
+    o.build()
+    threads = o.cpu_threads()
+    D = 1 << args.log_n
+    g1, _ = o.generators()
+    ks = o.random_fr_mont(3, 2)
+    powers = o.G1.gen_progression(g1, ks[0], ks[1], D, threads=threads)
+    p, w = o.random_fr_mont(11, D), o.random_fr_mont(12, D)
+    times = []
+    for i in range(max(0, min(args.warmup, 1)) + max(1, args.steps)):
+        t = time.perf_counter()
+        res = o.plonk_prove_wiring(o.SCHEME_SPDZ, p[None], w, powers, seed=i, threads=threads)
+        dt = (time.perf_counter() - t) * 1e3
+        assert res["status"] == 1
+        if i >= max(0, min(args.warmup, 1)):
+            times.append(dt)
+    ms = sum(times) / len(times)
+    cb = dict(value=ms, unit="ms", cores=threads, kind="port", log_n=args.log_n, steps_run=len(times),
+              sample=f"{len(times)} whole wiring proof(s) of one party over a 2^{args.log_n} domain on {threads} host threads, {ms:.1f} ms each")
+    print(json.dumps({"impl": "reference", "metric": PLONK_METRIC.format(args.log_n), "value": ms, "unit": "ms", "n_gpus": args.gpus,
+                      "steps": len(times), "warmup": max(0, min(args.warmup, 1)), "ms_per_step": ms, "higher_is_better": False, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "u64 limbs (Montgomery), integer", "data": "synthetic",
+                      "config": {"workload": f"plonk wiring argument spdz 2^{args.log_n} domain BLS12-377, one party's work on the host CPU (oracle port)",
+                                 "parties": args.gpus},
+                      "cpu_baseline": cb, "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+    return 0
+
+
+def run_plonk(args):
+    """BASELINE config 3 (Plonk SPDZ, 2^18, one party per GPU): the wiring argument - KZG10 commitment / opening MSMs, the
+    quotient transforms, batch division, prefix products and Beaver products on shares (mpc-plonk/src/lib.rs:110-258)."""
+    import numpy as np
+    import torch
+
+    import czk_b200
+    from czk_b200 import launch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the czk arm has no CPU fallback (use --impl reference for the CPU path)")
+    warmup = max(args.warmup, 3)
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        party = launch.Party()
+        party.ctx.batch_open(czk_b200.SCHEME_ADDITIVE, party.ctx.vec(4))
+        party.ctx.sync()
+    finally:
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    ctx, rank, world = party.ctx, party.rank, party.world
+    scheme = {"spdz": czk_b200.SCHEME_SPDZ, "additive": czk_b200.SCHEME_ADDITIVE, "plain": czk_b200.SCHEME_PLAIN}[args.scheme]
+    spdz = args.scheme == "spdz"
+    D = 1 << args.log_n
+    powers = ctx.bases_synthetic(1, 0x377, D, 0).precompute(0)  # committer key: device-generated points of the right shape
+    rng = np.random.Generator(np.random.PCG64(0x18))
+
+    def rand_fr(n):
+        a = rng.integers(0, 1 << 64, size=(n, 4), dtype=np.uint64)
+        a[:, 3] &= np.uint64((1 << 60) - 1)
+        return a
+
+    p_plain, w_host = rand_fr(D), rand_fr(D)  # same on every rank (same seed)
+    mine = launch.king_share_scatter(p_plain if rank == 0 else None, D, seed=0x5eed) if world > 1 else p_plain
+    p_pin = torch.from_numpy(mine.view(np.int64).copy()).pin_memory().numpy().view(np.uint64)
+    w_pin = torch.from_numpy(w_host.view(np.int64).copy()).pin_memory().numpy().view(np.uint64)
+    p_dev, w_dev = ctx.vec_from(mine), ctx.vec_from(w_host)
+    m_dev = ctx.vec_from(mine) if spdz else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{ctx.device}")
+
+    def step(resident, seed):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        if resident:
+            res = czk_b200.plonk_prove_wiring(ctx, scheme, powers, args.log_n, p_dev, m_dev, w_dev, seed=seed)
+        else:  # through host buffers: upload this party's shares and the public polynomial, read the proof back
+            pv, wv = ctx.vec_from(p_pin), ctx.vec_from(w_pin)
+            res = czk_b200.plonk_prove_wiring(ctx, scheme, powers, args.log_n, pv, ctx.vec_from(p_pin) if spdz else None, wv, seed=seed)
+        ctx.sync()
+        return (time.perf_counter() - t) * 1e3, res
+
+    for i in range(warmup):
+        step(True, i)
+    step(False, 99)
+
+    def timed(resident):
+        launch.barrier()
+        torch.cuda.synchronize()
+        l0 = ctx.launches
+        times, phases = [], []
+        for i in range(args.steps):
+            ms, res = step(resident, 1000 + i)
+            times.append(ms)
+            phases.append(res["phases_ms"])
+        launch.barrier()
+        torch.cuda.synchronize()
+        return launch.max_over_ranks(sum(times)) / args.steps, times, phases, ctx.launches - l0
+
+    sampler = ClockSampler(ctx.device)
+    sampler.start()
+    ms_res, t_res, phases, launches = timed(True)
+    ms_e2e, t_e2e, _, _ = timed(False)
+    clocks = sampler.stop()
+    if rank != 0:
+        party.close()
+        return 0
+    avg = lambda k: sum(p[k] for p in phases) / len(phases)
+    line = {"metric": PLONK_METRIC.format(args.log_n), "value": ms_res, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+            "ms_per_step": ms_res, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 limbs (Montgomery Fr/Fq), integer", "data": "synthetic",
+            "config": {"workload": f"plonk wiring argument {args.scheme} over a 2^{args.log_n} domain BLS12-377, one party per GPU "
+                                   "(4 KZG10 commitments, 9 openings, 16 transforms per component, batch division, prefix products, 2 Beaver products)",
+                       "parties": world, "l2": "256 MiB flush write between iterations",
+                       "transcript": "stand-in (SplitMix64 over absorbed limbs); the reference's Blake2s/ChaCha transcript plugs in through czk_plonk_transcript"},
+            "clocks": clocks,
+            "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": int((3 if spdz else 2) * D * 32), "d2h_bytes_per_step": int(2 * 1200)},
+            "gpu_launches": int(launches), "phases_ms": {k: avg(k) for k in phases[0]}, "times_ms": {"resident": t_res, "e2e": t_e2e}}
+    print(json.dumps(line))
+    party.close()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -181,7 +313,11 @@ def main():
                     help="real: CRS generated on the device from seeded toxic waste, the timed proof is verified with the pairing "
                          "check after the timed region; synthetic: device-generated bases of the same shapes (no verification)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="groth16", choices=["groth16", "plonk"],
+                    help="groth16: the BASELINE metric's proof (default). plonk: BASELINE config 3's wiring argument (use --log-n 18)")
     args = ap.parse_args()
+    if args.workload == "plonk":
+        return run_plonk_reference(args) if args.impl == "reference" else run_plonk(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -217,6 +353,7 @@ def main():
     imad_peak, _ = ctx.microbench(0, 8, 256, 2000)  # measured IMAD.WIDE.U32 issue rate: the integer roofline denominator
     key_kind = args.key
     pk = None
+    t_key = time.perf_counter()
     if key_kind == "real":
         try:
             rng = np.random.Generator(np.random.PCG64(0x377))
@@ -228,6 +365,13 @@ def main():
             key_kind = "synthetic"
     if pk is None:
         pk = czk_b200.ProvingKey.synthetic(ctx, n_sq, seed=0x377)
+    ctx.sync()
+    key_prepare_ms = (time.perf_counter() - t_key) * 1e3  # once per key, outside the timed region (like the reference's CRS)
+    key_bytes = {"points": 0, "table": 0}
+    for i in range(5):
+        b = pk.query(i).device_bytes()
+        key_bytes["points"] += b["points"]
+        key_bytes["table"] += b["table"]
     D = pk.domain_size
     start = np.array([0x1234567, 0x89abcdef, 0x55aa55aa, 0x0123], np.uint64)
     if args.scheme == "gsz":
@@ -278,6 +422,30 @@ def main():
     ms_e2e, times_e2e, phases_e2e, _, _, _ = timed(False, args.steps)
     clocks = sampler.stop()
 
+    # ---- the dominant kernel on its own: standalone MSMs of the h-query (2^21 - 1 terms) and l-query (2^20 terms) shapes
+    def standalone_msm(which, n_terms, reps=5):
+        rng = np.random.Generator(np.random.PCG64(0x5ca1a + which))
+        sc = rng.integers(0, 1 << 64, size=(n_terms, 4), dtype=np.uint64)
+        sc[:, 3] &= np.uint64((1 << 60) - 1)  # < 2^252 < r: valid Montgomery limbs
+        dsc = ctx.vec_from(sc)
+        q = pk.query(which)
+        for _ in range(2):
+            ctx.msm_bases(q, dsc)
+        ctx.msm_stats(1, reset=True)
+        wall = []
+        for _ in range(reps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            ctx.msm_bases(q, dsc)
+            wall.append((time.perf_counter() - t) * 1e3)
+        st = ctx.msm_stats(1)
+        return {"n": n_terms, "accumulate_ms": st["accumulate_ms"] / reps, "device_ms": st["msm_ms"] / reps, "wall_ms": sum(wall) / reps,
+                "entries": st["entries"] / reps}
+
+    alone_h = standalone_msm(3, D - 1)
+    alone_l = standalone_msm(4, n_sq)
+
     # acceptance check outside the timed region (mpc-snarks/src/proof.rs:141 verify_proof): one more proof, verified
     verified = None
     if key_kind == "real":
@@ -291,22 +459,25 @@ def main():
 
     avg = lambda key: sum(p[key] for p in phases) / len(phases)
     n_h = D - 1
-    msm_h_ms = avg("msm_h")
-    # dominant kernel: k_msm_accumulate<Fq> (bucket accumulation), CUDA events on the launching stream
-    acc_ms = st1["accumulate_ms"] / max(st1["launches"], 1)
-    terms_per_launch = st1["terms"] / max(st1["launches"], 1)
+    acc_ms = alone_h["accumulate_ms"]
     peaks = {}
     pf = ROOT / "MEASURED_PEAKS.json"
     if pf.exists():
         peaks = json.loads(pf.read_text())
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    alg_bytes = 128.0 * terms_per_launch  # 32 B scalar + 96 B affine base per G1 term
+    alg_bytes = 128.0 * n_h  # 32 B scalar + 96 B affine base per G1 term
     achieved_gbs = alg_bytes / (acc_ms * 1e-3) / 1e9 if acc_ms else 0.0
-    entries_per_launch = st1["entries"] / max(st1["launches"], 1)
     # N*W bucket additions; the batched-affine tree spends 6 products per addition + ~0.5 for the block-wide inversion
     # trees (the XYZZ walk: 8M + 2S = 10); one product = 276 wide multiply-adds (2*12^2 - 12: p0 = 1 rows need none)
-    wide_mads = entries_per_launch * 6.5 * 276
+    wide_mads = alone_h["entries"] * 6.5 * 276
     int_rate = wide_mads / (acc_ms * 1e-3) if acc_ms else 0.0
+    traffic, traffic_src = None, "no committed ncu capture found (profiles/r2_traffic.json)"
+    tf = ROOT / "profiles" / "r2_traffic.json"
+    if tf.exists():
+        tj = json.loads(tf.read_text())
+        traffic, traffic_src = tj.get("accumulate_g1_2_21_bytes"), tj.get("source")
+    # the G1 accumulations' share of the step, from kernel-alone times: one h-shaped + three l-shaped MSMs per proof
+    share = (alone_h["accumulate_ms"] + 3 * alone_l["accumulate_ms"]) / ms_res
     line = {
         "metric": METRIC, "value": ms_res, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": warmup,
         "ms_per_step": ms_res, "higher_is_better": False, "scaling": "weak",
@@ -319,24 +490,27 @@ def main():
                    "proof_verified": verified,
                    "published_reference_ms": PUBLISHED_MS.get(world)},
         "clocks": clocks,
-        "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": int((n_sq + 1) * 32), "d2h_bytes_per_step": int(2 * 48 * 8 + 6 + 5 * 16 * 192)},
+        "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": int((n_sq + 1) * 32), "d2h_bytes_per_step": int(2 * 48 * 8 + 6 + 5 * 17 * 192)},
         "gpu_launches": int(launches),
+        # per-key, outside the timed region ("CRS upload reported separately"): generating / uploading the key and
+        # building the merged-window tables 2^(cw) P_i the MSMs gather from
+        "key_prepare_ms": key_prepare_ms, "key_device_bytes": key_bytes,
         "roofline": {"kernel": ACC_KERNEL, "bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved_gbs / hbm_peak, "traffic": NCU_TRAFFIC_BYTES_PER_LAUNCH,
-                     "traffic_source": "profiles/r1_summary.md: ncu --set full dram__bytes_read+write summed over the rounds of one 2^21-1 term "
-                                       "accumulation, halved for the 2^20 term MSMs, mean over the step's 4 G1 MSMs; round 0 gathers each base "
-                                       "once per window from the precomputed table and every round streams points + prefix products, so "
-                                       "traffic >> the 128 B/term algorithmic figure",
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                     "frac": achieved_gbs / hbm_peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst figure: the kernel is timed alone)" if peaks else "fallback 6650 GB/s",
                      "note": "bucket accumulation is bound by integer-instruction dispatch (IMAD.WIDE pipe), not HBM: see roofline_int",
-                     "launch_ms": acc_ms, "launches_per_step": st1["launches"] / args.steps, "share_of_step": st1["accumulate_ms"] / args.steps / ms_res},
+                     "launch_ms": acc_ms, "launches_per_step": 4, "share_of_step": share,
+                     "share_note": "kernel-alone accumulation times of the step's four G1 MSMs (1 x 2^21-1 + 3 x 2^20 terms) / ms_per_step; "
+                                   "inside the step they overlap the G2 MSM and the witness map"},
         "roofline_int": {"kernel": ACC_KERNEL, "bound": "imad", "achieved": int_rate, "peak": imad_peak, "unit": "IMAD.WIDE/s",
                          "frac": int_rate / imad_peak if imad_peak else None,
                          "peak_source": "czk_microbench kind 0 (independent mad.wide.u32 chains), measured at bench start"},
-        "g1_msm_adds_per_s": ref_msm_adds(n_h) / (msm_h_ms * 1e-3),
-        "g1_msm": {"n": n_h, "ms": msm_h_ms, "adds_ref": ref_msm_adds(n_h)},
-        "g2_msm_ms": avg("msm_b_g2"), "msm_device_ms_per_step": {"g1": st1["msm_ms"] / args.steps, "g2": st2["msm_ms"] / args.steps},
+        "g1_msm_adds_per_s": ref_msm_adds(n_h) / (alone_h["wall_ms"] * 1e-3),
+        "g1_msm": {"n": n_h, "ms": alone_h["wall_ms"], "device_ms": alone_h["device_ms"], "accumulate_ms": acc_ms, "adds_ref": ref_msm_adds(n_h),
+                   "how": "standalone czk_msm_bases on the resident h-query (host call to result), L2 flushed between calls"},
+        "g1_msm_2_20": alone_l,
         "phases_ms": {k: avg(k) for k in phases[0]},
+        "phases_note": "witness_map and msm_* are device times of jobs that OVERLAP (context stream + two MSM lanes): they do not add up",
         "times_ms": {"resident": times_res, "e2e": times_e2e},
     }
     if not args.no_cpu_baseline and world == 1:  # the CPU leg runs on rank 0 of the 1-GPU run only

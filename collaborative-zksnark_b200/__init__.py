@@ -41,5 +41,8 @@ from .binding import (  # noqa: F401
     groth16_setup,
     groth16_setup_r1cs,
     pk_verifying_key,
+    plonk_prove_wiring,
+    PlonkTranscript,
+    PlonkWiringProof,
 )
 from .build import build as build_library  # noqa: F401

@@ -72,6 +72,7 @@ _SIGS = {
     "czk_bases_free": (None, [C.c_void_p, C.c_void_p]),
     "czk_bases_len": (C.c_size_t, [C.c_void_p]),
     "czk_bases_precompute": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint]),
+    "czk_bases_device_bytes": (C.c_int, [C.c_void_p, u64p]),
     "czk_msm_bases": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_size_t, u64p]),
     "czk_msm_bases_multi": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int, C.c_size_t,
                                       C.POINTER(u64p), C.POINTER(C.c_double)]),
@@ -121,8 +122,28 @@ _SIGS = {
     "czk_microbench": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
 }
 
-# include/czk_groth16.h
+class PlonkTranscript(C.Structure):
+    """czk_plonk_transcript (include/czk_plonk.h): the caller's Fiat-Shamir transcript as two callbacks."""
+    _fields_ = [("user", C.c_void_p), ("absorb_g1", C.c_void_p), ("challenge", C.c_void_p)]
+
+
+class PlonkWiringProof(C.Structure):
+    """czk_plonk_wiring_proof: commitments l1, t, q, l2_q; openings t(wr) t(r) t(w^(k-1)) l1(wr) q(r) l2_q(x) w(x) l1(x) p(x)."""
+    _fields_ = [("cmt_xy", (C.c_uint64 * 12) * 4), ("cmt_inf", C.c_uint8 * 4), ("open_val", (C.c_uint64 * 4) * 9),
+                ("open_pf_xy", (C.c_uint64 * 12) * 9), ("open_pf_inf", C.c_uint8 * 9), ("challenges", (C.c_uint64 * 4) * 4)]
+
+    def to_dict(self):
+        return dict(cmt_xy=np.array(self.cmt_xy, np.uint64).reshape(4, 12), cmt_inf=np.array(self.cmt_inf, np.uint8),
+                    open_val=np.array(self.open_val, np.uint64).reshape(9, 4), open_pf_xy=np.array(self.open_pf_xy, np.uint64).reshape(9, 12),
+                    open_pf_inf=np.array(self.open_pf_inf, np.uint8), challenges=np.array(self.challenges, np.uint64).reshape(4, 4))
+
+
+# include/czk_groth16.h, include/czk_plonk.h
 _OPTIONAL_SIGS = {
+    "czk_plonk_standin_transcript": (None, [C.POINTER(C.c_uint64), C.c_uint64, C.POINTER(PlonkTranscript)]),
+    "czk_plonk_prove_wiring": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.POINTER(PlonkTranscript), C.POINTER(PlonkWiringProof), C.POINTER(PlonkWiringProof),
+                                         C.POINTER(C.c_double)]),
     "czk_groth16_pk_upload": (C.c_int, [C.c_void_p, C.c_size_t] + [C.c_void_p] * 12 + [C.POINTER(C.c_void_p)]),
     "czk_groth16_pk_synthetic": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.POINTER(C.c_void_p)]),
     "czk_groth16_pk_free": (None, [C.c_void_p, C.c_void_p]),
@@ -260,6 +281,11 @@ class Bases:
         inf = np.empty(n, np.uint8)
         self.ctx._chk(self.ctx.lib.czk_bases_download(self.ctx.h, self.h, off, n, xy.ctypes.data, inf.ctypes.data))
         return xy, inf
+
+    def device_bytes(self) -> dict:
+        out = np.zeros(2, np.uint64)
+        self.ctx._chk(self.ctx.lib.czk_bases_device_bytes(self.h, out.ctypes.data_as(u64p)))
+        return {"points": int(out[0]), "table": int(out[1])}
 
     def precompute(self, c: int = 0):
         """Build the merged-window table (2^(c w) * P_i); later msm_bases calls use it."""
@@ -641,6 +667,24 @@ class ProvingKey:
         if self.h:
             self.ctx.lib.czk_groth16_pk_free(self.ctx.h, self.h)
             self.h = None
+
+
+def plonk_prove_wiring(ctx: "Context", scheme: int, powers: "Bases", log_d: int, p_sh: "DeviceVec", p_mac, w_pub: "DeviceVec",
+                       seed: int = 0, transcript: "PlonkTranscript | None" = None) -> dict:
+    """Prover::prove_wiring (mpc-plonk/src/lib.rs:199-258) on this party's shares; the stand-in transcript seeded with
+    `seed` unless the caller supplies its own callbacks.  Returns the revealed proof, this party's proof shares and the
+    phase times (transforms + share protocols, commitments, openings, reveal)."""
+    state = C.c_uint64(0)
+    tr = transcript
+    if tr is None:
+        tr = PlonkTranscript()
+        ctx.lib.czk_plonk_standin_transcript(C.byref(state), seed, C.byref(tr))
+    share, out = PlonkWiringProof(), PlonkWiringProof()
+    ph = (C.c_double * 4)()
+    ctx._chk(ctx.lib.czk_plonk_prove_wiring(ctx.h, scheme, powers.h, log_d, p_sh.h, p_mac.h if p_mac is not None else None, w_pub.h,
+                                            C.byref(tr), C.byref(share), C.byref(out), ph))
+    return dict(proof=out.to_dict(), proof_share=share.to_dict(),
+                phases_ms=dict(zip(("transforms_and_shares", "commitments", "openings", "reveal"), list(ph))))
 
 
 def groth16_witness_map(ctx: Context, scheme: int, n_sq: int, chain_sh) -> np.ndarray:

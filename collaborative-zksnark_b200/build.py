@@ -15,7 +15,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 CUFLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC,-fvisibility=hidden",
                   "-I", str(HERE.parent / "include"), "--expt-relaxed-constexpr"] + os.environ.get("CZK_EXTRA_NVCC_FLAGS", "").split()
-SOURCES = ["api.cu", "ntt.cu", "msm.cu", "msm_batched.cu", "fr_ops.cu", "shares.cu", "microbench.cu", "groth16.cu", "gsz.cu", "poly.cu", "serialize.cu", "pairing.cu", "fixed_base.cu"]
+SOURCES = ["api.cu", "ntt.cu", "msm.cu", "msm_batched.cu", "fr_ops.cu", "shares.cu", "microbench.cu", "groth16.cu", "gsz.cu", "poly.cu", "plonk.cu", "serialize.cu", "pairing.cu", "fixed_base.cu"]
 
 
 def _stale(target: Path, deps) -> bool:

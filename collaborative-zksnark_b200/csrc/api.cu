@@ -688,6 +688,14 @@ int czk_bases_precompute(czk_ctx* ctx, czk_bases* b, unsigned c) {
     return CZK_OK;
 }
 
+int czk_bases_device_bytes(const czk_bases* b, uint64_t out[2]) {
+    if (!b || !out) return CZK_ERR_ARG;
+    const uint64_t pb = b->curve == 1 ? 96 : 192;
+    out[0] = (uint64_t)b->n * pb + (b->inf ? b->n : 0);
+    out[1] = b->table ? (uint64_t)b->pre_w * b->n * pb : 0;
+    return CZK_OK;
+}
+
 // czk_msm_bases without the wait: the MSM is enqueued on `lane` (0 or 1) and runs concurrently with the other lane and with
 // the context stream; msm_collect returns its result.  Internal (ctx.hpp): the Groth16 prover keeps its five MSMs and the
 // witness map in flight together.

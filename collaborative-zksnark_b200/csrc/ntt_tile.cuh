@@ -16,7 +16,7 @@
 // 85-90) needs no bit-reversal pass at all: the scaling D^-1 g^i between them is applied where the DIT loads.
 //
 // This header compiles for the host too (tests/emu): the CPU test tier runs every phase of every pass thread by thread
-// against the oracle's restatement of radix2/fft.rs, which checks all the index arithmetic without a GPU.
+// against the CPU restatement of radix2/fft.rs kept with the tests, which checks all the index arithmetic without a GPU.
 #pragma once
 #include "fp.cuh"
 

@@ -117,6 +117,8 @@ CZK_API size_t czk_bases_len(const czk_bases* b);
 /* Precompute the merged-window table 2^(c w) * P_i for a resident base set (c = 0: chosen from its length).  One-off
  * cost per CRS query; afterwards czk_msm_bases uses one bucket set for all windows.  Same results. */
 CZK_API int czk_bases_precompute(czk_ctx* ctx, czk_bases* b, unsigned c);
+/* Bytes of device memory held by the base set: { points + flags, merged-window table } (the per-key cost of the table). */
+CZK_API int czk_bases_device_bytes(const czk_bases* b, uint64_t out[2]);
 /* MSM of bases[base_off .. base_off+n) by the device scalars sc[sc_off .. sc_off+n). */
 CZK_API int czk_msm_bases(czk_ctx* ctx, const czk_bases* b, size_t base_off, const czk_vec* sc, size_t sc_off,
                   int scalars_montgomery, size_t n, uint64_t* out_xyz);

@@ -36,8 +36,7 @@ def test_torchrun_multi_party_parity(scheme, nproc):
         pytest.skip(f"needs {nproc} GPUs, this box has {_gpus()}")
     r = _run(nproc, scheme, port=29641 + nproc)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    ok = [l for l in r.stdout.splitlines() if "parity ok" in l]
-    assert len(ok) == nproc, r.stdout[-3000:]
+    assert r.stdout.count("parity ok") == nproc, r.stdout[-3000:]  # (ranks share stdout: their lines may run together)
 
 
 def test_torchrun_corrupted_share_trips_the_mac_check():
@@ -46,4 +45,4 @@ def test_torchrun_corrupted_share_trips_the_mac_check():
         pytest.skip("needs 2 GPUs")
     r = _run(2, "spdz", extra=["--corrupt-mac"], port=29671)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
-    assert len([l for l in r.stdout.splitlines() if "corrupted MAC detected" in l]) == 2, r.stdout[-3000:]
+    assert r.stdout.count("corrupted MAC detected") == 2, r.stdout[-3000:]

@@ -3,6 +3,12 @@
 
     python tools/proof.py -p groth16 -c squaring --computation-size N local
     torchrun --nproc-per-node P tools/proof.py -p groth16 -c squaring --computation-size N mpc --alg spdz
+    torchrun --nproc-per-node P tools/proof.py -p plonk   -c squaring --computation-size N mpc --alg spdz
+
+-p plonk times the device data path of the Plonk prover that is built (the wiring argument, czk_plonk_prove_wiring:
+mpc-plonk/src/lib.rs:110-258,343-400) over a domain of 3 N wires rounded up to a power of two, with a stand-in transcript;
+-p marlin is accepted for flag compatibility and reports that its prover loop is not built (its leaves - MSM, NTT, share
+products - are the same library calls).
 
 `mpc --hosts F --party I` of the reference becomes one rank per party (RANK / WORLD_SIZE / LOCAL_RANK from
 torchrun); everything else keeps its meaning.  Prints the `End: ... timed section ...` line that
@@ -23,7 +29,7 @@ from czk_b200 import launch
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("-p", "--proof-system", default="groth16", choices=["groth16"])
+    ap.add_argument("-p", "--proof-system", default="groth16", choices=["groth16", "plonk", "marlin"])
     ap.add_argument("-c", "--computation", default="squaring", choices=["squaring"])
     ap.add_argument("--computation-size", type=int, default=10)
     sub = ap.add_subparsers(dest="mode", required=True)
@@ -34,9 +40,14 @@ def main():
     sub.add_parser("local")
     sub.add_parser("ark-local")
     args = ap.parse_args()
+    if args.proof_system == "marlin":
+        raise SystemExit("proof.py: -p marlin: the Marlin prover loop is not built on the device path (SURVEY.md section 8 scope); "
+                         "its MSM / NTT / share-product leaves are czk.h calls - see INTEGRATION.md")
     party = launch.Party()
     ctx, rank, world = party.ctx, party.rank, party.world
     n_sq = args.computation_size
+    if args.proof_system == "plonk":
+        return main_plonk(args, party)
     if args.mode == "mpc":
         scheme = {"spdz": czk_b200.SCHEME_SPDZ, "hbc": czk_b200.SCHEME_ADDITIVE, "gsz": czk_b200.SCHEME_GSZ}[args.alg]
     else:
@@ -69,6 +80,42 @@ def main():
     if rank == 0:
         unit = f"{dt:.3f}s" if dt >= 1 else (f"{dt * 1e3:.3f}ms" if dt >= 1e-3 else f"{dt * 1e6:.3f}µs")
         print(f"End:     timed section ............................................................{unit}")
+    print(f"Stats: {ctx.net_stats()}")
+    party.close()
+
+
+def main_plonk(args, party):
+    ctx, rank, world = party.ctx, party.rank, party.world
+    if args.mode == "mpc":
+        if args.alg == "gsz":
+            raise SystemExit("proof.py: -p plonk under gsz is not built (additive / SPDZ shares only)")
+        scheme = {"spdz": czk_b200.SCHEME_SPDZ, "hbc": czk_b200.SCHEME_ADDITIVE}[args.alg]
+    else:
+        assert world == 1, "local proving is a single process"
+        scheme = czk_b200.SCHEME_PLAIN
+    spdz = scheme == czk_b200.SCHEME_SPDZ
+    log_d = max(3, (3 * args.computation_size - 1).bit_length())  # circ.domains.wires: 3 wires per gate, next power of two
+    D = 1 << log_d
+    powers = ctx.bases_synthetic(1, 7, D, 0)
+    if D >= 1024:
+        powers.precompute(0)
+    rng = np.random.Generator(np.random.PCG64(3))
+    p = rng.integers(0, 1 << 64, size=(D, 4), dtype=np.uint64)
+    w = rng.integers(0, 1 << 64, size=(D, 4), dtype=np.uint64)
+    p[:, 3] &= np.uint64((1 << 60) - 1)
+    w[:, 3] &= np.uint64((1 << 60) - 1)
+    mine = launch.king_share_scatter(p if rank == 0 else None, D, seed=2)
+    args_ = (ctx, scheme, powers, log_d, ctx.vec_from(mine), ctx.vec_from(mine) if spdz else None, ctx.vec_from(w))
+    czk_b200.plonk_prove_wiring(*args_, seed=1)  # untimed first call: module loading, workspace, NCCL start-up
+    ctx.net_reset_stats()
+    launch.barrier()
+    t = time.perf_counter()
+    res = czk_b200.plonk_prove_wiring(*args_, seed=2)
+    dt = launch.max_over_ranks(time.perf_counter() - t)
+    if rank == 0:
+        unit = f"{dt:.3f}s" if dt >= 1 else (f"{dt * 1e3:.3f}ms" if dt >= 1e-3 else f"{dt * 1e6:.3f}µs")
+        print(f"End:     timed section ............................................................{unit}")
+        print(f"plonk wiring argument, domain 2^{log_d}: phases {res['phases_ms']}")
     print(f"Stats: {ctx.net_stats()}")
     party.close()
 
