@@ -45,7 +45,18 @@ int czk_ctx_create(int device, czk_ctx** out) {
     czk_ctx* ctx = new czk_ctx();
     ctx->device = device;
     CUDA_TRY(ctx, cudaSetDevice(device));
-    CUDA_TRY(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {
+        // the context stream (transforms, share protocols, collectives) outranks the MSM lanes: its short kernels get SM
+        // slots as soon as blocks of a long accumulation round retire, instead of queueing behind whole grids
+        int lo = 0, hi = 0;
+        CUDA_TRY(ctx, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        // measured (2^20 SPDZ proof, one B200): 56.5 ms with the context stream prioritised, 55.4 ms without - the witness map
+        // finishing early only moves the idle tail; equal priorities stay the default (CZK_STREAM_PRIORITY=1 to try again)
+        const char* env = getenv("CZK_STREAM_PRIORITY");
+        if (!(env && atoi(env) == 1)) hi = lo;
+        CUDA_TRY(ctx, cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, hi));
+        ctx->lane_priority = lo;
+    }
     {
         cudaMemPool_t pool;
         CUDA_TRY(ctx, cudaDeviceGetDefaultMemPool(&pool, device));
@@ -56,7 +67,7 @@ int czk_ctx_create(int device, czk_ctx** out) {
     CUDA_TRY(ctx, cudaMemset(ctx->flag, 0, 4));
     for (cudaEvent_t& e : ctx->ev_phase) CUDA_TRY(ctx, cudaEventCreate(&e));
     for (MsmLane& l : ctx->lanes) {
-        CUDA_TRY(ctx, cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        CUDA_TRY(ctx, cudaStreamCreateWithPriority(&l.stream, cudaStreamNonBlocking, ctx->lane_priority));
         CUDA_TRY(ctx, cudaEventCreateWithFlags(&l.ev_in, cudaEventDisableTiming));
         for (MsmSlot& sl : l.slots) {
             CUDA_TRY(ctx, cudaMallocHost(&sl.pinned, 256 * 96 * 4));  // up to 256 XYZZ points of G2

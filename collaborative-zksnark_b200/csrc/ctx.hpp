@@ -128,6 +128,7 @@ constexpr int CZK_MSM_LANES = 2;
 struct czk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    int lane_priority = 0;
     std::string err;
     std::map<int, Domain> domains;
     MsmLane lanes[CZK_MSM_LANES];

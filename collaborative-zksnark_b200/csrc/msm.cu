@@ -385,15 +385,16 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
     if (ws.ev[0]) cudaEventRecord(ws.ev[0], st);
     const uint32_t* gate = nullptr;
     // worth it only when buckets are long (merged windows over a large base set): the rounds' fixed latencies (one
-    // block-wide inversion each) must be paid back by the multiplications saved (measured: 2^19 terms 3.88 ms walk vs
-    // 2.88 ms tree, 2^20 terms 7.55 vs 5.15); CZK_BAT_MIN_ENTRIES / CZK_BAT_MIN_LOAD override for A/B runs
+    // block-wide inversion each) must be paid back by the multiplications saved (measured, whole MSM, with the rounds
+    // decided on the device: 2^17 G1 terms 1.83 ms walk vs 1.75 tree, 2^18 3.09 vs 2.60, 2^19 5.04 vs 3.88; 2^18 G2 terms
+    // 11.2 vs 6.9); CZK_BAT_MIN_ENTRIES / CZK_BAT_MIN_LOAD override for A/B runs
     static const size_t bat_min_entries = [] {
         const char* e = getenv("CZK_BAT_MIN_ENTRIES");
-        return e ? (size_t)atoll(e) : (size_t)6 << 20;  // 2^19 terms x 15 windows and up
+        return e ? (size_t)atoll(e) : (size_t)2 << 20;  // 2^18 terms x 15 windows and up
     }();
     static const size_t bat_min_load = [] {
         const char* e = getenv("CZK_BAT_MIN_LOAD");
-        return e ? (size_t)atoll(e) : (size_t)64;
+        return e ? (size_t)atoll(e) : (size_t)24;
     }();
     if (ws.batched && n && (ws.batched_always || (n * cfg.nwin >= bat_min_entries && n * cfg.nwin >= total * bat_min_load))) {
         // tree of batched affine additions (msm_batched.cu).  The longest bucket (queue word 4, written by k_msm_seg_counts)
