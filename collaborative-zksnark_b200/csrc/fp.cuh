@@ -325,25 +325,6 @@ struct Fp {
         reduce_once(cd.l);
     }
     CZK_HD static Fp sqr(const Fp& a) { return mul(a, a); }
-    // Same product with the a_i*b_j halves kept unfused (see chain_mad); `opaque_zero` must be a run-time zero the
-    // compiler cannot see through (loaded from memory).
-    CZK_HD static Fp mul_split(const Fp& a, const Fp& b, uint32_t opaque_zero) {
-        uint32_t even[N], odd[N], m[N];
-#pragma unroll
-        for (int i = 0; i < N; i++) m[i] = P::modc(i);
-#pragma unroll
-        for (int i = 0; i < N; i += 2) {
-            mont_row<P>(even, odd, a.l, b.l[i], m, i == 0, opaque_zero);
-            mont_row<P>(odd, even, a.l, b.l[i + 1], m, false, opaque_zero);
-        }
-        Fp r;
-        r.l[0] = add_cc(even[0], odd[1]);
-#pragma unroll
-        for (int i = 1; i < N - 1; i++) r.l[i] = addc_cc(even[i], odd[i + 1]);
-        r.l[N - 1] = addc(even[N - 1], 0);
-        reduce_once(r.l);
-        return r;
-    }
     // out-of-line copy: one body per kernel instead of one per call site.  Used wherever code size
     // (compile time, instruction cache) matters more than the call overhead: Fq2 and the cold kernels.
     CZK_HD_NOINLINE static Fp mul_ni(const Fp& a, const Fp& b) { return mul(a, b); }

@@ -3,7 +3,6 @@
 // multiplication and point addition rates at a chosen occupancy.
 #include <cuda_runtime.h>
 #include "ec.cuh"
-#include "fq13.cuh"
 #include "launch_count.hpp"
 
 namespace czk {
@@ -170,25 +169,6 @@ __global__ void k_mb_imad(uint64_t* out, int iters, uint32_t seed) {
     }
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
 }
-// kind 8: independent mad.hi chains
-__global__ void k_mb_imad_hi(uint64_t* out, int iters, uint32_t seed) {
-    uint32_t a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
-    uint32_t c0 = 1, c1 = 2, c2 = 3, c3 = 4, c4 = 5, c5 = 6, c6 = 7, c7 = 8;
-    for (int i = 0; i < iters; i++) {
-#pragma unroll
-        for (int k = 0; k < 8; k++) {
-            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(c0) : "r"(a), "r"(b));
-            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(c1) : "r"(a), "r"(b));
-            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(c2) : "r"(a), "r"(b));
-            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(c3) : "r"(a), "r"(b));
-            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(c4) : "r"(a), "r"(b));
-            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(c5) : "r"(a), "r"(b));
-            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(c6) : "r"(a), "r"(b));
-            asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(c7) : "r"(a), "r"(b));
-        }
-    }
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = c0 ^ c1 ^ c2 ^ c3 ^ c4 ^ c5 ^ c6 ^ c7;
-}
 
 template <class F>
 __global__ void k_mb_mul(uint64_t* out, int iters, uint32_t seed) {
@@ -255,48 +235,6 @@ __global__ void k_mb_mul_regmod(uint64_t* out, int iters, uint32_t seed) {
     for (int i = 0; i < 12; i++) acc ^= (uint64_t)(x.l[i] ^ y.l[i]) << (i & 31);
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
-__device__ uint32_t g_mb_zero = 0;
-__global__ void k_mb_mul_split(uint64_t* out, int iters, uint32_t seed) {
-    Fq x = Fq::one(), y = Fq::r2();
-    x.l[0] ^= seed + threadIdx.x;
-    y.l[1] ^= blockIdx.x;
-    const uint32_t z = *(volatile uint32_t*)&g_mb_zero;
-    for (int i = 0; i < iters; i++) {
-        x = Fq::mul_split(x, y, z);
-        y = Fq::mul_split(y, x, z);
-    }
-    uint64_t acc = 0;
-#pragma unroll
-    for (int i = 0; i < 12; i++) acc ^= (uint64_t)(x.l[i] ^ y.l[i]) << (i & 31);
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
-}
-__global__ void k_mb_mul13(uint64_t* out, int iters, uint32_t seed) {
-    Fq13 x = Fq13::one(), y = Fq13::one();
-    x.d[0] ^= (seed + threadIdx.x) & 0xffff;
-    y.d[1] ^= blockIdx.x & 0xffff;
-    for (int i = 0; i < iters; i++) {
-        x = Fq13::mul(x, y);
-        y = Fq13::mul(y, x);
-    }
-    uint64_t acc = 0;
-#pragma unroll
-    for (int i = 0; i < 13; i++) acc ^= (uint64_t)(x.d[i] ^ y.d[i]) << (i & 31);
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = acc;
-}
-__global__ void k_mb_madd13(uint64_t* out, int iters, uint32_t seed) {
-    XYZZ<Fq13> acc = XYZZ<Fq13>::from_affine(Fq13::one(), Fq13::one());
-    Fq13 px = Fq13::one(), py = Fq13::one();
-    px.d[0] ^= (seed + threadIdx.x) & 0xffff;
-    py.d[1] ^= blockIdx.x & 0xffff;
-    for (int i = 0; i < iters; i++) {
-        acc.add_affine(px, py);
-        px.d[2] = (px.d[2] + 1) & Fq13::MASK;
-    }
-    uint64_t r = 0;
-#pragma unroll
-    for (int i = 0; i < 13; i++) r ^= (uint64_t)(acc.x.d[i] ^ acc.y.d[i] ^ acc.zz.d[i] ^ acc.zzz.d[i]) << (i & 31);
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = r;
-}
 
 cudaError_t microbench_run(int kind, int blocks, int threads, int iters, uint64_t* scratch, double* ops_per_launch,
                            cudaStream_t st) {
@@ -310,14 +248,10 @@ cudaError_t microbench_run(int kind, int blocks, int threads, int iters, uint64_
         case 5: k_mb_wide_carry<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 24.0 * iters; break;
         case 6: k_mb_addc<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 96.0 * iters; break;
         case 7: k_mb_imad<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 64.0 * iters; break;
-        case 8: k_mb_imad_hi<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 64.0 * iters; break;
-        case 11: k_mb_mul_split<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 2.0 * iters; break;
         case 12: k_mb_mul_regmod<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 2.0 * iters; break;
         case 13: k_mb_wide_carry_clean<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 24.0 * iters; break;
         case 14: k_mb_wide_plus_add<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 16.0 * iters; break;
         case 15: k_mb_mul_x2<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 4.0 * iters; break;
-        case 9: k_mb_mul13<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 2.0 * iters; break;
-        case 10: k_mb_madd13<<<blocks, threads, 0, st>>>(scratch, iters, 12345u); per_thread = 1.0 * iters; break;
         default: return cudaErrorInvalidValue;
     }
     CZK_LAUNCHED();

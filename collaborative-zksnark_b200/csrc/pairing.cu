@@ -142,6 +142,21 @@ int czk_groth16_verify(const uint64_t alpha_g1[12], const uint64_t vk_g2[72], co
                        const uint64_t* public_inputs, const uint64_t proof[48], const uint8_t proof_inf[3], int* ok) {
     if (!alpha_g1 || !vk_g2 || !gamma_abc_g1 || !ninst || (ninst > 1 && !public_inputs) || !proof || !proof_inf || !ok)
         return fail(nullptr, CZK_ERR_ARG, "czk_groth16_verify: null argument");
+    // The reference's proof points are typed values that passed CanonicalDeserialize (on the curve, in the order-r subgroup);
+    // raw limbs get the same checks here, through the wire-format code that already implements them: a point that fails
+    // is an argument error, not a "does not verify" (the Miller loop's inversions are undefined off the subgroup).
+    {
+        uint8_t buf[192], inf = 0;
+        uint64_t back[24];
+        const struct { int g2; const uint64_t* xy; uint8_t isinf; const char* name; } pts[3] = {
+            {0, proof, proof_inf[0], "proof.a"}, {1, proof + 12, proof_inf[1], "proof.b"}, {0, proof + 36, proof_inf[2], "proof.c"}};
+        for (const auto& pt : pts) {
+            const uint8_t f = pt.isinf ? 1 : 0;
+            int rc = pt.g2 ? czk_g2_serialize(pt.xy, &f, 1, 0, buf) : czk_g1_serialize(pt.xy, &f, 1, 0, buf);
+            if (rc == CZK_OK) rc = pt.g2 ? czk_g2_deserialize(buf, 1, 0, 1, back, &inf) : czk_g1_deserialize(buf, 1, 0, 1, back, &inf);
+            if (rc != CZK_OK) return fail(nullptr, CZK_ERR_ARG, std::string("czk_groth16_verify: ") + pt.name + " is not a point of the prime-order subgroup");
+        }
+    }
     // acc = gamma_abc[0] + sum_i x_i gamma_abc[i]   (prepare_inputs, verifier.rs:23-43)
     HG1 acc = HG1::from_affine(HFq::from_limbs(gamma_abc_g1), HFq::from_limbs(gamma_abc_g1 + 6));
     for (size_t i = 1; i < ninst; i++) {

@@ -4,7 +4,6 @@
 #include <cstring>
 #include "../../collaborative-zksnark_b200/csrc/ec.cuh"
 #include "../../collaborative-zksnark_b200/csrc/msm_digits.cuh"
-#include "../../collaborative-zksnark_b200/csrc/fq13.cuh"
 #include "../../collaborative-zksnark_b200/csrc/fq_inverse.cuh"
 
 using namespace czk;
@@ -133,28 +132,6 @@ EXPORT void emu_signed_digits(int32_t* out, const uint64_t* scalar_canonical, un
     signed_digits(s, c, nwin, out);
 }
 
-// 13 x 29-bit digit field (csrc/fq13.cuh): op on values given / returned in the reference (12-limb, R = 2^384) form
-EXPORT void emu_fq13_binop(uint64_t* r, const uint64_t* a, const uint64_t* b, size_t n, int op) {
-    for (size_t i = 0; i < n; i++) {
-        Fq13 x = Fq13::from_std(ld<Fq>(a + 6 * i)), y = Fq13::from_std(ld<Fq>(b + 6 * i));
-        Fq13 z = op == 0 ? Fq13::mul(x, y) : op == 1 ? Fq13::add(x, y) : op == 2 ? Fq13::sub(x, y) : Fq13::neg(x);
-        st(r + 6 * i, z.to_std());
-    }
-}
-EXPORT int emu_g1_sum13(uint64_t* out_xy, const uint64_t* xy, const uint8_t* sign, size_t n) {
-    XYZZ<Fq13> acc = XYZZ<Fq13>::infinity();
-    for (size_t i = 0; i < n; i++) {
-        Fq13 x = Fq13::from_std(ld<Fq>(xy + 12 * i)), y = Fq13::from_std(ld<Fq>(xy + 12 * i + 6));
-        if (sign && sign[i]) y = Fq13::neg(y);
-        acc.add_affine(x, y);
-    }
-    if (acc.is_inf()) return 1;
-    XYZZ<Fq> s{acc.x.to_std(), acc.y.to_std(), acc.zz.to_std(), acc.zzz.to_std()};
-    Fq zi = Fq::inv_fermat(s.zz), zzzi = Fq::inv_fermat(s.zzz);
-    st(out_xy, Fq::mul(s.x, zi));
-    st(out_xy + 6, Fq::mul(s.y, zzzi));
-    return 0;
-}
 // The two-lane Fq2 product of the G2 bucket kernel (csrc/msm_batched.cu): lane 0 owns c0, lane 1 owns c1; each lane
 // computes ONE lazily reduced sum of two products (Fp::mul_sum2).  Here both lanes are evaluated one after the other.
 //   c0 = a0 b0 + (-5 a1) b1      c1 = a1 b0 + a0 b1

@@ -64,3 +64,24 @@ def test_groth16_verify_accepts_oracle_proofs_and_rejects_tampering(czk, oracle,
     # the proof survives the wire format
     back, inf = czk.groth16_proof_deserialize(czk.groth16_proof_serialize(res["proof"], res["proof_inf"]))
     assert czk.groth16_verify(pk, public, back, inf)
+
+
+def test_verify_rejects_points_off_the_curve_or_subgroup(czk, oracle, pymodel):
+    """czk_groth16_verify on raw limbs checks what the reference's typed, deserialised points guarantee: a proof element
+    that is not a point of the prime-order subgroup is an argument error (CZK_ERR_ARG), not a verdict."""
+    import random
+
+    rnd = random.Random(9)
+    n_sq = 4
+    toxic = [rnd.randrange(1, pymodel.R_MOD) for _ in range(7)]
+    pk = oracle.groth16_setup(n_sq, oracle.fr_from_ints(toxic))
+    chain = oracle.squaring_chain(oracle.fr_from_ints([rnd.randrange(pymodel.R_MOD)])[0], n_sq)
+    r, s = oracle.fr_from_ints([5]), oracle.fr_from_ints([7])
+    pf = oracle.groth16_prove(oracle.SCHEME_PLAIN, n_sq, [chain], r, s, pk)
+    proof, inf = pf["proof"].copy(), pf["proof_inf"].copy()
+    assert czk.groth16_verify(pk, chain[n_sq:n_sq + 1], proof, inf)
+    bad = proof.copy()
+    bad[6] ^= np.uint64(1)  # A.y: no longer on the curve
+    with pytest.raises(czk.CzkError) as e:
+        czk.groth16_verify(pk, chain[n_sq:n_sq + 1], bad, inf)
+    assert e.value.code == 2
