@@ -90,3 +90,35 @@ def test_device_groth16_golden(ctx, czk, oracle, e):
     got = czk.groth16_prove(ctx, czk.SCHEME_PLAIN, dpk, chain, r[0], s[0])
     assert digest(got["proof"]) == e["proof"]
     dpk.free()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# A second, independent implementation against the SAME frozen values: oracle/pymodel.py (Python big integers, textbook
+# affine group law, naive sum_i s_i P_i as in algebra/test-templates/src/msm.rs:6-14, a plain DFT) must reproduce every
+# golden MSM result and NTT digest.  The C oracle and this model share no code and no algorithm (Pippenger vs naive,
+# in-place radix-2 with derange vs recursive DFT), so agreement on the frozen vectors pins both to the mathematics.
+@pytest.mark.parametrize("e", VEC["msm"], ids=lambda e: f"{e['group']}-{e['n']}")
+def test_pymodel_msm_golden(oracle, pymodel, e):
+    G, xy, inf, sc = _msm_inputs(oracle, e)
+    pts = G.affine_to_ints(xy, inf)
+    scalars = oracle.fr_to_ints(sc)  # canonical integers
+    if e["group"] == "g1":
+        acc = None
+        for P, s in zip(pts, scalars):
+            if P is not None and s:
+                acc = pymodel.g1_add(acc, pymodel.g1_mul(P, s))
+    else:
+        acc = None
+        for P, s in zip(pts, scalars):
+            if P is not None and s:
+                acc = pymodel.g2_add(acc, pymodel.g2_mul(P, s))
+    assert acc == _pt(e["result"], e["group"])
+
+
+@pytest.mark.parametrize("e", VEC["ntt"], ids=lambda e: f"2^{e['log_d']}")
+def test_pymodel_ntt_golden(oracle, pymodel, e):
+    v = oracle.random_fr_mont(e["seed"], 1 << e["log_d"])
+    ints = oracle.fr_to_ints(v)
+    for name, inv, cos in (("fft", False, False), ("ifft", True, False), ("coset_fft", False, True), ("coset_ifft", True, True)):
+        out = pymodel.ntt(ints, inverse=inv, coset=cos)
+        assert digest(oracle.fr_from_ints(out)) == e[name], name
