@@ -690,9 +690,11 @@ int czk_bases_precompute(czk_ctx* ctx, czk_bases* b, unsigned c) {
         b->table = nullptr;
     }
     size_t pb = b->curve == 1 ? 96 : 192;
-    CUDA_TRY(ctx, cudaMalloc((void**)&b->table, (size_t)nwin * b->n * pb));
+    const unsigned ts = msm_table_stride_words(b->curve);
+    CUDA_TRY(ctx, cudaMalloc((void**)&b->table, (size_t)nwin * b->n * ts * 4));
+    if (ts * 4 != pb) CUDA_TRY(ctx, cudaMemsetAsync(b->table, 0, (size_t)nwin * b->n * ts * 4, ctx->stream));  // padding words
     // infinity bases must read as (0, 0) so the doubling chain leaves them alone; their scalars are zeroed anyway
-    CUDA_TRY(ctx, msm_precompute_table(b->curve, b->table, b->xy, b->n, c, nwin, ctx->stream));
+    CUDA_TRY(ctx, msm_precompute_table(b->curve, b->table, ts, b->xy, b->n, c, nwin, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     b->pre_c = c;
     b->pre_w = nwin;
@@ -703,7 +705,7 @@ int czk_bases_device_bytes(const czk_bases* b, uint64_t out[2]) {
     if (!b || !out) return CZK_ERR_ARG;
     const uint64_t pb = b->curve == 1 ? 96 : 192;
     out[0] = (uint64_t)b->n * pb + (b->inf ? b->n : 0);
-    out[1] = b->table ? (uint64_t)b->pre_w * b->n * pb : 0;
+    out[1] = b->table ? (uint64_t)b->pre_w * b->n * msm_table_stride_words(b->curve) * 4 : 0;
     return CZK_OK;
 }
 
@@ -715,7 +717,7 @@ int msm_bases_enqueue(czk_ctx* ctx, int lane, const czk_bases* b, size_t base_of
     if (!ctx || !b || !sc || !job || base_off + n > b->n || sc_off + n > sc->n) return fail(ctx, CZK_ERR_ARG, "czk_msm_bases: range");
     size_t pw = b->curve == 1 ? 24 : 48;
     if (b->table && n >= 1024) {
-        MsmConfig cfg = msm_merged_config(b->pre_c, b->n, base_off);
+        MsmConfig cfg = msm_merged_config(b->pre_c, b->n, base_off, msm_table_stride_words(b->curve));
         return msm_enqueue(ctx, lane, b->curve, b->table, b->inf ? b->inf + base_off : nullptr, (const uint32_t*)(sc->d + 4 * sc_off),
                            scalars_montgomery, n, &cfg, false, job);
     }
@@ -751,7 +753,7 @@ int czk_msm_bases_multi(czk_ctx* ctx, const czk_bases* const* b, int count, size
     if (tabled) {  // size the workspace for every set first, so that no later reservation moves the plan
         for (int k = 0; k < count; k++) {
             if (!b[k]->table || b[k]->pre_c != lead->pre_c || b[k]->n != lead->n) continue;
-            MsmConfig cfg = msm_merged_config(lead->pre_c, lead->n, base_off);
+            MsmConfig cfg = msm_merged_config(lead->pre_c, lead->n, base_off, msm_table_stride_words(b[k]->curve));
             CZK_TRY(ws_reserve(ctx, ctx->lanes[0], b[k]->curve, n, cfg));
         }
     }
@@ -780,7 +782,7 @@ int czk_msm_bases_multi(czk_ctx* ctx, const czk_bases* const* b, int count, size
             }
             return CZK_OK;
         }
-        MsmConfig cfg = msm_merged_config(o->pre_c, o->n, base_off);
+        MsmConfig cfg = msm_merged_config(o->pre_c, o->n, base_off, msm_table_stride_words(o->curve));
         CZK_TRY(msm_core(ctx, o->curve, o->table, o->inf ? o->inf + base_off : nullptr, (const uint32_t*)(sc->d + 4 * sc_off),
                          scalars_montgomery, n, out_xyz[k], &cfg, true));
         lap(k);

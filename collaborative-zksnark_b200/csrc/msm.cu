@@ -160,7 +160,8 @@ template <class F, bool PREFETCH, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                                          const uint4* __restrict__ items, uint32_t* __restrict__ queue,
                                                          const uint32_t* __restrict__ heavy, uint32_t* __restrict__ buckets,
-                                                         uint32_t* __restrict__ segsum, const uint32_t* __restrict__ gate) {
+                                                         uint32_t* __restrict__ segsum, const uint32_t* __restrict__ gate,
+                                                         const unsigned bstride) {
     constexpr int W = FieldIO<F>::W;
     if (gate && *gate == 0) return;  // the batched-affine path already produced the buckets
     const uint32_t nitems = queue[0], nheavy = queue[2];
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* __
                 }
                 if (PREFETCH && remaining) {
                     uint32_t e = sorted[pos];
-                    const uint32_t* p = bases + (size_t)(e & 0x7fffffffu) * (2 * W);
+                    const uint32_t* p = bases + (size_t)(e & 0x7fffffffu) * bstride;
                     nx = FieldIO<F>::load(p);
                     ny = FieldIO<F>::load(p + W);
                     nsign = e >> 31;
@@ -219,7 +220,7 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* __
                 sg = nsign;
             } else {  // G2: the prefetch registers would spill; load in place
                 uint32_t e = sorted[pos];
-                const uint32_t* p = bases + (size_t)(e & 0x7fffffffu) * (2 * W);
+                const uint32_t* p = bases + (size_t)(e & 0x7fffffffu) * bstride;
                 x = FieldIO<F>::load(p);
                 y = FieldIO<F>::load(p + W);
                 sg = e >> 31;
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* __
             pos++;
             if (PREFETCH && remaining) {  // issue the next point's loads before the long addition
                 uint32_t e = sorted[pos];
-                const uint32_t* p = bases + (size_t)(e & 0x7fffffffu) * (2 * W);
+                const uint32_t* p = bases + (size_t)(e & 0x7fffffffu) * bstride;
                 nx = FieldIO<F>::load(p);
                 ny = FieldIO<F>::load(p + W);
                 nsign = e >> 31;
@@ -337,6 +338,7 @@ template <class F>
 static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const uint32_t* scalars, bool mont, size_t n,
                              const MsmConfig& cfg, MsmWorkspace& ws, cudaStream_t st, bool reuse_plan) {
     size_t total = (size_t)cfg.bwin * cfg.nb;
+    const unsigned bstride = cfg.base_stride ? cfg.base_stride : 2u * FieldIO<F>::W;
     cudaError_t e;
     if (ws.ev[2]) cudaEventRecord(ws.ev[2], st);
     if (!reuse_plan) {  // steps 1-3: digits, histogram, scan, scatter
@@ -399,7 +401,7 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
     if (ws.batched && n && (ws.batched_always || (n * cfg.nwin >= bat_min_entries && n * cfg.nwin >= total * bat_min_load))) {
         // tree of batched affine additions (msm_batched.cu).  The longest bucket (queue word 4, written by k_msm_seg_counts)
         // decides the number of halving rounds on the device: nothing is read back, the whole MSM is enqueued in one go
-        if ((e = msm_batched_accumulate(FieldIO<F>::W == 12 ? 1 : 2, bases, ws.sorted, ws.offsets, ws.hist, total, n * cfg.nwin, ws.queue + 4,
+        if ((e = msm_batched_accumulate(FieldIO<F>::W == 12 ? 1 : 2, bases, bstride, ws.sorted, ws.offsets, ws.hist, total, n * cfg.nwin, ws.queue + 4,
                                         ws.bat_a, ws.bat_b, ws.bat_prefix, ws.buckets, ws.queue + 3, ws.sm_count, st)) != cudaSuccess)
             return e;
         gate = ws.queue + 3;
@@ -413,7 +415,7 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
         size_t cap = (size_t)ws.sm_count * 2;
         unsigned blocks = (unsigned)(want < cap ? want : cap);
         k_msm_accumulate<F, (FieldIO<F>::W == 12), 2><<<blocks, 128, 0, st>>>(bases, ws.sorted, (const uint4*)ws.items, ws.queue, ws.heavy,
-                                                                               ws.buckets, ws.segsum, gate);
+                                                                               ws.buckets, ws.segsum, gate, bstride);
         CZK_LAUNCHED();
     }
     if (ws.ev[1]) cudaEventRecord(ws.ev[1], st);
@@ -467,14 +469,14 @@ cudaError_t msm_flags_differ(const uint8_t* a, const uint8_t* b, size_t n, uint3
 // thread i: slab w holds 2^(c w) * P_i.  One doubling chain per base; every slab entry is normalised to affine
 // (Fermat inversion): a one-off cost per CRS query, amortised over every proof made with the key.
 template <class F>
-__global__ void __launch_bounds__(128) k_msm_precompute(uint32_t* __restrict__ table, const uint32_t* __restrict__ bases, size_t n,
-                                                         unsigned c, unsigned nwin) {
+__global__ void __launch_bounds__(128) k_msm_precompute(uint32_t* __restrict__ table, const unsigned ts, const uint32_t* __restrict__ bases,
+                                                         size_t n, unsigned c, unsigned nwin) {
     constexpr int W = FieldIO<F>::W;
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     F x = FieldIO<F>::load(bases + i * (2 * W)), y = FieldIO<F>::load(bases + i * (2 * W) + W);
-    FieldIO<F>::store(table + i * (2 * W), x);
-    FieldIO<F>::store(table + i * (2 * W) + W, y);
+    FieldIO<F>::store(table + i * ts, x);
+    FieldIO<F>::store(table + i * ts + W, y);
     XYZZ<F> acc = XYZZ<F>::from_affine(x, y);
     if (x.is_zero() && y.is_zero()) acc = XYZZ<F>::infinity();  // infinity placeholder: never addressed (scalar zeroed)
     for (unsigned w = 1; w < nwin; w++) {
@@ -486,18 +488,18 @@ __global__ void __launch_bounds__(128) k_msm_precompute(uint32_t* __restrict__ t
             oy = F::mul(acc.y, F::mul(inv, acc.zz));
             acc = XYZZ<F>::from_affine(ox, oy);
         }
-        FieldIO<F>::store(table + ((size_t)w * n + i) * (2 * W), ox);
-        FieldIO<F>::store(table + ((size_t)w * n + i) * (2 * W) + W, oy);
+        FieldIO<F>::store(table + ((size_t)w * n + i) * ts, ox);
+        FieldIO<F>::store(table + ((size_t)w * n + i) * ts + W, oy);
     }
 }
-cudaError_t msm_precompute_table(int curve, uint32_t* table, const uint32_t* bases, size_t n, unsigned c, unsigned nwin,
+cudaError_t msm_precompute_table(int curve, uint32_t* table, unsigned tstride, const uint32_t* bases, size_t n, unsigned c, unsigned nwin,
                                  cudaStream_t st) {
     if (!n) return cudaSuccess;
     unsigned blocks = (unsigned)((n + 127) / 128);
     if (curve == 1) {
-        k_msm_precompute<Fq><<<blocks, 128, 0, st>>>(table, bases, n, c, nwin);
+        k_msm_precompute<Fq><<<blocks, 128, 0, st>>>(table, tstride, bases, n, c, nwin);
     } else {
-        k_msm_precompute<Fq2><<<blocks, 128, 0, st>>>(table, bases, n, c, nwin);
+        k_msm_precompute<Fq2><<<blocks, 128, 0, st>>>(table, tstride, bases, n, c, nwin);
     }
     CZK_LAUNCHED();
     return cudaGetLastError();

@@ -34,6 +34,10 @@ struct MsmConfig {
     unsigned bwin = 0;
     size_t table_stride = 0;  // merged: points per window slab of the table (= length of the uploaded base array)
     size_t table_off = 0;     // merged: index of the first base of this MSM inside a slab
+    // words from one point record of `bases` to the next (0: packed x | y).  G1 table records are padded from 96 to 128
+    // bytes so that a gather touches exactly one 128-byte line: with packed records half of them straddle two lines and
+    // the measured DRAM traffic of round 0 was 1.5 lines per gather (profiles/r2_summary.md)
+    unsigned base_stride = 0;
 };
 
 // window size for the merged form: accumulation is n * ceil(254/c) additions, reduction ~3.3 * 2^(c-1)
@@ -45,7 +49,7 @@ inline unsigned msm_merged_window(size_t n) {
     unsigned c = lg >= 23 ? 20 : (lg >= 18 ? 17 : (lg >= 14 ? 16 : (lg > 10 ? lg - 2 : 8)));
     return c;
 }
-inline MsmConfig msm_merged_config(unsigned c, size_t stride, size_t off) {
+inline MsmConfig msm_merged_config(unsigned c, size_t stride, size_t off, unsigned base_stride = 0) {
     MsmConfig cfg;
     cfg.c = c;
     cfg.nwin = msm_num_windows(c);
@@ -59,6 +63,7 @@ inline MsmConfig msm_merged_config(unsigned c, size_t stride, size_t off) {
     cfg.bwin = 1;
     cfg.table_stride = stride;
     cfg.table_off = off;
+    cfg.base_stride = base_stride;
     return cfg;
 }
 
@@ -146,15 +151,19 @@ size_t msm_point_words(int curve);  // 4 coordinates
 // unless an addition without an affine formula was met, in which case *flag becomes non-zero and the caller's XYZZ
 // kernel must run.  pa / pb / prefix: scratch of the sizes msm_batched_bytes reports.
 size_t msm_batched_bytes(int curve, size_t entries, size_t nb, size_t* pa, size_t* pb, size_t* pre);
-cudaError_t msm_batched_accumulate(int curve, const uint32_t* bases, const uint32_t* sorted, const uint32_t* ends,
+// bstride: words between consecutive point records of `bases` (2 W when packed)
+cudaError_t msm_batched_accumulate(int curve, const uint32_t* bases, unsigned bstride, const uint32_t* sorted, const uint32_t* ends,
                                    const uint32_t* hist, size_t nb, size_t entries, const uint32_t* maxlen_dev, uint32_t* pa,
                                    uint32_t* pb, uint32_t* prefix, uint32_t* buckets, uint32_t* flag, int sm_count, cudaStream_t st);
 // out[i] = 1 / in[i] in Fq (Montgomery), 0 -> 0: the block inversion of the batched path, exposed for its parity test
 cudaError_t fq_inverse_batch(const uint32_t* in, uint32_t* out, size_t n, cudaStream_t st);
 
 // table[w * n + i] = 2^(c w) * bases[i] as affine points, w < nwin (slab 0 is a copy of the input)
-cudaError_t msm_precompute_table(int curve, uint32_t* table, const uint32_t* bases, size_t n, unsigned c, unsigned nwin,
+// tstride: words between consecutive records of the table (>= 2 W)
+cudaError_t msm_precompute_table(int curve, uint32_t* table, unsigned tstride, const uint32_t* bases, size_t n, unsigned c, unsigned nwin,
                                  cudaStream_t st);
+// record stride (words) of a merged-window table: G1 records are padded to one 128-byte line
+inline unsigned msm_table_stride_words(int curve) { return curve == 1 ? 32u : 48u; }
 
 // synthetic-input helper: out[i] = (k0 + i kstep + i^2 kquad) * base as affine points (x | y); quad2_xy = the affine
 // point 2 kquad * base (device memory).  The quadratic term matters: with a plain arithmetic progression every

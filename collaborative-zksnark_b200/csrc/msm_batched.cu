@@ -35,6 +35,7 @@ struct BatGeom {
     const uint32_t* hist;  // bucket lengths L_0
     uint32_t nb;           // buckets (all windows)
     int r;                 // the round whose array is the INPUT
+    uint32_t bstride;      // words between consecutive point records of `bases` (round 0 only)
 };
 __device__ __forceinline__ uint32_t bat_start(const BatGeom& g, uint32_t b, int r) {
     uint32_t s = g.ends[b] - g.hist[b];
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(BAT_THREADS, MINB)
     // descriptor of the slot whose small operands are in flight: bit 0 live, bit 1 pair; m_pos = its first input position
     uint32_t m_fl = 0, m_pos = 0;
     auto point_ptr = [&](uint32_t pos, uint32_t e) -> const uint32_t* {
-        return FIRST ? bases + (size_t)(e & 0x7fffffffu) * (2 * W) : in + (size_t)pos * (2 * W);
+        return FIRST ? bases + (size_t)(e & 0x7fffffffu) * g.bstride : in + (size_t)pos * (2 * W);
     };
     auto ldp = [&](const uint32_t* q) -> F { return FIRST ? FieldIO<F>::load(q) : FieldIO<F>::load_rw(q); };
     auto fetch_entries = [&](int par) {
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(G2L_THREADS, MINB)
     const Fq one = h ? Fq::zero() : Fq::one();  // this lane's component of 1
     uint32_t m_fl = 0, m_pos = 0;
     auto point_ptr = [&](uint32_t pos, uint32_t e) -> const uint32_t* {
-        return (FIRST ? bases + (size_t)(e & 0x7fffffffu) * (2 * W) : in + (size_t)pos * (2 * W)) + HW * h;
+        return (FIRST ? bases + (size_t)(e & 0x7fffffffu) * g.bstride : in + (size_t)pos * (2 * W)) + HW * h;
     };
     auto ldp = [&](const uint32_t* q) -> Fq { return FIRST ? FieldIO<Fq>::load(q) : FieldIO<Fq>::load_rw(q); };
     auto fetch_entries = [&](int par) {
@@ -756,7 +757,7 @@ size_t msm_batched_bytes(int curve, size_t entries, size_t nb, size_t* pa, size_
 #endif
 constexpr int G2L_MINB = 2;  // 2 blocks of 256 threads at 128 registers
 template <class F>
-static cudaError_t msm_batched_t(const uint32_t* bases, const uint32_t* sorted, const uint32_t* ends, const uint32_t* hist,
+static cudaError_t msm_batched_t(const uint32_t* bases, unsigned bstride, const uint32_t* sorted, const uint32_t* ends, const uint32_t* hist,
                                  size_t nb, size_t entries, const uint32_t* maxlen_p, uint32_t* pa, uint32_t* pb, uint32_t* prefix,
                                  uint32_t* buckets, uint32_t* flag, int sm_count, cudaStream_t st) {
     constexpr int MINB = BatTuning<F>::MINB;
@@ -768,7 +769,7 @@ static cudaError_t msm_batched_t(const uint32_t* bases, const uint32_t* sorted, 
     // caller caps it; rounds that are not needed return at once (bat_round_runs), and k_bat_finish walks whatever is left
     int launched = 1;
     while (launched < 26 && bat_len_after((uint32_t)(entries > 0xffffffffull ? 0xffffffffu : entries), launched) > walk) launched++;
-    BatGeom g{ends, hist, (uint32_t)nb, 0};
+    BatGeom g{ends, hist, (uint32_t)nb, 0, bstride ? bstride : 2u * FieldIO<F>::W};
     uint32_t* bufs[2] = {pa, pb};
     constexpr size_t smem = LANES ? g2l_smem_bytes() : bat_smem_bytes<F>();
     static const cudaError_t attr = [] {
@@ -806,12 +807,12 @@ static cudaError_t msm_batched_t(const uint32_t* bases, const uint32_t* sorted, 
     return cudaGetLastError();
 }
 
-cudaError_t msm_batched_accumulate(int curve, const uint32_t* bases, const uint32_t* sorted, const uint32_t* ends,
+cudaError_t msm_batched_accumulate(int curve, const uint32_t* bases, unsigned bstride, const uint32_t* sorted, const uint32_t* ends,
                                    const uint32_t* hist, size_t nb, size_t entries, const uint32_t* maxlen_dev, uint32_t* pa,
                                    uint32_t* pb, uint32_t* prefix, uint32_t* buckets, uint32_t* flag, int sm_count, cudaStream_t st) {
     if (curve == 1)
-        return msm_batched_t<Fq>(bases, sorted, ends, hist, nb, entries, maxlen_dev, pa, pb, prefix, buckets, flag, sm_count, st);
-    return msm_batched_t<Fq2>(bases, sorted, ends, hist, nb, entries, maxlen_dev, pa, pb, prefix, buckets, flag, sm_count, st);
+        return msm_batched_t<Fq>(bases, bstride, sorted, ends, hist, nb, entries, maxlen_dev, pa, pb, prefix, buckets, flag, sm_count, st);
+    return msm_batched_t<Fq2>(bases, bstride, sorted, ends, hist, nb, entries, maxlen_dev, pa, pb, prefix, buckets, flag, sm_count, st);
 }
 
 }  // namespace czk
