@@ -289,7 +289,7 @@ def run_plonk(args):
             "dtype": "u32 limbs (Montgomery Fr/Fq), integer", "data": "synthetic",
             "config": {"workload": f"plonk wiring argument {args.scheme} over a 2^{args.log_n} domain BLS12-377, one party per GPU "
                                    "(4 KZG10 commitments, 9 openings, 16 transforms per component, batch division, prefix products, 2 Beaver products)",
-                       "parties": world, "l2": "256 MiB flush write between iterations",
+                       "parties": world, "l2": "256 MiB flush write between iterations", "share_transport": ctx.share_transport,
                        "transcript": "stand-in (SplitMix64 over absorbed limbs); the reference's Blake2s/ChaCha transcript plugs in through czk_plonk_transcript"},
             "clocks": clocks,
             "e2e": {"value": ms_e2e, "unit": "ms", "h2d_bytes_per_step": int((3 if spdz else 2) * D * 32), "d2h_bytes_per_step": int(2 * 1200)},
@@ -485,6 +485,7 @@ def main():
         "dtype": "u32 limbs (Montgomery Fr/Fq), integer", "data": "synthetic",
         "config": {"workload": f"groth16 {args.scheme} 2^{args.log_n} constraints (D=2^{D.bit_length() - 1}) BLS12-377, one party per GPU",
                    "parties": world, "l2": "256 MiB flush write between iterations",
+                   "share_transport": ctx.share_transport,
                    "bases": ("real CRS generated on the device from seeded toxic waste (czk_groth16_setup); the proof is verified after the timed region"
                              if key_kind == "real" else "device-generated synthetic CRS of the reference's shapes"),
                    "proof_verified": verified,

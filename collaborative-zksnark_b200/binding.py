@@ -111,6 +111,7 @@ _SIGS = {
     "czk_gsz_check_products": (C.c_int, [C.c_void_p, u64p]),
     "czk_gsz_stats": (C.c_int, [C.c_void_p, u64p]),
     "czk_net_link_bytes": (C.c_int, [C.c_void_p, u64p]),
+    "czk_net_share_transport": (C.c_int, [C.c_void_p]),
     "czk_diag_sim_batch_open": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                                           C.c_size_t, C.POINTER(C.c_uint32)]),
     "czk_diag_sim_beaver_mul": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
@@ -492,6 +493,11 @@ class Context:
         n = x_sh.n if n is None else n
         self._chk(self.lib.czk_beaver_batch_mul(self.h, scheme, x_sh.h, x_mac.h if x_mac is not None else None, y_sh.h,
                                                 y_mac.h if y_mac is not None else None, n))
+
+    @property
+    def share_transport(self) -> str:
+        return {1: "nvlink peer memory (CUDA IPC)", -1: "nccl send/recv + all-gather", 0: "undecided / single party"}[
+            self.lib.czk_net_share_transport(self.h)]
 
     def ntt_batch(self, vecs, log_d: int, op: int):
         """The same transform over several device vectors in one grid per pass (czk_ntt_vec_batch).

@@ -894,6 +894,7 @@ int czk_net_init(czk_ctx* ctx, int rank, int nranks, const uint8_t nccl_unique_i
 }
 int czk_net_init_single(czk_ctx* ctx) { return czk_net_init(ctx, 0, 1, nullptr); }
 void czk_net_deinit(czk_ctx* ctx) {
+    if (ctx) sh_p2p_release(ctx);
     if (ctx && ctx->comm) {
         cudaStreamSynchronize(ctx->stream);
         nccl_api().CommDestroy(ctx->comm);

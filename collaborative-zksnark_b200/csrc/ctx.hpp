@@ -125,6 +125,15 @@ struct MsmJob {
 };
 constexpr int CZK_MSM_LANES = 2;
 
+// A buffer of this rank that the other ranks of the box address directly (CUDA IPC over NVLink peer memory): `local` is this
+// rank's allocation, peer[q] is rank q's allocation mapped into this process (peer[rank] == local).
+constexpr int CZK_P2P_MAX = 16;
+struct P2PBuf {
+    uint32_t* local = nullptr;
+    size_t cap = 0;
+    uint32_t* peer[CZK_P2P_MAX] = {nullptr};
+};
+
 struct czk_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -141,6 +150,10 @@ struct czk_ctx {
     ncclComm_t comm = nullptr;
     uint64_t stats[5] = {0, 0, 0, 0, 0};  // mpc-net's own accounting (what the reference would count)
     uint64_t link_bytes[2] = {0, 0};      // bytes this rank actually sent / received over NVLink
+    // share opens over peer memory (shares.cu): 0 = not probed yet, 1 = every rank can address every other, -1 = NCCL exchange
+    int p2p_state = 0;
+    P2PBuf p2p_send, p2p_opened, p2p_sigma;
+    uint32_t* p2p_sync = nullptr;  // N words: the tiny all-gather that orders the kernels of different ranks
     GszState gsz;
     // kernel timing of the MSM (CUDA events on the launching stream), per curve: [0] G1, [1] G2
     double acc_ms[2] = {0, 0}, msm_ms[2] = {0, 0}, acc_terms[2] = {0, 0}, acc_entries[2] = {0, 0};
@@ -155,6 +168,7 @@ int msm_collect(czk_ctx* ctx, MsmJob* job, uint64_t* out_xyz, double* device_ms)
 // shares.cu: the Beaver product without the final verdict read-back, and the read-back itself (one stream synchronisation)
 int sh_beaver_mul_enqueue(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_mac, const czk_vec* y_sh, const czk_vec* y_mac, size_t n);
 int sh_collect_flags(czk_ctx* ctx, const char* what);
+void sh_p2p_release(czk_ctx* ctx);  // unmap / free the peer-addressable buffers (before the communicator goes away)
 
 inline int fail(czk_ctx* ctx, int code, const std::string& msg) {
     czk_tls_error() = msg;

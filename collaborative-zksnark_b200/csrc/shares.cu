@@ -262,8 +262,10 @@ static ShPtrs sh_nccl_sources(const czk_ctx* ctx, const uint32_t* send, const ui
 
 // The whole job on this rank.  Leaves the opened values in j.opened[0 .. total) (on every rank) and, for SPDZ, the verdict of
 // this rank's slice in *j.flag; the caller reads the flags back (sh_collect_flags) when it needs the answer.
+static int sh_reserve(czk_ctx* ctx, const ShShape& s, ShJob& j);
 static int sh_run_nccl(czk_ctx* ctx, const ShShape& s, ShJob& j) {
     const int N = ctx->nranks;
+    CZK_TRY(sh_reserve(ctx, s, j));
     const bool spdz = s.scheme == CZK_SCHEME_SPDZ;
     const size_t slice_bytes = s.m * 32;
     CZK_TRY(sh_launch_pack(ctx, s, j));
@@ -296,6 +298,163 @@ static int sh_run_nccl(czk_ctx* ctx, const ShShape& s, ShJob& j) {
     return CZK_OK;
 }
 
+// ------------------------------------------------------------------------------------------ over NVLink peer memory
+// Inside one NVSwitch domain every rank can address every other rank's HBM.  The exchange buffers are then allocated once,
+// exported with CUDA IPC and mapped by every peer; an open needs NO bulk collective: the reduce kernel of rank q reads slice
+// q of every peer's send buffer through its NVLink mapping and writes the sum into every peer's `opened` buffer - the
+// reduce-scatter and the all-gather of the NCCL path fused into one kernel - and the sigma check reads the peers' sigma
+// slices the same way.  What remains of NCCL is a 4-byte all-gather between the kernels, used as the barrier that orders
+// "every rank has packed" before "any rank reads", and "every rank has written my opened buffer" before I read it.
+//   pack -> barrier -> reduce (P2P loads, P2P stores) -> barrier -> after_open -> barrier -> check (P2P loads)
+// Buffer reuse across consecutive opens is safe by the same barriers (a rank joins barrier 1 of open k + 1 only after its
+// own kernels of open k, so nobody's send / sigma buffer is rewritten while a peer still reads it).
+// CZK_SHARE_TRANSPORT=nccl keeps the send/recv exchange; the probe falls back to it when any rank cannot map any peer.
+static int sh_allgather_host(czk_ctx* ctx, const void* send, void* recv, size_t bytes) { return czk_net_allgather_host(ctx, send, recv, bytes); }
+
+void sh_p2p_release(czk_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    bool mapped = false;
+    for (P2PBuf* b : {&ctx->p2p_send, &ctx->p2p_opened, &ctx->p2p_sigma})
+        for (int q = 0; q < CZK_P2P_MAX; q++)
+            if (b->peer[q] && b->peer[q] != b->local) {
+                cudaIpcCloseMemHandle(b->peer[q]);
+                b->peer[q] = nullptr;
+                mapped = true;
+            }
+    if (mapped && ctx->comm && ctx->nranks > 1) {  // every rank has unmapped before anybody frees (deinit is collective)
+        int token = 1, tokens[CZK_P2P_MAX];
+        czk_net_allgather_host(ctx, &token, tokens, sizeof(int));
+    }
+    for (P2PBuf* b : {&ctx->p2p_send, &ctx->p2p_opened, &ctx->p2p_sigma}) {
+        cudaFree(b->local);
+        *b = P2PBuf();
+    }
+    cudaFree(ctx->p2p_sync);
+    ctx->p2p_sync = nullptr;
+    ctx->p2p_state = 0;
+}
+
+// decide once per communicator, collectively: every rank must be able to reach every other rank's device
+static int sh_p2p_probe(czk_ctx* ctx) {
+    if (ctx->p2p_state != 0) return CZK_OK;
+    const int N = ctx->nranks;
+    int ok = N > 1 && N <= CZK_P2P_MAX;
+    const char* env = getenv("CZK_SHARE_TRANSPORT");
+    if (env && std::string(env) == "nccl") ok = 0;
+    int devs[CZK_P2P_MAX] = {0};
+    int mine = ctx->device;
+    if (N > 1) CZK_TRY(sh_allgather_host(ctx, &mine, devs, sizeof(int)));
+    for (int q = 0; q < N && ok; q++) {
+        if (q == ctx->rank) continue;
+        if (devs[q] == ctx->device) {  // two ranks on one device cannot use IPC mappings of each other
+            ok = 0;
+            break;
+        }
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, ctx->device, devs[q]) != cudaSuccess || !can) ok = 0;
+    }
+    int all[CZK_P2P_MAX] = {0};
+    if (N > 1) CZK_TRY(sh_allgather_host(ctx, &ok, all, sizeof(int)));
+    for (int q = 0; q < N; q++) ok &= all[q];
+    if (ok) {
+        if (cudaMalloc((void**)&ctx->p2p_sync, 4 * CZK_P2P_MAX) != cudaSuccess) ok = 0;
+        else cudaMemsetAsync(ctx->p2p_sync, 0, 4 * CZK_P2P_MAX, ctx->stream);
+    }
+    ctx->p2p_state = ok ? 1 : -1;
+    return CZK_OK;
+}
+
+// grow a peer-addressable buffer: collective (every rank calls it with the same size at the same point of the protocol)
+static int sh_p2p_reserve(czk_ctx* ctx, P2PBuf& b, size_t bytes) {
+    if (bytes <= b.cap) return CZK_OK;
+    const int N = ctx->nranks;
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    // nobody may still be reading the old mapping: the host all-gathers below are the barrier
+    for (int q = 0; q < N; q++)
+        if (b.peer[q] && b.peer[q] != b.local) {
+            cudaIpcCloseMemHandle(b.peer[q]);
+            b.peer[q] = nullptr;
+        }
+    int token = 1, tokens[CZK_P2P_MAX];
+    CZK_TRY(sh_allgather_host(ctx, &token, tokens, sizeof(int)));  // every rank has unmapped
+    cudaFree(b.local);
+    b.local = nullptr;
+    b.cap = 0;
+    const size_t want = bytes + bytes / 8;
+    CUDA_TRY(ctx, cudaMalloc((void**)&b.local, want));
+    cudaIpcMemHandle_t mine, all[CZK_P2P_MAX];
+    CUDA_TRY(ctx, cudaIpcGetMemHandle(&mine, b.local));
+    CZK_TRY(sh_allgather_host(ctx, &mine, all, sizeof mine));
+    for (int q = 0; q < N; q++) {
+        if (q == ctx->rank) {
+            b.peer[q] = b.local;
+            continue;
+        }
+        void* p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, all[q], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(ctx, CZK_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
+        b.peer[q] = (uint32_t*)p;
+    }
+    b.cap = want;
+    return CZK_OK;
+}
+
+static int sh_barrier(czk_ctx* ctx) {
+    ncclResult_t r = nccl_api().AllGather(ctx->p2p_sync + ctx->rank, ctx->p2p_sync, 4, ncclUint8, ctx->comm, ctx->stream);
+    if (r != ncclSuccess) return fail(ctx, CZK_ERR_NCCL, std::string("ncclAllGather(barrier): ") + nccl_api().GetErrorString(r));
+    return CZK_OK;
+}
+
+// The whole job over peer memory.  Same contract as sh_run_nccl: opened values in j.opened[0 .. total) on every rank,
+// this rank's verdict in *j.flag.
+static int sh_run_p2p(czk_ctx* ctx, const ShShape& s, ShJob& j) {
+    const int N = ctx->nranks, me = ctx->rank;
+    const bool spdz = s.scheme == CZK_SCHEME_SPDZ;
+    const size_t bytes = s.padded * 32, slice_words = s.m * 8;
+    CZK_TRY(sh_p2p_reserve(ctx, ctx->p2p_send, bytes));
+    CZK_TRY(sh_p2p_reserve(ctx, ctx->p2p_opened, bytes));
+    if (spdz) CZK_TRY(sh_p2p_reserve(ctx, ctx->p2p_sigma, bytes));
+    j.send = ctx->p2p_send.local;
+    j.opened = ctx->p2p_opened.local;
+    j.sigma = spdz ? ctx->p2p_sigma.local : nullptr;
+    CZK_TRY(sh_launch_pack(ctx, s, j));
+    CZK_TRY(sh_barrier(ctx));  // every rank has packed
+    {
+        ShPtrs src{};
+        ShDsts dst{};
+        for (int p = 0; p < N; p++) {
+            src.p[p] = ctx->p2p_send.peer[p] + (size_t)me * slice_words;    // slice `me` of rank p's send buffer (NVLink loads)
+            dst.p[p] = ctx->p2p_opened.peer[p] + (size_t)me * slice_words;  // ... summed into every rank's opened buffer (NVLink stores)
+        }
+        k_sh_reduce_slices<<<sh_grid(s.m), 256, 0, ctx->stream>>>(dst, N, src, N, s.m); CZK_LAUNCHED();
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->link_bytes[0] += s.m * 32 * (uint64_t)(N - 1);  // stores into the peers
+        ctx->link_bytes[1] += s.m * 32 * (uint64_t)(N - 1);  // loads from the peers
+    }
+    CZK_TRY(sh_barrier(ctx));  // every rank has written its slice into my opened buffer
+    CZK_TRY(sh_launch_after_open(ctx, s, j));
+    if (spdz) {
+        CZK_TRY(sh_barrier(ctx));  // every rank's sigma is complete
+        ShPtrs src{};
+        for (int p = 0; p < N; p++) src.p[p] = ctx->p2p_sigma.peer[p] + (size_t)me * slice_words;
+        k_sh_check_zero<<<sh_grid(s.m), 256, 0, ctx->stream>>>(src, N, s.m, j.flag); CZK_LAUNCHED();
+        CUDA_TRY(ctx, cudaGetLastError());
+        ctx->link_bytes[1] += s.m * 32 * (uint64_t)(N - 1);
+    }
+    return CZK_OK;
+}
+
+// transport choice for this communicator (collective on first use)
+static int sh_run(czk_ctx* ctx, const ShShape& s, ShJob& j) {
+    if (ctx->nranks > 1) {
+        CZK_TRY(sh_p2p_probe(ctx));
+        if (ctx->p2p_state == 1) return sh_run_p2p(ctx, s, j);
+    }
+    return sh_run_nccl(ctx, s, j);
+}
+
 static int sh_reserve(czk_ctx* ctx, const ShShape& s, ShJob& j) {
     const size_t bytes = s.padded * 32;
     CZK_TRY(scratch_reserve(ctx, ctx->open_sx, bytes));
@@ -310,8 +469,6 @@ static int sh_reserve(czk_ctx* ctx, const ShShape& s, ShJob& j) {
         CZK_TRY(scratch_reserve(ctx, ctx->open_sigma, bytes));
         j.sigma = (uint32_t*)ctx->open_sigma.p;
     }
-    j.flag = ctx->flag;
-    j.rank = ctx->rank;
     return CZK_OK;
 }
 
@@ -352,11 +509,12 @@ int czk_batch_open(czk_ctx* ctx, int scheme, const czk_vec* sh, const czk_vec* m
     if (!n) return CZK_OK;
     const ShShape s = sh_shape(scheme, ctx->nranks, false, n);
     ShJob j;
-    CZK_TRY(sh_reserve(ctx, s, j));
+    j.flag = ctx->flag;
+    j.rank = ctx->rank;
     j.a_sh = (const uint32_t*)sh->d;
     j.a_mac = mac ? (const uint32_t*)mac->d : nullptr;
     sh_count_reference_open(ctx, scheme, n);
-    CZK_TRY(sh_run_nccl(ctx, s, j));
+    CZK_TRY(sh_run(ctx, s, j));
     CUDA_TRY(ctx, cudaMemcpyAsync(out_pub->d, j.opened, n * 32, cudaMemcpyDeviceToDevice, ctx->stream));
     if (scheme == CZK_SCHEME_SPDZ) return sh_collect_flags(ctx, "czk_batch_open");
     return CZK_OK;
@@ -385,7 +543,8 @@ int sh_beaver_mul_enqueue(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_ma
     if (!n) return CZK_OK;
     const ShShape s = sh_shape(scheme, ctx->nranks, true, n);
     ShJob j;
-    CZK_TRY(sh_reserve(ctx, s, j));
+    j.flag = ctx->flag;
+    j.rank = ctx->rank;
     j.a_sh = (const uint32_t*)x_sh->d;
     j.b_sh = (const uint32_t*)y_sh->d;
     j.a_mac = spdz ? (const uint32_t*)x_mac->d : nullptr;
@@ -394,8 +553,10 @@ int sh_beaver_mul_enqueue(czk_ctx* ctx, int scheme, czk_vec* x_sh, czk_vec* x_ma
     j.out_mac = spdz ? (uint32_t*)x_mac->d : nullptr;
     sh_count_reference_open(ctx, scheme, n);  // the reference opens s + x and o + y one after the other
     sh_count_reference_open(ctx, scheme, n);
-    return sh_run_nccl(ctx, s, j);
+    return sh_run(ctx, s, j);
 }
+
+int czk_net_share_transport(const czk_ctx* ctx) { return ctx ? ctx->p2p_state : 0; }
 
 int czk_net_link_bytes(const czk_ctx* ctx, uint64_t out[2]) {
     if (!ctx || !out) return CZK_ERR_ARG;

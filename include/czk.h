@@ -227,6 +227,11 @@ CZK_API int czk_gsz_stats(const czk_ctx* ctx, uint64_t out[2]);
  * of N-1 full messages, multi.rs:145-174 + channel.rs:50-75); the device path exchanges slices (see csrc/shares.cu), so
  * the two differ by design. */
 CZK_API int czk_net_link_bytes(const czk_ctx* ctx, uint64_t out[2]);
+/* How additive / SPDZ opens move their slices on this communicator: 1 = NVLink peer memory (every rank maps every other
+ * rank's exchange buffers with CUDA IPC; the reduce kernel loads from and stores to the peers directly, NCCL only orders the
+ * kernels), -1 = grouped ncclSend / ncclRecv + ncclAllGather (CZK_SHARE_TRANSPORT=nccl, or some peer not addressable),
+ * 0 = not decided yet (no open has run) or a single party. */
+CZK_API int czk_net_share_transport(const czk_ctx* ctx);
 /* N-party additive / SPDZ protocol arithmetic on ONE GPU: party q's vectors are sh[q] (mac[q]); the same kernels, slice
  * geometry and per-party constants as czk_batch_open / czk_beaver_batch_mul run for every simulated party, with the
  * collectives replaced by direct addressing between the parties' buffers.  flags_out[q] != 0: party q's slice of the

@@ -109,7 +109,7 @@ def main():
     assert (gotp["proof_share"]["open_pf_inf"] == expp["share_pf_inf"][rank]).all()
     kb.free()
     launch.barrier()
-    print(f"[rank {rank}/{world}] groth16 {args.scheme} n={n_sq}: parity ok; net {st}", flush=True)
+    print(f"[rank {rank}/{world}] groth16 {args.scheme} n={n_sq}: parity ok; net {st}; opens over {ctx.share_transport}; link bytes {ctx.net_link_bytes()}", flush=True)
     party.close()
 
 
