@@ -131,6 +131,20 @@ static int pk_finish(czk_ctx* ctx, czk_pk* pk) {
     return CZK_OK;
 }
 
+// a key under construction: freed (with whatever queries and tables it already holds) unless the constructor releases it
+struct PkGuard {
+    czk_ctx* ctx;
+    czk_pk* pk;
+    ~PkGuard() {
+        if (pk) czk_groth16_pk_free(ctx, pk);
+    }
+    czk_pk* release() {
+        czk_pk* p = pk;
+        pk = nullptr;
+        return p;
+    }
+};
+
 int czk_groth16_pk_upload(czk_ctx* ctx, size_t n_sq, const uint64_t* a_query, const uint8_t* a_inf, const uint64_t* b_g1_query,
                           const uint8_t* b1_inf, const uint64_t* b_g2_query, const uint8_t* b2_inf, const uint64_t* h_query,
                           const uint8_t* h_inf, const uint64_t* l_query, const uint8_t* l_inf, const uint64_t vk_g1[36],
@@ -138,6 +152,7 @@ int czk_groth16_pk_upload(czk_ctx* ctx, size_t n_sq, const uint64_t* a_query, co
     if (!ctx || !out || !n_sq || !a_query || !b_g1_query || !b_g2_query || !h_query || !l_query || !vk_g1 || !vk_g2)
         return fail(ctx, CZK_ERR_ARG, "czk_groth16_pk_upload: null argument");
     czk_pk* pk = new czk_pk();
+    PkGuard guard{ctx, pk};
     pk->n_sq = n_sq;
     pk->ncons = n_sq;
     pk->ninst = 2;
@@ -151,7 +166,7 @@ int czk_groth16_pk_upload(czk_ctx* ctx, size_t n_sq, const uint64_t* a_query, co
     std::memcpy(pk->vk_g1, vk_g1, sizeof pk->vk_g1);
     std::memcpy(pk->vk_g2, vk_g2, sizeof pk->vk_g2);
     CZK_TRY(pk_finish(ctx, pk));
-    *out = pk;
+    *out = guard.release();
     return CZK_OK;
 }
 
@@ -162,6 +177,7 @@ int czk_groth16_pk_upload_r1cs(czk_ctx* ctx, size_t ncons, size_t ninst, size_t 
     if (!ctx || !out || !ncons || !ninst || !a_query || !b_g1_query || !b_g2_query || !h_query || (nwit && !l_query) || !vk_g1 || !vk_g2)
         return fail(ctx, CZK_ERR_ARG, "czk_groth16_pk_upload_r1cs: null argument");
     czk_pk* pk = new czk_pk();
+    PkGuard guard{ctx, pk};
     pk->n_sq = 0;
     pk->ncons = ncons;
     pk->ninst = ninst;
@@ -179,7 +195,7 @@ int czk_groth16_pk_upload_r1cs(czk_ctx* ctx, size_t ncons, size_t ninst, size_t 
     std::memcpy(pk->vk_g1, vk_g1, sizeof pk->vk_g1);
     std::memcpy(pk->vk_g2, vk_g2, sizeof pk->vk_g2);
     CZK_TRY(pk_finish(ctx, pk));
-    *out = pk;
+    *out = guard.release();
     return CZK_OK;
 }
 
@@ -370,6 +386,7 @@ int czk_groth16_pk_gamma_abc(const czk_pk* pk, uint64_t* out, size_t ninst) {
 int czk_groth16_pk_synthetic(czk_ctx* ctx, size_t n_sq, uint64_t seed, czk_pk** out) {
     if (!ctx || !out || !n_sq) return fail(ctx, CZK_ERR_ARG, "czk_groth16_pk_synthetic: argument");
     czk_pk* pk = new czk_pk();
+    PkGuard guard{ctx, pk};
     pk->n_sq = n_sq;
     pk->ncons = n_sq;
     pk->ninst = 2;
@@ -390,7 +407,7 @@ int czk_groth16_pk_synthetic(czk_ctx* ctx, size_t n_sq, uint64_t seed, czk_pk** 
     czk_bases_free(ctx, v1);
     czk_bases_free(ctx, v2);
     CZK_TRY(pk_finish(ctx, pk));
-    *out = pk;
+    *out = guard.release();
     return CZK_OK;
 }
 

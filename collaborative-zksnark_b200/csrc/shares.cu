@@ -384,8 +384,11 @@ static int sh_p2p_reserve(czk_ctx* ctx, P2PBuf& b, size_t bytes) {
     b.cap = 0;
     const size_t want = bytes + bytes / 8;
     CUDA_TRY(ctx, cudaMalloc((void**)&b.local, want));
+    // export, exchange, map - and agree on the outcome: if ANY rank could not map ANY peer, every rank drops the peer-memory
+    // transport for this communicator (p2p_state = -1) and the caller goes through the NCCL exchange instead
     cudaIpcMemHandle_t mine, all[CZK_P2P_MAX];
-    CUDA_TRY(ctx, cudaIpcGetMemHandle(&mine, b.local));
+    std::memset(&mine, 0, sizeof mine);
+    int ok = cudaIpcGetMemHandle(&mine, b.local) == cudaSuccess;
     CZK_TRY(sh_allgather_host(ctx, &mine, all, sizeof mine));
     for (int q = 0; q < N; q++) {
         if (q == ctx->rank) {
@@ -393,9 +396,22 @@ static int sh_p2p_reserve(czk_ctx* ctx, P2PBuf& b, size_t bytes) {
             continue;
         }
         void* p = nullptr;
-        cudaError_t e = cudaIpcOpenMemHandle(&p, all[q], cudaIpcMemLazyEnablePeerAccess);
-        if (e != cudaSuccess) return fail(ctx, CZK_ERR_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e));
-        b.peer[q] = (uint32_t*)p;
+        if (ok && cudaIpcOpenMemHandle(&p, all[q], cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) b.peer[q] = (uint32_t*)p;
+        else ok = 0;
+    }
+    cudaGetLastError();  // a failed IPC call must not poison later error checks
+    int oks[CZK_P2P_MAX] = {0};
+    CZK_TRY(sh_allgather_host(ctx, &ok, oks, sizeof(int)));
+    for (int q = 0; q < N; q++) ok &= oks[q];
+    if (!ok) {
+        for (int q = 0; q < N; q++)
+            if (b.peer[q] && b.peer[q] != b.local) cudaIpcCloseMemHandle(b.peer[q]);
+        for (int q = 0; q < N; q++) b.peer[q] = nullptr;
+        CZK_TRY(sh_allgather_host(ctx, &token, tokens, sizeof(int)));  // every rank has unmapped before anybody frees
+        cudaFree(b.local);
+        b.local = nullptr;
+        ctx->p2p_state = -1;
+        return CZK_OK;
     }
     b.cap = want;
     return CZK_OK;
@@ -414,8 +430,9 @@ static int sh_run_p2p(czk_ctx* ctx, const ShShape& s, ShJob& j) {
     const bool spdz = s.scheme == CZK_SCHEME_SPDZ;
     const size_t bytes = s.padded * 32, slice_words = s.m * 8;
     CZK_TRY(sh_p2p_reserve(ctx, ctx->p2p_send, bytes));
-    CZK_TRY(sh_p2p_reserve(ctx, ctx->p2p_opened, bytes));
-    if (spdz) CZK_TRY(sh_p2p_reserve(ctx, ctx->p2p_sigma, bytes));
+    if (ctx->p2p_state == 1) CZK_TRY(sh_p2p_reserve(ctx, ctx->p2p_opened, bytes));
+    if (ctx->p2p_state == 1 && spdz) CZK_TRY(sh_p2p_reserve(ctx, ctx->p2p_sigma, bytes));
+    if (ctx->p2p_state != 1) return sh_run_nccl(ctx, s, j);  // the mapping failed somewhere: agreed by all ranks (see sh_p2p_reserve)
     j.send = ctx->p2p_send.local;
     j.opened = ctx->p2p_opened.local;
     j.sigma = spdz ? ctx->p2p_sigma.local : nullptr;
