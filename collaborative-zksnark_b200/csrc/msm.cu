@@ -2,6 +2,7 @@
 #include "msm.cuh"
 
 #include <cstdlib>
+#include <cstring>
 
 #include "launch_count.hpp"
 #include "msm_io.cuh"
@@ -308,6 +309,66 @@ __global__ void __launch_bounds__(128) k_msm_bit_sums(const uint32_t* __restrict
     store_point<F>(partial + ((size_t)j * T + t) * (4 * W), acc);
 }
 
+// ------------------------------------------------------------------ 5a''. the same slice sums through a two-level grid
+// Write the weight v in [0, nb) as v = hi * L + lo (L = 2^lo_bits, H = nb / L; v = 0 has no bucket).  With the row sums
+// R_hi = sum_lo B_v and the column sums C_lo = sum_hi B_v, slice j < lo_bits is the sum of the C_lo whose index has bit j
+// set and slice lo_bits + j the sum of the R_hi whose index has bit j set; the top slice is the single bucket of weight
+// nb.  Two adds per bucket instead of (c - 1) / 2: the bit-slice kernel above is throughput bound on G2.
+// Block b < H sums row b, block H + b sums column b; GRID_THREADS threads stride over the L (or H) members, then a tree.
+constexpr int GRID_THREADS = 64;
+template <class F>
+__device__ __forceinline__ XYZZ<F> block_tree_sum(XYZZ<F> acc, XYZZ<F>* sm, unsigned tid) {
+    sm[tid] = acc;
+    __syncthreads();
+    for (unsigned s = GRID_THREADS / 2; s > 0; s >>= 1) {
+        if (tid < s) {
+            XYZZ<F> a = sm[tid];
+            a.add(sm[tid + s]);
+            sm[tid] = a;
+        }
+        __syncthreads();
+    }
+    return sm[0];
+}
+template <class F>
+__global__ void __launch_bounds__(GRID_THREADS) k_msm_grid_sums(const uint32_t* __restrict__ buckets, uint32_t* __restrict__ grid,
+                                                                 unsigned lo_bits, unsigned hi_bits) {
+    constexpr int W = FieldIO<F>::W;
+    __shared__ XYZZ<F> sm[GRID_THREADS];
+    const unsigned L = 1u << lo_bits, H = 1u << hi_bits, b = blockIdx.x, tid = threadIdx.x;
+    const bool row = b < H;
+    const unsigned fixed = row ? b : b - H, count = row ? L : H;
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    for (unsigned k = tid; k < count; k += GRID_THREADS) {
+        unsigned v = row ? fixed * L + k : k * L + fixed;
+        if (v) acc.add(load_point<F>(buckets + (size_t)(v - 1) * (4 * W)));
+    }
+    acc = block_tree_sum<F>(acc, sm, tid);
+    if (tid == 0) store_point<F>(grid + (size_t)b * (4 * W), acc);
+}
+// block j: slice j from the grid sums (grid[0..H) rows, grid[H..H+L) columns); the top slice copies bucket nb
+template <class F>
+__global__ void __launch_bounds__(GRID_THREADS) k_msm_grid_slices(const uint32_t* __restrict__ grid, const uint32_t* __restrict__ buckets,
+                                                                   uint32_t* __restrict__ out, unsigned lo_bits, unsigned hi_bits) {
+    constexpr int W = FieldIO<F>::W;
+    __shared__ XYZZ<F> sm[GRID_THREADS];
+    const unsigned L = 1u << lo_bits, H = 1u << hi_bits, j = blockIdx.x, tid = threadIdx.x;
+    XYZZ<F> acc = XYZZ<F>::infinity();
+    if (j == lo_bits + hi_bits) {
+        if (tid == 0) acc = load_point<F>(buckets + (size_t)(H * L - 1) * (4 * W));
+    } else {
+        const bool col = j < lo_bits;
+        const unsigned bit = col ? j : j - lo_bits, count = (col ? L : H) / 2;
+        const uint32_t* src = col ? grid + (size_t)H * (4 * W) : grid;
+        for (unsigned k = tid; k < count; k += GRID_THREADS) {
+            unsigned idx = ((((k >> bit) << 1) | 1u) << bit) | (k & ((1u << bit) - 1));
+            acc.add(load_point<F>(src + (size_t)idx * (4 * W)));
+        }
+    }
+    acc = block_tree_sum<F>(acc, sm, tid);
+    if (tid == 0) store_point<F>(out + (size_t)j * (4 * W), acc);
+}
+
 // ------------------------------------------------------------------ 5b. tree sums of the chunk results
 // block b sums in[b*count .. (b+1)*count) -> out[b]; run twice (chunks -> groups -> window) so that the first
 // level has windows*groups blocks instead of one block per window
@@ -428,6 +489,14 @@ static cudaError_t msm_run_t(const uint32_t* bases, const uint8_t* inf, const ui
     if (msm_uses_bit_sums(cfg)) {
         // merged windows: c bit-slice sums (the host tail recombines them with c - 1 doublings)
         nsums = cfg.c;
+        static const bool use_grid = [] { const char* e = getenv("CZK_MSM_REDUCE"); return !(e && !strcmp(e, "bits")); }();
+        if (use_grid) {
+            const unsigned top = 31 - __builtin_clz(cfg.nb), lo_bits = top / 2, hi_bits = top - lo_bits;
+            k_msm_grid_sums<F><<<(1u << lo_bits) + (1u << hi_bits), GRID_THREADS, 0, st>>>(ws.buckets, ws.partial, lo_bits, hi_bits); CZK_LAUNCHED();
+            k_msm_grid_slices<F><<<nsums, GRID_THREADS, 0, st>>>(ws.partial, ws.buckets, ws.winsum, lo_bits, hi_bits); CZK_LAUNCHED();
+            if (ws.ev[3]) cudaEventRecord(ws.ev[3], st);
+            return cudaGetLastError();
+        }
         nchunks = msm_bitsum_threads(cfg);
         rthreads = (size_t)nsums * nchunks;
         k_msm_bit_sums<F><<<dim3(nchunks / 128, nsums), 128, 0, st>>>(ws.buckets, ws.partial, cfg.nb, nchunks); CZK_LAUNCHED();
