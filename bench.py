@@ -178,7 +178,9 @@ def run_plonk_reference(args):
 
     o.build()
     threads = o.cpu_threads()
-    D = 1 << args.log_n
+    mixed = args.plonk_domain == "mixed"
+    D = (3 if mixed else 1) << args.log_n
+    dom = f"3*2^{args.log_n} (mixed-radix wire domain of 2^{args.log_n} gates)" if mixed else f"2^{args.log_n}"
     g1, _ = o.generators()
     ks = o.random_fr_mont(3, 2)
     powers = o.G1.gen_progression(g1, ks[0], ks[1], D, threads=threads)
@@ -193,11 +195,11 @@ def run_plonk_reference(args):
             times.append(dt)
     ms = sum(times) / len(times)
     cb = dict(value=ms, unit="ms", cores=threads, kind="port", log_n=args.log_n, steps_run=len(times),
-              sample=f"{len(times)} whole wiring proof(s) of one party over a 2^{args.log_n} domain on {threads} host threads, {ms:.1f} ms each")
+              sample=f"{len(times)} whole wiring proof(s) of one party over a {dom} domain on {threads} host threads, {ms:.1f} ms each")
     print(json.dumps({"impl": "reference", "metric": PLONK_METRIC.format(args.log_n), "value": ms, "unit": "ms", "n_gpus": args.gpus,
                       "steps": len(times), "warmup": max(0, min(args.warmup, 1)), "ms_per_step": ms, "higher_is_better": False, "scaling": "weak",
                       "vs_baseline": None, "dtype": "u64 limbs (Montgomery), integer", "data": "synthetic",
-                      "config": {"workload": f"plonk wiring argument spdz 2^{args.log_n} domain BLS12-377, one party's work on the host CPU (oracle port)",
+                      "config": {"workload": f"plonk wiring argument spdz over a {dom} domain BLS12-377, one party's work on the host CPU (oracle port)",
                                  "parties": args.gpus},
                       "cpu_baseline": cb, "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
     return 0
@@ -229,7 +231,9 @@ def run_plonk(args):
     ctx, rank, world = party.ctx, party.rank, party.world
     scheme = {"spdz": czk_b200.SCHEME_SPDZ, "additive": czk_b200.SCHEME_ADDITIVE, "plain": czk_b200.SCHEME_PLAIN}[args.scheme]
     spdz = args.scheme == "spdz"
-    D = 1 << args.log_n
+    mixed = args.plonk_domain == "mixed"
+    D = (3 if mixed else 1) << args.log_n
+    dom = f"3*2^{args.log_n} (mixed-radix wire domain of 2^{args.log_n} gates)" if mixed else f"2^{args.log_n}"
     powers = ctx.bases_synthetic(1, 0x377, D, 0).precompute(0)  # committer key: device-generated points of the right shape
     rng = np.random.Generator(np.random.PCG64(0x18))
 
@@ -251,10 +255,11 @@ def run_plonk(args):
         torch.cuda.synchronize()
         t = time.perf_counter()
         if resident:
-            res = czk_b200.plonk_prove_wiring(ctx, scheme, powers, args.log_n, p_dev, m_dev, w_dev, seed=seed)
+            res = czk_b200.plonk_prove_wiring(ctx, scheme, powers, args.log_n, p_dev, m_dev, w_dev, seed=seed, mixed=mixed)
         else:  # through host buffers: upload this party's shares and the public polynomial, read the proof back
             pv, wv = ctx.vec_from(p_pin), ctx.vec_from(w_pin)
-            res = czk_b200.plonk_prove_wiring(ctx, scheme, powers, args.log_n, pv, ctx.vec_from(p_pin) if spdz else None, wv, seed=seed)
+            res = czk_b200.plonk_prove_wiring(ctx, scheme, powers, args.log_n, pv, ctx.vec_from(p_pin) if spdz else None, wv, seed=seed,
+                                              mixed=mixed)
         ctx.sync()
         return (time.perf_counter() - t) * 1e3, res
 
@@ -287,7 +292,7 @@ def run_plonk(args):
     line = {"metric": PLONK_METRIC.format(args.log_n), "value": ms_res, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": warmup,
             "ms_per_step": ms_res, "higher_is_better": False, "scaling": "weak", "vs_baseline": None,
             "dtype": "u32 limbs (Montgomery Fr/Fq), integer", "data": "synthetic",
-            "config": {"workload": f"plonk wiring argument {args.scheme} over a 2^{args.log_n} domain BLS12-377, one party per GPU "
+            "config": {"workload": f"plonk wiring argument {args.scheme} over a {dom} domain BLS12-377, one party per GPU "
                                    "(4 KZG10 commitments, 9 openings, 16 transforms per component, batch division, prefix products, 2 Beaver products)",
                        "parties": world, "l2": "256 MiB flush write between iterations", "share_transport": ctx.share_transport,
                        "transcript": "stand-in (SplitMix64 over absorbed limbs); the reference's Blake2s/ChaCha transcript plugs in through czk_plonk_transcript"},
@@ -313,6 +318,8 @@ def main():
                     help="real: CRS generated on the device from seeded toxic waste, the timed proof is verified with the pairing "
                          "check after the timed region; synthetic: device-generated bases of the same shapes (no verification)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--plonk-domain", default="mixed", choices=["mixed", "radix2"],
+                    help="plonk workload: wire domain of 3 * 2^log_n points (the reference's MixedRadixEvaluationDomain for 2^log_n gates) or 2^log_n")
     ap.add_argument("--workload", default="groth16", choices=["groth16", "plonk"],
                     help="groth16: the BASELINE metric's proof (default). plonk: BASELINE config 3's wiring argument (use --log-n 18)")
     args = ap.parse_args()

@@ -12,6 +12,7 @@ from .binding import (  # noqa: F401
     load_library,
     library_path,
     domain_params,
+    mixed_domain_params,
     SCHEME_PLAIN,
     SCHEME_ADDITIVE,
     SCHEME_SPDZ,

@@ -60,6 +60,9 @@ _SIGS = {
     "czk_ntt_fr_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint, C.c_int]),
     "czk_ntt_vec_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint, C.c_int]),
     "czk_domain_params": (C.c_int, [C.c_uint, u64p, u64p, u64p, u64p]),
+    "czk_ntt_mixed_fr_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint, C.c_int]),
+    "czk_ntt_mixed_vec_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint, C.c_int]),
+    "czk_mixed_domain_params": (C.c_int, [C.c_uint, u64p, u64p, u64p, u64p]),
     "czk_vec_add": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "czk_vec_sub": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "czk_vec_mul": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
@@ -145,6 +148,9 @@ _OPTIONAL_SIGS = {
     "czk_plonk_prove_wiring": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.POINTER(PlonkTranscript), C.POINTER(PlonkWiringProof), C.POINTER(PlonkWiringProof),
                                          C.POINTER(C.c_double)]),
+    "czk_plonk_prove_wiring_mixed": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_uint, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.POINTER(PlonkTranscript), C.POINTER(PlonkWiringProof), C.POINTER(PlonkWiringProof),
+                                               C.POINTER(C.c_double)]),
     "czk_groth16_pk_upload": (C.c_int, [C.c_void_p, C.c_size_t] + [C.c_void_p] * 12 + [C.POINTER(C.c_void_p)]),
     "czk_groth16_pk_synthetic": (C.c_int, [C.c_void_p, C.c_size_t, C.c_uint64, C.POINTER(C.c_void_p)]),
     "czk_groth16_pk_free": (None, [C.c_void_p, C.c_void_p]),
@@ -213,6 +219,16 @@ def domain_params(log_d: int):
     lib = load_library()
     outs = [np.zeros(4, np.uint64) for _ in range(4)]
     rc = lib.czk_domain_params(log_d, *[o.ctypes.data_as(u64p) for o in outs])
+    if rc:
+        raise CzkError(rc, lib.czk_last_error(None).decode())
+    return dict(group_gen=outs[0], group_gen_inv=outs[1], size_inv=outs[2], generator_inv=outs[3])
+
+
+def mixed_domain_params(log_m: int):
+    """Constants of MixedRadixEvaluationDomain::new(3 * 2^log_m)."""
+    lib = load_library()
+    outs = [np.zeros(4, np.uint64) for _ in range(4)]
+    rc = lib.czk_mixed_domain_params(log_m, *[o.ctypes.data_as(u64p) for o in outs])
     if rc:
         raise CzkError(rc, lib.czk_last_error(None).decode())
     return dict(group_gen=outs[0], group_gen_inv=outs[1], size_inv=outs[2], generator_inv=outs[3])
@@ -504,6 +520,10 @@ class Context:
         op: NTT_FFT / NTT_IFFT / NTT_COSET_FFT / NTT_COSET_IFFT / NTT_IFFT_COSET_FFT."""
         self._chk(self.lib.czk_ntt_vec_batch(self.h, self._handles(vecs), len(vecs), log_d, op))
 
+    def ntt_mixed_batch(self, vecs, log_m: int, op: int):
+        """MixedRadixEvaluationDomain transforms over 3 * 2^log_m points (czk_ntt_mixed_vec_batch), same ops."""
+        self._chk(self.lib.czk_ntt_mixed_vec_batch(self.h, self._handles(vecs), len(vecs), log_m, op))
+
     def net_link_bytes(self):
         out = np.zeros(2, np.uint64)
         self.lib.czk_net_link_bytes(self.h, out.ctypes.data_as(u64p))
@@ -676,10 +696,11 @@ class ProvingKey:
 
 
 def plonk_prove_wiring(ctx: "Context", scheme: int, powers: "Bases", log_d: int, p_sh: "DeviceVec", p_mac, w_pub: "DeviceVec",
-                       seed: int = 0, transcript: "PlonkTranscript | None" = None) -> dict:
+                       seed: int = 0, transcript: "PlonkTranscript | None" = None, mixed: bool = False) -> dict:
     """Prover::prove_wiring (mpc-plonk/src/lib.rs:199-258) on this party's shares; the stand-in transcript seeded with
-    `seed` unless the caller supplies its own callbacks.  Returns the revealed proof, this party's proof shares and the
-    phase times (transforms + share protocols, commitments, openings, reveal)."""
+    `seed` unless the caller supplies its own callbacks.  mixed: the domain has 3 * 2^log_d points (the reference's
+    MixedRadixEvaluationDomain wire domain) instead of 2^log_d.  Returns the revealed proof, this party's proof shares and
+    the phase times (transforms + share protocols, commitments, openings, reveal)."""
     state = C.c_uint64(0)
     tr = transcript
     if tr is None:
@@ -687,8 +708,9 @@ def plonk_prove_wiring(ctx: "Context", scheme: int, powers: "Bases", log_d: int,
         ctx.lib.czk_plonk_standin_transcript(C.byref(state), seed, C.byref(tr))
     share, out = PlonkWiringProof(), PlonkWiringProof()
     ph = (C.c_double * 4)()
-    ctx._chk(ctx.lib.czk_plonk_prove_wiring(ctx.h, scheme, powers.h, log_d, p_sh.h, p_mac.h if p_mac is not None else None, w_pub.h,
-                                            C.byref(tr), C.byref(share), C.byref(out), ph))
+    fn = ctx.lib.czk_plonk_prove_wiring_mixed if mixed else ctx.lib.czk_plonk_prove_wiring
+    ctx._chk(fn(ctx.h, scheme, powers.h, log_d, p_sh.h, p_mac.h if p_mac is not None else None, w_pub.h,
+                C.byref(tr), C.byref(share), C.byref(out), ph))
     return dict(proof=out.to_dict(), proof_share=share.to_dict(),
                 phases_ms=dict(zip(("transforms_and_shares", "commitments", "openings", "reveal"), list(ph))))
 

@@ -115,6 +115,10 @@ void czk_ctx_destroy(czk_ctx* ctx) {
         cudaFree(d.gi_lo);
         cudaFree(d.gi_hi);
     }
+    for (auto& kv : ctx->mixed_domains) {
+        cudaFree(kv.second.wpow);
+        cudaFree(kv.second.wipow);
+    }
     for (MsmLane& l : ctx->lanes) {
         if (l.stream) cudaStreamSynchronize(l.stream);
         for (int i = 0; i < 4; i++) l.ws.ev[i] = nullptr;  // owned by the slots
@@ -130,7 +134,7 @@ void czk_ctx_destroy(czk_ctx* ctx) {
     }
     gsz_release(ctx);
     for (Scratch* s : {&ctx->up_bases, &ctx->up_inf, &ctx->up_scalars, &ctx->up_vec, &ctx->open_gather, &ctx->open_sigma,
-                       &ctx->open_sx, &ctx->open_oy, &ctx->open_d, &ctx->open_dm})
+                       &ctx->open_sx, &ctx->open_oy, &ctx->open_d, &ctx->open_dm, &ctx->mixed})
         cudaFree(s->p);
     cudaFree(ctx->flag);
     for (cudaEvent_t e : ctx->ev_phase)
@@ -336,6 +340,119 @@ int czk_ntt_vec_batch(czk_ctx* ctx, czk_vec* const* vecs, int count, unsigned lo
         v[(size_t)i] = vecs[i]->d;
     }
     return czk_ntt_fr_batch(ctx, v.data(), count, log_d, op);
+}
+
+// ------------------------------------------------------------------------------------------ mixed-radix NTT (3 * 2^k)
+// FftField::get_root_of_unity(3 * 2^log_m) (algebra/ff/src/fields/mod.rs:337-367, large-subgroup branch)
+static HFr mixed_root(unsigned log_m) {
+    HFr w = HFr::from_limbs(FrParams::LARGE_ROOT_64);
+    for (unsigned i = log_m; i < FrParams::TWO_ADICITY; i++) w = HFr::sqr(w);
+    return w;
+}
+int czk_mixed_domain_params(unsigned log_m, uint64_t group_gen[4], uint64_t group_gen_inv[4], uint64_t size_inv[4],
+                            uint64_t generator_inv[4]) {
+    if (log_m > FrParams::TWO_ADICITY) return fail(nullptr, CZK_ERR_ARG, "domain larger than 3 * 2^47");
+    HFr w = mixed_root(log_m);
+    w.to_limbs(group_gen);
+    HFr::inv(w).to_limbs(group_gen_inv);
+    HFr::inv(HFr::from_u64((uint64_t)3 << log_m)).to_limbs(size_inv);
+    HFr::inv(HFr::from_limbs(FrParams::GENERATOR_64)).to_limbs(generator_inv);
+    return CZK_OK;
+}
+static int get_mixed_domain(czk_ctx* ctx, int log_m, MixedDomain** out) {
+    auto it = ctx->mixed_domains.find(log_m);
+    if (it != ctx->mixed_domains.end()) {
+        *out = &it->second;
+        return CZK_OK;
+    }
+    MixedDomain d;
+    d.log_m = log_m;
+    const size_t M = (size_t)1 << log_m;
+    d.group_gen = mixed_root((unsigned)log_m);
+    d.group_gen_inv = HFr::inv(d.group_gen);
+    d.size_inv = HFr::inv(HFr::from_u64((uint64_t)3 << log_m));
+    d.third_inv = HFr::inv(HFr::from_u64(3));
+    d.zeta = HFr::pow_u64(d.group_gen, (uint64_t)M);
+    d.zeta_inv = HFr::inv(d.zeta);
+    HFr one = HFr::one();
+    CUDA_TRY(ctx, cudaMalloc((void**)&d.wpow, M * 32));
+    CUDA_TRY(ctx, cudaMalloc((void**)&d.wipow, M * 32));
+    CUDA_TRY(ctx, ntt_build_powers(d.wpow, d.group_gen.l, one.l, M, ctx->stream));
+    CUDA_TRY(ctx, ntt_build_powers(d.wipow, d.group_gen_inv.l, one.l, M, ctx->stream));
+    auto ins = ctx->mixed_domains.emplace(log_m, d);
+    *out = &ins.first->second;
+    return CZK_OK;
+}
+// a[i] *= c g^i for i < n on a raw device pointer (two-level power table built on the fly)
+static int distribute_powers_dev(czk_ctx* ctx, uint32_t* a, const HFr& g, const HFr& c, size_t n) {
+    if (!n) return CZK_OK;
+    const int lo_log = 10;
+    size_t nlo = (size_t)1 << lo_log, nhi = (n + nlo - 1) >> lo_log;
+    CZK_TRY(scratch_reserve(ctx, ctx->open_sigma, (nlo + nhi) * 32));
+    uint32_t* lo = (uint32_t*)ctx->open_sigma.p;
+    uint32_t* hi = lo + nlo * 8;
+    HFr one = HFr::one();
+    CUDA_TRY(ctx, ntt_build_powers(lo, g.l, one.l, nlo, ctx->stream));
+    HFr ghi = HFr::pow_u64(g, (uint64_t)nlo);
+    CUDA_TRY(ctx, ntt_build_powers(hi, ghi.l, c.l, nhi, ctx->stream));
+    CUDA_TRY(ctx, fr_scale_by_tables(a, lo, hi, lo_log, n, ctx->stream));
+    return CZK_OK;
+}
+// The four transforms of MixedRadixEvaluationDomain (mixed_radix.rs:130-157, domain/mod.rs:139-142) over 3 * 2^log_m
+// points for `count` vectors: de-interleave -> 3 * count radix-2 transforms in one batch -> combine (ntt.cu).
+// CZK_NTT_IFFT_COSET_FFT runs as the two transforms one after the other.
+static int ntt_mixed_batch_dev(czk_ctx* ctx, uint32_t* const* data, int count, unsigned log_m, int op) {
+    if (!ctx || (count > 0 && !data) || count < 0) return fail(ctx, CZK_ERR_ARG, "czk_ntt_mixed: null argument");
+    if (log_m > 28) return fail(ctx, CZK_ERR_ARG, "czk_ntt_mixed: log_m > 28 unsupported");
+    if (op < 0 || op > CZK_NTT_IFFT_COSET_FFT) return fail(ctx, CZK_ERR_ARG, "czk_ntt_mixed: unknown transform");
+    if (count == 0) return CZK_OK;
+    if (op == CZK_NTT_IFFT_COSET_FFT) {
+        CZK_TRY(ntt_mixed_batch_dev(ctx, data, count, log_m, CZK_NTT_IFFT));
+        return ntt_mixed_batch_dev(ctx, data, count, log_m, CZK_NTT_COSET_FFT);
+    }
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    MixedDomain* d;
+    CZK_TRY(get_mixed_domain(ctx, (int)log_m, &d));
+    const size_t M = (size_t)1 << log_m, N = 3 * M;
+    const bool inverse = op == CZK_NTT_IFFT || op == CZK_NTT_COSET_IFFT;
+    const HFr g = HFr::from_limbs(FrParams::GENERATOR_64), one = HFr::one();
+    CZK_TRY(scratch_reserve(ctx, ctx->mixed, (size_t)count * N * 32));
+    uint32_t* sub = (uint32_t*)ctx->mixed.p;
+    std::vector<uint32_t*> parts((size_t)count * 3);
+    for (int i = 0; i < count; i++) {
+        if (op == CZK_NTT_COSET_FFT) CZK_TRY(distribute_powers_dev(ctx, data[i], g, one, N));
+        CUDA_TRY(ctx, ntt_mixed_split(data[i], sub + (size_t)i * N * 8, M, ctx->stream));
+        for (int r = 0; r < 3; r++) parts[(size_t)i * 3 + r] = sub + ((size_t)i * N + (size_t)r * M) * 8;
+    }
+    // the radix-2 inverse scales by M^-1; the remaining 3^-1 rides on the combining pass
+    CZK_TRY(ntt_batch_dev(ctx, parts.data(), count * 3, log_m, inverse ? CZK_NTT_IFFT : CZK_NTT_FFT));
+    for (int i = 0; i < count; i++) {
+        CUDA_TRY(ctx, ntt_mixed_combine(sub + (size_t)i * N * 8, data[i], inverse ? d->wipow : d->wpow, inverse ? d->zeta_inv.l : d->zeta.l,
+                                        inverse ? d->third_inv.l : nullptr, M, ctx->stream));
+        if (op == CZK_NTT_COSET_IFFT) CZK_TRY(distribute_powers_dev(ctx, data[i], HFr::inv(g), one, N));
+    }
+    return CZK_OK;
+}
+int czk_ntt_mixed_fr_batch(czk_ctx* ctx, uint64_t* const* dev_vecs, int count, unsigned log_m, int op) {
+    if (!ctx || (count > 0 && !dev_vecs) || count < 0) return fail(ctx, CZK_ERR_ARG, "czk_ntt_mixed_fr_batch: null argument");
+    std::vector<uint32_t*> v((size_t)count);
+    for (int i = 0; i < count; i++) {
+        if (!dev_vecs[i]) return fail(ctx, CZK_ERR_ARG, "czk_ntt_mixed_fr_batch: null vector");
+        v[(size_t)i] = reinterpret_cast<uint32_t*>(dev_vecs[i]);
+        for (int j = 0; j < i; j++)
+            if (dev_vecs[j] == dev_vecs[i]) return fail(ctx, CZK_ERR_ARG, "czk_ntt_mixed_fr_batch: the same vector twice");
+    }
+    return ntt_mixed_batch_dev(ctx, v.data(), count, log_m, op);
+}
+int czk_ntt_mixed_vec_batch(czk_ctx* ctx, czk_vec* const* vecs, int count, unsigned log_m, int op) {
+    if (!ctx || (count > 0 && !vecs) || count < 0) return fail(ctx, CZK_ERR_ARG, "czk_ntt_mixed_vec_batch: null argument");
+    if (log_m > 28) return fail(ctx, CZK_ERR_ARG, "czk_ntt_mixed_vec_batch: log_m > 28 unsupported");
+    std::vector<uint64_t*> v((size_t)count);
+    for (int i = 0; i < count; i++) {
+        if (!vecs[i] || vecs[i]->n < ((size_t)3 << log_m)) return fail(ctx, CZK_ERR_ARG, "czk_ntt_mixed_vec_batch: vector shorter than the domain");
+        v[(size_t)i] = vecs[i]->d;
+    }
+    return czk_ntt_mixed_fr_batch(ctx, v.data(), count, log_m, op);
 }
 
 int czk_ntt_vec(czk_ctx* ctx, czk_vec* v, unsigned log_d, int inverse, int coset) {

@@ -79,6 +79,12 @@ struct Domain {
     int lo_log = 0;
     HFr size_inv, group_gen, group_gen_inv, generator_inv;
 };
+// MixedRadixEvaluationDomain of 3 * 2^log_m points: w = get_root_of_unity(3 M), tables w^j and w^-j (j < M)
+struct MixedDomain {
+    int log_m = 0;
+    uint32_t *wpow = nullptr, *wipow = nullptr;
+    HFr group_gen, group_gen_inv, size_inv, third_inv, zeta, zeta_inv;
+};
 struct Scratch {
     void* p = nullptr;
     size_t cap = 0;
@@ -140,9 +146,11 @@ struct czk_ctx {
     int lane_priority = 0;
     std::string err;
     std::map<int, Domain> domains;
+    std::map<int, MixedDomain> mixed_domains;
     MsmLane lanes[CZK_MSM_LANES];
     Scratch up_bases, up_inf, up_scalars, up_vec;  // staging for the host-pointer entry points
     Scratch open_gather, open_sigma, open_sx, open_oy, open_d, open_dm;
+    Scratch mixed;  // the three de-interleaved subsequences of every vector of a mixed-radix batch
     uint32_t* flag = nullptr;
     cudaEvent_t ev_phase[2] = {nullptr, nullptr};  // witness-map start / stop on the context stream (phase report)
     // network

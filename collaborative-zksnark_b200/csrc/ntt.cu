@@ -295,4 +295,53 @@ cudaError_t ntt_bitrev_scale(uint32_t* data, int log_d, int mode, const uint64_t
     return cudaGetLastError();
 }
 
+// --------------------------------------------------------------------------------------------- mixed radix (3 * 2^k)
+// MixedRadixEvaluationDomain (algebra/poly/src/domain/mixed_radix.rs) for Fr's small subgroup base 3: a transform over
+// N = 3 M points (M = 2^k) with w = get_root_of_unity(N).  Writing the input index as 3 a + r,
+//   X[j + s M] = Y_0[j] + zeta^s w^j Y_1[j] + zeta^(2 s) w^(2 j) Y_2[j],   Y_r = DFT_M of x[3 a + r] under w^3,
+// with zeta = w^M a primitive cube root of unity and w^3 the radix-2 domain's own generator: de-interleave, three radix-2
+// transforms of M points (one batched grid of the tile kernels above), one combining pass.  The reference's serial
+// permute + radix-3 + radix-2 passes compute the same DFT; nothing of their order is kept.
+__global__ void k_mr_split(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, size_t M) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 3 * M) return;
+    st_fr(out, (i % 3) * M + i / 3, ld_fr(in, i));
+}
+// wpow[j] = w^j (or w^-j with zeta^-1 for the inverse), j < M; scale: multiply everything by c (3^-1 on the way back)
+__global__ void k_mr_combine(const uint32_t* __restrict__ y, uint32_t* __restrict__ out, const uint32_t* __restrict__ wpow, Fr4 zeta4,
+                             Fr4 c4, int scale, size_t M) {
+    size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= M) return;
+    Fr w = ldg_fr(wpow, j);
+    Fr y0 = ld_fr(y, j), y1 = ld_fr(y, M + j), y2 = ld_fr(y, 2 * M + j);
+    if (scale) {
+        Fr c = fr_from_u64x4(c4.v);
+        y0 = Fr::mul(y0, c);
+        y1 = Fr::mul(y1, c);
+        y2 = Fr::mul(y2, c);
+    }
+    Fr t1 = Fr::mul(y1, w), t2 = Fr::mul(y2, Fr::mul(w, w));
+    Fr zeta = fr_from_u64x4(zeta4.v);
+    Fr z1 = Fr::mul(t1, zeta), z2 = Fr::mul(t2, zeta);
+    // 1 + zeta + zeta^2 = 0: zeta^2 t = -(t + zeta t)
+    Fr zz1 = Fr::neg(Fr::add(t1, z1)), zz2 = Fr::neg(Fr::add(t2, z2));
+    st_fr(out, j, Fr::add(y0, Fr::add(t1, t2)));
+    st_fr(out, M + j, Fr::add(y0, Fr::add(z1, zz2)));
+    st_fr(out, 2 * M + j, Fr::add(y0, Fr::add(zz1, z2)));
+}
+cudaError_t ntt_mixed_split(const uint32_t* in, uint32_t* out, size_t M, cudaStream_t st) {
+    k_mr_split<<<(unsigned)((3 * M + 255) / 256), 256, 0, st>>>(in, out, M); CZK_LAUNCHED();
+    return cudaGetLastError();
+}
+cudaError_t ntt_mixed_combine(const uint32_t* y, uint32_t* out, const uint32_t* wpow, const uint64_t zeta[4], const uint64_t c[4], size_t M,
+                              cudaStream_t st) {
+    Fr4 z{}, cc{};
+    for (int i = 0; i < 4; i++) {
+        z.v[i] = zeta[i];
+        cc.v[i] = c ? c[i] : 0;
+    }
+    k_mr_combine<<<(unsigned)((M + 127) / 128), 128, 0, st>>>(y, out, wpow, z, cc, c ? 1 : 0, M); CZK_LAUNCHED();
+    return cudaGetLastError();
+}
+
 }  // namespace czk

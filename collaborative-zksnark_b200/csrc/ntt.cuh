@@ -42,4 +42,10 @@ cudaError_t ntt_scale_by_powers(uint32_t* data, const uint32_t* lo, const uint32
 cudaError_t ntt_bitrev_scale(uint32_t* data, int log_d, int mode, const uint64_t c[4], const uint32_t* lo,
                              const uint32_t* hi, int lo_log, cudaStream_t st);
 
+// mixed radix (N = 3 M, M = 2^k): out[r M + a] = in[3 a + r]; and the combining pass after the three radix-2 transforms
+// (wpow[j] = w^j, j < M; zeta = w^M; c: optional constant multiplied into every output)
+cudaError_t ntt_mixed_split(const uint32_t* in, uint32_t* out, size_t M, cudaStream_t st);
+cudaError_t ntt_mixed_combine(const uint32_t* y, uint32_t* out, const uint32_t* wpow, const uint64_t zeta[4], const uint64_t c[4], size_t M,
+                              cudaStream_t st);
+
 }  // namespace czk

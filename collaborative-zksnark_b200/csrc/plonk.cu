@@ -53,7 +53,8 @@ struct Prover {
     int scheme;
     bool spdz, shared;
     const czk_bases* powers;
-    unsigned log_d;
+    unsigned log_d;  // D = 2^log_d, or 3 * 2^log_d when mixed
+    bool mixed;
     size_t D;
     const czk_plonk_transcript* tr;
     std::vector<czk_vec*> owned;
@@ -98,6 +99,7 @@ struct Prover {
             if (spdz) all.push_back(v->mac);
         }
         for (czk_vec* p : pubs) all.push_back(p);
+        if (mixed) return czk_ntt_mixed_vec_batch(ctx, all.data(), (int)all.size(), log_d, op);
         return czk_ntt_vec_batch(ctx, all.data(), (int)all.size(), log_d, op);
     }
     int distribute_powers(SVec& v, const HFr& g) {
@@ -118,9 +120,10 @@ struct Prover {
         if (spdz) CZK_TRY(czk_vec_sub(ctx, a.mac, b.mac, D));
         return CZK_OK;
     }
-    int div_vanishing(SVec& a) {
-        CZK_TRY(czk_vec_divide_by_vanishing_on_coset(ctx, a.sh, log_d));
-        if (spdz) CZK_TRY(czk_vec_divide_by_vanishing_on_coset(ctx, a.mac, log_d));
+    int div_vanishing(SVec& a) {  // evals *= 1 / (g^D - 1)   (domain/mod.rs:184-191, any multiplicative-subgroup domain)
+        const HFr zi = HFr::inv(HFr::sub(HFr::pow_u64(HFr::from_limbs(FrParams::GENERATOR_64), (uint64_t)D), HFr::one()));
+        CZK_TRY(czk_vec_scale(ctx, a.sh, zi.l, D));
+        if (spdz) CZK_TRY(czk_vec_scale(ctx, a.mac, zi.l, D));
         return CZK_OK;
     }
     int mul(SVec& a, const SVec& b) { return czk_beaver_batch_mul(ctx, scheme, a.sh, a.mac, b.sh, b.mac, D); }
@@ -184,13 +187,13 @@ void czk_plonk_standin_transcript(uint64_t* state, uint64_t seed, czk_plonk_tran
     out->challenge = standin_challenge;
 }
 
-int czk_plonk_prove_wiring(czk_ctx* ctx, int scheme, const czk_bases* powers, unsigned log_d, const czk_vec* p_sh, const czk_vec* p_mac,
-                           const czk_vec* w_pub, const czk_plonk_transcript* transcript, czk_plonk_wiring_proof* out_share,
-                           czk_plonk_wiring_proof* out, double* phases_ms) {
+static int prove_wiring_impl(czk_ctx* ctx, int scheme, const czk_bases* powers, unsigned log_d, bool mixed, const czk_vec* p_sh,
+                             const czk_vec* p_mac, const czk_vec* w_pub, const czk_plonk_transcript* transcript,
+                             czk_plonk_wiring_proof* out_share, czk_plonk_wiring_proof* out, double* phases_ms) {
     if (!ctx || !powers || !p_sh || !w_pub || !transcript || !transcript->absorb_g1 || !transcript->challenge || !out_share || !out)
         return fail(ctx, CZK_ERR_ARG, "czk_plonk_prove_wiring: null argument");
-    if (log_d > 28) return fail(ctx, CZK_ERR_ARG, "czk_plonk_prove_wiring: domain too large");
-    const size_t D = (size_t)1 << log_d;
+    if (log_d > (mixed ? 26u : 28u)) return fail(ctx, CZK_ERR_ARG, "czk_plonk_prove_wiring: domain too large");
+    const size_t D = (size_t)(mixed ? 3 : 1) << log_d;
     const bool spdz = scheme == CZK_SCHEME_SPDZ;
     if (scheme != CZK_SCHEME_PLAIN && scheme != CZK_SCHEME_ADDITIVE && !spdz) return fail(ctx, CZK_ERR_ARG, "czk_plonk_prove_wiring: scheme");
     if (scheme == CZK_SCHEME_PLAIN && ctx->nranks != 1) return fail(ctx, CZK_ERR_ARG, "plain scheme needs a 1-party context");
@@ -199,9 +202,10 @@ int czk_plonk_prove_wiring(czk_ctx* ctx, int scheme, const czk_bases* powers, un
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
     std::memset(out, 0, sizeof *out);
     std::memset(out_share, 0, sizeof *out_share);
-    Prover P{ctx, scheme, spdz, scheme != CZK_SCHEME_PLAIN, powers, log_d, D, transcript, {}, {}};
+    Prover P{ctx, scheme, spdz, scheme != CZK_SCHEME_PLAIN, powers, log_d, mixed, D, transcript, {}, {}};
     uint64_t dom[4][4];
-    CZK_TRY(czk_domain_params(log_d, dom[0], dom[1], dom[2], dom[3]));
+    if (mixed) CZK_TRY(czk_mixed_domain_params(log_d, dom[0], dom[1], dom[2], dom[3]));
+    else CZK_TRY(czk_domain_params(log_d, dom[0], dom[1], dom[2], dom[3]));
     const HFr w = HFr::from_limbs(dom[0]), w_inv = HFr::from_limbs(dom[1]);
     double t_commit = 0, t_open = 0, t_reveal = 0, t_all = now_ms();
     auto timed = [&](double& acc, int rc, double t0) {
@@ -313,4 +317,16 @@ int czk_plonk_prove_wiring(czk_ctx* ctx, int scheme, const czk_bases* powers, un
         phases_ms[3] = t_reveal;
     }
     return CZK_OK;
+}
+
+int czk_plonk_prove_wiring(czk_ctx* ctx, int scheme, const czk_bases* powers, unsigned log_d, const czk_vec* p_sh, const czk_vec* p_mac,
+                           const czk_vec* w_pub, const czk_plonk_transcript* transcript, czk_plonk_wiring_proof* out_share,
+                           czk_plonk_wiring_proof* out, double* phases_ms) {
+    return prove_wiring_impl(ctx, scheme, powers, log_d, false, p_sh, p_mac, w_pub, transcript, out_share, out, phases_ms);
+}
+// the reference's own wire domain: MixedRadixEvaluationDomain::new(3 * n_gates) = 3 * 2^log_m points (relations/flat.rs:282-300)
+int czk_plonk_prove_wiring_mixed(czk_ctx* ctx, int scheme, const czk_bases* powers, unsigned log_m, const czk_vec* p_sh, const czk_vec* p_mac,
+                                 const czk_vec* w_pub, const czk_plonk_transcript* transcript, czk_plonk_wiring_proof* out_share,
+                                 czk_plonk_wiring_proof* out, double* phases_ms) {
+    return prove_wiring_impl(ctx, scheme, powers, log_m, true, p_sh, p_mac, w_pub, transcript, out_share, out, phases_ms);
 }

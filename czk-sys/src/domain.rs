@@ -46,3 +46,20 @@ pub fn domain_constants(log_size: u32) -> ([u64; 4], [u64; 4], [u64; 4], [u64; 4
     assert_eq!(rc, ffi::CZK_OK, "czk_domain_params");
     (g, gi, si, geni)
 }
+
+/// `MixedRadixEvaluationDomain` of 3 * 2^log_m points (algebra/poly/src/domain/mixed_radix.rs:130-157): the Plonk prover's
+/// wire domain (mpc-plonk/src/relations/flat.rs:282-300).  Same ops, device-resident vectors of 3 * 2^log_m elements.
+///
+/// ```ignore
+/// // mixed_radix.rs, fft_in_place:  if self.size == 3 << self.log_size_of_group { upload; transform_batch_mixed(..); download }
+/// ```
+pub fn transform_batch_mixed(log_m: u32, vecs: &[&DevVec], op: i32) {
+    let ptrs: Vec<*mut ffi::czk_vec> = vecs.iter().map(|v| v.ptr).collect();
+    with_ctx(|c| check(c, "czk_ntt_mixed_vec_batch", unsafe { ffi::czk_ntt_mixed_vec_batch(c, ptrs.as_ptr(), ptrs.len() as i32, log_m, op) }));
+}
+pub fn mixed_domain_constants(log_m: u32) -> ([u64; 4], [u64; 4], [u64; 4], [u64; 4]) {
+    let (mut g, mut gi, mut si, mut geni) = ([0u64; 4], [0u64; 4], [0u64; 4], [0u64; 4]);
+    let rc = unsafe { ffi::czk_mixed_domain_params(log_m, g.as_mut_ptr(), gi.as_mut_ptr(), si.as_mut_ptr(), geni.as_mut_ptr()) };
+    assert_eq!(rc, ffi::CZK_OK, "czk_mixed_domain_params");
+    (g, gi, si, geni)
+}

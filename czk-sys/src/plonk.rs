@@ -28,8 +28,22 @@ fn fq(l: &[u64]) -> Fq {
 }
 
 /// p: this party's shares of the wire polynomial's coefficients (value, and MAC under SPDZ); w: pk.w (public).
-pub fn prove_wiring(scheme: i32, powers_of_g: &Bases, log_size: u32, p_sh: &DevVec, p_mac: Option<&DevVec>, w: &DevVec,
+/// `domain_size` is `circ.domains.wires.size()`: 3 * 2^k for the reference's mixed-radix wire domain, or a power of two.
+pub fn prove_wiring(scheme: i32, powers_of_g: &Bases, domain_size: usize, p_sh: &DevVec, p_mac: Option<&DevVec>, w: &DevVec,
                     fs_rng: &mut Transcript) -> (ffi::czk_plonk_wiring_proof, ffi::czk_plonk_wiring_proof) {
+    let log_size = domain_size.trailing_zeros();
+    if domain_size == 3usize << log_size {
+        let tr = ffi::czk_plonk_transcript { user: fs_rng as *mut _ as *mut c_void, absorb_g1: Some(absorb_g1), challenge: Some(challenge) };
+        let mut share: ffi::czk_plonk_wiring_proof = unsafe { std::mem::zeroed() };
+        let mut revealed: ffi::czk_plonk_wiring_proof = unsafe { std::mem::zeroed() };
+        with_ctx(|c| check(c, "czk_plonk_prove_wiring_mixed", unsafe {
+            ffi::czk_plonk_prove_wiring_mixed(c, scheme, powers_of_g.ptr, log_size, p_sh.ptr,
+                                              p_mac.map(|m| m.ptr as *const _).unwrap_or(std::ptr::null()), w.ptr, &tr, &mut share, &mut revealed,
+                                              std::ptr::null_mut())
+        }));
+        return (share, revealed);
+    }
+    assert_eq!(domain_size, 1usize << log_size, "wire domain must have 2^k or 3 * 2^k points");
     let tr = ffi::czk_plonk_transcript { user: fs_rng as *mut _ as *mut c_void, absorb_g1: Some(absorb_g1), challenge: Some(challenge) };
     let mut share: ffi::czk_plonk_wiring_proof = unsafe { std::mem::zeroed() };
     let mut revealed: ffi::czk_plonk_wiring_proof = unsafe { std::mem::zeroed() };

@@ -89,6 +89,18 @@ CZK_API int czk_ntt_vec_batch(czk_ctx* ctx, czk_vec* const* vecs, int count, uns
 CZK_API int czk_domain_params(unsigned log_d, uint64_t group_gen[4], uint64_t group_gen_inv[4], uint64_t size_inv[4],
                       uint64_t generator_inv[4]);
 
+/* ---- mixed-radix domains: 3 * 2^log_m points ------------------------------------------------------
+ * Replaces MixedRadixEvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place (algebra/poly/src/domain/mixed_radix.rs:
+ * 130-157, domain/mod.rs:139-142) for Fr's small subgroup base 3 - the wire domain of the Plonk prover
+ * (mpc-plonk/src/relations/flat.rs:282-300).  Natural order in and out, out[j] = sum_i in[i] w^(ij) with
+ * w = get_root_of_unity(3 * 2^log_m); every vector holds 3 * 2^log_m elements.  op as above (CZK_NTT_IFFT_COSET_FFT runs as
+ * the two transforms in sequence). */
+CZK_API int czk_ntt_mixed_fr_batch(czk_ctx* ctx, uint64_t* const* dev_vecs, int count, unsigned log_m, int op);
+CZK_API int czk_ntt_mixed_vec_batch(czk_ctx* ctx, czk_vec* const* vecs, int count, unsigned log_m, int op);
+/* Domain constants as MixedRadixEvaluationDomain::new computes them (mixed_radix.rs:64-105). */
+CZK_API int czk_mixed_domain_params(unsigned log_m, uint64_t group_gen[4], uint64_t group_gen_inv[4], uint64_t size_inv[4],
+                            uint64_t generator_inv[4]);
+
 /* ---- pointwise Fr helpers used between the transforms -------------------------------------------
  * domain/mod.rs:93-126 (distribute_powers), :184-191 (divide_by_vanishing_poly_on_coset_in_place),
  * mpc-snarks/src/groth/r1cs_to_qap.rs:92,105-109.                                                */

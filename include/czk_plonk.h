@@ -52,6 +52,11 @@ typedef struct czk_plonk_wiring_proof {
 CZK_API int czk_plonk_prove_wiring(czk_ctx* ctx, int scheme, const czk_bases* powers, unsigned log_d, const czk_vec* p_sh,
                                    const czk_vec* p_mac, const czk_vec* w_pub, const czk_plonk_transcript* transcript,
                                    czk_plonk_wiring_proof* out_share, czk_plonk_wiring_proof* out, double* phases_ms);
+/* The same argument over the reference's own wire domain, MixedRadixEvaluationDomain::new(3 * n_gates) = 3 * 2^log_m points
+ * (mpc-plonk/src/relations/flat.rs:282-300): every vector and the committer key hold >= 3 * 2^log_m elements. */
+CZK_API int czk_plonk_prove_wiring_mixed(czk_ctx* ctx, int scheme, const czk_bases* powers, unsigned log_m, const czk_vec* p_sh,
+                                         const czk_vec* p_mac, const czk_vec* w_pub, const czk_plonk_transcript* transcript,
+                                         czk_plonk_wiring_proof* out_share, czk_plonk_wiring_proof* out, double* phases_ms);
 
 #ifdef __cplusplus
 }

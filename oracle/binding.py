@@ -21,7 +21,7 @@ u8p = C.POINTER(C.c_uint8)
 
 def build(force: bool = False) -> Path:
     so = _HERE / "libczk_oracle.so"
-    srcs = [_HERE / n for n in ("czk_oracle.c", "czk_oracle_groth16.inc", "czk_oracle_plonk.inc", "fp_tmpl.h", "ec_tmpl.h", "Makefile")]
+    srcs = [_HERE / n for n in ("czk_oracle.c", "czk_oracle_groth16.inc", "czk_oracle_plonk.inc", "czk_oracle_mixed.inc", "fp_tmpl.h", "ec_tmpl.h", "Makefile")]
     if force or not so.exists() or any(s.stat().st_mtime > so.stat().st_mtime for s in srcs):
         subprocess.run(["make", "-C", str(_HERE), "-s"], check=True)
     return so
@@ -223,6 +223,22 @@ def ntt(data: np.ndarray, inverse=False, coset=False, threads=1) -> np.ndarray:
     ok = lib().orc_ntt(_p(a), C.c_uint(log_d), C.c_int(int(inverse)), C.c_int(int(coset)), C.c_int(threads))
     assert ok
     return a
+
+
+def ntt_mixed(data: np.ndarray, inverse=False, coset=False) -> np.ndarray:
+    """MixedRadixEvaluationDomain transforms (algebra/poly/src/domain/mixed_radix.rs): data is (2^k, 4) or (3 * 2^k, 4)
+    Montgomery Fr, natural order in and out.  Returns a transformed copy."""
+    a = np.array(data, dtype=np.uint64, order="C").reshape(-1, 4)
+    ok = lib().orc_ntt_mixed(_p(a), C.c_size_t(a.shape[0]), C.c_int(int(inverse)), C.c_int(int(coset)))
+    assert ok, "not a mixed-radix domain size"
+    return a
+
+
+def mixed_domain_params(size: int):
+    """(group_gen, group_gen_inv, size_inv, generator_inv) of MixedRadixEvaluationDomain::new(size), Montgomery limbs."""
+    out = [np.zeros(4, np.uint64) for _ in range(4)]
+    assert lib().orc_mixed_domain_params(C.c_size_t(size), *[_p(o) for o in out])
+    return tuple(out)
 
 
 def serial_radix2_fft(data: np.ndarray, inverse=False) -> np.ndarray:
@@ -465,9 +481,7 @@ def plonk_prove_wiring(scheme, p_shares, w_pub, powers_xy, powers_inf=None, seed
     shares of the wire polynomial, w_pub: (D, 4) public wiring polynomial, powers_xy: >= D KZG10 powers_of_g.
     Returns the revealed proof, every party's opening-proof shares and the status (1 ok, 0 zero divisor, -1 MAC failure)."""
     p_shares = np.ascontiguousarray(p_shares, np.uint64)
-    n, D = p_shares.shape[0], p_shares.shape[1]
-    log_d = D.bit_length() - 1
-    assert 1 << log_d == D
+    n, D = p_shares.shape[0], p_shares.shape[1]  # D = 2^k, or 3 * 2^k (the reference's mixed-radix wire domain)
     w_pub = np.ascontiguousarray(w_pub, np.uint64).reshape(D, 4)
     powers_xy = np.ascontiguousarray(powers_xy, np.uint64)
     assert powers_xy.shape[0] >= D
@@ -475,9 +489,9 @@ def plonk_prove_wiring(scheme, p_shares, w_pub, powers_xy, powers_inf=None, seed
     out = dict(cmt_xy=np.zeros((4, 12), np.uint64), cmt_inf=np.zeros(4, np.uint8), open_val=np.zeros((9, 4), np.uint64),
                open_pf_xy=np.zeros((9, 12), np.uint64), open_pf_inf=np.zeros(9, np.uint8), challenges=np.zeros((4, 4), np.uint64))
     sh_xy, sh_inf = np.zeros((n, 9, 12), np.uint64), np.zeros((n, 9), np.uint8)
-    f = lib().orc_plonk_prove_wiring
+    f = lib().orc_plonk_prove_wiring_size
     f.restype = C.c_int
-    st = f(C.c_int(scheme), C.c_int(n), C.c_uint(log_d), _p(powers_xy), _p8(powers_inf) if powers_inf is not None else None, ptrs, _p(w_pub),
+    st = f(C.c_int(scheme), C.c_int(n), C.c_size_t(D), _p(powers_xy), _p8(powers_inf) if powers_inf is not None else None, ptrs, _p(w_pub),
            C.c_uint64(seed), _p(out["cmt_xy"]), _p8(out["cmt_inf"]), _p(out["open_val"]), _p(out["open_pf_xy"]), _p8(out["open_pf_inf"]),
            _p(sh_xy), _p8(sh_inf), _p(out["challenges"]), C.c_int(threads))
     return dict(status=st, proof=out, share_pf_xy=sh_xy, share_pf_inf=sh_inf)

@@ -673,4 +673,5 @@ EXPORT int orc_divide_by_vanishing_on_coset(uint64_t *data, unsigned log_d, int 
 }
 
 #include "czk_oracle_groth16.inc"
+#include "czk_oracle_mixed.inc"
 #include "czk_oracle_plonk.inc"

@@ -26,21 +26,22 @@ def make_points(G, n, seed, threads=8):
     return G.gen_progression(gxy[0], ks[0], ks[1], n, threads=threads)
 
 
-def plonk_wiring_instance(log_d, seed):
-    """A VALID wiring instance over the domain of size 2^log_d: a permutation sigma made of short cycles, wire values that
+def plonk_wiring_instance(log_d, seed, size=None):
+    """A VALID wiring instance over the domain of size 2^log_d (or of `size` = 3 * 2^k points, the reference's mixed-radix
+    wire domain): a permutation sigma made of short cycles, wire values that
     are constant on every cycle, p = interpolate(values), w = interpolate(omega^sigma(i)) - so that
     prod_i (p_i + y w_i + z) / (p_i + y omega^i + z) = 1 and the unit-product argument has something true to prove.
     Returns (p_coeffs, w_coeffs) as Montgomery Fr arrays."""
     import random
 
-    D = 1 << log_d
+    D = size if size is not None else 1 << log_d
     rnd = random.Random(seed)
-    dp = o.domain_params(D)
+    group_gen = o.mixed_domain_params(D)[0]  # == Radix2EvaluationDomain's for a power of two
     omega_pows = np.zeros((D, 4), np.uint64)
     cur = o.fr_from_ints([1])[0]
     for i in range(D):
         omega_pows[i] = cur
-        cur = o.fr_mul(cur[None, :], dp["group_gen"][None, :])[0]
+        cur = o.fr_mul(cur[None, :], group_gen[None, :])[0]
     idx = list(range(D))
     rnd.shuffle(idx)
     sigma = list(range(D))
@@ -56,6 +57,8 @@ def plonk_wiring_instance(log_d, seed):
         pos += ln
     p_evals = o.fr_from_ints(vals)
     w_evals = omega_pows[sigma]
+    if D & (D - 1):
+        return o.ntt_mixed(p_evals, inverse=True), o.ntt_mixed(np.ascontiguousarray(w_evals), inverse=True)
     return o.ntt(p_evals, inverse=True), o.ntt(np.ascontiguousarray(w_evals), inverse=True)
 
 

@@ -94,20 +94,22 @@ def main():
     sys.path.insert(0, str(ROOT / "tests"))
     from helpers import kzg_powers, plonk_wiring_instance
 
-    log_d = 8
-    powers = kzg_powers(1 << log_d, 0xfeed)
-    pp, ww = plonk_wiring_instance(log_d, seed=4)
-    psh = czk_b200.king_share_batch(pp, world, seed=17)
-    expp = o.plonk_prove_wiring(oscheme, psh, ww, powers, seed=5, threads=max(1, o.cpu_threads() // world))
-    assert expp["status"] == 1
-    kb = ctx.bases_upload(1, powers)
-    gotp = czk_b200.plonk_prove_wiring(ctx, scheme, kb, log_d, ctx.vec_from(psh[rank]), ctx.vec_from(psh[rank]) if spdz else None,
-                                       ctx.vec_from(ww), seed=5)
-    for key in expp["proof"]:
-        assert (gotp["proof"][key] == expp["proof"][key]).all(), f"rank {rank}: plonk wiring proof differs at {key}"
-    assert (gotp["proof_share"]["open_pf_xy"] == expp["share_pf_xy"][rank]).all(), f"rank {rank}: plonk opening-proof shares differ"
-    assert (gotp["proof_share"]["open_pf_inf"] == expp["share_pf_inf"][rank]).all()
-    kb.free()
+    # twice: a power-of-two domain, and the reference's own wire-domain shape (3 * 2^k points, mixed radix)
+    for log_d, mixed in ((8, False), (6, True)):
+        D = (3 if mixed else 1) << log_d
+        powers = kzg_powers(D, 0xfeed + mixed)
+        pp, ww = plonk_wiring_instance(None, seed=4 + mixed, size=D)
+        psh = czk_b200.king_share_batch(pp, world, seed=17)
+        expp = o.plonk_prove_wiring(oscheme, psh, ww, powers, seed=5, threads=max(1, o.cpu_threads() // world))
+        assert expp["status"] == 1
+        kb = ctx.bases_upload(1, powers)
+        gotp = czk_b200.plonk_prove_wiring(ctx, scheme, kb, log_d, ctx.vec_from(psh[rank]), ctx.vec_from(psh[rank]) if spdz else None,
+                                           ctx.vec_from(ww), seed=5, mixed=mixed)
+        for key in expp["proof"]:
+            assert (gotp["proof"][key] == expp["proof"][key]).all(), f"rank {rank}: plonk wiring proof differs at {key} (mixed={mixed})"
+        assert (gotp["proof_share"]["open_pf_xy"] == expp["share_pf_xy"][rank]).all(), f"rank {rank}: plonk opening-proof shares differ"
+        assert (gotp["proof_share"]["open_pf_inf"] == expp["share_pf_inf"][rank]).all()
+        kb.free()
     launch.barrier()
     print(f"[rank {rank}/{world}] groth16 {args.scheme} n={n_sq}: parity ok; net {st}; opens over {ctx.share_transport}; link bytes {ctx.net_link_bytes()}", flush=True)
     party.close()

@@ -157,3 +157,58 @@ def test_ntt_batch_rejects_bad_arguments(ctx, czk, oracle):
     with pytest.raises(czk.CzkError):
         ctx.ntt_batch([v], 4, 7)  # no such transform
     ctx.ntt_batch([], 4, czk.NTT_FFT)  # nothing to do
+
+
+@pytest.mark.parametrize("log_m", [0, 1, 2, 3, 5, 9, 12, 15])
+def test_mixed_radix_ntt_matches_oracle(ctx, czk, oracle, log_m):
+    """czk_ntt_mixed_vec_batch over 3 * 2^log_m points (the Plonk prover's wire domain) against the oracle's restatement of
+    MixedRadixEvaluationDomain (algebra/poly/src/domain/mixed_radix.rs): all ops, several vectors per call."""
+    n = 3 << log_m
+    count = 3 if log_m <= 9 else 2
+    vs = [oracle.random_fr_mont(0xa00 + 5 * log_m + i, n) for i in range(count)]
+    for op in (czk.NTT_FFT, czk.NTT_IFFT, czk.NTT_COSET_FFT, czk.NTT_COSET_IFFT, czk.NTT_IFFT_COSET_FFT):
+        dv = [ctx.vec_from(v) for v in vs]
+        ctx.ntt_mixed_batch(dv, log_m, op)
+        for v, d in zip(vs, dv):
+            if op == czk.NTT_IFFT_COSET_FFT:
+                exp = oracle.ntt_mixed(oracle.ntt_mixed(v, True, False), False, True)
+            else:
+                exp = oracle.ntt_mixed(v, bool(op & 1), bool(op & 2))
+            assert (d.numpy() == exp).all(), (log_m, op)
+
+
+def test_mixed_radix_ntt_2_20_roundtrip_and_evaluation(ctx, czk, oracle, pymodel):
+    """3 * 2^20 points: iFFT(FFT(x)) = x, coset round trip, and X[j] = p(w^j) at a few j by Horner (size-independent checks)."""
+    log_m = 20
+    n = 3 << log_m
+    x = oracle.random_fr_mont(0xbeef, n)
+    d = ctx.vec_from(x)
+    ctx.ntt_mixed_batch([d], log_m, czk.NTT_FFT)
+    y = d.numpy()
+    w = czk.mixed_domain_params(log_m)["group_gen"]
+    for j in (0, 1, 3, (1 << log_m) + 5, n - 1):
+        assert (oracle.poly_eval(x, oracle.fr_pow_u64(w, j)) == y[j]).all(), j
+    ctx.ntt_mixed_batch([d], log_m, czk.NTT_IFFT)
+    assert (d.numpy() == x).all()
+    ctx.ntt_mixed_batch([d], log_m, czk.NTT_COSET_FFT)
+    ctx.ntt_mixed_batch([d], log_m, czk.NTT_COSET_IFFT)
+    assert (d.numpy() == x).all()
+
+
+def test_mixed_domain_params_match_oracle(czk, oracle):
+    for log_m in (0, 1, 7, 20):
+        got = czk.mixed_domain_params(log_m)
+        exp = oracle.mixed_domain_params(3 << log_m)
+        for k, e in zip(("group_gen", "group_gen_inv", "size_inv", "generator_inv"), exp):
+            assert (got[k] == e).all(), (log_m, k)
+
+
+def test_mixed_radix_ntt_rejects_bad_arguments(ctx, czk, oracle):
+    v = ctx.vec_from(oracle.random_fr_mont(1, 24))
+    with pytest.raises(czk.CzkError):
+        ctx.ntt_mixed_batch([v, v], 3, czk.NTT_FFT)
+    with pytest.raises(czk.CzkError):
+        ctx.ntt_mixed_batch([v], 4, czk.NTT_FFT)  # 48 points needed
+    with pytest.raises(czk.CzkError):
+        ctx.ntt_mixed_batch([v], 3, 9)
+    ctx.ntt_mixed_batch([], 3, czk.NTT_FFT)

@@ -106,15 +106,15 @@ def _g1_mul(oracle, xy, inf, k_int):
     return out, isinf
 
 
-@pytest.mark.parametrize("log_d", [3, 6])
-def test_plonk_wiring_proof_identities_and_kzg(oracle, pymodel, log_d):
+@pytest.mark.parametrize("D", [8, 64, 12, 48])
+def test_plonk_wiring_proof_identities_and_kzg(oracle, pymodel, D):
+    """Power-of-two domains and the reference's own wire domain shape, 3 * 2^k (MixedRadixEvaluationDomain)."""
     from helpers import kzg_powers, plonk_wiring_instance
 
     R = pymodel.R_MOD
-    D = 1 << log_d
-    tau = 0x1234567 + log_d
+    tau = 0x1234567 + D
     powers = kzg_powers(D, tau)
-    p, w = plonk_wiring_instance(log_d, seed=5 + log_d)
+    p, w = plonk_wiring_instance(None, seed=5 + D, size=D)
     res = oracle.plonk_prove_wiring(oracle.SCHEME_PLAIN, p[None], w, powers, seed=77)
     assert res["status"] == 1
     pf = res["proof"]
@@ -126,8 +126,8 @@ def test_plonk_wiring_proof_identities_and_kzg(oracle, pymodel, log_d):
     assert (t_wr - t_r * f_wr - Z(r) * q_r) % R == 0                       # lib.rs:184-187
     assert ((p_x + y * x + z) * l1_x - (p_x + y * w_x + z) - l2q_x * Z(x)) % R == 0  # lib.rs:246-249
     # KZG10 openings in the exponent: (tau - point) * W == C - value * G
-    dp = oracle.domain_params(D)
-    omega, omega_inv = oracle.fr_to_ints([dp["group_gen"], dp["group_gen_inv"]])
+    dp = oracle.mixed_domain_params(D)
+    omega, omega_inv = oracle.fr_to_ints([dp[0], dp[1]])
     g1, _ = oracle.generators()
     one = oracle.fr_from_ints([1])[0]
     p_cmt, p_cmt_inf = oracle.G1.msm(powers, None, p)
@@ -143,14 +143,12 @@ def test_plonk_wiring_proof_identities_and_kzg(oracle, pymodel, log_d):
         assert (None if lhs_inf else oracle.G1.affine_to_ints(lhs)[0]) == rhs, (slot, name)
 
 
-@pytest.mark.parametrize("scheme_name,parties", [("additive", 2), ("spdz", 2), ("spdz", 3), ("additive", 4)])
-def test_plonk_wiring_n_party_reveals_the_single_prover_proof(oracle, scheme_name, parties):
+@pytest.mark.parametrize("scheme_name,parties,D", [("additive", 2, 32), ("spdz", 2, 32), ("spdz", 3, 32), ("additive", 4, 32), ("spdz", 2, 24)])
+def test_plonk_wiring_n_party_reveals_the_single_prover_proof(oracle, scheme_name, parties, D):
     from helpers import kzg_powers, plonk_wiring_instance
 
-    log_d = 5
-    D = 1 << log_d
     powers = kzg_powers(D, 0xabcdef)
-    p, w = plonk_wiring_instance(log_d, seed=21)
+    p, w = plonk_wiring_instance(None, seed=21, size=D)
     single = oracle.plonk_prove_wiring(oracle.SCHEME_PLAIN, p[None], w, powers, seed=3)
     shares = oracle.king_share_batch(p, parties, seed=9)
     scheme = oracle.SCHEME_SPDZ if scheme_name == "spdz" else oracle.SCHEME_ADDITIVE

@@ -5,8 +5,9 @@
     torchrun --nproc-per-node P tools/proof.py -p groth16 -c squaring --computation-size N mpc --alg spdz
     torchrun --nproc-per-node P tools/proof.py -p plonk   -c squaring --computation-size N mpc --alg spdz
 
--p plonk times the device data path of the Plonk prover that is built (the wiring argument, czk_plonk_prove_wiring:
-mpc-plonk/src/lib.rs:110-258,343-400) over a domain of 3 N wires rounded up to a power of two, with a stand-in transcript;
+-p plonk times the device data path of the Plonk prover that is built (the wiring argument, czk_plonk_prove_wiring_mixed:
+mpc-plonk/src/lib.rs:110-258,343-400) over the reference's wire domain (3 * 2^k points for N <= 2^k gates, mixed radix), with a
+stand-in transcript;
 -p marlin is accepted for flag compatibility and reports that its prover loop is not built (its leaves - MSM, NTT, share
 products - are the same library calls).
 
@@ -94,8 +95,10 @@ def main_plonk(args, party):
         assert world == 1, "local proving is a single process"
         scheme = czk_b200.SCHEME_PLAIN
     spdz = scheme == czk_b200.SCHEME_SPDZ
-    log_d = max(3, (3 * args.computation_size - 1).bit_length())  # circ.domains.wires: 3 wires per gate, next power of two
-    D = 1 << log_d
+    # circ.domains: gates = Radix2EvaluationDomain::new(n_gates) (the circuit is padded to a power of two, proof.rs:232),
+    # wires = MixedRadixEvaluationDomain::new(3 * n_gates) (relations/flat.rs:287-300)
+    log_d = max(0, (args.computation_size - 1).bit_length())
+    D = 3 << log_d
     powers = ctx.bases_synthetic(1, 7, D, 0)
     if D >= 1024:
         powers.precompute(0)
@@ -106,16 +109,16 @@ def main_plonk(args, party):
     w[:, 3] &= np.uint64((1 << 60) - 1)
     mine = launch.king_share_scatter(p if rank == 0 else None, D, seed=2)
     args_ = (ctx, scheme, powers, log_d, ctx.vec_from(mine), ctx.vec_from(mine) if spdz else None, ctx.vec_from(w))
-    czk_b200.plonk_prove_wiring(*args_, seed=1)  # untimed first call: module loading, workspace, NCCL start-up
+    czk_b200.plonk_prove_wiring(*args_, seed=1, mixed=True)  # untimed first call: module loading, workspace, NCCL start-up
     ctx.net_reset_stats()
     launch.barrier()
     t = time.perf_counter()
-    res = czk_b200.plonk_prove_wiring(*args_, seed=2)
+    res = czk_b200.plonk_prove_wiring(*args_, seed=2, mixed=True)
     dt = launch.max_over_ranks(time.perf_counter() - t)
     if rank == 0:
         unit = f"{dt:.3f}s" if dt >= 1 else (f"{dt * 1e3:.3f}ms" if dt >= 1e-3 else f"{dt * 1e6:.3f}µs")
         print(f"End:     timed section ............................................................{unit}")
-        print(f"plonk wiring argument, domain 2^{log_d}: phases {res['phases_ms']}")
+        print(f"plonk wiring argument, wire domain 3*2^{log_d}: phases {res['phases_ms']}")
     print(f"Stats: {ctx.net_stats()}")
     party.close()
 

@@ -2,6 +2,7 @@
 # --set full pages of the dominant kernels (exported to CSV on the box: the reports exceed the 64 MiB that travels back).
 mkdir -p gpurun_out /tmp/ncu
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -4 > gpurun_out/r2_pytest_gpu.log; cat gpurun_out/r2_pytest_gpu.log
+timeout 300 python -c 'import __graft_entry__ as g; g.smoke(); print("smoke ok")' 2>&1 | tail -2 > gpurun_out/r2_smoke.log; cat gpurun_out/r2_smoke.log
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/r2_bench_1gpu.json 2> gpurun_out/r2_bench_1gpu.err; tail -c 300 gpurun_out/r2_bench_1gpu.json
 timeout 900 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/r2_bench_reference.json 2> gpurun_out/r2_bench_reference.err; cut -c1-400 gpurun_out/r2_bench_reference.json
 timeout 300 python bench.py --workload plonk --log-n 18 --steps 5 --warmup 3 > gpurun_out/r2_bench_plonk_1gpu.json 2>/dev/null
