@@ -159,7 +159,9 @@ def main():
         (OUT / b.name).write_text(line + "\n")
     for extra in ("mb.log", "sweep_parity.json", f"{TAG}_pytest_gpu.log", f"{TAG}_ntt_once.log", f"{TAG}_ab_bingcd.log", f"{TAG}_g2ab.log",
                   f"{TAG}_step5.log", f"{TAG}_step7.log", f"{TAG}_step8.log", f"{TAG}_step9.log", f"{TAG}_mp2.log", f"{TAG}_mp8.log",
-                  f"{TAG}_mp_spdz_8.log", f"{TAG}_mp_gsz_8.log", "mp_pytest_additive_2.log", "mp_pytest_spdz_2.log", "mp_pytest_gsz_2.log"):
+                  f"{TAG}_step11.log", f"{TAG}_step12.log", f"{TAG}_step13.log", f"{TAG}_pytest_mixed.log", f"{TAG}_smoke.log",
+                  f"{TAG}_mp2c.log", f"{TAG}_mp4b.log", f"{TAG}_mp8b.log", f"{TAG}_mp_spdz_2.log", f"{TAG}_mp_spdz_4.log", f"{TAG}_mp_gsz_2.log",
+                  f"{TAG}_mp_gsz_4.log", f"{TAG}_mp_spdz_8.log", f"{TAG}_mp_gsz_8.log", "mp_pytest_additive_2.log", "mp_pytest_spdz_2.log", "mp_pytest_gsz_2.log"):
         p = G / extra
         if p.exists():
             md += [f"## `{extra}`", "", "```", p.read_text()[:6000], "```", ""]
