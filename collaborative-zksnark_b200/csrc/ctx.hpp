@@ -85,6 +85,12 @@ struct MixedDomain {
     uint32_t *wpow = nullptr, *wipow = nullptr;
     HFr group_gen, group_gen_inv, size_inv, third_inv, zeta, zeta_inv;
 };
+// what the last GSZ group product check opened (czk_groth16_gsz_last_checks)
+struct GszCheckOut {
+    uint64_t group_x[4] = {0, 0, 0, 0};
+    uint64_t group_yz[24] = {};
+    uint8_t group_inf[2] = {0, 0};
+};
 struct Scratch {
     void* p = nullptr;
     size_t cap = 0;
@@ -152,6 +158,8 @@ struct czk_ctx {
     Scratch open_gather, open_sigma, open_sx, open_oy, open_d, open_dm;
     Scratch mixed;  // the three de-interleaved subsequences of every vector of a mixed-radix batch
     uint32_t* flag = nullptr;
+    double phases[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // host-side phase times of the last proof (czk_groth16_last_phases)
+    GszCheckOut gsz_check;
     cudaEvent_t ev_phase[2] = {nullptr, nullptr};  // witness-map start / stop on the context stream (phase report)
     // network
     int rank = 0, nranks = 1;

@@ -29,7 +29,6 @@ struct czk_pk {
 static double now_ms() {
     return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
-static thread_local double g_phases[8];
 
 // A constraint system in CSR form on the device (the reference's ConstraintMatrices, relations/src/r1cs): for matrix
 // m in {A, B, C}, row i holds entries row_ptr[m][i] .. row_ptr[m][i+1] of (col[m], coeff[m]).
@@ -69,7 +68,14 @@ int czk_r1cs_upload(czk_ctx* ctx, size_t ncons, size_t ninst, size_t nwit, const
                     const uint32_t* const col[3], const uint64_t* const coeff[3], czk_r1cs** out) {
     if (!ctx || !out || !row_ptr || !col || !coeff || !ncons || !ninst) return fail(ctx, CZK_ERR_ARG, "czk_r1cs_upload: argument");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
-    czk_r1cs* r = new czk_r1cs();
+    struct Guard {
+        czk_ctx* ctx;
+        czk_r1cs* r;
+        ~Guard() {
+            if (r) czk_r1cs_free(ctx, r);
+        }
+    } guard{ctx, new czk_r1cs()};
+    czk_r1cs* r = guard.r;
     r->ncons = ncons;
     r->ninst = ninst;
     r->nwit = nwit;
@@ -91,6 +97,7 @@ int czk_r1cs_upload(czk_ctx* ctx, size_t ncons, size_t ninst, size_t nwit, const
         }
     }
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    guard.r = nullptr;
     *out = r;
     return CZK_OK;
 }
@@ -424,8 +431,9 @@ int czk_groth16_pk_vk(const czk_pk* pk, uint64_t vk_g1[36], uint64_t vk_g2[72]) 
     std::memcpy(vk_g2, pk->vk_g2, sizeof pk->vk_g2);
     return CZK_OK;
 }
-int czk_groth16_last_phases(const czk_ctx*, double out_ms[8]) {
-    for (int i = 0; i < 8; i++) out_ms[i] = g_phases[i];
+int czk_groth16_last_phases(const czk_ctx* ctx, double out_ms[8]) {
+    if (!ctx || !out_ms) return CZK_ERR_ARG;
+    for (int i = 0; i < 8; i++) out_ms[i] = ctx->phases[i];
     return CZK_OK;
 }
 
@@ -481,7 +489,7 @@ static int witness_map_dev(czk_ctx* ctx, int scheme, size_t n_sq, unsigned log_d
             CZK_TRY(czk_vec_copy(ctx, v.bm, 0, v.b, 0, D));
             CZK_TRY(czk_vec_copy(ctx, v.cm, 0, v.c, 0, D));
         }
-        g_phases[0] = now_ms() - t0;
+        ctx->phases[0] = now_ms() - t0;
         if (after_inputs) CZK_TRY(after_inputs());
         return witness_map_transforms(ctx, scheme, log_d, v, defer_check);
     }
@@ -511,7 +519,7 @@ static int witness_map_dev(czk_ctx* ctx, int scheme, size_t n_sq, unsigned log_d
         CZK_TRY(czk_vec_copy(ctx, v.bm, 0, v.b, 0, D));
         CZK_TRY(czk_vec_copy(ctx, v.cm, 0, v.c, 0, D));
     }
-    g_phases[0] = now_ms() - t0;
+    ctx->phases[0] = now_ms() - t0;
     if (after_inputs) CZK_TRY(after_inputs());
     return witness_map_transforms(ctx, scheme, log_d, v, defer_check);
 }
@@ -547,7 +555,7 @@ static int witness_map_transforms(czk_ctx* ctx, int scheme, unsigned log_d, Shar
     if (ctx->ev_phase[1]) CUDA_TRY(ctx, cudaEventRecord(ctx->ev_phase[1], ctx->stream));
     if (!defer_check) {
         CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        g_phases[1] = now_ms() - t0;
+        ctx->phases[1] = now_ms() - t0;
     }
     return CZK_OK;
 }
@@ -680,12 +688,6 @@ int gsz_mult1(czk_ctx* ctx, const HFr& x, const HFr& y, HFr* out);
 int czk_gsz_open_scalar_internal(czk_ctx* ctx, const HFr& v, HFr* out);
 int czk_gsz_prepare_internal(czk_ctx* ctx);
 
-struct GszCheckOut {
-    uint64_t group_x[4];
-    uint64_t group_yz[24];
-    uint8_t group_inf[2];
-};
-static thread_local GszCheckOut g_gsz_check;
 
 template <class HF>
 static HPoint<HF> pt_scale(const HPoint<HF>& p, const HFr& s) {
@@ -808,12 +810,12 @@ static int gsz_g1_product_check(czk_ctx* ctx, std::vector<HFr> x, std::vector<HG
     ctx->gsz.opens += 2;
     CZK_TRY((gsz_group_open<HFq, 6>(ctx, yb, ctx->gsz.t, &fy)));
     CZK_TRY((gsz_group_open<HFq, 6>(ctx, ib, ctx->gsz.t, &fz)));
-    fx.to_limbs(g_gsz_check.group_x);
-    g_gsz_check.group_inf[0] = (uint8_t)GShare<HFq, 6>::to_affine_limbs(fy, g_gsz_check.group_yz);
-    g_gsz_check.group_inf[1] = (uint8_t)GShare<HFq, 6>::to_affine_limbs(fz, g_gsz_check.group_yz + 12);
+    fx.to_limbs(ctx->gsz_check.group_x);
+    ctx->gsz_check.group_inf[0] = (uint8_t)GShare<HFq, 6>::to_affine_limbs(fy, ctx->gsz_check.group_yz);
+    ctx->gsz_check.group_inf[1] = (uint8_t)GShare<HFq, 6>::to_affine_limbs(fz, ctx->gsz_check.group_yz + 12);
     uint64_t chk[12];
     int chk_inf = GShare<HFq, 6>::to_affine_limbs(pt_scale(fy, fx), chk);
-    if (chk_inf != (int)g_gsz_check.group_inf[1] || std::memcmp(chk, g_gsz_check.group_yz + 12, sizeof chk) != 0)
+    if (chk_inf != (int)ctx->gsz_check.group_inf[1] || std::memcmp(chk, ctx->gsz_check.group_yz + 12, sizeof chk) != 0)
         return fail(ctx, CZK_ERR_PROTOCOL, "GSZ group product check failed (gsz20/mod.rs:1326 assert_eq!)");
     return CZK_OK;
 }
@@ -902,7 +904,7 @@ static int prove_tail_gsz(czk_ctx* ctx, const czk_pk* pk, const TailPre& pre, co
     proof_inf[0] = (uint8_t)S1::to_affine_limbs(A, proof);
     proof_inf[1] = (uint8_t)S2::to_affine_limbs(B, proof + 12);
     proof_inf[2] = (uint8_t)S1::to_affine_limbs(Cc, proof + 36);
-    g_phases[7] = now_ms() - t0;
+    ctx->phases[7] = now_ms() - t0;
     return CZK_OK;
 }
 
@@ -910,9 +912,9 @@ int czk_groth16_gsz_last_checks(const czk_ctx* ctx, uint64_t field_xyz[12], uint
                                 uint8_t group_inf[2], uint64_t counts[2]) {
     if (!ctx) return CZK_ERR_ARG;
     if (field_xyz) std::memcpy(field_xyz, ctx->gsz.last_check, sizeof ctx->gsz.last_check);
-    if (group_x) std::memcpy(group_x, g_gsz_check.group_x, sizeof g_gsz_check.group_x);
-    if (group_yz) std::memcpy(group_yz, g_gsz_check.group_yz, sizeof g_gsz_check.group_yz);
-    if (group_inf) std::memcpy(group_inf, g_gsz_check.group_inf, 2);
+    if (group_x) std::memcpy(group_x, ctx->gsz_check.group_x, sizeof ctx->gsz_check.group_x);
+    if (group_yz) std::memcpy(group_yz, ctx->gsz_check.group_yz, sizeof ctx->gsz_check.group_yz);
+    if (group_inf) std::memcpy(group_inf, ctx->gsz_check.group_inf, 2);
     if (counts) {
         counts[0] = ctx->gsz.king_computes;
         counts[1] = ctx->gsz.opens;
@@ -931,7 +933,7 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     typedef GShare<HFq2, 12> S2;
     const size_t n_sq = pk->n_sq, D = pk->D;
     if (!cs && !n_sq) return fail(ctx, CZK_ERR_ARG, "czk_groth16_prove: this key was uploaded for a general circuit - use czk_groth16_prove_r1cs");
-    for (int i = 0; i < 8; i++) g_phases[i] = 0;
+    for (int i = 0; i < 8; i++) ctx->phases[i] = 0;
     std::future<TailPre> tail_pre;
     try {
         tail_pre = std::async(std::launch::async, tail_precompute, pk, r_sh, s_sh);
@@ -978,22 +980,22 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     S2 b2_acc;
     // collect in each lane's enqueue order; the phase figures are each job's device time on its own stream (the jobs overlap,
     // so they do not add up to the proof time)
-    if ((rc = msm_collect(ctx, &job_l, o1, &g_phases[3])) != CZK_OK) return fin(rc);
+    if ((rc = msm_collect(ctx, &job_l, o1, &ctx->phases[3])) != CZK_OK) return fin(rc);
     l_acc.sh = l_acc.mac = S1::from_jac_out(o1);
-    if ((rc = msm_collect(ctx, &job_b2, o2, &g_phases[6])) != CZK_OK) return fin(rc);
+    if ((rc = msm_collect(ctx, &job_b2, o2, &ctx->phases[6])) != CZK_OK) return fin(rc);
     b2_acc.sh = b2_acc.mac = S2::from_jac_out(o2);
-    if ((rc = msm_collect(ctx, &job_b1, o1, &g_phases[5])) != CZK_OK) return fin(rc);
+    if ((rc = msm_collect(ctx, &job_b1, o1, &ctx->phases[5])) != CZK_OK) return fin(rc);
     b1_acc.sh = b1_acc.mac = S1::from_jac_out(o1);
-    if ((rc = msm_collect(ctx, &job_a, o1, &g_phases[4])) != CZK_OK) return fin(rc);
+    if ((rc = msm_collect(ctx, &job_a, o1, &ctx->phases[4])) != CZK_OK) return fin(rc);
     a_acc.sh = a_acc.mac = S1::from_jac_out(o1);
-    if ((rc = msm_collect(ctx, &job_h, o1, &g_phases[2])) != CZK_OK) return fin(rc);
+    if ((rc = msm_collect(ctx, &job_h, o1, &ctx->phases[2])) != CZK_OK) return fin(rc);
     h_acc.sh = h_acc.mac = S1::from_jac_out(o1);
     // the h MSM waited for the witness map, so the context stream is idle now: the SPDZ MAC verdict of the Beaver product
     // (spdz.rs:182) is read here, once per proof
     if (scheme == CZK_SCHEME_SPDZ && (rc = sh_collect_flags(ctx, "czk_groth16_prove (witness-map product)")) != CZK_OK) return fin(rc);
     {
         float wm = 0;
-        if (ctx->ev_phase[0] && cudaEventElapsedTime(&wm, ctx->ev_phase[0], ctx->ev_phase[1]) == cudaSuccess) g_phases[1] = wm;
+        if (ctx->ev_phase[0] && cudaEventElapsedTime(&wm, ctx->ev_phase[0], ctx->ev_phase[1]) == cudaSuccess) ctx->phases[1] = wm;
     }
     free_share_vecs(ctx, v);
 
@@ -1060,6 +1062,6 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     proof_inf[0] = (uint8_t)S1::to_affine_limbs(A, proof);
     proof_inf[1] = (uint8_t)S2::to_affine_limbs(B, proof + 12);
     proof_inf[2] = (uint8_t)S1::to_affine_limbs(Cc, proof + 36);
-    g_phases[7] = now_ms() - t0;
+    ctx->phases[7] = now_ms() - t0;
     return CZK_OK;
 }

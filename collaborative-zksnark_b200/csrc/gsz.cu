@@ -336,6 +336,17 @@ int czk_gsz_king_compute(czk_ctx* ctx, czk_vec* v, unsigned degree, size_t n) {
     return gsz_check_flag(ctx, "czk_gsz_king_compute");
 }
 
+// stream-ordered device buffers that must not outlive an error return
+struct AsyncFree {
+    cudaStream_t st;
+    void* p[3] = {nullptr, nullptr, nullptr};
+    ~AsyncFree() {
+        for (void* q : p)
+            if (q) cudaFreeAsync(q, st);
+    }
+    void release() { p[0] = p[1] = p[2] = nullptr; }
+};
+
 int czk_gsz_batch_mul(czk_ctx* ctx, czk_vec* x, const czk_vec* y, size_t n, int queue_check) {
     if (!ctx || !x || !y || n > x->n || n > y->n) return fail(ctx, CZK_ERR_ARG, "czk_gsz_batch_mul: range");
     CUDA_TRY(ctx, cudaSetDevice(ctx->device));
@@ -343,11 +354,15 @@ int czk_gsz_batch_mul(czk_ctx* ctx, czk_vec* x, const czk_vec* y, size_t n, int 
     if (!n) return CZK_OK;
     GszState& g = ctx->gsz;
     GszTriple tr;
+    AsyncFree guard{ctx->stream};
     if (queue_check) {  // GszFieldTriple(x, y, z) kept for hadamard_check (:585-592)
         tr.n = n;
         CUDA_TRY(ctx, cudaMallocAsync((void**)&tr.x, n * 32, ctx->stream));
+        guard.p[0] = tr.x;
         CUDA_TRY(ctx, cudaMallocAsync((void**)&tr.y, n * 32, ctx->stream));
+        guard.p[1] = tr.y;
         CUDA_TRY(ctx, cudaMallocAsync((void**)&tr.z, n * 32, ctx->stream));
+        guard.p[2] = tr.z;
         CUDA_TRY(ctx, cudaMemcpyAsync(tr.x, x->d, n * 32, cudaMemcpyDeviceToDevice, ctx->stream));
         CUDA_TRY(ctx, cudaMemcpyAsync(tr.y, y->d, n * 32, cudaMemcpyDeviceToDevice, ctx->stream));
     }
@@ -362,6 +377,7 @@ int czk_gsz_batch_mul(czk_ctx* ctx, czk_vec* x, const czk_vec* y, size_t n, int 
     if (queue_check) {
         CUDA_TRY(ctx, cudaMemcpyAsync(tr.z, x->d, n * 32, cudaMemcpyDeviceToDevice, ctx->stream));
         g.queue.push_back(tr);
+        guard.release();  // the queue owns them now
     }
     return gsz_check_flag(ctx, "czk_gsz_batch_mul");
 }
@@ -412,6 +428,8 @@ int czk_gsz_check_products(czk_ctx* ctx, uint64_t final3[12]) {
     uint32_t *x = (uint32_t*)g.pad_x.p, *y = (uint32_t*)g.pad_y.p;
     uint32_t* z = nullptr;
     CUDA_TRY(ctx, cudaMallocAsync((void**)&z, k * 32, ctx->stream));
+    AsyncFree z_guard{ctx->stream};
+    z_guard.p[0] = z;
     size_t off = 0;
     for (GszTriple& t : g.queue) {
         CUDA_TRY(ctx, cudaMemcpyAsync(x + off * 8, t.x, t.n * 32, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -445,6 +463,7 @@ int czk_gsz_check_products(czk_ctx* ctx, uint64_t final3[12]) {
     HFr ip;
     CUDA_TRY(ctx, cudaMemcpyAsync(ip.l, d, 32, cudaMemcpyDeviceToHost, ctx->stream));
     CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    z_guard.release();
     CUDA_TRY(ctx, cudaFreeAsync(z, ctx->stream));
     size_t len = k;
     while (len > 1) {
