@@ -830,13 +830,13 @@ int czk_bases_device_bytes(const czk_bases* b, uint64_t out[2]) {
 // the context stream; msm_collect returns its result.  Internal (ctx.hpp): the Groth16 prover keeps its five MSMs and the
 // witness map in flight together.
 int msm_bases_enqueue(czk_ctx* ctx, int lane, const czk_bases* b, size_t base_off, const czk_vec* sc, size_t sc_off,
-                      int scalars_montgomery, size_t n, MsmJob* job) {
+                      int scalars_montgomery, size_t n, MsmJob* job, bool reuse_plan) {
     if (!ctx || !b || !sc || !job || base_off + n > b->n || sc_off + n > sc->n) return fail(ctx, CZK_ERR_ARG, "czk_msm_bases: range");
     size_t pw = b->curve == 1 ? 24 : 48;
     if (b->table && n >= 1024) {
         MsmConfig cfg = msm_merged_config(b->pre_c, b->n, base_off, msm_table_stride_words(b->curve));
         return msm_enqueue(ctx, lane, b->curve, b->table, b->inf ? b->inf + base_off : nullptr, (const uint32_t*)(sc->d + 4 * sc_off),
-                           scalars_montgomery, n, &cfg, false, job);
+                           scalars_montgomery, n, &cfg, reuse_plan, job);
     }
     return msm_enqueue(ctx, lane, b->curve, b->xy + base_off * pw, b->inf ? b->inf + base_off : nullptr,
                        (const uint32_t*)(sc->d + 4 * sc_off), scalars_montgomery, n, nullptr, false, job);

@@ -178,7 +178,7 @@ struct czk_ctx {
 
 // asynchronous MSM over resident bases (api.cu): enqueue on lane 0 / 1, collect in enqueue order per lane
 int msm_bases_enqueue(czk_ctx* ctx, int lane, const czk_bases* b, size_t base_off, const czk_vec* sc, size_t sc_off,
-                      int scalars_montgomery, size_t n, MsmJob* job);
+                      int scalars_montgomery, size_t n, MsmJob* job, bool reuse_plan = false);
 int msm_collect(czk_ctx* ctx, MsmJob* job, uint64_t* out_xyz, double* device_ms);
 
 // shares.cu: the Beaver product without the final verdict read-back, and the read-back itself (one stream synchronisation)

@@ -24,6 +24,9 @@ struct czk_pk {
     uint64_t a0[12], b10[12], b20[24];
     uint8_t a0_inf = 0, b10_inf = 0, b20_inf = 0;
     std::vector<uint64_t> gamma_abc;  // ninst x 12 limbs when the key was generated here (czk_groth16_setup*), else empty
+    // the a- and b_g1-query MSMs take the same scalars; when the two queries also agree on which bases are infinity (and on
+    // table shape) the second one reuses the first one's digit sort (msm_run's reuse_plan)
+    bool ab_share_plan = false;
 };
 
 static double now_ms() {
@@ -135,6 +138,21 @@ static int pk_finish(czk_ctx* ctx, czk_pk* pk) {
     pk->b10_inf = inf;
     CZK_TRY(czk_bases_download(ctx, pk->q[2], 0, 1, pk->b20, &inf));
     pk->b20_inf = inf;
+    const czk_bases *qa = pk->q[0], *qb = pk->q[1];
+    const char* share_env = getenv("CZK_AB_SHARE_PLAN");
+    pk->ab_share_plan = false;
+    if (!(share_env && atoi(share_env) == 0) && qa->table && qb->table && qa->pre_c == qb->pre_c && qa->n == qb->n && qa->n > 1 &&
+        (qa->inf != nullptr) == (qb->inf != nullptr)) {
+        uint32_t differ = 0;
+        if (qa->inf) {  // entry 0 is added on the host (calculate_coeff): the MSMs start at base 1
+            CUDA_TRY(ctx, cudaMemsetAsync(ctx->flag, 0, 4, ctx->stream));
+            CUDA_TRY(ctx, msm_flags_differ(qa->inf + 1, qb->inf + 1, qa->n - 1, ctx->flag, ctx->stream));
+            CUDA_TRY(ctx, cudaMemcpyAsync(&differ, ctx->flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+            if (differ) CUDA_TRY(ctx, cudaMemsetAsync(ctx->flag, 0, 4, ctx->stream));  // its other users expect it clear
+        }
+        pk->ab_share_plan = differ == 0;
+    }
     return CZK_OK;
 }
 
@@ -946,7 +964,7 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     // ---- the five MSMs (prover.rs:104,108,132,143,155); share-local, no communication.
     // SPDZ computes sh and mac as the same MSM of the value shares (spdz.rs:440-446): done once, used twice.
     // Four of them take only the assignment, so they are enqueued BEFORE the witness map, on the context's two MSM lanes
-    // (lane 0: l, b_g1, then h; lane 1: b_g2, a): the transforms run on the context stream under their accumulation rounds,
+    // (lane 0: a, b_g1 on a's digit sort, then h; lane 1: b_g2, l): the transforms run on the context stream under their accumulation rounds,
     // and the serial stretches of one MSM (digit sort, finish walk, bucket reduction, host tail) run under another's rounds.
     // Nothing is read back between the kernels of an MSM, so the host only waits when it collects.
     MsmJob job_h, job_l, job_a, job_b1, job_b2;
@@ -961,10 +979,11 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
         const size_t wit_off = cs ? pk->ninst : 0, n_wit = pk->nwit;
         const czk_vec* asg_vec = cs ? v.full : v.assign;
         const size_t asg_off = cs ? 1 : 0, n_asg = pk->ninst + pk->nwit - 1;
-        CZK_TRY(msm_bases_enqueue(ctx, 0, pk->q[4], 0, wit_vec, wit_off, 1, n_wit, &job_l));
+        // a and b_g1 back to back on one lane: same scalars, so b_g1 runs on a's digit sort when the key allows it
+        CZK_TRY(msm_bases_enqueue(ctx, 0, pk->q[0], 1, asg_vec, asg_off, 1, n_asg, &job_a));
         CZK_TRY(msm_bases_enqueue(ctx, 1, pk->q[2], 1, asg_vec, asg_off, 1, n_asg, &job_b2));
-        CZK_TRY(msm_bases_enqueue(ctx, 0, pk->q[1], 1, asg_vec, asg_off, 1, n_asg, &job_b1));
-        CZK_TRY(msm_bases_enqueue(ctx, 1, pk->q[0], 1, asg_vec, asg_off, 1, n_asg, &job_a));
+        CZK_TRY(msm_bases_enqueue(ctx, 0, pk->q[1], 1, asg_vec, asg_off, 1, n_asg, &job_b1, pk->ab_share_plan));
+        CZK_TRY(msm_bases_enqueue(ctx, 1, pk->q[4], 0, wit_vec, wit_off, 1, n_wit, &job_l));
         return CZK_OK;
     };
     int rc = witness_map_dev(ctx, scheme, n_sq, pk->log_d, chain_sh, chain_dev, v, cs, full_sh, enqueue_witness_msms, true);
@@ -980,14 +999,14 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     S2 b2_acc;
     // collect in each lane's enqueue order; the phase figures are each job's device time on its own stream (the jobs overlap,
     // so they do not add up to the proof time)
-    if ((rc = msm_collect(ctx, &job_l, o1, &ctx->phases[3])) != CZK_OK) return fin(rc);
-    l_acc.sh = l_acc.mac = S1::from_jac_out(o1);
+    if ((rc = msm_collect(ctx, &job_a, o1, &ctx->phases[4])) != CZK_OK) return fin(rc);
+    a_acc.sh = a_acc.mac = S1::from_jac_out(o1);
     if ((rc = msm_collect(ctx, &job_b2, o2, &ctx->phases[6])) != CZK_OK) return fin(rc);
     b2_acc.sh = b2_acc.mac = S2::from_jac_out(o2);
     if ((rc = msm_collect(ctx, &job_b1, o1, &ctx->phases[5])) != CZK_OK) return fin(rc);
     b1_acc.sh = b1_acc.mac = S1::from_jac_out(o1);
-    if ((rc = msm_collect(ctx, &job_a, o1, &ctx->phases[4])) != CZK_OK) return fin(rc);
-    a_acc.sh = a_acc.mac = S1::from_jac_out(o1);
+    if ((rc = msm_collect(ctx, &job_l, o1, &ctx->phases[3])) != CZK_OK) return fin(rc);
+    l_acc.sh = l_acc.mac = S1::from_jac_out(o1);
     if ((rc = msm_collect(ctx, &job_h, o1, &ctx->phases[2])) != CZK_OK) return fin(rc);
     h_acc.sh = h_acc.mac = S1::from_jac_out(o1);
     // the h MSM waited for the witness map, so the context stream is idle now: the SPDZ MAC verdict of the Beaver product
