@@ -69,6 +69,7 @@ struct Prover {
     ~Prover() {
         bool in_flight = false;
         for (Pending& pd : pending) in_flight |= pd.job.lane >= 0;
+        for (PendingCommit& pc : commits) in_flight |= pc.job.lane >= 0;
         if (in_flight) {  // error path: nothing of this call may still be running when its vectors are freed
             czk_ctx_sync(ctx);
             for (MsmLane& l : ctx->lanes) l.collected = l.enqueued;
@@ -128,17 +129,43 @@ struct Prover {
     }
     int mul(SVec& a, const SVec& b) { return czk_beaver_batch_mul(ctx, scheme, a.sh, a.mac, b.sh, b.mac, D); }
 
-    // commit (lib.rs:367-400): MSM of this party's coefficient shares, publicize (group open), absorb
-    int commit(const SVec& poly, uint64_t cmt_xy[12], uint8_t* cmt_inf) {
-        uint64_t o[18];
-        CZK_TRY(czk_msm_bases(ctx, powers, 0, poly.sh, 0, 1, D, o));
-        S1 s;
-        s.sh = s.mac = S1::from_jac_out(o);  // spdz.rs:440-446: both MSMs run on the value shares
-        HG1 opened;
-        CZK_TRY((group_open<HFq, 6>(ctx, scheme, s, &opened)));
-        *cmt_inf = (uint8_t)S1::to_affine_limbs(opened, cmt_xy);
-        tr->absorb_g1(tr->user, cmt_xy, *cmt_inf);
+    // commit (lib.rs:367-400): MSM of this party's coefficient shares, publicize (group open), absorb.  Split in two so that
+    // a commitment nothing waits for yet (l1, t: no challenge is drawn before the q commitment) runs on an MSM lane under
+    // the transforms and share protocols that follow; commit_finish keeps the reference's absorb order.
+    struct PendingCommit {
+        MsmJob job;
+        uint64_t* cmt_xy;
+        uint8_t* cmt_inf;
+    };
+    std::vector<PendingCommit> commits;
+    int commit_enqueue(const SVec& poly, int lane, uint64_t cmt_xy[12], uint8_t* cmt_inf) {
+        PendingCommit pc;
+        pc.cmt_xy = cmt_xy;
+        pc.cmt_inf = cmt_inf;
+        pc.job.lane = -1;
+        if (ctx->lanes[lane].enqueued - ctx->lanes[lane].collected >= CZK_MSM_SLOTS) return fail(ctx, CZK_ERR_ARG, "plonk: commitment queue full");
+        CZK_TRY(msm_bases_enqueue(ctx, lane, powers, 0, poly.sh, 0, 1, D, &pc.job));
+        commits.push_back(pc);
         return CZK_OK;
+    }
+    int commit_finish() {  // in enqueue order = the order the reference commits in
+        for (PendingCommit& pc : commits) {
+            uint64_t o[18];
+            CZK_TRY(msm_collect(ctx, &pc.job, o, nullptr));
+            pc.job.lane = -1;
+            S1 s;
+            s.sh = s.mac = S1::from_jac_out(o);  // spdz.rs:440-446: both MSMs run on the value shares
+            HG1 opened;
+            CZK_TRY((group_open<HFq, 6>(ctx, scheme, s, &opened)));
+            *pc.cmt_inf = (uint8_t)S1::to_affine_limbs(opened, pc.cmt_xy);
+            tr->absorb_g1(tr->user, pc.cmt_xy, *pc.cmt_inf);
+        }
+        commits.clear();
+        return CZK_OK;
+    }
+    int commit(const SVec& poly, uint64_t cmt_xy[12], uint8_t* cmt_inf) {
+        CZK_TRY(commit_enqueue(poly, 0, cmt_xy, cmt_inf));
+        return commit_finish();
     }
 
     // eval (lib.rs:343-365): KZG10 open at x.  The witness polynomial's MSM is only ENQUEUED (lane = slot & 1); the value is
@@ -248,14 +275,14 @@ static int prove_wiring_impl(czk_ctx* ctx, int scheme, const czk_bases* powers, 
     CZK_TRY(P.copy(l1, l1e));
     CZK_TRY(P.ntt({&l1}, CZK_NTT_IFFT));
     double t0 = now_ms();
-    CZK_TRY(timed(t_commit, P.commit(l1, out->cmt_xy[0], &out->cmt_inf[0]), t0));
+    CZK_TRY(timed(t_commit, P.commit_enqueue(l1, 0, out->cmt_xy[0], &out->cmt_inf[0]), t0));  // absorbed before t and q, below
     // ---- prove_unit_product(f = l1)
     CZK_TRY(P.copy(t, l1));
     CZK_TRY(P.ntt({&t}, CZK_NTT_FFT));  // f.evaluate_over_domain_by_ref
     CZK_TRY(czk_share_partial_products(ctx, scheme, t.sh, t.mac, D));
     CZK_TRY(P.ntt({&t}, CZK_NTT_IFFT));
     t0 = now_ms();
-    CZK_TRY(timed(t_commit, P.commit(t, out->cmt_xy[1], &out->cmt_inf[1]), t0));
+    CZK_TRY(timed(t_commit, P.commit_enqueue(t, 1, out->cmt_xy[1], &out->cmt_inf[1]), t0));
     CZK_TRY(P.copy(fe, l1));
     CZK_TRY(P.distribute_powers(fe, w));
     CZK_TRY(P.copy(tc, t));
@@ -267,7 +294,7 @@ static int prove_wiring_impl(czk_ctx* ctx, int scheme, const czk_bases* powers, 
     CZK_TRY(P.div_vanishing(tw));
     CZK_TRY(P.ntt({&tw}, CZK_NTT_COSET_IFFT));  // q
     t0 = now_ms();
-    CZK_TRY(timed(t_commit, P.commit(tw, out->cmt_xy[2], &out->cmt_inf[2]), t0));
+    CZK_TRY(timed(t_commit, P.commit(tw, out->cmt_xy[2], &out->cmt_inf[2]), t0));  // collects l1, t, q in that order
     const HFr r = draw(2);
     const HFr wr = HFr::mul(w, r);
     t0 = now_ms();
