@@ -56,3 +56,18 @@ def test_czk_arm_refuses_to_run_without_a_gpu():
     r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1"], capture_output=True, text=True, cwd=str(ROOT), timeout=300)
     assert r.returncode != 0 and r.stdout.strip() == ""
     assert "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
+
+
+def test_plonk_reference_arm_both_domain_shapes():
+    """--workload plonk: the wiring argument on the host CPU over the reference's 3 * 2^k-point wire domain (default) and
+    over a power-of-two domain; one JSON line each, labelled with the domain it ran."""
+    for extra, needle in ((["--plonk-domain", "mixed"], "3*2^4"), (["--plonk-domain", "radix2"], "over a 2^4 domain")):
+        r = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--workload", "plonk", "--log-n", "4", "--steps", "1",
+                            "--warmup", "0"] + extra, capture_output=True, text=True, cwd=str(ROOT), timeout=300)
+        assert r.returncode == 0, r.stderr[-2000:]
+        lines = [l for l in r.stdout.splitlines() if l.strip()]
+        assert len(lines) == 1
+        d = json.loads(lines[0])
+        assert d["impl"] == "reference" and d["metric"] == "plonk_wiring_proof_ms_2^4_bls12_377" and d["value"] > 0
+        assert needle in d["config"]["workload"] and needle.replace("over a ", "") in d["cpu_baseline"]["sample"]
+        assert d["e2e"]["h2d_bytes_per_step"] == 0
