@@ -114,6 +114,7 @@ void czk_ctx_destroy(czk_ctx* ctx) {
         cudaFree(d.g_hi_sinv);
         cudaFree(d.gi_lo);
         cudaFree(d.gi_hi);
+        cudaFree(d.g_sinv_br);
     }
     for (auto& kv : ctx->mixed_domains) {
         cudaFree(kv.second.wpow);
@@ -281,9 +282,23 @@ static int ntt_batch_dev(czk_ctx* ctx, uint32_t* const* data, int count, unsigne
         uint32_t* const* v = data + at;
         if (op == CZK_NTT_IFFT_COSET_FFT && log_d > 2) {
             CUDA_TRY(ctx, ntt_run_tiles(v, cnt, d->tw, (int)log_d, true, false, none, none, ctx->stream));  // natural -> bit-reversed
-            // D^-1 g^i on the way into the forward transform; position p holds coefficient bitrev(p)
-            CUDA_TRY(ctx, ntt_run_tiles(v, cnt, d->tw, (int)log_d, false, true, scale_tables(d->g_lo, d->g_hi_sinv, d->lo_log, true), none,
-                                        ctx->stream));
+            // D^-1 g^i on the way into the forward transform; position p holds coefficient bitrev(p).  One table entry per
+            // position (32 B x D, built once per domain): a coalesced load and one product where the two-level tables cost two
+            // scattered loads and two products
+            static const bool direct = [] { const char* e = getenv("CZK_NTT_DIRECT_SCALE"); return !(e && atoi(e) == 0); }();
+            if (direct && !d->g_sinv_br && log_d >= 10) {
+                HFr g = HFr::from_limbs(FrParams::GENERATOR_64);
+                CUDA_TRY(ctx, cudaMalloc((void**)&d->g_sinv_br, ((size_t)1 << log_d) * 32));
+                CUDA_TRY(ctx, ntt_build_powers(d->g_sinv_br, g.l, d->size_inv.l, (size_t)1 << log_d, ctx->stream));
+                CUDA_TRY(ctx, ntt_bitrev_scale(d->g_sinv_br, (int)log_d, 0, nullptr, nullptr, nullptr, 0, ctx->stream));
+            }
+            NttScale pre_dit = scale_tables(d->g_lo, d->g_hi_sinv, d->lo_log, true);
+            if (d->g_sinv_br) {
+                pre_dit = NttScale();
+                pre_dit.mode = 3;
+                pre_dit.lo = d->g_sinv_br;
+            }
+            CUDA_TRY(ctx, ntt_run_tiles(v, cnt, d->tw, (int)log_d, false, true, pre_dit, none, ctx->stream));
             continue;
         }
         if (op == CZK_NTT_IFFT_COSET_FFT) {  // <= 4 points: the tiny kernel works in natural order

@@ -76,6 +76,7 @@ struct Domain {
     int log_d = 0;
     uint32_t* tw = nullptr;
     uint32_t *g_lo = nullptr, *g_hi = nullptr, *gi_lo = nullptr, *gi_hi = nullptr, *g_hi_sinv = nullptr;
+    uint32_t* g_sinv_br = nullptr;  // D^-1 g^bitrev(p) at position p: the fused iFFT -> coset FFT pair's scaling, built on first use
     int lo_log = 0;
     HFr size_inv, group_gen, group_gen_inv, generator_inv;
 };

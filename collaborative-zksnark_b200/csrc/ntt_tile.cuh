@@ -69,7 +69,7 @@ inline NttPlan ntt_make_plan(int log_d, int tile_log = NTT_TILE_LOG) {
 // lo[i & (2^lo_log - 1)] * hi[i >> lo_log] for the element's NATURAL index i (= the bit reversal of its position when
 // the data is in bit-reversed order at that point).
 struct NttScale {
-    int mode = 0;  // 0 none, 1 constant, 2 two-level power table
+    int mode = 0;  // 0 none, 1 constant, 2 two-level power table, 3 one factor per POSITION read from `lo` (already permuted)
     int bitrev = 0;
     uint32_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     const uint32_t* lo = nullptr;
@@ -129,6 +129,7 @@ CZK_HD uint32_t ntt_bitrev(uint32_t v, int bits) {
 template <class TW>
 CZK_HD Fr ntt_scale_factor(const NttScale& sc, size_t pos, int n, TW ldtw) {
     if (sc.mode == 1) return ntt_ld_words(sc.c);
+    if (sc.mode == 3) return ldtw(sc.lo, pos);
     const size_t i = sc.bitrev ? (size_t)ntt_bitrev((uint32_t)pos, n) : pos;
     return Fr::mul(ldtw(sc.lo, i & (((size_t)1 << sc.lo_log) - 1)), ldtw(sc.hi, i >> sc.lo_log));
 }
