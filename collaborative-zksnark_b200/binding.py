@@ -60,6 +60,7 @@ _SIGS = {
     "czk_ntt_fr_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint, C.c_int]),
     "czk_ntt_vec_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint, C.c_int]),
     "czk_domain_params": (C.c_int, [C.c_uint, u64p, u64p, u64p, u64p]),
+    "czk_ntt_mixed_fr": (C.c_int, [C.c_void_p, u64p, C.c_uint, C.c_int, C.c_int]),
     "czk_ntt_mixed_fr_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint, C.c_int]),
     "czk_ntt_mixed_vec_batch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_int, C.c_uint, C.c_int]),
     "czk_mixed_domain_params": (C.c_int, [C.c_uint, u64p, u64p, u64p, u64p]),
@@ -519,6 +520,15 @@ class Context:
         """The same transform over several device vectors in one grid per pass (czk_ntt_vec_batch).
         op: NTT_FFT / NTT_IFFT / NTT_COSET_FFT / NTT_COSET_IFFT / NTT_IFFT_COSET_FFT."""
         self._chk(self.lib.czk_ntt_vec_batch(self.h, self._handles(vecs), len(vecs), log_d, op))
+
+    def ntt_mixed(self, data, inverse=False, coset=False) -> np.ndarray:
+        """Host array of 3 * 2^k Montgomery Fr elements through czk_ntt_mixed_fr; returns a transformed copy."""
+        a = np.array(data, dtype=np.uint64, order="C").reshape(-1, 4)
+        n = a.shape[0]
+        log_m = (n // 3).bit_length() - 1
+        assert n == 3 << log_m, "length must be 3 * 2^k"
+        self._chk(self.lib.czk_ntt_mixed_fr(self.h, a.ctypes.data_as(u64p), log_m, int(inverse), int(coset)))
+        return a
 
     def ntt_mixed_batch(self, vecs, log_m: int, op: int):
         """MixedRadixEvaluationDomain transforms over 3 * 2^log_m points (czk_ntt_mixed_vec_batch), same ops."""

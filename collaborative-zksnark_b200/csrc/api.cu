@@ -470,6 +470,21 @@ int czk_ntt_mixed_vec_batch(czk_ctx* ctx, czk_vec* const* vecs, int count, unsig
     return czk_ntt_mixed_fr_batch(ctx, v.data(), count, log_m, op);
 }
 
+// host vector of 3 * 2^log_m plain field elements, in place (what MixedRadixEvaluationDomain::fft_in_place::<Fr> does)
+int czk_ntt_mixed_fr(czk_ctx* ctx, uint64_t* host_data, unsigned log_m, int inverse, int coset) {
+    if (!ctx || !host_data) return fail(ctx, CZK_ERR_ARG, "czk_ntt_mixed_fr: null argument");
+    if (log_m > 28) return fail(ctx, CZK_ERR_ARG, "czk_ntt_mixed_fr: log_m > 28 unsupported");
+    size_t bytes = ((size_t)3 << log_m) * 32;
+    CUDA_TRY(ctx, cudaSetDevice(ctx->device));
+    CZK_TRY(scratch_reserve(ctx, ctx->up_vec, bytes));
+    CUDA_TRY(ctx, cudaMemcpyAsync(ctx->up_vec.p, host_data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    uint32_t* v = (uint32_t*)ctx->up_vec.p;
+    CZK_TRY(ntt_mixed_batch_dev(ctx, &v, 1, log_m, (inverse ? 1 : 0) | (coset ? 2 : 0)));
+    CUDA_TRY(ctx, cudaMemcpyAsync(host_data, ctx->up_vec.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    return CZK_OK;
+}
+
 int czk_ntt_vec(czk_ctx* ctx, czk_vec* v, unsigned log_d, int inverse, int coset) {
     if (!v || v->n < ((size_t)1 << log_d)) return fail(ctx, CZK_ERR_ARG, "czk_ntt_vec: vector shorter than the domain");
     return czk_ntt_fr_dev(ctx, v->d, log_d, inverse, coset);

@@ -63,3 +63,10 @@ pub fn mixed_domain_constants(log_m: u32) -> ([u64; 4], [u64; 4], [u64; 4], [u64
     assert_eq!(rc, ffi::CZK_OK, "czk_mixed_domain_params");
     (g, gi, si, geni)
 }
+/// In-place mixed-radix transform of a host vector of plain field elements (`fft_in_place::<Fr>` of a 3 * 2^k-point domain).
+pub fn transform_in_place_mixed(log_m: u32, coeffs: &mut Vec<Fr>, op: i32) {
+    assert!(coeffs.len() <= 3usize << log_m);
+    coeffs.resize(3usize << log_m, Fr::from(0u64));
+    let (inverse, coset) = (op & 1, (op >> 1) & 1);
+    with_ctx(|c| check(c, "czk_ntt_mixed_fr", unsafe { ffi::czk_ntt_mixed_fr(c, fr_limbs_mut(coeffs).as_mut_ptr(), log_m, inverse, coset) }));
+}

@@ -95,6 +95,8 @@ CZK_API int czk_domain_params(unsigned log_d, uint64_t group_gen[4], uint64_t gr
  * (mpc-plonk/src/relations/flat.rs:282-300).  Natural order in and out, out[j] = sum_i in[i] w^(ij) with
  * w = get_root_of_unity(3 * 2^log_m); every vector holds 3 * 2^log_m elements.  op as above (CZK_NTT_IFFT_COSET_FFT runs as
  * the two transforms in sequence). */
+/* host vector of 3 * 2^log_m elements, in place (fft_in_place::<Fr> on plain field elements) */
+CZK_API int czk_ntt_mixed_fr(czk_ctx* ctx, uint64_t* host_data, unsigned log_m, int inverse, int coset);
 CZK_API int czk_ntt_mixed_fr_batch(czk_ctx* ctx, uint64_t* const* dev_vecs, int count, unsigned log_m, int op);
 CZK_API int czk_ntt_mixed_vec_batch(czk_ctx* ctx, czk_vec* const* vecs, int count, unsigned log_m, int op);
 /* Domain constants as MixedRadixEvaluationDomain::new computes them (mixed_radix.rs:64-105). */

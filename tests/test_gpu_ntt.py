@@ -212,3 +212,10 @@ def test_mixed_radix_ntt_rejects_bad_arguments(ctx, czk, oracle):
     with pytest.raises(czk.CzkError):
         ctx.ntt_mixed_batch([v], 3, 9)
     ctx.ntt_mixed_batch([], 3, czk.NTT_FFT)
+
+
+def test_mixed_radix_ntt_host_entry(ctx, oracle):
+    x = oracle.random_fr_mont(0xc0de, 3 << 7)
+    for inverse in (False, True):
+        for coset in (False, True):
+            assert (ctx.ntt_mixed(x, inverse, coset) == oracle.ntt_mixed(x, inverse, coset)).all(), (inverse, coset)
