@@ -628,6 +628,28 @@ static int group_scale_shared(czk_ctx* ctx, int scheme, GShare<HF, LIMBS>& self,
     return CZK_OK;
 }
 
+// The local half of GroupShare::scale once sx = open(self) and oy = open(other + y) are known (see group_scale_shared):
+// out = z - scale_pub_group(sx, y) - x.scale_pub_scalar(oy), then out.shift(sx * oy), with x = 0, y = 1@king, z = 0
+template <class HF, int LIMBS>
+static GShare<HF, LIMBS> group_scale_finish(const czk_ctx* ctx, const HPoint<HF>& sx, const HFr& oy) {
+    typedef HPoint<HF> P;
+    GShare<HF, LIMBS> out;
+    out.sh = P::infinity();
+    out.mac = P::infinity();
+    if (ctx->rank == 0) {
+        P neg = sx;
+        neg.negate();
+        out.sh.add(neg);
+        out.mac.add(neg);
+        uint64_t k[4];
+        oy.from_mont().to_limbs(k);
+        P sxoy = P::mul(sx, k, 4);
+        out.sh.add(sxoy);
+        out.mac.add(sxoy);
+    }
+    return out;
+}
+
 template <class HF, int LIMBS>
 static void shift_pub(const czk_ctx* ctx, int scheme, GShare<HF, LIMBS>& s, const HPoint<HF>& el) {
     if (scheme == CZK_SCHEME_PLAIN || ctx->rank == 0) {
@@ -1030,7 +1052,6 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     // from_add_shared scalars: mac = share (key 1), so scale_pub_group gives sh == mac (spdz.rs:419-423)
     S1 rsd;
     rsd.sh = rsd.mac = pre.r_delta;  // delta_g1 * r
-    CZK_TRY((group_scale_shared<HFq, 6>(ctx, scheme, rsd, s, s)));  // ... * s
     // A = r*delta + a_query[0] + MSM + alpha   (calculate_coeff, prover.rs:216-232)
     S1 g_a;
     g_a.sh = g_a.mac = pre.r_delta;
@@ -1038,8 +1059,6 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     g_a.sh.add(a_acc.sh);
     g_a.mac.add(a_acc.mac);
     shift_pub(ctx, scheme, g_a, alpha_g1);
-    S1 s_g_a = g_a;
-    CZK_TRY((group_scale_shared<HFq, 6>(ctx, scheme, s_g_a, s, s)));
     S1 g1_b;
     g1_b.sh = g1_b.mac = pre.s_delta;
     shift_pub(ctx, scheme, g1_b, S1::from_affine_limbs(pk->b10, pk->b10_inf));
@@ -1052,8 +1071,26 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     g2_b.sh.add(b2_acc.sh);
     g2_b.mac.add(b2_acc.mac);
     shift_pub(ctx, scheme, g2_b, beta_g2);
-    S1 r_g1_b = g1_b;
-    CZK_TRY((group_scale_shared<HFq, 6>(ctx, scheme, r_g1_b, r, r)));
+    // The three shared-scalar x shared-point products (r s delta, s A, r B1: GroupShare::scale, share/group.rs:70-109) are
+    // independent: their six openings (the point and the masked scalar of each) travel in one exchange, their MAC checks in
+    // another (group_shares.hpp, open_many) - the reference's 12 broadcasts, counted as such, in 2 all-gathers.
+    S1 s_g_a, r_g1_b;
+    if (scheme == CZK_SCHEME_PLAIN) {
+        s_g_a = g_a;
+        r_g1_b = g1_b;
+        CZK_TRY((group_scale_shared<HFq, 6>(ctx, scheme, rsd, s, s)));
+        CZK_TRY((group_scale_shared<HFq, 6>(ctx, scheme, s_g_a, s, s)));
+        CZK_TRY((group_scale_shared<HFq, 6>(ctx, scheme, r_g1_b, r, r)));
+    } else {
+        const HFr y = ctx->rank == 0 ? HFr::one() : HFr::zero();
+        std::vector<OpenItem> it = {OpenItem::point(rsd),  OpenItem::field(HFr::add(s, y), HFr::add(s, y)),
+                                    OpenItem::point(g_a),  OpenItem::field(HFr::add(s, y), HFr::add(s, y)),
+                                    OpenItem::point(g1_b), OpenItem::field(HFr::add(r, y), HFr::add(r, y))};
+        CZK_TRY(open_many(ctx, scheme, it));
+        rsd = group_scale_finish<HFq, 6>(ctx, it[0].g1_out, it[1].f_out);
+        s_g_a = group_scale_finish<HFq, 6>(ctx, it[2].g1_out, it[3].f_out);
+        r_g1_b = group_scale_finish<HFq, 6>(ctx, it[4].g1_out, it[5].f_out);
+    }
     // C = s*A + r*B1 - r*s*delta + L + H
     S1 g_c = s_g_a;
     g_c.sh.add(r_g1_b.sh);
@@ -1075,9 +1112,13 @@ static int prove_impl(czk_ctx* ctx, int scheme, const czk_pk* pk, const uint64_t
     // pf.reveal() (groth16/src/reveal.rs:7-12)
     HG1 A, Cc;
     HG2 B;
-    CZK_TRY((group_open<HFq, 6>(ctx, scheme, g_a, &A)));
-    CZK_TRY((group_open<HFq2, 12>(ctx, scheme, g2_b, &B)));
-    CZK_TRY((group_open<HFq, 6>(ctx, scheme, g_c, &Cc)));
+    {
+        std::vector<OpenItem> it = {OpenItem::point(g_a), OpenItem::point(g2_b), OpenItem::point(g_c)};
+        CZK_TRY(open_many(ctx, scheme, it));  // the three reveals in one exchange (+ one for the MAC checks)
+        A = it[0].g1_out;
+        B = it[1].g2_out;
+        Cc = it[2].g1_out;
+    }
     proof_inf[0] = (uint8_t)S1::to_affine_limbs(A, proof);
     proof_inf[1] = (uint8_t)S2::to_affine_limbs(B, proof + 12);
     proof_inf[2] = (uint8_t)S1::to_affine_limbs(Cc, proof + 36);

@@ -62,6 +62,7 @@ struct Prover {
         MsmJob job;
         int slot;
         bool is_public;
+        HFr y_sh, y_mac;  // this party's share of the evaluation (publicized with the proofs, in finish_evals)
     };
     std::vector<Pending> pending;
     typedef GShare<HFq, 6> S1;
@@ -183,23 +184,39 @@ struct Prover {
         const int lane = slot & 1;
         if (ctx->lanes[lane].enqueued - ctx->lanes[lane].collected >= CZK_MSM_SLOTS) return fail(ctx, CZK_ERR_ARG, "plonk: opening queue full");
         CZK_TRY(msm_bases_enqueue(ctx, lane, powers, 0, q, 0, 1, D > 1 ? D - 1 : 0, &pd.job));
+        pd.y_sh = HFr::from_limbs(ev);
+        pd.y_mac = spdz ? HFr::from_limbs(evm) : pd.y_sh;
         pending.push_back(pd);
-        HFr y = HFr::from_limbs(ev);
-        if (!is_public) CZK_TRY(field_open1(ctx, scheme, HFr::from_limbs(ev), spdz ? HFr::from_limbs(evm) : HFr::from_limbs(ev), &y));  // y.publicize()
-        y.to_limbs(out->open_val[slot]);
+        if (is_public) pd.y_sh.to_limbs(out->open_val[slot]);
         return CZK_OK;
     }
+    // Collect the opening MSMs enqueued since `first`, then publicize the evaluations (y.publicize(), lib.rs:360-362) and
+    // reveal the proofs (reveal.rs) of all of them in ONE exchange (+ one for the SPDZ MAC checks): group_shares.hpp, open_many.
     int finish_evals(czk_plonk_wiring_proof* share, czk_plonk_wiring_proof* out, size_t first) {
+        std::vector<OpenItem> items;
+        std::vector<size_t> who;
         for (size_t i = first; i < pending.size(); i++) {
             Pending& pd = pending[i];
             uint64_t o[18];
             CZK_TRY(msm_collect(ctx, &pd.job, o, nullptr));
+            pd.job.lane = -1;
             S1 s;
             s.sh = s.mac = S1::from_jac_out(o);
             share->open_pf_inf[pd.slot] = (uint8_t)S1::to_affine_limbs(s.sh, share->open_pf_xy[pd.slot]);
-            HG1 opened = s.sh;
-            if (!pd.is_public) CZK_TRY((group_open<HFq, 6>(ctx, scheme, s, &opened)));  // Proof::reveal
-            out->open_pf_inf[pd.slot] = (uint8_t)S1::to_affine_limbs(opened, out->open_pf_xy[pd.slot]);
+            if (pd.is_public) {
+                out->open_pf_inf[pd.slot] = share->open_pf_inf[pd.slot];
+                std::memcpy(out->open_pf_xy[pd.slot], share->open_pf_xy[pd.slot], sizeof out->open_pf_xy[pd.slot]);
+                continue;
+            }
+            items.push_back(OpenItem::field(pd.y_sh, pd.y_mac));
+            items.push_back(OpenItem::point(s));
+            who.push_back(i);
+        }
+        CZK_TRY(open_many(ctx, scheme, items));
+        for (size_t k = 0; k < who.size(); k++) {
+            const Pending& pd = pending[who[k]];
+            items[2 * k].f_out.to_limbs(out->open_val[pd.slot]);
+            out->open_pf_inf[pd.slot] = (uint8_t)S1::to_affine_limbs(items[2 * k + 1].g1_out, out->open_pf_xy[pd.slot]);
         }
         return CZK_OK;
     }
