@@ -190,3 +190,31 @@ def test_ntt_tile_phases_match_oracle(emu, oracle, n, tile_log):
         else:
             exp = oracle.ntt(oracle.ntt(x, inverse=True, coset=False), inverse=False, coset=True)
         assert (got == exp).all(), (n, tile_log, op)
+
+
+@pytest.mark.parametrize("top", [12, 13, 16])
+def test_two_level_grid_reduction_index_maps(top):
+    """The index maps of k_msm_grid_sums / k_msm_grid_slices (csrc/msm.cu), restated in Python over integers standing in for
+    points: with v = hi * L + lo, the row sums R_hi and column sums C_lo give every bit-slice sum S_j, and
+    sum_j 2^j S_j = sum_v v B_v (what the host tail's Horner recombination computes).  The kernels themselves are covered
+    bit for bit by the GPU parity tests; this pins the arithmetic identity they rely on, for even and odd bit counts."""
+    import random
+
+    rnd = random.Random(top)
+    nb = 1 << top
+    lo_bits = top // 2
+    hi_bits = top - lo_bits
+    L, H = 1 << lo_bits, 1 << hi_bits
+    B = [rnd.randrange(1 << 40) for _ in range(nb)]  # B[v - 1] is the bucket of weight v, v = 1 .. nb
+    R = [sum(B[h * L + k - 1] for k in range(L) if h * L + k) for h in range(H)]
+    C = [sum(B[k * L + l - 1] for k in range(H) if k * L + l) for l in range(L)]
+    S = []
+    for j in range(top + 1):
+        if j == top:
+            S.append(B[H * L - 1])
+            continue
+        col = j < lo_bits
+        bit = j if col else j - lo_bits
+        src, count = (C, L // 2) if col else (R, H // 2)
+        S.append(sum(src[((((k >> bit) << 1) | 1) << bit) | (k & ((1 << bit) - 1))] for k in range(count)))
+    assert sum(s << j for j, s in enumerate(S)) == sum(v * B[v - 1] for v in range(1, nb + 1))
