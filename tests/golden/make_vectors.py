@@ -20,7 +20,7 @@ sys.path.insert(0, str(ROOT / "tests"))
 import numpy as np
 
 from oracle import binding as o
-from helpers import make_points
+from helpers import kzg_powers, make_points, plonk_wiring_instance
 
 
 def digest(arr) -> str:
@@ -68,6 +68,28 @@ def main():
         out["groth16"].append(dict(n_sq=n_sq, proof=digest(res["proof"]), h=digest(res["h"][0]),
                                    a=hexpt(o.G1, res["proof"][:12]), c=hexpt(o.G1, res["proof"][36:48]),
                                    pk_digest=digest(np.concatenate([pk[k].reshape(-1) for k in ("a_query", "b_g1_query", "b_g2_query", "h_query", "l_query")]))))
+    # mixed-radix NTT (3 * 2^log_m points): random_fr_mont(seed, 3 << log_m) through the four transforms
+    out["ntt_mixed"] = []
+    for log_m, seed in ((5, 41), (8, 42)):
+        v = o.random_fr_mont(seed, 3 << log_m)
+        e = dict(log_m=log_m, seed=seed)
+        for name, inv, cos in (("fft", False, False), ("ifft", True, False), ("coset_fft", False, True), ("coset_ifft", True, True)):
+            e[name] = digest(o.ntt_mixed(v, inv, cos))
+        out["ntt_mixed"].append(e)
+    # Plonk wiring argument: kzg_powers(D, tau), plonk_wiring_instance(size=D, seed), stand-in transcript seed 77;
+    # n-party entries share p with king_share_batch(p, parties, seed=9)
+    out["plonk_wiring"] = []
+    for D, parties, scheme in ((64, 1, "plain"), (48, 1, "plain"), (48, 2, "spdz")):
+        tau, seed = 0x60 + D, 50 + D
+        powers = kzg_powers(D, tau)
+        p, w = plonk_wiring_instance(None, seed=seed, size=D)
+        shares = p[None] if parties == 1 else o.king_share_batch(p, parties, seed=9)
+        res = o.plonk_prove_wiring(o.SCHEME_PLAIN if scheme == "plain" else o.SCHEME_SPDZ, shares, w, powers, seed=77, threads=2)
+        assert res["status"] == 1
+        pf = res["proof"]
+        out["plonk_wiring"].append(dict(D=D, parties=parties, scheme=scheme, tau=tau, instance_seed=seed, transcript_seed=77,
+                                        cmt=digest(pf["cmt_xy"]), open_val=digest(pf["open_val"]), open_pf=digest(pf["open_pf_xy"]),
+                                        challenges=digest(pf["challenges"]), share_pf=digest(res["share_pf_xy"])))
     (Path(__file__).resolve().parent / "vectors.json").write_text(json.dumps(out, indent=1))
     print("wrote tests/golden/vectors.json")
 

@@ -7,7 +7,7 @@ from pathlib import Path
 import numpy as np
 import pytest
 
-from helpers import jac_to_affine_ints, make_points
+from helpers import jac_to_affine_ints, kzg_powers, make_points, plonk_wiring_instance
 
 VEC = json.loads((Path(__file__).resolve().parent / "golden" / "vectors.json").read_text())
 
@@ -122,3 +122,85 @@ def test_pymodel_ntt_golden(oracle, pymodel, e):
     for name, inv, cos in (("fft", False, False), ("ifft", True, False), ("coset_fft", False, True), ("coset_ifft", True, True)):
         out = pymodel.ntt(ints, inverse=inv, coset=cos)
         assert digest(oracle.fr_from_ints(out)) == e[name], name
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# mixed-radix transforms (3 * 2^k points) and the Plonk wiring argument
+_FLAVOURS = (("fft", False, False), ("ifft", True, False), ("coset_fft", False, True), ("coset_ifft", True, True))
+
+
+@pytest.mark.parametrize("e", VEC["ntt_mixed"], ids=lambda e: f"3*2^{e['log_m']}")
+def test_oracle_ntt_mixed_golden(oracle, e):
+    v = oracle.random_fr_mont(e["seed"], 3 << e["log_m"])
+    for name, inv, cos in _FLAVOURS:
+        assert digest(oracle.ntt_mixed(v, inv, cos)) == e[name], name
+
+
+@pytest.mark.parametrize("e", VEC["ntt_mixed"], ids=lambda e: f"3*2^{e['log_m']}")
+def test_plain_dft_ntt_mixed_golden(oracle, pymodel, e):
+    """The frozen digests are the plain O(n^2) DFT under get_root_of_unity(n) in Python integers (no shared code with the C
+    restatement of the reference's permute / radix-3 / radix-2 passes)."""
+    R = pymodel.R_MOD
+    n = 3 << e["log_m"]
+    x = oracle.fr_to_ints(oracle.random_fr_mont(e["seed"], n))
+    w, w_inv, n_inv, g_inv = [oracle.fr_to_ints([t])[0] for t in oracle.mixed_domain_params(n)]
+    g = pow(g_inv, R - 2, R)
+
+    def dft(vals, root):
+        pw = [1] * n
+        for i in range(1, n):
+            pw[i] = pw[i - 1] * root % R
+        return [sum(vals[i] * pw[(i * j) % n] for i in range(n)) % R for j in range(n)]
+
+    gp = [pow(g, i, R) for i in range(n)]
+    gip = [pow(g_inv, i, R) for i in range(n)]
+    want = {"fft": dft(x, w), "ifft": [v * n_inv % R for v in dft(x, w_inv)],
+            "coset_fft": dft([a * b % R for a, b in zip(x, gp)], w),
+            "coset_ifft": [v * n_inv % R * b % R for v, b in zip(dft(x, w_inv), gip)]}
+    for name, _, _ in _FLAVOURS:
+        assert digest(oracle.fr_from_ints(want[name])) == e[name], name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("e", VEC["ntt_mixed"], ids=lambda e: f"3*2^{e['log_m']}")
+def test_device_ntt_mixed_golden(ctx, oracle, e):
+    v = oracle.random_fr_mont(e["seed"], 3 << e["log_m"])
+    for name, inv, cos in _FLAVOURS:
+        assert digest(ctx.ntt_mixed(v, inv, cos)) == e[name], name
+
+
+def _wiring_inputs(oracle, e):
+    powers = kzg_powers(e["D"], e["tau"])
+    p, w = plonk_wiring_instance(None, seed=e["instance_seed"], size=e["D"])
+    return powers, p, w
+
+
+@pytest.mark.parametrize("e", VEC["plonk_wiring"], ids=lambda e: f"{e['scheme']}-{e['parties']}p-D{e['D']}")
+def test_oracle_plonk_wiring_golden(oracle, e):
+    powers, p, w = _wiring_inputs(oracle, e)
+    shares = p[None] if e["parties"] == 1 else oracle.king_share_batch(p, e["parties"], seed=9)
+    scheme = oracle.SCHEME_PLAIN if e["scheme"] == "plain" else oracle.SCHEME_SPDZ
+    res = oracle.plonk_prove_wiring(scheme, shares, w, powers, seed=e["transcript_seed"], threads=2)
+    assert res["status"] == 1
+    pf = res["proof"]
+    got = dict(cmt=digest(pf["cmt_xy"]), open_val=digest(pf["open_val"]), open_pf=digest(pf["open_pf_xy"]),
+               challenges=digest(pf["challenges"]), share_pf=digest(res["share_pf_xy"]))
+    assert got == {k: e[k] for k in got}
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("e", [e for e in VEC["plonk_wiring"] if e["parties"] == 1], ids=lambda e: f"{e['scheme']}-D{e['D']}")
+def test_device_plonk_wiring_golden(ctx, czk, oracle, e):
+    ctx.net_init(0, 1, None)
+    powers, p, w = _wiring_inputs(oracle, e)
+    D = e["D"]
+    mixed = bool(D & (D - 1))
+    log = (D // 3 if mixed else D).bit_length() - 1
+    b = ctx.bases_upload(1, powers)
+    try:
+        got = czk.plonk_prove_wiring(ctx, czk.SCHEME_PLAIN, b, log, ctx.vec_from(p), None, ctx.vec_from(w), seed=e["transcript_seed"], mixed=mixed)
+    finally:
+        b.free()
+    pf = got["proof"]
+    assert digest(pf["cmt_xy"]) == e["cmt"] and digest(pf["open_val"]) == e["open_val"]
+    assert digest(pf["open_pf_xy"]) == e["open_pf"] and digest(pf["challenges"]) == e["challenges"]
