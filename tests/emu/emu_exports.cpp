@@ -228,6 +228,16 @@ EXPORT int emu_ntt(uint64_t* data, int n, int op, int tile_log, const uint64_t* 
         host_run_tiles(data, tw.data(), n, false, true, tables(g_lo, g_hi_sinv, true), none, tile_log);
         return 1;
     }
+    if (op == 5) {  // the same pair with the product's one-factor-per-position table (api.cu: g_sinv_br[p] = D^-1 g^bitrev(p))
+        std::vector<uint32_t> nat = powers(g, sinv, d), br(nat.size());
+        for (size_t pos = 0; pos < d; pos++) std::memcpy(&br[8 * pos], &nat[8 * (size_t)ntt_bitrev((uint32_t)pos, n)], 32);
+        NttScale direct;
+        direct.mode = 3;
+        direct.lo = br.data();
+        host_run_tiles(data, tw.data(), n, true, false, none, none, tile_log);
+        host_run_tiles(data, tw.data(), n, false, true, direct, none, tile_log);
+        return 1;
+    }
     host_run_tiles(data, tw.data(), n, inverse, false, op == 2 ? tables(g_lo, g_hi, false) : none, none, tile_log);
     // k_bitrev_scale: swap into natural order, the inverse scalings ride along
     std::vector<uint64_t> tmp(data, data + 4 * d);

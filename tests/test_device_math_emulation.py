@@ -182,7 +182,7 @@ def test_ntt_tile_phases_match_oracle(emu, oracle, n, tile_log):
     x = oracle.random_fr_mont(0x47 + n, d)
     f = emu.emu_ntt
     f.restype = C.c_int
-    for op in range(5):
+    for op in range(6):  # 4: the fused pair with two-level scale tables, 5: with the pre-permuted one-factor-per-position table
         got = x.copy()
         assert f(P(got), n, op, tile_log, P(dp["group_gen"]), P(gen22), P(dp["generator_inv"]), P(dp["size_inv"])) == 1
         if op < 4:
