@@ -312,22 +312,12 @@ __global__ void k_mr_combine(const uint32_t* __restrict__ y, uint32_t* __restric
                              Fr4 c4, int scale, size_t M) {
     size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= M) return;
-    Fr w = ldg_fr(wpow, j);
-    Fr y0 = ld_fr(y, j), y1 = ld_fr(y, M + j), y2 = ld_fr(y, 2 * M + j);
-    if (scale) {
-        Fr c = fr_from_u64x4(c4.v);
-        y0 = Fr::mul(y0, c);
-        y1 = Fr::mul(y1, c);
-        y2 = Fr::mul(y2, c);
-    }
-    Fr t1 = Fr::mul(y1, w), t2 = Fr::mul(y2, Fr::mul(w, w));
-    Fr zeta = fr_from_u64x4(zeta4.v);
-    Fr z1 = Fr::mul(t1, zeta), z2 = Fr::mul(t2, zeta);
-    // 1 + zeta + zeta^2 = 0: zeta^2 t = -(t + zeta t)
-    Fr zz1 = Fr::neg(Fr::add(t1, z1)), zz2 = Fr::neg(Fr::add(t2, z2));
-    st_fr(out, j, Fr::add(y0, Fr::add(t1, t2)));
-    st_fr(out, M + j, Fr::add(y0, Fr::add(z1, zz2)));
-    st_fr(out, 2 * M + j, Fr::add(y0, Fr::add(zz1, z2)));
+    const Fr yv[3] = {ld_fr(y, j), ld_fr(y, M + j), ld_fr(y, 2 * M + j)};
+    Fr out3[3];
+    ntt_mixed_combine3(yv, ldg_fr(wpow, j), fr_from_u64x4(zeta4.v), fr_from_u64x4(c4.v), scale != 0, out3);
+    st_fr(out, j, out3[0]);
+    st_fr(out, M + j, out3[1]);
+    st_fr(out, 2 * M + j, out3[2]);
 }
 cudaError_t ntt_mixed_split(const uint32_t* in, uint32_t* out, size_t M, cudaStream_t st) {
     k_mr_split<<<(unsigned)((3 * M + 255) / 256), 256, 0, st>>>(in, out, M); CZK_LAUNCHED();

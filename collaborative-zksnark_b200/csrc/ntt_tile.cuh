@@ -203,4 +203,22 @@ CZK_HD void ntt_phase_thread(Tile& tile, unsigned u, const NttTileGeom& g, bool 
     for (int k = 0; k < 8; k++) tile.store(e0 | ((unsigned)k << kp), x[k]);
 }
 
+// The combining step of a mixed-radix transform over 3 M points (ntt.cu, k_mr_combine): from the three radix-2 outputs at
+// index j (y[r] = Y_r[j]), w = omega^j and zeta = omega^M, X[j + s M] = y0 + zeta^s w y1 + zeta^(2 s) w^2 y2 for s = 0, 1, 2.
+// scale: multiply everything by c (3^-1 on the inverse).  Two products by zeta: zeta^2 t = -(t + zeta t).
+CZK_HD void ntt_mixed_combine3(const Fr y[3], const Fr& w, const Fr& zeta, const Fr& c, bool scale, Fr out[3]) {
+    Fr y0 = y[0], y1 = y[1], y2 = y[2];
+    if (scale) {
+        y0 = Fr::mul(y0, c);
+        y1 = Fr::mul(y1, c);
+        y2 = Fr::mul(y2, c);
+    }
+    const Fr t1 = Fr::mul(y1, w), t2 = Fr::mul(y2, Fr::mul(w, w));
+    const Fr z1 = Fr::mul(t1, zeta), z2 = Fr::mul(t2, zeta);
+    const Fr zz1 = Fr::neg(Fr::add(t1, z1)), zz2 = Fr::neg(Fr::add(t2, z2));
+    out[0] = Fr::add(y0, Fr::add(t1, t2));
+    out[1] = Fr::add(y0, Fr::add(z1, zz2));
+    out[2] = Fr::add(y0, Fr::add(zz1, z2));
+}
+
 }  // namespace czk

@@ -250,3 +250,27 @@ EXPORT int emu_ntt(uint64_t* data, int n, int op, int tile_log, const uint64_t* 
     }
     return 1;
 }
+
+// A whole mixed-radix transform over 3 * 2^n points the way the device runs it (api.cu, ntt_mixed_batch_dev): de-interleave,
+// three radix-2 transforms through the tile emulation above (op 0 forward / 1 inverse, natural order out), then
+// ntt_mixed_combine3 - the device's own combining arithmetic - with w^j (or w^-j), zeta = w^M and 3^-1 on the inverse.
+// omega2 / size_inv2: the radix-2 domain of 2^n points; omega3: get_root_of_unity(3 * 2^n) (or its inverse for inverse = 1).
+EXPORT int emu_ntt_mixed(uint64_t* data, int n, int inverse, int tile_log, const uint64_t* omega2, const uint64_t* gen, const uint64_t* gen_inv,
+                         const uint64_t* size_inv2, const uint64_t* omega3, const uint64_t* third_inv) {
+    const size_t M = (size_t)1 << n;
+    std::vector<uint64_t> sub(3 * M * 4);
+    for (size_t i = 0; i < 3 * M; i++) std::memcpy(&sub[((i % 3) * M + i / 3) * 4], data + 4 * i, 32);
+    for (int r = 0; r < 3; r++)
+        if (!emu_ntt(sub.data() + r * M * 4, n, inverse ? 1 : 0, tile_log, omega2, gen, gen_inv, size_inv2)) return 0;
+    const Fr w = ld<Fr>(omega3), c = ld<Fr>(third_inv), zeta = Fr::pow_u64(w, M);
+    Fr wj = Fr::one();
+    for (size_t j = 0; j < M; j++) {
+        const Fr y[3] = {ld<Fr>(sub.data() + 4 * j), ld<Fr>(sub.data() + 4 * (M + j)), ld<Fr>(sub.data() + 4 * (2 * M + j))};
+        Fr out[3];
+        ntt_mixed_combine3(y, wj, zeta, c, inverse != 0, out);
+        for (int s3 = 0; s3 < 3; s3++) st(data + 4 * (j + (size_t)s3 * M), out[s3]);
+        wj = Fr::mul(wj, w);
+    }
+    return 1;
+}
+

@@ -218,3 +218,23 @@ def test_two_level_grid_reduction_index_maps(top):
         src, count = (C, L // 2) if col else (R, H // 2)
         S.append(sum(src[((((k >> bit) << 1) | 1) << bit) | (k & ((1 << bit) - 1))] for k in range(count)))
     assert sum(s << j for j, s in enumerate(S)) == sum(v * B[v - 1] for v in range(1, nb + 1))
+
+
+@pytest.mark.parametrize("n,tile_log", [(4, 4), (7, 5), (9, 11)])
+@pytest.mark.parametrize("inverse", [0, 1])
+def test_mixed_radix_transform_emulated(emu, oracle, pymodel, n, tile_log, inverse):
+    """The device's mixed-radix transform over 3 * 2^n points on the host: de-interleave, the tile kernels' own phase code for
+    the three radix-2 transforms, and ntt_mixed_combine3 (the arithmetic of k_mr_combine) - against the oracle's restatement
+    of MixedRadixEvaluationDomain."""
+    M, N = 1 << n, 3 << n
+    dp = oracle.domain_params(M)
+    gen22 = oracle.fr_from_ints([22])[0]
+    w3, w3_inv, _, _ = oracle.mixed_domain_params(N)
+    third_inv = oracle.fr_from_ints([pow(3, pymodel.R_MOD - 2, pymodel.R_MOD)])[0]
+    x = oracle.random_fr_mont(0x61 + n, N)
+    got = x.copy()
+    f = emu.emu_ntt_mixed
+    f.restype = C.c_int
+    assert f(P(got), n, inverse, tile_log, P(dp["group_gen"]), P(gen22), P(dp["generator_inv"]), P(dp["size_inv"]),
+             P(w3_inv if inverse else w3), P(third_inv)) == 1
+    assert (got == oracle.ntt_mixed(x, inverse=bool(inverse))).all()
